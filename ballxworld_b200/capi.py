@@ -1,0 +1,344 @@
+"""ctypes binding of csrc/libbxw_cuda.so — one method per entry point of include/bxw_cuda.h."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "csrc", "libbxw_cuda.so")
+
+VERTEX_DTYPE = np.dtype(
+    [
+        ("position", "<u4"),
+        ("color", "<u4"),
+        ("texcoord", "<f4", (3,)),
+        ("index", "<i4"),
+        ("barycentric_color_offset", "<f4", (4,)),
+    ]
+)
+SPAN_DTYPE = np.dtype([("v_off", "<u8"), ("i_off", "<u8"), ("v_count", "<u4"), ("i_count", "<u4")])
+CHANGE_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("z", "<i4"), ("from", "<u4"), ("to", "<u4")])
+assert VERTEX_DTYPE.itemsize == 40 and SPAN_DTYPE.itemsize == 24 and CHANGE_DTYPE.itemsize == 20
+
+ERROR_NAMES = {
+    -1: "BXW_E_INVALID",
+    -2: "BXW_E_CUDA",
+    -3: "BXW_E_NOMEM",
+    -4: "BXW_E_UNKNOWN_ID",
+    -5: "BXW_E_NOSPACE",
+    -6: "BXW_E_BAD_RLE",
+    -7: "BXW_E_NO_REGISTRY",
+}
+
+
+class BxwError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"{ERROR_NAMES.get(code, code)}: {message}")
+        self.code = code
+
+
+class BlockDef(C.Structure):
+    _fields_ = [
+        ("present", C.c_uint8),
+        ("mesh_kind", C.c_uint8),
+        ("debug_color", C.c_float * 3),
+        ("tex", C.c_uint32 * 6),
+    ]
+
+
+def library_path():
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def load_library():
+    """Loads the CUDA library. Fails loudly when it has not been built: there is no other implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(
+            f"{_LIB_PATH} is missing: build it with `python -m ballxworld_b200.build` (nvcc, sm_100a). "
+            "ballxworld_b200 has no CPU fallback."
+        )
+    L = C.CDLL(_LIB_PATH)
+    vp, u32p, u64p = C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+    sig = {
+        "bxw_create": ([C.c_int, C.POINTER(vp)], C.c_int),
+        "bxw_destroy": ([vp], None),
+        "bxw_last_error": ([vp], C.c_char_p),
+        "bxw_set_stream": ([vp, vp], C.c_int),
+        "bxw_synchronize": ([vp], C.c_int),
+        "bxw_kernel_launches": ([vp], C.c_uint64),
+        "bxw_set_registry": ([vp, C.POINTER(BlockDef), C.c_uint32], C.c_int),
+        "bxw_set_gen_ids": ([vp] + [C.c_uint16] * 5, C.c_int),
+        "bxw_gen_chunk": ([vp, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, vp], C.c_int),
+        "bxw_mesh_chunk27": ([vp, C.POINTER(vp), vp], C.c_int),
+        "bxw_mesh_chunk27_rle": ([vp, C.POINTER(vp), C.POINTER(C.c_size_t), vp], C.c_int),
+        "bxw_mesh_fetch": ([vp, vp, vp], C.c_int),
+        "bxw_is_chunk_trivial": ([vp, vp, C.c_size_t, C.POINTER(C.c_int)], C.c_int),
+        "bxw_rle_bound": ([C.c_size_t], C.c_size_t),
+        "bxw_rle_compress": ([vp, vp, C.c_size_t, vp, vp], C.c_int),
+        "bxw_rle_decompress": ([vp, vp, vp, C.c_size_t, vp], C.c_int),
+        "bxw_region_create": ([vp, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32], C.c_int),
+        "bxw_region_destroy": ([vp], C.c_int),
+        "bxw_region_generate": ([vp, C.c_uint64, C.c_int], C.c_int),
+        "bxw_region_heightmap": ([vp, vp, vp, vp], C.c_int),
+        "bxw_region_upload_chunk": ([vp, C.c_int32, C.c_int32, C.c_int32, vp], C.c_int),
+        "bxw_region_download_chunk": ([vp, C.c_int32, C.c_int32, C.c_int32, vp], C.c_int),
+        "bxw_region_mesh_reserve": ([vp, C.c_uint64, C.c_uint64], C.c_int),
+        "bxw_region_mesh": ([vp, u64p, u64p], C.c_int),
+        "bxw_region_generate_and_mesh": ([vp, C.c_uint64, C.c_int, u64p, u64p], C.c_int),
+        "bxw_region_mesh_spans": ([vp, vp], C.c_int),
+        "bxw_region_mesh_fetch": ([vp, vp, C.c_uint64, vp, C.c_uint64], C.c_int),
+        "bxw_region_apply_changes": ([vp, vp, C.c_uint32, u32p], C.c_int),
+        "bxw_region_remesh_dirty": ([vp, u32p], C.c_int),
+        "bxw_region_halo_bytes": ([vp], C.c_size_t),
+        "bxw_region_halo_export": ([vp, C.c_int, vp], C.c_int),
+        "bxw_region_halo_import": ([vp, C.c_int, vp], C.c_int),
+        "bxw_region_device_ptrs": ([vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)], C.c_int),
+        "bxw_terragen_noise2": ([vp, C.c_uint64, vp, vp, C.c_size_t, vp], C.c_int),
+        "bxw_timer_start": ([vp], C.c_int),
+        "bxw_timer_stop_ms": ([vp, C.POINTER(C.c_float)], C.c_int),
+        "bxw_mesh_kernel_time_ms": ([vp, C.POINTER(C.c_float), u64p, C.c_int], C.c_int),
+    }
+    for name, (argtypes, restype) in sig.items():
+        fn = getattr(L, name)  # AttributeError = the library does not export what the header declares
+        fn.argtypes = argtypes
+        fn.restype = restype
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = None  # filled lazily for tests
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u32(a, n=None):
+    a = np.ascontiguousarray(a, dtype=np.uint32)
+    if n is not None and a.size != n:
+        raise ValueError(f"expected {n} u32 words, got {a.size}")
+    return a
+
+
+class Context:
+    """One bxw_ctx: bound to one CUDA device; calls must be serialised by the caller."""
+
+    def __init__(self, device=0):
+        self.L = load_library()
+        h = C.c_void_p()
+        rc = self.L.bxw_create(device, C.byref(h))
+        if rc != 0:
+            raise BxwError(rc, f"bxw_create(device={device}) failed (no usable sm_100 CUDA device?)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.bxw_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise BxwError(rc, self.L.bxw_last_error(self.h).decode())
+
+    # ---- context ----
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self.L.bxw_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        self._ck(self.L.bxw_synchronize(self.h))
+
+    def kernel_launches(self):
+        return int(self.L.bxw_kernel_launches(self.h))
+
+    def set_registry(self, defs):
+        """defs: sequence of dicts {present, mesh_kind, debug_color[3], tex[6]} indexed by block id."""
+        arr = (BlockDef * len(defs))()
+        for i, d in enumerate(defs):
+            arr[i].present = int(d.get("present", 1))
+            arr[i].mesh_kind = int(d["mesh_kind"])
+            for k in range(3):
+                arr[i].debug_color[k] = float(d["debug_color"][k])
+            for k in range(6):
+                arr[i].tex[k] = int(d["tex"][k])
+        self._ck(self.L.bxw_set_registry(self.h, arr, len(defs)))
+
+    def set_gen_ids(self, void, grass, dirt, stone, snow_grass):
+        self._ck(self.L.bxw_set_gen_ids(self.h, void, grass, dirt, stone, snow_grass))
+
+    # ---- per-chunk drop-ins ----
+    def gen_chunk(self, seed, cx, cy, cz, out=None):
+        out = np.empty(32768, dtype=np.uint32) if out is None else out
+        self._ck(self.L.bxw_gen_chunk(self.h, seed, cx, cy, cz, _ptr(out)))
+        return out
+
+    def _fetch(self, span):
+        v = np.empty(int(span["v_count"]), dtype=VERTEX_DTYPE)
+        ix = np.empty(int(span["i_count"]), dtype=np.uint32)
+        self._ck(self.L.bxw_mesh_fetch(self.h, _ptr(v), _ptr(ix)))
+        return v, ix
+
+    def mesh_chunk27(self, dense27):
+        arrs = [_u32(a, 32768) for a in dense27]
+        if len(arrs) != 27:
+            raise ValueError("mesh_chunk27 needs 27 chunks")
+        ptrs = (C.c_void_p * 27)(*[a.ctypes.data for a in arrs])
+        span = np.zeros(1, dtype=SPAN_DTYPE)
+        self._ck(self.L.bxw_mesh_chunk27(self.h, ptrs, _ptr(span)))
+        return self._fetch(span[0])
+
+    def mesh_chunk27_rle(self, rle27):
+        arrs = [_u32(a) for a in rle27]
+        if len(arrs) != 27:
+            raise ValueError("mesh_chunk27_rle needs 27 chunks")
+        ptrs = (C.c_void_p * 27)(*[a.ctypes.data for a in arrs])
+        lens = (C.c_size_t * 27)(*[a.size for a in arrs])
+        span = np.zeros(1, dtype=SPAN_DTYPE)
+        self._ck(self.L.bxw_mesh_chunk27_rle(self.h, ptrs, lens, _ptr(span)))
+        return self._fetch(span[0])
+
+    def is_chunk_trivial(self, rle_words):
+        w = _u32(rle_words)
+        out = C.c_int()
+        self._ck(self.L.bxw_is_chunk_trivial(self.h, _ptr(w), w.size, C.byref(out)))
+        return bool(out.value)
+
+    # ---- RLE codec ----
+    def rle_compress(self, dense):
+        """dense: (n, 32768) u32 -> (words, offsets[n+1])"""
+        d = np.ascontiguousarray(dense, dtype=np.uint32).reshape(-1, 32768)
+        n = d.shape[0]
+        words = np.empty(self.L.bxw_rle_bound(n), dtype=np.uint32)
+        offs = np.empty(n + 1, dtype=np.uint64)
+        self._ck(self.L.bxw_rle_compress(self.h, _ptr(d), n, _ptr(words), _ptr(offs)))
+        return words[: int(offs[n])].copy(), offs
+
+    def rle_decompress(self, words, offsets):
+        w = _u32(words)
+        o = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = o.size - 1
+        out = np.empty((n, 32768), dtype=np.uint32)
+        self._ck(self.L.bxw_rle_decompress(self.h, _ptr(w), _ptr(o), n, _ptr(out)))
+        return out
+
+    # ---- region ----
+    def region_create(self, cx0, cy0, cz0, nx, ny, nz):
+        self._ck(self.L.bxw_region_create(self.h, cx0, cy0, cz0, nx, ny, nz))
+        self.region_dims = (nx, ny, nz)
+        self.region_origin = (cx0, cy0, cz0)
+
+    def region_destroy(self):
+        self._ck(self.L.bxw_region_destroy(self.h))
+
+    def region_generate(self, seed, precision=64):
+        self._ck(self.L.bxw_region_generate(self.h, seed, precision))
+
+    def region_heightmap(self, raw=False):
+        nx, ny, nz = self.region_dims
+        W, D = (nx + 2) * 32, (nz + 2) * 32
+        h = np.empty((D, W), dtype=np.int32)
+        e = np.empty((D, W), dtype=np.uint8)
+        r = np.empty((D, W), dtype=np.float64) if raw else None
+        self._ck(self.L.bxw_region_heightmap(self.h, _ptr(h), _ptr(e), _ptr(r) if raw else None))
+        return (h, e, r) if raw else (h, e)
+
+    def region_upload_chunk(self, lx, ly, lz, blocks):
+        b = _u32(blocks, 32768)
+        self._ck(self.L.bxw_region_upload_chunk(self.h, lx, ly, lz, _ptr(b)))
+
+    def region_download_chunk(self, lx, ly, lz):
+        out = np.empty(32768, dtype=np.uint32)
+        self._ck(self.L.bxw_region_download_chunk(self.h, lx, ly, lz, _ptr(out)))
+        return out
+
+    def region_mesh_reserve(self, max_vertices, max_indices):
+        self._ck(self.L.bxw_region_mesh_reserve(self.h, max_vertices, max_indices))
+
+    def region_mesh(self):
+        v, i = C.c_uint64(), C.c_uint64()
+        self._ck(self.L.bxw_region_mesh(self.h, C.byref(v), C.byref(i)))
+        return v.value, i.value
+
+    def region_generate_and_mesh(self, seed, precision=64):
+        v, i = C.c_uint64(), C.c_uint64()
+        self._ck(self.L.bxw_region_generate_and_mesh(self.h, seed, precision, C.byref(v), C.byref(i)))
+        return v.value, i.value
+
+    def region_mesh_spans(self):
+        nx, ny, nz = self.region_dims
+        spans = np.empty(nx * ny * nz, dtype=SPAN_DTYPE)
+        self._ck(self.L.bxw_region_mesh_spans(self.h, _ptr(spans)))
+        return spans
+
+    def region_mesh_fetch(self, n_vertices, n_indices, vertices=None, indices=None):
+        v = np.empty(n_vertices, dtype=VERTEX_DTYPE) if vertices is None else vertices
+        ix = np.empty(n_indices, dtype=np.uint32) if indices is None else indices
+        self._ck(self.L.bxw_region_mesh_fetch(self.h, _ptr(v), n_vertices, _ptr(ix), n_indices))
+        return v, ix
+
+    def region_mesh_fetch_ptr(self, vptr, n_vertices, iptr, n_indices):
+        self._ck(self.L.bxw_region_mesh_fetch(self.h, C.c_void_p(vptr), n_vertices, C.c_void_p(iptr), n_indices))
+
+    def region_apply_changes(self, changes):
+        ch = np.ascontiguousarray(changes, dtype=CHANGE_DTYPE)
+        nd = C.c_uint32()
+        self._ck(self.L.bxw_region_apply_changes(self.h, _ptr(ch), ch.size, C.byref(nd)))
+        return nd.value
+
+    def region_remesh_dirty(self):
+        n = C.c_uint32()
+        self._ck(self.L.bxw_region_remesh_dirty(self.h, C.byref(n)))
+        return n.value
+
+    def region_halo_bytes(self):
+        return int(self.L.bxw_region_halo_bytes(self.h))
+
+    def region_halo_export(self, face, dev_ptr):
+        self._ck(self.L.bxw_region_halo_export(self.h, face, C.c_void_p(dev_ptr)))
+
+    def region_halo_import(self, face, dev_ptr):
+        self._ck(self.L.bxw_region_halo_import(self.h, face, C.c_void_p(dev_ptr)))
+
+    def region_device_ptrs(self):
+        b, v, i = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._ck(self.L.bxw_region_device_ptrs(self.h, C.byref(b), C.byref(v), C.byref(i)))
+        return b.value, v.value, i.value
+
+    def terragen_noise2(self, seed, xs, ys):
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        ys = np.ascontiguousarray(ys, dtype=np.float64)
+        out = np.empty(xs.size, dtype=np.float64)
+        self._ck(self.L.bxw_terragen_noise2(self.h, seed, _ptr(xs), _ptr(ys), xs.size, _ptr(out)))
+        return out
+
+    # ---- timing ----
+    def timer_start(self):
+        self._ck(self.L.bxw_timer_start(self.h))
+
+    def timer_stop_ms(self):
+        ms = C.c_float()
+        self._ck(self.L.bxw_timer_stop_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def mesh_kernel_time_ms(self, reset=False):
+        ms, n = C.c_float(), C.c_uint64()
+        self._ck(self.L.bxw_mesh_kernel_time_ms(self.h, C.byref(ms), C.byref(n), 1 if reset else 0))
+        return ms.value, n.value

@@ -1,0 +1,697 @@
+// bxw_api.cu — the extern "C" boundary of libbxw_cuda.so (include/bxw_cuda.h): context, registry, GPU-resident
+// region storage, and the host-side orchestration of the kernels. No CPU fallback anywhere: every entry point that
+// produces blocks or meshes launches the sm_100a kernels.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "device_common.cuh"
+
+using namespace bxw;
+
+namespace {
+
+struct Region {
+    bool live = false;
+    int32_t cx0 = 0, cy0 = 0, cz0 = 0; // world chunk coordinate of interior chunk (0,0,0)
+    uint32_t nx = 0, ny = 0, nz = 0;   // interior dims
+    int SX = 0, SY = 0, SZ = 0;        // storage dims (shell included)
+    uint32_t *blocks = nullptr;
+    int32_t *hmap = nullptr;
+    double *raw = nullptr;
+    bool have_hmap = false;
+    CellPointDev *cells = nullptr;
+    size_t cells_cap = 0;
+    uint32_t *work = nullptr, *work_span = nullptr; // full interior work list
+    uint32_t n_work = 0;
+    bxw_mesh_span *spans = nullptr;
+    bxw_vertex *varena = nullptr;
+    uint32_t *iarena = nullptr;
+    unsigned long long v_cap = 0, i_cap = 0;
+    bool reserved = false;
+    MeshCounters *counters = nullptr;
+    MeshCounters *h_counters = nullptr; // pinned
+    uint8_t *dirty = nullptr;           // [n_work] interior dirty flags
+    uint32_t *dirty_work = nullptr, *dirty_span = nullptr, *dirty_count = nullptr;
+    size_t n_storage() const { return (size_t)SX * SY * SZ; }
+};
+
+} // namespace
+
+struct bxw_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    // registry
+    uint32_t reg_n = 0;
+    std::vector<bxw_block_def> reg_host;
+    uint8_t *d_kind = nullptr;
+    float *d_texf = nullptr, *d_color = nullptr;
+    bool have_gen_ids = false;
+    uint16_t gen_ids[5] = {0, 0, 0, 0, 0};
+    // tables
+    MeshTables *d_tables = nullptr;
+    GenTables *d_gen = nullptr;
+    bool gen_seed_valid = false;
+    uint64_t gen_seed = 0;
+    // regions
+    Region region;  // the user's region
+    Region scratch; // 3x3x3 storage behind the per-chunk drop-ins
+    // timing
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_m0 = nullptr, ev_m1 = nullptr;
+    double mesh_ms = 0.0;
+    uint64_t mesh_launches = 0;
+};
+
+namespace {
+
+int fail(bxw_ctx *c, int code, const char *fmt, ...) {
+    if (c) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        c->err = buf;
+    }
+    return code;
+}
+
+#define CK(call)                                                                                            \
+    do {                                                                                                    \
+        cudaError_t e_ = (call);                                                                            \
+        if (e_ != cudaSuccess) return fail(ctx, BXW_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+DeviceRegistry dev_registry(const bxw_ctx *c) {
+    DeviceRegistry r;
+    r.kind = c->d_kind;
+    r.texf = c->d_texf;
+    r.color = c->d_color;
+    r.n = c->reg_n;
+    return r;
+}
+
+// ---- host restatement of the seeding arithmetic the generator needs (third-party crates, see oracle/noise.c) ----
+uint32_t splitmix_next_u32(uint64_t &x) { // rand_xoshiro 0.6.0 SplitMix64::next_u32
+    x += 0x9e3779b97f4a7c15ULL;
+    uint64_t z = x;
+    z = (z ^ (z >> 33)) * 0x62A9D9ED799705F5ULL;
+    z = (z ^ (z >> 28)) * 0xCB24D0A5C88C35B3ULL;
+    return (uint32_t)(z >> 32);
+}
+
+void permutation_table(uint32_t seed, uint8_t out[256]) { // noise 0.8.2 PermutationTable::new
+    uint32_t s[4] = {1u, seed, seed, seed}; // XorShiftRng::from_seed([1,0,0,0, seed x3] LE)
+    auto next = [&]() {
+        uint32_t t = s[0] ^ (s[0] << 11);
+        s[0] = s[1];
+        s[1] = s[2];
+        s[2] = s[3];
+        s[3] = s[3] ^ (s[3] >> 19) ^ (t ^ (t >> 8));
+        return s[3];
+    };
+    for (int i = 0; i < 256; i++) out[i] = (uint8_t)i;
+    for (uint32_t i = 255; i >= 1; i--) { // rand 0.7.3 SliceRandom::shuffle + UniformInt::sample_single
+        const uint32_t range = i + 1;
+        const uint32_t zone = (range << __builtin_clz(range)) - 1u;
+        uint32_t hi;
+        for (;;) {
+            const uint64_t m = (uint64_t)next() * range;
+            hi = (uint32_t)(m >> 32);
+            if ((uint32_t)m <= zone) break;
+        }
+        const uint8_t tmp = out[i];
+        out[i] = out[hi];
+        out[hi] = tmp;
+    }
+}
+
+int ensure_gen_tables(bxw_ctx *ctx, uint64_t seed) {
+    if (ctx->gen_seed_valid && ctx->gen_seed == seed) return BXW_OK;
+    GenTables t;
+    uint64_t sd = seed; // SplitMix64::seed_from_u64 (stdgen.rs:106)
+    for (int i = 0; i < 7; i++) permutation_table(splitmix_next_u32(sd), t.perm[i]);
+    if (!ctx->d_gen) CK(cudaMalloc(&ctx->d_gen, sizeof(GenTables)));
+    CK(cudaMemcpyAsync(ctx->d_gen, &t, sizeof t, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream)); // t is a stack object
+    ctx->gen_seed = seed;
+    ctx->gen_seed_valid = true;
+    return BXW_OK;
+}
+
+void region_free(Region &r) {
+    cudaFree(r.blocks);
+    cudaFree(r.hmap);
+    cudaFree(r.raw);
+    cudaFree(r.cells);
+    cudaFree(r.work);
+    cudaFree(r.work_span);
+    cudaFree(r.spans);
+    cudaFree(r.varena);
+    cudaFree(r.iarena);
+    cudaFree(r.counters);
+    cudaFree(r.dirty);
+    cudaFree(r.dirty_work);
+    cudaFree(r.dirty_span);
+    cudaFree(r.dirty_count);
+    if (r.h_counters) cudaFreeHost(r.h_counters);
+    r = Region();
+}
+
+int region_alloc(bxw_ctx *ctx, Region &r, int32_t cx0, int32_t cy0, int32_t cz0, uint32_t nx, uint32_t ny, uint32_t nz) {
+    region_free(r);
+    r.cx0 = cx0;
+    r.cy0 = cy0;
+    r.cz0 = cz0;
+    r.nx = nx;
+    r.ny = ny;
+    r.nz = nz;
+    r.SX = (int)nx + 2;
+    r.SY = (int)ny + 2;
+    r.SZ = (int)nz + 2;
+    const size_t nst = r.n_storage();
+    if (nst >= (1ull << 32)) return fail(ctx, BXW_E_INVALID, "region too large");
+    r.n_work = nx * ny * nz;
+    CK(cudaMalloc(&r.blocks, nst * kChunkVoxels * sizeof(uint32_t)));
+    CK(cudaMalloc(&r.hmap, (size_t)r.SX * 32 * r.SZ * 32 * sizeof(int32_t)));
+    CK(cudaMalloc(&r.work, r.n_work * sizeof(uint32_t)));
+    CK(cudaMalloc(&r.work_span, r.n_work * sizeof(uint32_t)));
+    CK(cudaMalloc(&r.spans, r.n_work * sizeof(bxw_mesh_span)));
+    CK(cudaMalloc(&r.counters, sizeof(MeshCounters)));
+    CK(cudaMallocHost(&r.h_counters, sizeof(MeshCounters)));
+    CK(cudaMalloc(&r.dirty, r.n_work));
+    CK(cudaMalloc(&r.dirty_work, r.n_work * sizeof(uint32_t)));
+    CK(cudaMalloc(&r.dirty_span, r.n_work * sizeof(uint32_t)));
+    CK(cudaMalloc(&r.dirty_count, sizeof(uint32_t)));
+    CK(cudaMemsetAsync(r.spans, 0, r.n_work * sizeof(bxw_mesh_span), ctx->stream));
+    CK(cudaMemsetAsync(r.dirty, 0, r.n_work, ctx->stream));
+    CK(cudaMemsetAsync(r.counters, 0, sizeof(MeshCounters), ctx->stream));
+    // interior work list: span slot = ix + nx*(iz + nz*iy); processing order x, then z, then y
+    std::vector<uint32_t> w(r.n_work), ws(r.n_work);
+    size_t k = 0;
+    for (uint32_t iy = 0; iy < ny; iy++)
+        for (uint32_t iz = 0; iz < nz; iz++)
+            for (uint32_t ix = 0; ix < nx; ix++) {
+                w[k] = (uint32_t)((ix + 1) + r.SX * ((iz + 1) + r.SZ * (iy + 1)));
+                ws[k] = (uint32_t)(ix + nx * (iz + nz * iy));
+                k++;
+            }
+    CK(cudaMemcpyAsync(r.work, w.data(), r.n_work * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(r.work_span, ws.data(), r.n_work * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    r.live = true;
+    return BXW_OK;
+}
+
+int region_generate(bxw_ctx *ctx, Region &r, uint64_t seed, int precision, bool want_raw) {
+    if (precision != 32 && precision != 64) return fail(ctx, BXW_E_INVALID, "precision must be 32 or 64");
+    if (!ctx->have_gen_ids) return fail(ctx, BXW_E_NO_REGISTRY, "bxw_set_gen_ids not called");
+    int rc = ensure_gen_tables(ctx, seed);
+    if (rc) return rc;
+    const int32_t W = r.SX * 32, D = r.SZ * 32;
+    const int32_t x0 = (r.cx0 - 1) * 32, z0 = (r.cz0 - 1) * 32;
+    const int32_t cell_x0 = x0 / 128 - 1, cell_z0 = z0 / 128 - 1; // truncating, as stdgen.rs:150
+    const int32_t cell_x1 = (x0 + W - 1) / 128 + 1, cell_z1 = (z0 + D - 1) / 128 + 1;
+    const int32_t cw = cell_x1 - cell_x0 + 1, cd = cell_z1 - cell_z0 + 1;
+    const size_t need = (size_t)cw * cd * 4;
+    if (need > r.cells_cap) {
+        cudaFree(r.cells);
+        r.cells = nullptr;
+        CK(cudaMalloc(&r.cells, need * sizeof(CellPointDev)));
+        r.cells_cap = need;
+    }
+    if (want_raw && !r.raw) CK(cudaMalloc(&r.raw, (size_t)W * D * sizeof(double)));
+    launch_cellpoints_kernel(seed, cell_x0, cell_z0, cw, cd, ctx->d_gen, r.cells, precision, ctx->stream);
+    GenParams gp;
+    gp.seed = seed;
+    gp.x0 = x0;
+    gp.z0 = z0;
+    gp.W = W;
+    gp.D = D;
+    gp.cell_x0 = cell_x0;
+    gp.cell_z0 = cell_z0;
+    gp.cells_w = cw;
+    gp.cells_d = cd;
+    gp.cells = r.cells;
+    gp.tables = ctx->d_gen;
+    gp.hmap = r.hmap;
+    gp.raw = want_raw ? r.raw : nullptr;
+    launch_heightmap_kernel(gp, precision, ctx->stream);
+    FillParams fp;
+    fp.hmap = r.hmap;
+    fp.W = W;
+    fp.blocks = r.blocks;
+    fp.SX = r.SX;
+    fp.SY = r.SY;
+    fp.SZ = r.SZ;
+    fp.cy_min = r.cy0 - 1;
+    fp.id_void = (uint32_t)ctx->gen_ids[0] << 16;
+    fp.id_grass = (uint32_t)ctx->gen_ids[1] << 16;
+    fp.id_dirt = (uint32_t)ctx->gen_ids[2] << 16;
+    fp.id_stone = (uint32_t)ctx->gen_ids[3] << 16;
+    fp.id_snow = (uint32_t)ctx->gen_ids[4] << 16;
+    launch_fill_kernel(fp, ctx->stream);
+    ctx->launches += 3;
+    CK(cudaGetLastError());
+    r.have_hmap = true;
+    return BXW_OK;
+}
+
+int arena_resize(bxw_ctx *ctx, Region &r, unsigned long long v_cap, unsigned long long i_cap, unsigned long long keep_v,
+                 unsigned long long keep_i) {
+    bxw_vertex *nv = nullptr;
+    uint32_t *ni = nullptr;
+    if (v_cap < 64) v_cap = 64;
+    if (i_cap < 64) i_cap = 64;
+    CK(cudaMalloc(&nv, v_cap * sizeof(bxw_vertex)));
+    CK(cudaMalloc(&ni, i_cap * sizeof(uint32_t)));
+    if (keep_v && r.varena) CK(cudaMemcpyAsync(nv, r.varena, keep_v * sizeof(bxw_vertex), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (keep_i && r.iarena) CK(cudaMemcpyAsync(ni, r.iarena, keep_i * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(r.varena);
+    cudaFree(r.iarena);
+    r.varena = nv;
+    r.iarena = ni;
+    r.v_cap = v_cap;
+    r.i_cap = i_cap;
+    return BXW_OK;
+}
+
+// Runs the mesher over a work list. append=false restarts arena allocation at 0.
+int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *work_span, uint32_t n_work, bool append) {
+    if (!ctx->d_kind) return fail(ctx, BXW_E_NO_REGISTRY, "bxw_set_registry not called");
+    MeshParams p;
+    p.blocks = r.blocks;
+    p.SX = r.SX;
+    p.SY = r.SY;
+    p.SZ = r.SZ;
+    p.work = work;
+    p.work_span = work_span;
+    p.n_work = n_work;
+    p.spans = r.spans;
+    p.counters = r.counters;
+    p.tables = ctx->d_tables;
+    p.reg = dev_registry(ctx);
+    unsigned long long base_v = 0, base_i = 0;
+    if (append) {
+        CK(cudaMemcpyAsync(r.h_counters, r.counters, sizeof(MeshCounters), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        base_v = r.h_counters->v_alloc;
+        base_i = r.h_counters->i_alloc;
+    }
+    for (int attempt = 0; attempt < 3; attempt++) {
+        MeshCounters init;
+        init.v_alloc = base_v;
+        init.i_alloc = base_i;
+        init.flags = 0;
+        init.work_next = 0;
+        *r.h_counters = init;
+        CK(cudaMemcpyAsync(r.counters, r.h_counters, sizeof(MeshCounters), cudaMemcpyHostToDevice, ctx->stream));
+        const bool count_only = (r.varena == nullptr);
+        p.varena = r.varena;
+        p.iarena = r.iarena;
+        p.v_cap = r.v_cap;
+        p.i_cap = r.i_cap;
+        p.count_only = count_only ? 1 : 0;
+        CK(cudaEventRecord(ctx->ev_m0, ctx->stream));
+        launch_mesh_kernel(p, ctx->sm_count, ctx->stream);
+        CK(cudaEventRecord(ctx->ev_m1, ctx->stream));
+        ctx->launches += 1;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(r.h_counters, r.counters, sizeof(MeshCounters), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev_m0, ctx->ev_m1));
+        if (!count_only) {
+            ctx->mesh_ms += ms;
+            ctx->mesh_launches += 1;
+        }
+        if (r.h_counters->flags & kFlagUnknownId)
+            return fail(ctx, BXW_E_UNKNOWN_ID, "a voxel references a block id without a registry definition");
+        const unsigned long long need_v = r.h_counters->v_alloc, need_i = r.h_counters->i_alloc;
+        if (count_only || (r.h_counters->flags & kFlagArenaOverflow)) {
+            // size the arena from the measured need (+ slack so small edits can append) and run again
+            int rc = arena_resize(ctx, r, need_v + need_v / 8 + 4096, need_i + need_i / 8 + 8192, base_v, base_i);
+            if (rc) return rc;
+            continue;
+        }
+        return BXW_OK;
+    }
+    return fail(ctx, BXW_E_NOSPACE, "mesh arena sizing did not converge");
+}
+
+int ensure_scratch(bxw_ctx *ctx) {
+    if (ctx->scratch.live) return BXW_OK;
+    return region_alloc(ctx, ctx->scratch, 0, 0, 0, 1, 1, 1);
+}
+
+size_t storage_index(const Region &r, int32_t lx, int32_t ly, int32_t lz) {
+    return (size_t)(lx + 1) + (size_t)r.SX * ((size_t)(lz + 1) + (size_t)r.SZ * (size_t)(ly + 1));
+}
+
+bool local_ok(const Region &r, int32_t lx, int32_t ly, int32_t lz) {
+    return lx >= -1 && ly >= -1 && lz >= -1 && lx <= (int32_t)r.nx && ly <= (int32_t)r.ny && lz <= (int32_t)r.nz;
+}
+
+int not_implemented(bxw_ctx *ctx, const char *what) { return fail(ctx, BXW_E_INVALID, "%s: not implemented in this build", what); }
+
+} // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int bxw_create(int device, bxw_ctx **out) {
+    if (!out) return BXW_E_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return BXW_E_CUDA;
+    bxw_ctx *ctx = new (std::nothrow) bxw_ctx();
+    if (!ctx) return BXW_E_NOMEM;
+    ctx->device = device;
+    auto bail = [&](int code) {
+        bxw_destroy(ctx);
+        return code;
+    };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(BXW_E_CUDA);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(BXW_E_CUDA);
+    if (prop.major < 10) { // sm_100a cubins only
+        return bail(BXW_E_CUDA);
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(BXW_E_CUDA);
+    ctx->stream = ctx->own_stream;
+    if (cudaEventCreate(&ctx->ev_a) != cudaSuccess || cudaEventCreate(&ctx->ev_b) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev_m0) != cudaSuccess || cudaEventCreate(&ctx->ev_m1) != cudaSuccess)
+        return bail(BXW_E_CUDA);
+    MeshTables *t = new (std::nothrow) MeshTables();
+    if (!t) return bail(BXW_E_NOMEM);
+    build_mesh_tables(*t);
+    cudaError_t e = cudaMalloc(&ctx->d_tables, sizeof(MeshTables));
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->d_tables, t, sizeof(MeshTables), cudaMemcpyHostToDevice);
+    delete t;
+    if (e != cudaSuccess) return bail(BXW_E_CUDA);
+    *out = ctx;
+    return BXW_OK;
+}
+
+void bxw_destroy(bxw_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    region_free(ctx->region);
+    region_free(ctx->scratch);
+    cudaFree(ctx->d_kind);
+    cudaFree(ctx->d_texf);
+    cudaFree(ctx->d_color);
+    cudaFree(ctx->d_tables);
+    cudaFree(ctx->d_gen);
+    if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+    if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+    if (ctx->ev_m0) cudaEventDestroy(ctx->ev_m0);
+    if (ctx->ev_m1) cudaEventDestroy(ctx->ev_m1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char *bxw_last_error(const bxw_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int bxw_set_stream(bxw_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return BXW_E_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return BXW_OK;
+}
+
+int bxw_synchronize(bxw_ctx *ctx) {
+    if (!ctx) return BXW_E_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BXW_OK;
+}
+
+uint64_t bxw_kernel_launches(const bxw_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int bxw_set_registry(bxw_ctx *ctx, const bxw_block_def *defs, uint32_t n) {
+    if (!ctx || !defs || n == 0 || n > 65536) return fail(ctx, BXW_E_INVALID, "bad registry");
+    std::vector<uint8_t> kind(n);
+    std::vector<float> texf((size_t)n * 6), color((size_t)n * 3);
+    for (uint32_t i = 0; i < n; i++) {
+        kind[i] = defs[i].present ? (defs[i].mesh_kind ? 2 : 1) : 0;
+        for (int k = 0; k < 6; k++) texf[(size_t)i * 6 + k] = (float)defs[i].tex[k]; // `texid as f32` (voxmesh.rs:167)
+        for (int k = 0; k < 3; k++) color[(size_t)i * 3 + k] = defs[i].debug_color[k];
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_kind);
+    cudaFree(ctx->d_texf);
+    cudaFree(ctx->d_color);
+    ctx->d_kind = nullptr;
+    ctx->d_texf = ctx->d_color = nullptr;
+    CK(cudaMalloc(&ctx->d_kind, n));
+    CK(cudaMalloc(&ctx->d_texf, (size_t)n * 6 * sizeof(float)));
+    CK(cudaMalloc(&ctx->d_color, (size_t)n * 3 * sizeof(float)));
+    CK(cudaMemcpy(ctx->d_kind, kind.data(), n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_texf, texf.data(), texf.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_color, color.data(), color.size() * sizeof(float), cudaMemcpyHostToDevice));
+    ctx->reg_n = n;
+    ctx->reg_host.assign(defs, defs + n);
+    return BXW_OK;
+}
+
+int bxw_set_gen_ids(bxw_ctx *ctx, uint16_t void_id, uint16_t grass, uint16_t dirt, uint16_t stone, uint16_t snow_grass) {
+    if (!ctx) return BXW_E_INVALID;
+    ctx->gen_ids[0] = void_id;
+    ctx->gen_ids[1] = grass;
+    ctx->gen_ids[2] = dirt;
+    ctx->gen_ids[3] = stone;
+    ctx->gen_ids[4] = snow_grass;
+    ctx->have_gen_ids = true;
+    return BXW_OK;
+}
+
+int bxw_gen_chunk(bxw_ctx *ctx, uint64_t seed, int32_t cx, int32_t cy, int32_t cz, uint32_t *blocks_yzx) {
+    if (!ctx || !blocks_yzx) return fail(ctx, BXW_E_INVALID, "null argument");
+    int rc = ensure_scratch(ctx);
+    if (rc) return rc;
+    // reuse the scratch region's storage slot 0 as a 1x1x1 box positioned at (cx,cy,cz)
+    Region box = ctx->scratch;
+    box.SX = box.SY = box.SZ = 1;
+    box.cx0 = cx + 1;
+    box.cy0 = cy + 1;
+    box.cz0 = cz + 1;
+    box.raw = nullptr;
+    rc = region_generate(ctx, box, seed, 64, false);
+    ctx->scratch.cells = box.cells; // region_generate may have grown the cell table
+    ctx->scratch.cells_cap = box.cells_cap;
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(blocks_yzx, box.blocks, kChunkVoxels * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BXW_OK;
+}
+
+int bxw_mesh_chunk27(bxw_ctx *ctx, const uint32_t *const dense[27], bxw_mesh_span *counts) {
+    if (!ctx || !dense || !counts) return fail(ctx, BXW_E_INVALID, "null argument");
+    int rc = ensure_scratch(ctx);
+    if (rc) return rc;
+    Region &r = ctx->scratch;
+    for (int i = 0; i < 27; i++) {
+        if (!dense[i]) return fail(ctx, BXW_E_INVALID, "dense[%d] is null", i);
+        // slot rx + 3 rz + 9 ry (voxmesh.rs:72) is exactly the 3x3x3 storage order sx + 3*(sz + 3*sy)
+        CK(cudaMemcpyAsync(r.blocks + (size_t)i * kChunkVoxels, dense[i], kChunkVoxels * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    rc = region_mesh(ctx, r, r.work, r.work_span, 1, false);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(counts, r.spans, sizeof(bxw_mesh_span), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BXW_OK;
+}
+
+int bxw_mesh_chunk27_rle(bxw_ctx *ctx, const uint32_t *const rle[27], const size_t rle_len[27], bxw_mesh_span *counts) {
+    (void)rle;
+    (void)rle_len;
+    (void)counts;
+    return not_implemented(ctx, "bxw_mesh_chunk27_rle");
+}
+
+int bxw_mesh_fetch(bxw_ctx *ctx, bxw_vertex *vertices, uint32_t *indices) {
+    if (!ctx || !ctx->scratch.live) return fail(ctx, BXW_E_INVALID, "no mesh to fetch");
+    Region &r = ctx->scratch;
+    bxw_mesh_span sp;
+    CK(cudaMemcpyAsync(&sp, r.spans, sizeof sp, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (sp.v_count && vertices)
+        CK(cudaMemcpyAsync(vertices, r.varena + sp.v_off, (size_t)sp.v_count * sizeof(bxw_vertex), cudaMemcpyDeviceToHost, ctx->stream));
+    if (sp.i_count && indices)
+        CK(cudaMemcpyAsync(indices, r.iarena + sp.i_off, (size_t)sp.i_count * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BXW_OK;
+}
+
+int bxw_is_chunk_trivial(bxw_ctx *ctx, const uint32_t *rle, size_t rle_len, int *out_trivial) {
+    // voxmesh.rs:16-25: uniform chunk (3 RLE words, v v n) whose block has no mesh
+    if (!ctx || !rle || !out_trivial) return fail(ctx, BXW_E_INVALID, "null argument");
+    if (ctx->reg_host.empty()) return fail(ctx, BXW_E_NO_REGISTRY, "bxw_set_registry not called");
+    *out_trivial = 0;
+    if (rle_len == 3 && rle[0] == rle[1]) {
+        const uint32_t id = rle[0] >> 16;
+        if (id >= ctx->reg_n || !ctx->reg_host[id].present) return fail(ctx, BXW_E_UNKNOWN_ID, "unknown block id %u", id);
+        if (ctx->reg_host[id].mesh_kind == 0) *out_trivial = 1;
+    }
+    return BXW_OK;
+}
+
+size_t bxw_rle_bound(size_t n_chunks) { return n_chunks * (size_t)(kChunkVoxels + kChunkVoxels / 2 + 1); }
+
+int bxw_rle_compress(bxw_ctx *ctx, const uint32_t *, size_t, uint32_t *, uint64_t *) { return not_implemented(ctx, "bxw_rle_compress"); }
+int bxw_rle_decompress(bxw_ctx *ctx, const uint32_t *, const uint64_t *, size_t, uint32_t *) { return not_implemented(ctx, "bxw_rle_decompress"); }
+
+int bxw_region_create(bxw_ctx *ctx, int32_t cx0, int32_t cy0, int32_t cz0, uint32_t nx, uint32_t ny, uint32_t nz) {
+    if (!ctx || nx == 0 || ny == 0 || nz == 0) return fail(ctx, BXW_E_INVALID, "bad region dims");
+    return region_alloc(ctx, ctx->region, cx0, cy0, cz0, nx, ny, nz);
+}
+
+int bxw_region_destroy(bxw_ctx *ctx) {
+    if (!ctx) return BXW_E_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    region_free(ctx->region);
+    return BXW_OK;
+}
+
+int bxw_region_generate(bxw_ctx *ctx, uint64_t seed, int precision) {
+    if (!ctx || !ctx->region.live) return fail(ctx, BXW_E_INVALID, "no region");
+    return region_generate(ctx, ctx->region, seed, precision, false);
+}
+
+int bxw_region_heightmap(bxw_ctx *ctx, int32_t *height, uint8_t *elevation, double *raw_height) {
+    if (!ctx || !ctx->region.live || !ctx->region.have_hmap) return fail(ctx, BXW_E_INVALID, "no generated region");
+    Region &r = ctx->region;
+    const size_t n = (size_t)r.SX * 32 * r.SZ * 32;
+    if (raw_height) {
+        // recompute with the raw output enabled (same kernels, same seed/precision=64)
+        int rc = region_generate(ctx, r, ctx->gen_seed, 64, true);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(raw_height, r.raw, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    std::vector<int32_t> packed(n);
+    CK(cudaMemcpyAsync(packed.data(), r.hmap, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < n; i++) {
+        if (height) height[i] = packed[i] >> 2;
+        if (elevation) elevation[i] = (uint8_t)(packed[i] & 3);
+    }
+    return BXW_OK;
+}
+
+int bxw_region_upload_chunk(bxw_ctx *ctx, int32_t lx, int32_t ly, int32_t lz, const uint32_t *blocks_yzx) {
+    if (!ctx || !ctx->region.live || !blocks_yzx) return fail(ctx, BXW_E_INVALID, "no region / null");
+    Region &r = ctx->region;
+    if (!local_ok(r, lx, ly, lz)) return fail(ctx, BXW_E_INVALID, "chunk (%d,%d,%d) outside region+shell", lx, ly, lz);
+    CK(cudaMemcpyAsync(r.blocks + storage_index(r, lx, ly, lz) * kChunkVoxels, blocks_yzx, kChunkVoxels * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BXW_OK;
+}
+
+int bxw_region_download_chunk(bxw_ctx *ctx, int32_t lx, int32_t ly, int32_t lz, uint32_t *blocks_yzx) {
+    if (!ctx || !ctx->region.live || !blocks_yzx) return fail(ctx, BXW_E_INVALID, "no region / null");
+    Region &r = ctx->region;
+    if (!local_ok(r, lx, ly, lz)) return fail(ctx, BXW_E_INVALID, "chunk (%d,%d,%d) outside region+shell", lx, ly, lz);
+    CK(cudaMemcpyAsync(blocks_yzx, r.blocks + storage_index(r, lx, ly, lz) * kChunkVoxels, kChunkVoxels * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BXW_OK;
+}
+
+int bxw_region_mesh_reserve(bxw_ctx *ctx, uint64_t max_vertices, uint64_t max_indices) {
+    if (!ctx || !ctx->region.live) return fail(ctx, BXW_E_INVALID, "no region");
+    int rc = arena_resize(ctx, ctx->region, max_vertices, max_indices, 0, 0);
+    if (rc == BXW_OK) ctx->region.reserved = true;
+    return rc;
+}
+
+int bxw_region_mesh(bxw_ctx *ctx, uint64_t *arena_vertices, uint64_t *arena_indices) {
+    if (!ctx || !ctx->region.live) return fail(ctx, BXW_E_INVALID, "no region");
+    Region &r = ctx->region;
+    int rc = region_mesh(ctx, r, r.work, r.work_span, r.n_work, false);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(r.dirty, 0, r.n_work, ctx->stream));
+    if (arena_vertices) *arena_vertices = r.h_counters->v_alloc;
+    if (arena_indices) *arena_indices = r.h_counters->i_alloc;
+    return BXW_OK;
+}
+
+int bxw_region_generate_and_mesh(bxw_ctx *ctx, uint64_t seed, int precision, uint64_t *arena_vertices, uint64_t *arena_indices) {
+    int rc = bxw_region_generate(ctx, seed, precision);
+    if (rc) return rc;
+    return bxw_region_mesh(ctx, arena_vertices, arena_indices);
+}
+
+int bxw_region_mesh_spans(bxw_ctx *ctx, bxw_mesh_span *spans) {
+    if (!ctx || !ctx->region.live || !spans) return fail(ctx, BXW_E_INVALID, "no region / null");
+    Region &r = ctx->region;
+    CK(cudaMemcpyAsync(spans, r.spans, r.n_work * sizeof(bxw_mesh_span), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BXW_OK;
+}
+
+int bxw_region_mesh_fetch(bxw_ctx *ctx, bxw_vertex *vertices, uint64_t n_vertices, uint32_t *indices, uint64_t n_indices) {
+    if (!ctx || !ctx->region.live) return fail(ctx, BXW_E_INVALID, "no region");
+    Region &r = ctx->region;
+    if (n_vertices > r.v_cap || n_indices > r.i_cap) return fail(ctx, BXW_E_INVALID, "fetch exceeds arena");
+    if (n_vertices && vertices) CK(cudaMemcpyAsync(vertices, r.varena, n_vertices * sizeof(bxw_vertex), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_indices && indices) CK(cudaMemcpyAsync(indices, r.iarena, n_indices * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BXW_OK;
+}
+
+int bxw_region_apply_changes(bxw_ctx *ctx, const bxw_voxel_change *, uint32_t, uint32_t *) { return not_implemented(ctx, "bxw_region_apply_changes"); }
+int bxw_region_remesh_dirty(bxw_ctx *ctx, uint32_t *) { return not_implemented(ctx, "bxw_region_remesh_dirty"); }
+
+size_t bxw_region_halo_bytes(const bxw_ctx *ctx) {
+    if (!ctx || !ctx->region.live) return 0;
+    return (size_t)ctx->region.SZ * 32 * ctx->region.SY * 32 * sizeof(uint32_t);
+}
+int bxw_region_halo_export(bxw_ctx *ctx, int, void *) { return not_implemented(ctx, "bxw_region_halo_export"); }
+int bxw_region_halo_import(bxw_ctx *ctx, int, const void *) { return not_implemented(ctx, "bxw_region_halo_import"); }
+
+int bxw_region_device_ptrs(bxw_ctx *ctx, void **blocks, void **vertices, void **indices) {
+    if (!ctx || !ctx->region.live) return fail(ctx, BXW_E_INVALID, "no region");
+    if (blocks) *blocks = ctx->region.blocks;
+    if (vertices) *vertices = ctx->region.varena;
+    if (indices) *indices = ctx->region.iarena;
+    return BXW_OK;
+}
+
+int bxw_terragen_noise2(bxw_ctx *ctx, uint64_t, const double *, const double *, size_t, double *) { return not_implemented(ctx, "bxw_terragen_noise2"); }
+
+int bxw_timer_start(bxw_ctx *ctx) {
+    if (!ctx) return BXW_E_INVALID;
+    CK(cudaEventRecord(ctx->ev_a, ctx->stream));
+    return BXW_OK;
+}
+
+int bxw_timer_stop_ms(bxw_ctx *ctx, float *ms) {
+    if (!ctx || !ms) return BXW_E_INVALID;
+    CK(cudaEventRecord(ctx->ev_b, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev_b));
+    CK(cudaEventElapsedTime(ms, ctx->ev_a, ctx->ev_b));
+    return BXW_OK;
+}
+
+int bxw_mesh_kernel_time_ms(bxw_ctx *ctx, float *ms, uint64_t *launches, int reset) {
+    if (!ctx) return BXW_E_INVALID;
+    if (ms) *ms = (float)ctx->mesh_ms;
+    if (launches) *launches = ctx->mesh_launches;
+    if (reset) {
+        ctx->mesh_ms = 0.0;
+        ctx->mesh_launches = 0;
+    }
+    return BXW_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,87 @@
+// device_common.cuh — shared device-side declarations of libbxw_cuda (sm_100a only).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/bxw_cuda.h"
+#include "tables.hpp"
+
+namespace bxw {
+
+constexpr int kChunkDim = 32;
+constexpr int kChunkVoxels = 32768;
+
+// Registry as the kernels see it (voxregistry.rs:141-143 lookups become array reads).
+struct DeviceRegistry {
+    const uint8_t *kind;   // [n] 0 = absent, 1 = VoxelMesh::None, 2 = VoxelMesh::CubeAndSlopes
+    const float *texf;     // [n][6] texture id as f32 (voxmesh.rs:167 `texid as f32`)
+    const float *color;    // [n][3] debug_color
+    uint32_t n;
+};
+
+// error / status flags accumulated by kernels (atomicOr into MeshCounters::flags)
+constexpr unsigned long long kFlagUnknownId = 1ull;
+constexpr unsigned long long kFlagArenaOverflow = 2ull;
+
+struct MeshCounters {
+    unsigned long long v_alloc; // next free vertex slot in the arena
+    unsigned long long i_alloc; // next free index slot
+    unsigned long long flags;
+    unsigned long long work_next; // dynamic work-list cursor
+};
+
+struct MeshParams {
+    const uint32_t *blocks; // region storage: chunk c at blocks + c*32768, voxel x + 32 z + 1024 y
+    int SX, SY, SZ;         // storage dims in chunks (shell included); chunk index sx + SX*(sz + SZ*sy)
+    const uint32_t *work;   // [n_work] storage chunk index of each chunk to mesh
+    const uint32_t *work_span; // [n_work] span slot of each work item
+    uint32_t n_work;
+    bxw_mesh_span *spans;
+    bxw_vertex *varena;
+    uint32_t *iarena;
+    unsigned long long v_cap, i_cap;
+    MeshCounters *counters;
+    const MeshTables *tables;
+    DeviceRegistry reg;
+    int count_only; // 1: fill spans' counts only (offsets = running totals), no vertex/index writes
+};
+
+void launch_mesh_kernel(const MeshParams &p, int sm_count, cudaStream_t stream);
+int mesh_kernel_max_ctas_per_sm();
+
+// generation -------------------------------------------------------------------------------------------------
+struct GenTables {
+    uint8_t perm[7][256]; // height_map_gen[0..5], elevation_map_gen, moisture_map_gen (stdgen.rs:82-84,103-114)
+};
+
+struct CellPointDev {
+    int32_t px, pz;
+    double elevation_class;
+};
+
+struct GenParams {
+    uint64_t seed;
+    int32_t x0, z0;      // world voxel coordinate of column (0,0) of the height map
+    int32_t W, D;        // columns along x, z
+    int32_t cell_x0, cell_z0, cells_w, cells_d; // super-cell table origin / extent (stdgen.rs:15,149-161)
+    const CellPointDev *cells; // [cells_d][cells_w][4]
+    const GenTables *tables;
+    int32_t *hmap;       // [D][W] height*4 + elevation
+    double *raw;         // optional [D][W] raw f64 height
+};
+
+void launch_cellpoints_kernel(uint64_t seed, int32_t cell_x0, int32_t cell_z0, int32_t cells_w, int32_t cells_d,
+                              const GenTables *tables, CellPointDev *cells, int precision, cudaStream_t stream);
+void launch_heightmap_kernel(const GenParams &p, int precision, cudaStream_t stream);
+
+struct FillParams {
+    const int32_t *hmap; // [D][W]
+    int32_t W;
+    uint32_t *blocks;
+    int SX, SY, SZ;
+    int32_t cy_min;      // world chunk y of storage layer 0
+    uint32_t id_void, id_grass, id_dirt, id_stone, id_snow; // already shifted datums (id << 16)
+};
+void launch_fill_kernel(const FillParams &p, cudaStream_t stream);
+
+} // namespace bxw

@@ -1,0 +1,349 @@
+// gen_kernel.cu — bxw_world::stdgen::StdGenerator as sm_100a kernels.
+//
+// The reference evaluates calc_voxel_params for the 1024 columns of EVERY chunk (stdgen.rs:335-347), so a vertical
+// stack of chunks recomputes the same columns; here the column parameters are computed once per (x,z) of the
+// region (heightmap kernel), then a fill kernel streams the block ids of whole vertical stacks with 16-byte
+// coalesced stores (stdgen.rs:349-373).
+//
+// The f64 path performs exactly the IEEE operations of the reference, in its order, with explicit
+// round-to-nearest intrinsics so that nvcc never contracts a*b+c into an FMA (Rust/LLVM does not contract).
+#include "device_common.cuh"
+
+namespace bxw {
+namespace {
+
+// ---- noise 0.8.2 super_simplex_2d constants (see oracle/noise.c for provenance: crate source not vendored) ----
+__constant__ double c_lat_off[32][2];
+__constant__ signed char c_lat_pt[32][2];
+
+constexpr double kToReal = -0.211324865405187;
+constexpr double kToSimplex = 0.366025403784439;
+constexpr double kNorm = 1.0 / 0.05428295288661623;
+constexpr double kDiag = 0.70710678118654752440;
+
+#define LA 0.788675134594813
+#define LB 0.211324865405187
+#define LC 0.577350269189626
+#define LD 1.366025403784439
+#define LE 0.36602540378443904
+const double h_lat_off[32][2] = {
+    {0.0, 0.0}, {-LC, -LC}, {LA, -LB},  {-LB, LA}, {0.0, 0.0}, {-LC, -LC}, {LB, -LA},  {-LA, LB},
+    {0.0, 0.0}, {-LC, -LC}, {-LA, LB},  {-LB, LA}, {0.0, 0.0}, {-LC, -LC}, {-LD, -LE}, {-LA, LB},
+    {0.0, 0.0}, {-LC, -LC}, {LA, -LB},  {LB, -LA}, {0.0, 0.0}, {-LC, -LC}, {LB, -LA},  {-LE, -LD},
+    {0.0, 0.0}, {-LC, -LC}, {-LA, LB},  {LB, -LA}, {0.0, 0.0}, {-LC, -LC}, {-LD, -LE}, {-LE, -LD},
+};
+const signed char h_lat_pt[32][2] = {
+    {0, 0}, {1, 1}, {-1, 0}, {0, -1}, {0, 0}, {1, 1}, {0, 1}, {1, 0}, {0, 0}, {1, 1}, {1, 0},  {0, -1}, {0, 0}, {1, 1}, {2, 1}, {1, 0},
+    {0, 0}, {1, 1}, {-1, 0}, {0, 1},  {0, 0}, {1, 1}, {0, 1}, {1, 2}, {0, 0}, {1, 1}, {1, 0},  {0, 1},  {0, 0}, {1, 1}, {2, 1}, {1, 2},
+};
+
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+
+// noise::SuperSimplex::get([x, y]) (f64)
+__device__ double super_simplex_2d(const uint8_t *__restrict__ perm, double px, double py) {
+    const double to_simplex_offset = dmul(dadd(px, py), kToSimplex);
+    const double sx = dadd(px, to_simplex_offset), sy = dadd(py, to_simplex_offset);
+    const double bxf = floor(sx), byf = floor(sy);
+    const long long bxi = __double2ll_rz(bxf), byi = __double2ll_rz(byf);
+    const double rx = dsub(sx, bxf), ry = dsub(sy, byf);
+    const double region_sum = floor(dadd(rx, ry));
+    const double half_rs = dmul(region_sum, 0.5);
+    unsigned index = (region_sum >= 1.0 ? 1u : 0u) << 2;
+    index |= (dsub(dadd(dsub(rx, dmul(ry, 0.5)), 1.0), half_rs) >= 1.0 ? 1u : 0u) << 3;
+    index |= (dsub(dadd(dsub(ry, dmul(rx, 0.5)), 1.0), half_rs) >= 1.0 ? 1u : 0u) << 4;
+    const double to_real_offset = dmul(dadd(rx, ry), kToReal);
+    const double qx = dadd(rx, to_real_offset), qy = dadd(ry, to_real_offset);
+    double value = 0.0;
+#pragma unroll
+    for (unsigned k = 0; k < 4; k++) {
+        const double dx = dadd(qx, c_lat_off[index + k][0]), dy = dadd(qy, c_lat_off[index + k][1]);
+        const double attn = dsub(2.0 / 3.0, dadd(dmul(dx, dx), dmul(dy, dy)));
+        if (attn > 0.0) {
+            const long long lx = bxi + c_lat_pt[index + k][0], ly = byi + c_lat_pt[index + k][1];
+            const unsigned h = __ldg(perm + (__ldg(perm + (unsigned)(lx & 0xff)) ^ (unsigned)(ly & 0xff)));
+            double gx, gy;
+            switch (h & 7u) { // gradient::grad2
+            case 0: gx = 1.0; gy = 0.0; break;
+            case 1: gx = -1.0; gy = 0.0; break;
+            case 2: gx = 0.0; gy = 1.0; break;
+            case 3: gx = 0.0; gy = -1.0; break;
+            case 4: gx = kDiag; gy = kDiag; break;
+            case 5: gx = -kDiag; gy = kDiag; break;
+            case 6: gx = kDiag; gy = -kDiag; break;
+            default: gx = -kDiag; gy = -kDiag; break;
+            }
+            const double a2 = dmul(attn, attn);
+            value = dadd(value, dmul(dmul(a2, a2), dadd(dmul(gx, dx), dmul(gy, dy))));
+        }
+    }
+    return dmul(value, kNorm);
+}
+
+// FP32 evaluation of the same noise (north_star-literal variant). Lattice decisions are taken in f32 too.
+__device__ float super_simplex_2d_f32(const uint8_t *__restrict__ perm, float px, float py) {
+    const float to_simplex_offset = __fmul_rn(__fadd_rn(px, py), (float)kToSimplex);
+    const float sx = __fadd_rn(px, to_simplex_offset), sy = __fadd_rn(py, to_simplex_offset);
+    const float bxf = floorf(sx), byf = floorf(sy);
+    const int bxi = __float2int_rz(bxf), byi = __float2int_rz(byf);
+    const float rx = __fsub_rn(sx, bxf), ry = __fsub_rn(sy, byf);
+    const float region_sum = floorf(__fadd_rn(rx, ry));
+    const float half_rs = __fmul_rn(region_sum, 0.5f);
+    unsigned index = (region_sum >= 1.0f ? 1u : 0u) << 2;
+    index |= (__fsub_rn(__fadd_rn(__fsub_rn(rx, __fmul_rn(ry, 0.5f)), 1.0f), half_rs) >= 1.0f ? 1u : 0u) << 3;
+    index |= (__fsub_rn(__fadd_rn(__fsub_rn(ry, __fmul_rn(rx, 0.5f)), 1.0f), half_rs) >= 1.0f ? 1u : 0u) << 4;
+    const float to_real_offset = __fmul_rn(__fadd_rn(rx, ry), (float)kToReal);
+    const float qx = __fadd_rn(rx, to_real_offset), qy = __fadd_rn(ry, to_real_offset);
+    float value = 0.0f;
+#pragma unroll
+    for (unsigned k = 0; k < 4; k++) {
+        const float dx = __fadd_rn(qx, (float)c_lat_off[index + k][0]), dy = __fadd_rn(qy, (float)c_lat_off[index + k][1]);
+        const float attn = __fsub_rn(2.0f / 3.0f, __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+        if (attn > 0.0f) {
+            const int lx = bxi + c_lat_pt[index + k][0], ly = byi + c_lat_pt[index + k][1];
+            const unsigned h = __ldg(perm + (__ldg(perm + (unsigned)(lx & 0xff)) ^ (unsigned)(ly & 0xff)));
+            const float diag = (float)kDiag;
+            const float gx = (h & 4u) ? ((h & 1u) ? -diag : diag) : ((h & 2u) ? 0.0f : ((h & 1u) ? -1.0f : 1.0f));
+            const float gy = (h & 4u) ? ((h & 2u) ? -diag : diag) : ((h & 2u) ? ((h & 1u) ? -1.0f : 1.0f) : 0.0f);
+            const float a2 = __fmul_rn(attn, attn);
+            value = __fadd_rn(value, __fmul_rn(__fmul_rn(a2, a2), __fadd_rn(__fmul_rn(gx, dx), __fmul_rn(gy, dy))));
+        }
+    }
+    return __fmul_rn(value, (float)kNorm);
+}
+
+// precision-generic noise returning double
+template <int PREC>
+__device__ __forceinline__ double noise_at(const uint8_t *perm, double px, double py) {
+    if (PREC == 32) return (double)super_simplex_2d_f32(perm, (float)px, (float)py);
+    return super_simplex_2d(perm, px, py);
+}
+
+template <int PREC>
+__device__ __forceinline__ double elevation_noise(const GenTables *T, int32_t x, int32_t z) {
+    // stdgen.rs:171-175: GLOBAL_BIOME_SCALE * GLOBAL_SCALE_MOD = 2560
+    const double sf = 256.0 * 10.0;
+    return ddiv(dadd(noise_at<PREC>(T->perm[5], ddiv((double)x, sf), ddiv((double)z, sf)), 1.0), 2.0);
+}
+
+template <int PREC>
+__device__ __forceinline__ double h_n(const GenTables *T, int i, double px, double pz) {
+    return ddiv(dadd(noise_at<PREC>(T->perm[i], px, pz), 1.0), 2.0); // stdgen.rs:178-180
+}
+template <int PREC>
+__device__ __forceinline__ double h_rn(const GenTables *T, int i, double px, double pz) {
+    return dmul(2.0, dsub(0.5, fabs(dsub(0.5, h_n<PREC>(T, i, px, pz))))); // stdgen.rs:183-185
+}
+
+template <int PREC>
+__device__ double plains_height(const GenTables *T, int32_t x, int32_t z) {
+    // stdgen.rs:187-192
+    const double sf = 10.0 * 120.0;
+    const double px = ddiv((double)x, sf), pz = ddiv((double)z, sf);
+    const double a = dmul(0.75, h_n<PREC>(T, 0, px, pz));
+    const double b = dmul(0.25, h_n<PREC>(T, 1, dmul(px, 2.0), dmul(pz, 2.0)));
+    return dadd(dmul(dadd(a, b), 5.0), 10.0);
+}
+
+template <int PREC>
+__device__ double hills_height(const GenTables *T, int32_t x, int32_t z) {
+    // stdgen.rs:194-200
+    const double sf = 10.0 * 160.0;
+    const double px = ddiv((double)x, sf), pz = ddiv((double)z, sf);
+    const double a = dmul(0.60, h_n<PREC>(T, 0, px, pz));
+    const double b = dmul(0.25, h_n<PREC>(T, 1, dmul(px, 1.5), dmul(pz, 1.5)));
+    const double c = dmul(0.15, h_n<PREC>(T, 2, dmul(px, 3.0), dmul(pz, 3.0)));
+    return dadd(dmul(dadd(dadd(a, b), c), 30.0), 15.0);
+}
+
+template <int PREC>
+__device__ double mountains_height(const GenTables *T, int32_t x, int32_t z) {
+    // stdgen.rs:202-213
+    const double sf = 10.0 * 200.0;
+    const double px = ddiv((double)x, sf), pz = ddiv((double)z, sf);
+    const double h0 = dmul(0.50, h_rn<PREC>(T, 0, px, pz));
+    const double h01 = dadd(dmul(0.25, h_rn<PREC>(T, 1, dmul(px, 2.0), dmul(pz, 2.0))), h0);
+    const double q = ddiv(h01, 0.75);
+    const double t1 = dmul(dmul(q, 0.15), h_n<PREC>(T, 2, dmul(px, 5.0), dmul(pz, 5.0)));
+    const double t2 = dmul(dmul(q, 0.05), h_rn<PREC>(T, 3, dmul(px, 9.0), dmul(pz, 9.0)));
+    return dadd(dmul(dadd(dadd(h01, t1), t2), 750.0), 40.0);
+}
+
+__device__ __forceinline__ uint64_t sm64_next(uint64_t &x) {
+    x += 0x9e3779b97f4a7c15ULL;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+
+// CellGen::get_cell_points (stdgen.rs:116-147): one thread per super-cell
+template <int PREC>
+__global__ void cellpoints_kernel(uint64_t seed, int32_t cell_x0, int32_t cell_z0, int32_t cells_w, int32_t cells_d,
+                                  const GenTables *T, CellPointDev *cells) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cells_w * cells_d) return;
+    const int32_t cx = cell_x0 + i % cells_w, cz = cell_z0 + i / cells_w;
+    uint64_t s = seed ^ ((((uint64_t)(int64_t)cx) << 32) | (((uint64_t)(int64_t)cz) & 0xFFFFFFFFULL));
+    uint64_t st[4]; // Xoshiro256StarStar::seed_from_u64 (rand_xoshiro 0.6.0)
+    for (int k = 0; k < 4; k++) st[k] = sm64_next(s);
+    const int bx[4] = {32, 96, 0, 64}, bz[4] = {32, 32, 96, 96};
+    for (int k = 0; k < 4; k++) {
+        uint32_t r[2];
+        for (int q = 0; q < 2; q++) {
+            const uint64_t res = rotl64(st[1] * 5, 7) * 9;
+            const uint64_t t = st[1] << 17;
+            st[2] ^= st[0];
+            st[3] ^= st[1];
+            st[1] ^= st[2];
+            st[0] ^= st[3];
+            st[2] ^= t;
+            st[3] = rotl64(st[3], 45);
+            r[q] = (uint32_t)(res >> 32);
+        }
+        CellPointDev cp;
+        cp.px = cx * 128 + bx[k] + ((int32_t)(r[0] % 32u) - 16);
+        cp.pz = cz * 128 + bz[k] + ((int32_t)(r[1] % 32u) - 16);
+        cp.elevation_class = elevation_noise<PREC>(T, cp.px, cp.pz);
+        cells[i * 4 + k] = cp;
+    }
+}
+
+// CellGen::calc_voxel_params (stdgen.rs:215-276): one thread per column
+template <int PREC>
+__global__ void __launch_bounds__(128) heightmap_kernel(GenParams p) {
+    const int ix = blockIdx.x * blockDim.x + threadIdx.x;
+    const int iz = blockIdx.y;
+    if (ix >= p.W) return;
+    const int32_t x = p.x0 + ix, z = p.z0 + iz;
+    const GenTables *T = p.tables;
+
+    // find_nearest_cell_points(pos, 1) (stdgen.rs:149-169): truncating division, first minimum wins
+    const int32_t cellx = x / 128, cellz = z / 128;
+    int32_t best = 0x7FFFFFFF;
+    double cec = 0.0;
+    bool have = false;
+    for (int cdx = -1; cdx <= 1; cdx++)
+        for (int cdy = -1; cdy <= 1; cdy++) {
+            const CellPointDev *c = p.cells + ((size_t)(cellz + cdy - p.cell_z0) * p.cells_w + (cellx + cdx - p.cell_x0)) * 4;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int32_t dx = c[k].px - x, dz = c[k].pz - z;
+                const int32_t dist = dx * dx + dz * dz;
+                if (!have || dist < best) {
+                    have = true;
+                    best = dist;
+                    cec = c[k].elevation_class;
+                }
+            }
+        }
+    const double ec = elevation_noise<PREC>(T, x, z);
+    double height;
+    if (ec < 0.4) {
+        height = plains_height<PREC>(T, x, z);
+    } else if (ec < 0.5) {
+        const double nlin = ddiv(dsub(ec, 0.4), 0.1);
+        const double olin = dsub(1.0, nlin);
+        const double ph = plains_height<PREC>(T, x, z);
+        const double hh = hills_height<PREC>(T, x, z);
+        height = dadd(dmul(olin, ph), dmul(nlin, hh));
+    } else if (ec < 0.7) {
+        height = hills_height<PREC>(T, x, z);
+    } else if (ec < 0.8) {
+        const double nlin = ddiv(dsub(ec, 0.7), 0.1);
+        const double olin = dsub(1.0, nlin);
+        const double hh = hills_height<PREC>(T, x, z);
+        const double mh = mountains_height<PREC>(T, x, z);
+        height = dadd(dmul(olin, hh), dmul(nlin, mh));
+    } else {
+        height = mountains_height<PREC>(T, x, z);
+    }
+    int elevation;
+    if (cec < 0.4) {
+        elevation = 0;
+    } else if (cec < 0.5) {
+        elevation = noise_at<PREC>(T->perm[4], (double)x, (double)z) < 0.0 ? 0 : 1;
+    } else if (cec < 0.7) {
+        elevation = 1;
+    } else if (cec < 0.8) {
+        elevation = noise_at<PREC>(T->perm[4], (double)x, (double)z) < 0.0 ? 1 : 2;
+    } else {
+        elevation = 2;
+    }
+    // height.round() as i32 (stdgen.rs:272): half away from zero, saturating
+    double r = round(height);
+    int32_t h;
+    if (!(r == r)) h = 0;
+    else if (r >= 536870911.0) h = 536870911; // packed into 30 bits below; the terrain never approaches this
+    else if (r <= -536870912.0) h = -536870912;
+    else h = (int32_t)r;
+    p.hmap[(size_t)iz * p.W + ix] = h * 4 + elevation;
+    if (p.raw) p.raw[(size_t)iz * p.W + ix] = height;
+}
+
+// StdGenerator::generate_chunk block selection (stdgen.rs:349-373) for a vertical stack of chunks.
+// CTA = one (sx,sz) chunk column; thread = 4 consecutive x of one z row; loops over all layers.
+__global__ void __launch_bounds__(256) fill_kernel(FillParams p) {
+    const int sx = blockIdx.x, sz = blockIdx.y;
+    const int q = threadIdx.x & 7, zr = threadIdx.x >> 3;
+    const int4 hm = __ldg(reinterpret_cast<const int4 *>(p.hmap + (size_t)(sz * 32 + zr) * p.W + sx * 32 + q * 4));
+    const int hh[4] = {hm.x >> 2, hm.y >> 2, hm.z >> 2, hm.w >> 2};
+    const int el[4] = {hm.x & 3, hm.y & 3, hm.z & 3, hm.w & 3};
+    for (int sy = 0; sy < p.SY; sy++) {
+        uint4 *dst = reinterpret_cast<uint4 *>(p.blocks + ((size_t)(sx + p.SX * (sz + p.SZ * sy))) * kChunkVoxels + zr * 32 + q * 4);
+        const int ybase = (p.cy_min + sy) * 32;
+#pragma unroll 4
+        for (int yc = 0; yc < 32; yc++) {
+            const int y = ybase + yc;
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int h = hh[k];
+                uint32_t v;
+                if (y == h) v = (el[k] == 2 && y > 80) ? p.id_snow : p.id_grass;
+                else if (y < h - 5) v = p.id_stone;
+                else if (y < h) v = p.id_dirt;
+                else v = p.id_void;
+                o[k] = v;
+            }
+            dst[yc * 256] = make_uint4(o[0], o[1], o[2], o[3]); // 1024 voxels per y layer = 256 uint4
+        }
+    }
+}
+
+bool g_const_uploaded = false;
+void ensure_constants() {
+    if (g_const_uploaded) return;
+    cudaMemcpyToSymbol(c_lat_off, h_lat_off, sizeof h_lat_off);
+    cudaMemcpyToSymbol(c_lat_pt, h_lat_pt, sizeof h_lat_pt);
+    g_const_uploaded = true;
+}
+
+} // namespace
+
+void launch_cellpoints_kernel(uint64_t seed, int32_t cell_x0, int32_t cell_z0, int32_t cells_w, int32_t cells_d,
+                              const GenTables *tables, CellPointDev *cells, int precision, cudaStream_t stream) {
+    ensure_constants();
+    const int n = cells_w * cells_d;
+    if (precision == 32)
+        cellpoints_kernel<32><<<(n + 127) / 128, 128, 0, stream>>>(seed, cell_x0, cell_z0, cells_w, cells_d, tables, cells);
+    else
+        cellpoints_kernel<64><<<(n + 127) / 128, 128, 0, stream>>>(seed, cell_x0, cell_z0, cells_w, cells_d, tables, cells);
+}
+
+void launch_heightmap_kernel(const GenParams &p, int precision, cudaStream_t stream) {
+    ensure_constants();
+    dim3 grid((p.W + 127) / 128, p.D);
+    if (precision == 32) heightmap_kernel<32><<<grid, 128, 0, stream>>>(p);
+    else heightmap_kernel<64><<<grid, 128, 0, stream>>>(p);
+}
+
+void launch_fill_kernel(const FillParams &p, cudaStream_t stream) {
+    dim3 grid(p.SX, p.SZ);
+    fill_kernel<<<grid, 256, 0, stream>>>(p);
+}
+
+} // namespace bxw

@@ -1,0 +1,35 @@
+// tables.hpp — geometry lookup tables of the mesher, pre-rotated into world space per (shape, orientation) class.
+//
+// Source of the data: bxw_world/src/blocks/stdshapes.rs (VoxelShapeDef tables, :103-700) and
+// bxw_util/src/direction.rs (OctahedralOrientation, :165-347). The reference looks a side up at run time as
+// sides[orientation.unapply_to_dir(world_dir)] and rotates every vertex / AO offset by orientation.to_matrixi()
+// (src/client/render/voxmesh.rs:105-106, 125-139); here all 24 rotations are applied once on the host so the
+// kernels index [class][world_dir][vertex] directly.
+#pragma once
+#include <cstdint>
+
+namespace bxw {
+
+// class 0 = no mesh (VOXEL_NO_SHAPE); class 1 + shape*24 + orientation, shape 0 cube,1 slope,2 corner,3 inner corner
+constexpr int kNumClasses = 97;
+
+// ctab[class]: bits 0-5 CC (side facing world dir d can_clip), 6-11 EC (emits && can_be_clipped),
+//              12-17 EU (emits && !can_be_clipped), 18-29 per-dir vertex-count code (2 bits: 0 none,1 three,2 four,3 six)
+// stab[class][d]: bits 0-2 local side, 3-5 n_verts, 6-8 n_indices, 9-20 barycentric sign codes (2 bits/vertex: sign+1)
+// vtab[class][d][j] (64-bit):
+//   bits 0-2 corner (x,y,z in {0,1}: vertex = cell + corner), 3 texcoord u, 4 texcoord v, 5-7 barycentric >0.1 flags (x,y,z),
+//   8-9 sign+1, 10-12 n_ao, 13+6k.. AO sample k: (dx+1) | (dy+1)<<2 | (dz+1)<<4
+struct MeshTables {
+    uint32_t ctab[kNumClasses];
+    uint32_t stab[kNumClasses][6];
+    unsigned long long vtab[kNumClasses][6][6];
+    float ao_lut[8]; // ao after k occluding samples: sequential f32 multiplies by 0.88 (voxmesh.rs:27,129-137)
+};
+
+void build_mesh_tables(MeshTables &t);
+
+// orientation helpers (direction.rs:267-293, 312-314), exposed for host-side use / tests
+void orientation_matrix(int idx, int m[9]); // row-major
+int orientation_unapply(int idx, int dir);
+
+} // namespace bxw

@@ -1,0 +1,68 @@
+"""Batched, GPU-resident form of the chunk handlers.
+
+The reference schedules one task per chunk through ChunkDataHandler::create_chunk_update_task
+(bxw_world/src/worldmgr.rs:49-77; WorldBlocks generation.rs:96-148; MeshDataHandler voxrender.rs:224-418) and
+applies edits with World::apply_voxel_changes (worldmgr.rs:312-357). A Region does the same work for a whole box of
+chunks per call, keeping block storage and meshes on the device.
+"""
+import numpy as np
+
+from .capi import CHANGE_DTYPE
+from .world import ChunkBuffers, StdGenerator, default_context
+
+
+class Region:
+    def __init__(self, origin, dims, registry, ctx=None):
+        """origin: world chunk coordinate of interior chunk (0,0,0); dims: (nx, ny, nz) interior chunks."""
+        self.ctx = ctx or default_context()
+        self.origin = tuple(origin)
+        self.dims = tuple(dims)
+        self.registry = registry
+        registry.bind(self.ctx)
+        self.ctx.region_create(*self.origin, *self.dims)
+        self.arena = (0, 0)
+
+    def generate(self, seed=0, precision=64):
+        self.ctx.set_gen_ids(*StdGenerator.resolve_ids(self.registry))
+        self.ctx.region_generate(seed, precision)
+
+    def mesh(self):
+        self.registry.bind(self.ctx)
+        self.arena = self.ctx.region_mesh()
+        return self.arena
+
+    def generate_and_mesh(self, seed=0, precision=64):
+        self.registry.bind(self.ctx)
+        self.ctx.set_gen_ids(*StdGenerator.resolve_ids(self.registry))
+        self.arena = self.ctx.region_generate_and_mesh(seed, precision)
+        return self.arena
+
+    def spans(self):
+        return self.ctx.region_mesh_spans()
+
+    def fetch(self):
+        return self.ctx.region_mesh_fetch(*self.arena)
+
+    def chunk_buffers(self, spans, vertices, indices, ix, iy, iz):
+        nx, ny, nz = self.dims
+        s = spans[ix + nx * (iz + nz * iy)]
+        return ChunkBuffers(vertices[int(s["v_off"]): int(s["v_off"]) + int(s["v_count"])],
+                            indices[int(s["i_off"]): int(s["i_off"]) + int(s["i_count"])])
+
+    def upload_chunk(self, lx, ly, lz, blocks):
+        self.ctx.region_upload_chunk(lx, ly, lz, blocks)
+
+    def download_chunk(self, lx, ly, lz):
+        return self.ctx.region_download_chunk(lx, ly, lz)
+
+    def apply_voxel_changes(self, changes):
+        """changes: iterable of (x, y, z, from, to) global block positions, applied in order (worldmgr.rs:312-357)."""
+        ch = np.array([tuple(c) for c in changes], dtype=CHANGE_DTYPE) if not isinstance(changes, np.ndarray) else changes
+        return self.ctx.region_apply_changes(ch)
+
+    def remesh_dirty(self):
+        n = self.ctx.region_remesh_dirty()
+        return n
+
+    def close(self):
+        self.ctx.region_destroy()

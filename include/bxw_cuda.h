@@ -1,0 +1,170 @@
+/*
+ * bxw_cuda.h — C ABI of libbxw_cuda.so: BallX World's chunk pipeline (generate -> GPU-resident store -> mesh)
+ * as hand-written sm_100a kernels.
+ *
+ * The reference (eigenraven/ballxworld, Rust) has no FFI of its own; the seam this ABI replaces is three Rust
+ * items (file:line relative to the reference tree):
+ *   1. bxw_world::stdgen::StdGenerator::{new, generate_chunk}          bxw_world/src/stdgen.rs:297-374
+ *   2. client::render::voxmesh::{mesh_from_chunk, is_chunk_trivial}     src/client/render/voxmesh.rs:16-190
+ *   3. the ChunkDataHandler plugin trait both sit behind               bxw_world/src/worldmgr.rs:49-77
+ *      (WorldBlocks: bxw_world/src/generation.rs:11-203; MeshDataHandler: src/client/render/voxrender.rs:192-448;
+ *      edits: World::apply_voxel_changes bxw_world/src/worldmgr.rs:312-357)
+ * INTEGRATION.md shows the Rust-side bindings (extern "C" block + shims) a maintainer would add.
+ *
+ * Conventions: every function returns 0 (BXW_OK) or a negative BXW_E* code and never unwinds; out-pointers are
+ * caller-owned; one context per CUDA device; calls on one context must be serialised by the caller (the Rust
+ * side wraps the context in a Mutex). There is NO CPU fallback: without a usable CUDA device bxw_create fails.
+ */
+#ifndef BXW_CUDA_H
+#define BXW_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BXW_CHUNK_DIM 32
+#define BXW_CHUNK_VOXELS 32768
+
+enum {
+    BXW_OK = 0,
+    BXW_E_INVALID = -1,    /* bad argument / call order */
+    BXW_E_CUDA = -2,       /* CUDA runtime error; see bxw_last_error */
+    BXW_E_NOMEM = -3,      /* host or device allocation failed */
+    BXW_E_UNKNOWN_ID = -4, /* a voxel's block id has no registry definition (reference panics: voxregistry.rs:141-143) */
+    BXW_E_NOSPACE = -5,    /* mesh arena too small and auto-grow disabled */
+    BXW_E_BAD_RLE = -6,    /* RLE stream does not decode to 32768 voxels (lib.rs:296-302) */
+    BXW_E_NO_REGISTRY = -7 /* registry / generator ids not set */
+};
+
+typedef struct bxw_ctx bxw_ctx;
+
+/* VoxelDefinition fields the path reads (bxw_world/src/lib.rs:629-639). mesh_kind: 0 VoxelMesh::None,
+ * 1 VoxelMesh::CubeAndSlopes (lib.rs:651-655). tex[] is TextureMapping by signed axis index (lib.rs:624-626). */
+typedef struct {
+    uint8_t present;
+    uint8_t mesh_kind;
+    float debug_color[3];
+    uint32_t tex[6];
+} bxw_block_def;
+
+/* vox::VoxelVertex, #[repr(C)], 40 bytes (src/client/render/voxrender.rs:39-49) */
+typedef struct {
+    uint32_t position; /* W2 X10 Y10 Z10 */
+    uint32_t color;    /* R8 G8 B8 A8 */
+    float texcoord[3];
+    int32_t index;
+    float barycentric_color_offset[4];
+} bxw_vertex;
+
+/* VoxelChange as consumed by World::apply_voxel_changes (bxw_world/src/worldmgr.rs:312-357,
+ * bxw_world/src/generation.rs:39-64): compare-and-swap of one voxel at a global block position. */
+typedef struct {
+    int32_t x, y, z;
+    uint32_t from, to;
+} bxw_voxel_change;
+
+/* Where one chunk's ChunkBuffers{vertices, indices} (voxrender.rs:34-37) live inside the mesh arena.
+ * Indices are chunk-relative exactly as in the reference (voxmesh.rs:123,175). */
+typedef struct {
+    uint64_t v_off, i_off; /* in vertices / indices from the start of the arena */
+    uint32_t v_count, i_count;
+} bxw_mesh_span;
+
+/* ---- context ---- */
+int bxw_create(int device, bxw_ctx **out);
+void bxw_destroy(bxw_ctx *ctx);
+const char *bxw_last_error(const bxw_ctx *ctx);
+/* Launch all work on an externally owned cudaStream_t (e.g. torch's current stream); NULL = the context's own. */
+int bxw_set_stream(bxw_ctx *ctx, void *cuda_stream);
+int bxw_synchronize(bxw_ctx *ctx);
+/* Number of this library's kernels launched since creation (bench.py's gpu_launches evidence). */
+uint64_t bxw_kernel_launches(const bxw_ctx *ctx);
+
+/* ---- registry (replaces &VoxelRegistry arguments; voxregistry.rs:94-143, blocks/mod.rs:6-65) ---- */
+int bxw_set_registry(bxw_ctx *ctx, const bxw_block_def *defs, uint32_t n); /* ids 0..n-1 */
+/* The five names StdGenerator::generate_chunk resolves (stdgen.rs:307-326), as ids. */
+int bxw_set_gen_ids(bxw_ctx *ctx, uint16_t void_id, uint16_t grass, uint16_t dirt, uint16_t stone,
+                    uint16_t snow_grass);
+
+/* ---- per-chunk drop-ins (host pointers) ---- */
+/* StdGenerator::new(seed).generate_chunk(chunk{position=(cx,cy,cz)}, registry)  (stdgen.rs:297-374).
+ * Overwrites all 32768 voxels of blocks_yzx (index x + 32 z + 1024 y, lib.rs:104-108). */
+int bxw_gen_chunk(bxw_ctx *ctx, uint64_t seed, int32_t cx, int32_t cy, int32_t cz, uint32_t *blocks_yzx);
+/* mesh_from_chunk(registry, chunks[27]) (voxmesh.rs:45-190) with the 27 neighbours given dense, in
+ * iter_neighbors(cpos, true) order: slot = rx + 3 rz + 9 ry (worldmgr.rs:748-759, voxmesh.rs:72).
+ * counts->v_count / i_count receive the buffer sizes; fetch with bxw_mesh_fetch. */
+int bxw_mesh_chunk27(bxw_ctx *ctx, const uint32_t *const dense[27], bxw_mesh_span *counts);
+/* Same, neighbours given as VChunk RLE streams (lib.rs:237-345); decoded on the device. */
+int bxw_mesh_chunk27_rle(bxw_ctx *ctx, const uint32_t *const rle[27], const size_t rle_len[27],
+                         bxw_mesh_span *counts);
+int bxw_mesh_fetch(bxw_ctx *ctx, bxw_vertex *vertices, uint32_t *indices);
+/* is_chunk_trivial(chunk, registry) (voxmesh.rs:16-25); host-side, no device work. */
+int bxw_is_chunk_trivial(bxw_ctx *ctx, const uint32_t *rle, size_t rle_len, int *out_trivial);
+
+/* ---- VChunk RLE codec on the device (bxw_world/src/lib.rs:263-345), host buffers ---- */
+/* compress_rle of n_chunks dense chunks; out_words must hold n_chunks*32768*... see bxw_rle_bound(). offsets
+ * gets n_chunks+1 word offsets. */
+size_t bxw_rle_bound(size_t n_chunks);
+int bxw_rle_compress(bxw_ctx *ctx, const uint32_t *dense, size_t n_chunks, uint32_t *out_words,
+                     uint64_t *out_offsets);
+int bxw_rle_decompress(bxw_ctx *ctx, const uint32_t *words, const uint64_t *offsets, size_t n_chunks,
+                       uint32_t *out_dense);
+
+/* ---- region form: GPU-resident block storage + batched kernels (the form that reaches the roofline) ---- */
+/* A region is the box of nx*ny*nz chunks whose minimum chunk is (cx0,cy0,cz0), stored together with a 1-chunk
+ * shell so every interior chunk has its 26 neighbours (the reference's precondition, worldmgr.rs:761-790).
+ * Local chunk coordinates l* run over -1..n* (shell included). One region per context. */
+int bxw_region_create(bxw_ctx *ctx, int32_t cx0, int32_t cy0, int32_t cz0, uint32_t nx, uint32_t ny, uint32_t nz);
+int bxw_region_destroy(bxw_ctx *ctx);
+/* Fill every chunk (shell included) with StdGenerator(seed) terrain. precision: 64 = f64 noise exactly as the
+ * reference computes it; 32 = FP32 noise evaluation (north_star-literal variant; may flip voxels whose noise value
+ * sits within rounding of a selection threshold). */
+int bxw_region_generate(bxw_ctx *ctx, uint64_t seed, int precision);
+/* Column parameters of the last generate: height (round(h) as i32) and elevation class (0 LowLand,1 Hill,
+ * 2 Mountain) for the (nx+2)*32 x (nz+2)*32 columns, row-major [z][x]; raw f64 height optional (may be NULL). */
+int bxw_region_heightmap(bxw_ctx *ctx, int32_t *height, uint8_t *elevation, double *raw_height);
+int bxw_region_upload_chunk(bxw_ctx *ctx, int32_t lx, int32_t ly, int32_t lz, const uint32_t *blocks_yzx);
+int bxw_region_download_chunk(bxw_ctx *ctx, int32_t lx, int32_t ly, int32_t lz, uint32_t *blocks_yzx);
+/* Mesh arena capacity (vertices / indices). Without a reservation bxw_region_mesh sizes it with a count pass. */
+int bxw_region_mesh_reserve(bxw_ctx *ctx, uint64_t max_vertices, uint64_t max_indices);
+/* Mesh every interior chunk (mesh_from_chunk semantics per chunk). Totals include alignment padding between
+ * chunks, i.e. they are the arena extents to fetch. */
+int bxw_region_mesh(bxw_ctx *ctx, uint64_t *arena_vertices, uint64_t *arena_indices);
+/* Fused StdGenerator + mesher over the pristine region: blocks are written once and meshed from on-chip data. */
+int bxw_region_generate_and_mesh(bxw_ctx *ctx, uint64_t seed, int precision, uint64_t *arena_vertices,
+                                 uint64_t *arena_indices);
+/* spans: nx*ny*nz entries, chunk order x + nx*(z + nz*y). */
+int bxw_region_mesh_spans(bxw_ctx *ctx, bxw_mesh_span *spans);
+/* Copy arena extents [0,arena_vertices) / [0,arena_indices) to host (pinned memory recommended). */
+int bxw_region_mesh_fetch(bxw_ctx *ctx, bxw_vertex *vertices, uint64_t n_vertices, uint32_t *indices,
+                          uint64_t n_indices);
+/* World::apply_voxel_changes (worldmgr.rs:312-357): CAS each change in order, mark touching_chunks
+ * (lib.rs:110-135) dirty. n_dirty = interior chunks now dirty. */
+int bxw_region_apply_changes(bxw_ctx *ctx, const bxw_voxel_change *changes, uint32_t n, uint32_t *n_dirty);
+/* Re-mesh the dirty interior chunks into fresh arena space; their spans are updated. */
+int bxw_region_remesh_dirty(bxw_ctx *ctx, uint32_t *n_remeshed);
+/* Multi-GPU slab boundary: the 1-voxel plane adjacent to face 0 (x-) or 1 (x+) of the interior, packed for the
+ * neighbouring rank ((nz+2)*32 x (ny+2)*32 u32, [y][z]). export packs interior boundary voxels into dev_buf;
+ * import writes a received plane into this region's shell. dev_buf is device memory (e.g. a torch tensor). */
+size_t bxw_region_halo_bytes(const bxw_ctx *ctx);
+int bxw_region_halo_export(bxw_ctx *ctx, int face, void *dev_buf);
+int bxw_region_halo_import(bxw_ctx *ctx, int face, const void *dev_buf);
+/* Device pointers for zero-copy consumers (e.g. graphics interop); valid until the next mesh/destroy call. */
+int bxw_region_device_ptrs(bxw_ctx *ctx, void **blocks, void **vertices, void **indices);
+
+/* ---- bxw_terragen in-tree SuperSimplex (bxw_terragen/src/supersimplex.rs:20-107), batched ---- */
+int bxw_terragen_noise2(bxw_ctx *ctx, uint64_t seed, const double *xs, const double *ys, size_t n, double *out);
+
+/* ---- device timing helpers (CUDA events on the context's stream) ---- */
+int bxw_timer_start(bxw_ctx *ctx);
+int bxw_timer_stop_ms(bxw_ctx *ctx, float *ms); /* records, synchronises, returns elapsed */
+/* Accumulated device time of the mesher kernel since the last reset (events around each launch). */
+int bxw_mesh_kernel_time_ms(bxw_ctx *ctx, float *ms, uint64_t *launches, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,142 @@
+"""Parity of the CUDA mesher (through the C ABI) against the oracle: bit-exact vertices and indices."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def assert_mesh_equal(got, want, what=""):
+    gv, gi = got
+    wv, wi = want
+    assert len(gv) == len(wv) and len(gi) == len(wi), f"{what}: counts {len(gv)},{len(gi)} vs oracle {len(wv)},{len(wi)}"
+    # bitwise comparison, floats included
+    assert gv.tobytes() == wv.tobytes(), f"{what}: vertex bytes differ (first at {first_diff(gv, wv)})"
+    assert np.array_equal(gi, wi), f"{what}: indices differ"
+
+
+def first_diff(a, b):
+    a8 = np.frombuffer(a.tobytes(), dtype=np.uint8).reshape(-1, 40)
+    b8 = np.frombuffer(b.tobytes(), dtype=np.uint8).reshape(-1, 40)
+    bad = np.nonzero((a8 != b8).any(axis=1))[0]
+    if len(bad) == 0:
+        return None
+    k = int(bad[0])
+    return k, a[k], b[k]
+
+
+def neighborhood(oracle, cx, cy, cz, **kw):
+    out = []
+    for dy in (-1, 0, 1):
+        for dz in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                out.append(oracle.random_chunk(cx + dx, cy + dy, cz + dz, **kw))
+    return out
+
+
+def test_lone_grass_cube_kat(ctx, oracle):
+    """SURVEY.md App. C.5 known answer + oracle equality."""
+    d = [np.zeros(32768, np.uint32) for _ in range(27)]
+    d[13][5 + 32 * 7 + 1024 * 6] = 1 << 16
+    v, ix = ctx.mesh_chunk27(d)
+    assert len(v) == 24 and len(ix) == 36
+    assert [int(p) for p in v["position"][:4]] == [0x05018080, 0x0501C080, 0x0501C070, 0x05018070]
+    assert [int(p) for p in v["index"][:4]] == [0x000C18E5, 0x000818E5, 0x000A18E5, 0x000818E5]
+    assert int(v["color"][0]) == 0xFFFFFFFF and float(v["texcoord"][0][2]) == 16.0
+    assert list(ix[:12]) == [0, 1, 2, 2, 3, 0, 4, 5, 6, 6, 7, 4]
+    assert_mesh_equal((v, ix), oracle.mesh_from_dense27(oracle.OracleRegistry(), d), "lone cube")
+
+
+@pytest.mark.parametrize("pos", [(0, 0, 0), (3, -2, 5), (-7, 1, -1)])
+@pytest.mark.parametrize("thr", [128, 250, 16])
+def test_random_shapes_chunk27(ctx, oracle, pos, thr):
+    """cfg 2 style input: hashed random ids, all shapes, all 24 orientations, incl. halo influence."""
+    d = neighborhood(oracle, *pos, seed=1, void_threshold=thr)
+    got = ctx.mesh_chunk27(d)
+    want = oracle.mesh_from_dense27(oracle.OracleRegistry(), d)
+    assert len(want[0]) > 0
+    assert_mesh_equal(got, want, f"random {pos} thr={thr}")
+
+
+def test_uniform_and_empty(ctx, oracle):
+    reg = oracle.OracleRegistry()
+    void = [np.zeros(32768, np.uint32) for _ in range(27)]
+    v, ix = ctx.mesh_chunk27(void)
+    assert len(v) == 0 and len(ix) == 0
+    stone = [np.full(32768, 4 << 16, np.uint32) for _ in range(27)]
+    v, ix = ctx.mesh_chunk27(stone)
+    assert len(v) == 0 and len(ix) == 0
+    # solid centre in a void neighbourhood: the full 6*1024 faces
+    d = [np.zeros(32768, np.uint32) for _ in range(27)]
+    d[13] = np.full(32768, 4 << 16, np.uint32)
+    assert_mesh_equal(ctx.mesh_chunk27(d), oracle.mesh_from_dense27(reg, d), "solid centre")
+    # void centre, solid neighbours: nothing (void emits nothing)
+    d = [np.full(32768, 3 << 16, np.uint32) for _ in range(27)]
+    d[13] = np.zeros(32768, np.uint32)
+    v, ix = ctx.mesh_chunk27(d)
+    assert len(v) == 0
+
+
+def test_maximum_output_chunk(ctx, oracle):
+    """3-D checkerboard of cubes: every face visible -> 16384 cubes x 24 vertices."""
+    g = np.indices((32, 32, 32)).sum(axis=0) & 1
+    d = [np.zeros(32768, np.uint32) for _ in range(27)]
+    d[13] = np.where(g.reshape(-1) == 1, np.uint32(6 << 16), np.uint32(0)).astype(np.uint32)
+    got = ctx.mesh_chunk27(d)
+    assert len(got[0]) == 16384 * 24 and len(got[1]) == 16384 * 36
+    assert_mesh_equal(got, oracle.mesh_from_dense27(oracle.OracleRegistry(), d), "checkerboard")
+
+
+def test_odd_meta_values(ctx, oracle):
+    """shape > 3 -> cube, orientation >= 24 -> default (stdshapes.rs:54-70); meta on a None-mesh block ignored."""
+    rng = np.random.default_rng(7)
+    d = []
+    for _ in range(27):
+        ids = rng.integers(0, 8, 32768).astype(np.uint32)
+        meta = rng.integers(0, 65536, 32768).astype(np.uint32)
+        keep = rng.random(32768) < 0.3
+        d.append(np.where(keep, (ids << 16) | meta, 0).astype(np.uint32))
+    assert_mesh_equal(ctx.mesh_chunk27(d), oracle.mesh_from_dense27(oracle.OracleRegistry(), d), "odd meta")
+
+
+def test_unknown_block_id_is_an_error(ctx):
+    import ballxworld_b200 as bxw
+
+    d = [np.zeros(32768, np.uint32) for _ in range(27)]
+    # id 200 is not registered; the reference panics (voxregistry.rs:141-143). Slot 4 is the -y neighbour: only its
+    # y=31 layer is part of the 34^3 table, so the bad voxel must sit there to be seen at all.
+    d[4][4 + 32 * 3 + 1024 * 31] = 200 << 16
+    with pytest.raises(bxw.BxwError) as e:
+        ctx.mesh_chunk27(d)
+    assert e.value.code == -4
+
+
+def test_region_mesh_matches_oracle(ctx, oracle):
+    """Region form: upload random chunks (shell included), mesh all interior chunks, compare each with the oracle."""
+    nx, ny, nz = 4, 3, 2
+    ctx.region_create(10, -1, 20, nx, ny, nz)
+    chunks = {}
+    for ly in range(-1, ny + 1):
+        for lz in range(-1, nz + 1):
+            for lx in range(-1, nx + 1):
+                thr = 128 if (lx + ly + lz) % 3 else 245
+                c = oracle.random_chunk(10 + lx, -1 + ly, 20 + lz, seed=5, void_threshold=thr)
+                chunks[(lx, ly, lz)] = c
+                ctx.region_upload_chunk(lx, ly, lz, c)
+    av, ai = ctx.region_mesh()
+    spans = ctx.region_mesh_spans()
+    V, I = ctx.region_mesh_fetch(av, ai)
+    reg = oracle.OracleRegistry()
+    tot_v = 0
+    for iy in range(ny):
+        for iz in range(nz):
+            for ix in range(nx):
+                s = spans[ix + nx * (iz + nz * iy)]
+                d = [chunks[(ix + dx, iy + dy, iz + dz)] for dy in (-1, 0, 1) for dz in (-1, 0, 1) for dx in (-1, 0, 1)]
+                want = oracle.mesh_from_dense27(reg, d)
+                got = (V[int(s["v_off"]): int(s["v_off"]) + int(s["v_count"])], I[int(s["i_off"]): int(s["i_off"]) + int(s["i_count"])])
+                assert_mesh_equal(got, want, f"region chunk {(ix, iy, iz)}")
+                tot_v += len(want[0])
+    assert tot_v > 0
+    # download returns what was uploaded
+    assert np.array_equal(ctx.region_download_chunk(0, 0, 0), chunks[(0, 0, 0)])
+    ctx.region_destroy()
