@@ -1,0 +1,389 @@
+// aux_kernels.cu — the small kernels around the two hot ones: slab-boundary halo pack/unpack (multi-GPU), voxel
+// edits + dirty tracking (World::apply_voxel_changes), the VChunk RLE codec, and bxw_terragen's SuperSimplex.
+#include "aux_kernels.cuh"
+
+namespace bxw {
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------
+// Halo planes. One x = const voxel plane over the whole storage extent in y and z (shell rows included so that
+// edges and corners travel too: AO samples diagonal neighbours, stdshapes.rs:131-152). Layout [gy][gz].
+// ------------------------------------------------------------------------------------------------------------
+__global__ void halo_plane_kernel(uint32_t *blocks, int SX, int SY, int SZ, int sx, int lx, uint32_t *plane, int import) {
+    const int gz = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gy = blockIdx.y;
+    if (gz >= SZ * 32) return;
+    const int sy = gy >> 5, ly = gy & 31, sz = gz >> 5, lz = gz & 31;
+    uint32_t *v = blocks + ((size_t)(sx + SX * (sz + SZ * sy))) * kChunkVoxels + lx + 32 * lz + 1024 * ly;
+    uint32_t *p = plane + (size_t)gy * (SZ * 32) + gz;
+    if (import) *v = *p;
+    else *p = *v;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Edits. The host groups the changes by voxel (stable), one thread replays one voxel's changes in order:
+// `if chunk.blocks_yzx[bidx] == change.from { = change.to }` (generation.rs:52-57). Every change marks
+// bpos.touching_chunks() dirty whether or not it applied (worldmgr.rs:329-334, lib.rs:110-135).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void apply_changes_kernel(EditParams p) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.n_runs) return;
+    const uint32_t b = p.run_start[r], e = p.run_start[r + 1];
+    const bxw_voxel_change c0 = p.changes[b];
+    // storage-local voxel coordinates (the host dropped changes outside the storage box)
+    const int gx = c0.x - p.x_min, gy = c0.y - p.y_min, gz = c0.z - p.z_min;
+    const int sx = gx >> 5, sy = gy >> 5, sz = gz >> 5, lx = gx & 31, ly = gy & 31, lz = gz & 31;
+    uint32_t *v = p.blocks + ((size_t)(sx + p.SX * (sz + p.SZ * sy))) * kChunkVoxels + lx + 32 * lz + 1024 * ly;
+    uint32_t cur = *v;
+    for (uint32_t k = b; k < e; k++) {
+        const bxw_voxel_change c = p.changes[k];
+        if (cur == c.from) cur = c.to;
+    }
+    *v = cur;
+    auto mark = [&](int cx, int cy, int cz) { // interior chunks only carry meshes
+        if (cx >= 1 && cx <= p.SX - 2 && cy >= 1 && cy <= p.SY - 2 && cz >= 1 && cz <= p.SZ - 2)
+            p.dirty[(cx - 1) + (p.SX - 2) * ((cz - 1) + (p.SZ - 2) * (cy - 1))] = 1;
+    };
+    mark(sx, sy, sz);
+    if (lx == 0) mark(sx - 1, sy, sz);
+    if (lx == 31) mark(sx + 1, sy, sz);
+    if (ly == 0) mark(sx, sy - 1, sz);
+    if (ly == 31) mark(sx, sy + 1, sz);
+    if (lz == 0) mark(sx, sy, sz - 1);
+    if (lz == 31) mark(sx, sy, sz + 1);
+}
+
+__global__ void dirty_list_kernel(uint8_t *dirty, uint32_t n, int nx, int nz, int SX, int SZ, uint32_t *work, uint32_t *work_span,
+                                  uint32_t *count, int clear) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !dirty[i]) return;
+    if (clear) dirty[i] = 0;
+    const uint32_t k = atomicAdd(count, 1u);
+    const uint32_t ix = i % nx, iz = (i / nx) % nz, iy = i / (nx * nz);
+    work[k] = (ix + 1) + SX * ((iz + 1) + SZ * (iy + 1));
+    work_span[k] = i;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// VChunk RLE (bxw_world/src/lib.rs:263-345). compress_rle emits, for every maximal run of a value v of length L,
+// [v] if L == 1 and [v, v, L-2] otherwise (a count word follows every equal pair; the state machine at
+// lib.rs:268-291 never pairs across a count). One CTA per chunk.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int RT = 256;            // threads per CTA
+constexpr int RSEG = 32768 / RT;   // 128 contiguous voxels per thread
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *warp_tot, uint32_t &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t a = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += a;
+    }
+    __syncthreads();
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+    for (int k = 0; k < RT / 32; k++) {
+        uint32_t t = warp_tot[k];
+        if (k < warp) base += t;
+        tot += t;
+    }
+    total = tot;
+    return base + incl - v;
+}
+
+// words a run starting at voxel i contributes, given the dense data; run heads only
+template <bool WRITE>
+__global__ void __launch_bounds__(RT) rle_compress_kernel(const uint32_t *dense, size_t n_chunks, const uint64_t *offsets,
+                                                          uint32_t *out_words, uint32_t *out_len) {
+    __shared__ uint32_t warp_tot[RT / 32];
+    const size_t c = blockIdx.x;
+    if (c >= n_chunks) return;
+    const uint32_t *d = dense + c * kChunkVoxels;
+    const int t = threadIdx.x;
+    const int b = t * RSEG;
+    // Each thread owns the run HEADS inside its segment; a run's length may extend past the segment.
+    // pass 1: count words for heads in this segment
+    uint32_t words = 0;
+    uint32_t prev = b ? d[b - 1] : 0;
+    for (int i = b; i < b + RSEG; i++) {
+        const uint32_t v = d[i];
+        const bool head = (i == 0) || (v != prev);
+        if (head) {
+            const bool longrun = (i + 1 < kChunkVoxels) && d[i + 1] == v;
+            words += longrun ? 3u : 1u;
+        }
+        prev = v;
+    }
+    uint32_t total;
+    uint32_t off = block_exclusive_scan(words, warp_tot, total);
+    if (!WRITE) {
+        if (t == 0) out_len[c] = total;
+        return;
+    }
+    uint32_t *o = out_words + offsets[c];
+    prev = b ? d[b - 1] : 0;
+    for (int i = b; i < b + RSEG; i++) {
+        const uint32_t v = d[i];
+        const bool head = (i == 0) || (v != prev);
+        if (head) {
+            int j = i + 1;
+            if (j < kChunkVoxels && d[j] == v) {
+                while (j < kChunkVoxels && d[j] == v) j++; // run length (may cross segments; long runs are rare per thread)
+                o[off] = v;
+                o[off + 1] = v;
+                o[off + 2] = (uint32_t)(j - i - 2);
+                off += 3;
+            } else {
+                o[off++] = v;
+            }
+        }
+        prev = v;
+    }
+}
+
+__global__ void offsets_scan_kernel(const uint32_t *len, size_t n, uint64_t *offsets) {
+    // single CTA: exclusive scan of per-chunk word counts into 64-bit offsets (n+1 entries)
+    __shared__ uint64_t carry;
+    __shared__ uint32_t warp_tot[RT / 32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (size_t base = 0; base < n; base += RT) {
+        const size_t i = base + threadIdx.x;
+        const uint32_t v = i < n ? len[i] : 0u;
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan(v, warp_tot, total);
+        if (i < n) offsets[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offsets[n] = carry;
+}
+
+// decompress_rle (lib.rs:304-345). The parse state before word i is one of N (no previous value), V (previous word
+// is a value that may pair) or C (a count is expected); the transition depends only on whether w[i] == w[i-1]:
+//   C -> N,  N -> V,  V -> (w[i]==w[i-1] ? C : V).
+// Each thread folds the transitions of its contiguous word segment for all three start states, the CTA scans the
+// composed maps, and each thread then replays its segment from its true start state.
+__device__ __forceinline__ int rle_step(int s, bool eq) { return s == 2 ? 0 : (s == 0 ? 1 : (eq ? 2 : 1)); }
+
+__global__ void __launch_bounds__(RT) rle_decompress_kernel(const uint32_t *words, const uint64_t *offsets, size_t n_chunks,
+                                                            uint32_t *out_dense, uint32_t *status) {
+    __shared__ uint32_t warp_tot[RT / 32];
+    __shared__ uint8_t seg_map[RT];   // 2 bits per start state -> end state
+    __shared__ uint8_t seg_start[RT];
+    __shared__ uint32_t n_long;
+    __shared__ uint32_t long_runs[256][3]; // value, start, length of runs too long for one thread
+    __shared__ int bad;
+    const size_t c = blockIdx.x;
+    if (c >= n_chunks) return;
+    const uint32_t *w = words + offsets[c];
+    const uint64_t len64 = offsets[c + 1] - offsets[c];
+    uint32_t *out = out_dense + c * kChunkVoxels;
+    const int t = threadIdx.x;
+    if (t == 0) {
+        bad = 0;
+        n_long = 0;
+    }
+    __syncthreads();
+    if (len64 < 3 || len64 > 49152) { // lib.rs:305-307; an encoder never exceeds 1.5 words/voxel
+        if (t == 0) status[c] = 4;
+        return;
+    }
+    const uint32_t len = (uint32_t)len64;
+    const uint32_t seg = (len + RT - 1) / RT;
+    const uint32_t b = min(len, t * seg), e = min(len, b + seg);
+    // fold
+    int m[3] = {0, 1, 2};
+    for (uint32_t i = b; i < e; i++) {
+        const bool eq = i > 0 && w[i] == w[i - 1];
+#pragma unroll
+        for (int k = 0; k < 3; k++) m[k] = rle_step(m[k], eq);
+    }
+    seg_map[t] = (uint8_t)(m[0] | (m[1] << 2) | (m[2] << 4));
+    __syncthreads();
+    if (t == 0) {
+        int s = 0; // decompress_rle starts with no previous value
+        for (int k = 0; k < RT; k++) {
+            seg_start[k] = (uint8_t)s;
+            s = (seg_map[k] >> (2 * s)) & 3;
+        }
+        if (s == 2) bad = 3; // stream ends where a count is expected: MissingRleRepeatN
+    }
+    __syncthreads();
+    // count voxels produced by this segment
+    int s = seg_start[t];
+    uint64_t vox = 0;
+    for (uint32_t i = b; i < e; i++) {
+        const bool eq = i > 0 && w[i] == w[i - 1];
+        vox += (s == 2) ? (uint64_t)w[i] : 1ull;
+        s = rle_step(s, eq);
+    }
+    if (vox > 65536) {
+        vox = 65536; // clamp so the 32-bit scan cannot wrap; flagged below through the total
+        bad = 2;
+    }
+    uint32_t total;
+    uint32_t pos = block_exclusive_scan((uint32_t)vox, warp_tot, total);
+    __syncthreads();
+    if (bad || total != (uint32_t)kChunkVoxels) {
+        if (t == 0) status[c] = bad ? (uint32_t)bad : (total > (uint32_t)kChunkVoxels ? 2u : 4u);
+        return;
+    }
+    // write
+    s = seg_start[t];
+    for (uint32_t i = b; i < e; i++) {
+        const bool eq = i > 0 && w[i] == w[i - 1];
+        if (s == 2) {
+            const uint32_t n = w[i], v = w[i - 1];
+            if (n >= 64) {
+                const uint32_t q = atomicAdd(&n_long, 1u);
+                if (q < 256) {
+                    long_runs[q][0] = v;
+                    long_runs[q][1] = pos;
+                    long_runs[q][2] = n;
+                } else {
+                    for (uint32_t k = 0; k < n; k++) out[pos + k] = v; // more than 256 long runs cannot fit 32768 voxels at n>=64... defensive
+                }
+            } else {
+                for (uint32_t k = 0; k < n; k++) out[pos + k] = v;
+            }
+            pos += n;
+        } else {
+            out[pos++] = w[i];
+        }
+        s = rle_step(s, eq);
+    }
+    __syncthreads();
+    const uint32_t nl = min(n_long, 256u);
+    for (uint32_t q = 0; q < nl; q++) {
+        const uint32_t v = long_runs[q][0], st = long_runs[q][1], n = long_runs[q][2];
+        for (uint32_t k = t; k < n; k += RT) out[st + k] = v;
+    }
+    if (t == 0) status[c] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// bxw_terragen::SuperSimplex::noise2 (bxw_terragen/src/supersimplex.rs:53-107), one point per thread.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void terragen_noise2_kernel(const TerragenTables *T, const double *xs, const double *ys, size_t n, double *out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = xs[i], y = ys[i];
+    const double s = __dmul_rn(__dadd_rn(x, y), 0.366025403784439);
+    const double xs_ = __dadd_rn(x, s), ys_ = __dadd_rn(y, s);
+    // widefloor_f64_i32 (math.rs:68-78): truncating cast, minus one where x < trunc(x)
+    int32_t xsb = __double2int_rz(xs_), ysb = __double2int_rz(ys_);
+    if (xs_ < (double)xsb) xsb -= 1;
+    if (ys_ < (double)ysb) ysb -= 1;
+    const double xsi = __dsub_rn(xs_, (double)xsb), ysi = __dsub_rn(ys_, (double)ysb);
+    const int32_t a = __double2int_rz(__dadd_rn(xsi, ysi));
+    const double af = (double)a;
+    const double half_a = __ddiv_rn(af, 2.0);
+    const int32_t index = (a << 2) |
+                          (__double2int_rz(__dsub_rn(__dadd_rn(__dsub_rn(xsi, __ddiv_rn(ysi, 2.0)), 1.0), half_a)) << 3) |
+                          (__double2int_rz(__dsub_rn(__dadd_rn(__dsub_rn(ysi, __ddiv_rn(xsi, 2.0)), 1.0), half_a)) << 4);
+    const double ssi = __dmul_rn(__dadd_rn(xsi, ysi), -0.211324865405187);
+    const double xi = __dadd_rn(xsi, ssi), yi = __dadd_rn(ysi, ssi);
+    double value = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int li = (index + k) & 31;
+        const double dx = __dadd_rn(xi, T->lat_dx[li]), dy = __dadd_rn(yi, T->lat_dy[li]);
+        const double attn = __dsub_rn(__dsub_rn(2.0 / 3.0, __dmul_rn(dx, dx)), __dmul_rn(dy, dy));
+        if (attn > 0.0) {
+            const unsigned pxm = (unsigned)((xsb + T->lat_x[li]) & 2047), pym = (unsigned)((ysb + T->lat_y[li]) & 2047);
+            const unsigned gi = (unsigned)T->perm[pxm] ^ pym;
+            const double ex = __dadd_rn(__dmul_rn(T->gx[gi], dx), __dmul_rn(T->gy[gi], dy));
+            const double a2 = __dmul_rn(attn, attn);
+            value = __dadd_rn(value, __dmul_rn(__dmul_rn(a2, a2), ex));
+        }
+    }
+    out[i] = value;
+}
+
+} // namespace
+
+void launch_halo_plane(uint32_t *blocks, int SX, int SY, int SZ, int sx, int lx, uint32_t *plane, int import, cudaStream_t stream) {
+    dim3 grid((SZ * 32 + 127) / 128, SY * 32);
+    halo_plane_kernel<<<grid, 128, 0, stream>>>(blocks, SX, SY, SZ, sx, lx, plane, import);
+}
+
+void launch_apply_changes(const EditParams &p, cudaStream_t stream) {
+    if (p.n_runs == 0) return;
+    apply_changes_kernel<<<(p.n_runs + 127) / 128, 128, 0, stream>>>(p);
+}
+
+void launch_dirty_list(uint8_t *dirty, uint32_t n, int nx, int nz, int SX, int SZ, uint32_t *work, uint32_t *work_span, uint32_t *count,
+                       int clear, cudaStream_t stream) {
+    dirty_list_kernel<<<(n + 255) / 256, 256, 0, stream>>>(dirty, n, nx, nz, SX, SZ, work, work_span, count, clear);
+}
+
+void launch_rle_compress(const uint32_t *dense, size_t n_chunks, uint32_t *len, uint64_t *offsets, uint32_t *out_words, int phase,
+                         cudaStream_t stream) {
+    if (phase == 0) {
+        rle_compress_kernel<false><<<(unsigned)n_chunks, RT, 0, stream>>>(dense, n_chunks, nullptr, nullptr, len);
+        offsets_scan_kernel<<<1, RT, 0, stream>>>(len, n_chunks, offsets);
+    } else {
+        rle_compress_kernel<true><<<(unsigned)n_chunks, RT, 0, stream>>>(dense, n_chunks, offsets, out_words, nullptr);
+    }
+}
+
+void launch_rle_decompress(const uint32_t *words, const uint64_t *offsets, size_t n_chunks, uint32_t *out_dense, uint32_t *status,
+                           cudaStream_t stream) {
+    rle_decompress_kernel<<<(unsigned)n_chunks, RT, 0, stream>>>(words, offsets, n_chunks, out_dense, status);
+}
+
+void launch_terragen_noise2(const TerragenTables *T, const double *xs, const double *ys, size_t n, double *out, cudaStream_t stream) {
+    terragen_noise2_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(T, xs, ys, n, out);
+}
+
+void build_terragen_tables(uint64_t seed, TerragenTables &t) {
+    // SuperSimplex::new (supersimplex.rs:20-43) and lookup_2d (:121-274)
+    static const double grad2[24][2] = {
+        {0.130526192220052, 0.99144486137381},    {0.38268343236509, 0.923879532511287},   {0.608761429008721, 0.793353340291235},
+        {0.793353340291235, 0.608761429008721},   {0.923879532511287, 0.38268343236509},   {0.99144486137381, 0.130526192220051},
+        {0.99144486137381, -0.130526192220051},   {0.923879532511287, -0.38268343236509},  {0.793353340291235, -0.60876142900872},
+        {0.608761429008721, -0.793353340291235},  {0.38268343236509, -0.923879532511287},  {0.130526192220052, -0.99144486137381},
+        {-0.130526192220052, -0.99144486137381},  {-0.38268343236509, -0.923879532511287}, {-0.608761429008721, -0.793353340291235},
+        {-0.793353340291235, -0.608761429008721}, {-0.923879532511287, -0.38268343236509}, {-0.99144486137381, -0.130526192220052},
+        {-0.99144486137381, 0.130526192220051},   {-0.923879532511287, 0.38268343236509},  {-0.793353340291235, 0.608761429008721},
+        {-0.608761429008721, 0.793353340291235},  {-0.38268343236509, 0.923879532511287},  {-0.130526192220052, 0.99144486137381}};
+    const double N2 = 0.05481866495625118;
+    uint16_t source[2048];
+    for (int i = 0; i < 2048; i++) source[i] = (uint16_t)i;
+    for (int i = 2047; i >= 0; i--) {
+        seed = seed * 6364136223846793005ULL + 1442695040888963407ULL;
+        const uint64_t r = (seed + 31ULL) % ((uint64_t)i + 1ULL);
+        t.perm[i] = source[r];
+        t.gx[i] = grad2[t.perm[i] % 24][0] / N2;
+        t.gy[i] = grad2[t.perm[i] % 24][1] / N2;
+        source[r] = source[i];
+    }
+    for (int i = 0; i < 8; i++) {
+        int i1, j1, i2, j2;
+        if ((i & 1) == 0) {
+            i1 = (i & 2) == 0 ? -1 : 1;
+            j1 = 0;
+            i2 = 0;
+            j2 = (i & 4) == 0 ? -1 : 1;
+        } else {
+            i1 = (i & 2) != 0 ? 2 : 0;
+            j1 = 1;
+            i2 = 1;
+            j2 = (i & 4) != 0 ? 2 : 0;
+        }
+        const int px[4] = {0, 1, i1, i2}, py[4] = {0, 1, j1, j2};
+        for (int k = 0; k < 4; k++) {
+            const double ssv = (double)(px[k] + py[k]) * -0.211324865405187;
+            t.lat_x[i * 4 + k] = px[k];
+            t.lat_y[i * 4 + k] = py[k];
+            t.lat_dx[i * 4 + k] = (double)(-px[k]) - ssv;
+            t.lat_dy[i * 4 + k] = (double)(-py[k]) - ssv;
+        }
+    }
+}
+
+} // namespace bxw
