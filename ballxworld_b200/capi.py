@@ -88,6 +88,7 @@ def load_library():
         "bxw_region_heightmap": ([vp, vp, vp, vp], C.c_int),
         "bxw_region_upload_chunk": ([vp, C.c_int32, C.c_int32, C.c_int32, vp], C.c_int),
         "bxw_region_download_chunk": ([vp, C.c_int32, C.c_int32, C.c_int32, vp], C.c_int),
+        "bxw_region_fill_synthetic": ([vp, C.c_uint64, C.c_uint32], C.c_int),
         "bxw_region_mesh_reserve": ([vp, C.c_uint64, C.c_uint64], C.c_int),
         "bxw_region_mesh": ([vp, u64p, u64p], C.c_int),
         "bxw_region_generate_and_mesh": ([vp, C.c_uint64, C.c_int, u64p, u64p], C.c_int),
@@ -268,6 +269,9 @@ class Context:
         out = np.empty(32768, dtype=np.uint32)
         self._ck(self.L.bxw_region_download_chunk(self.h, lx, ly, lz, _ptr(out)))
         return out
+
+    def region_fill_synthetic(self, seed=1, void_threshold=128):
+        self._ck(self.L.bxw_region_fill_synthetic(self.h, seed, void_threshold))
 
     def region_mesh_reserve(self, max_vertices, max_indices):
         self._ck(self.L.bxw_region_mesh_reserve(self.h, max_vertices, max_indices))

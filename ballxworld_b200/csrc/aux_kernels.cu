@@ -304,7 +304,37 @@ __global__ void terragen_noise2_kernel(const TerragenTables *T, const double *xs
     out[i] = value;
 }
 
+// Synthetic input of BASELINE config 2: every voxel is a pure function of its global position.
+__global__ void fill_synthetic_kernel(uint32_t *blocks, int SX, int SY, int SZ, int32_t cx_min, int32_t cy_min, int32_t cz_min,
+                                      uint64_t seed, uint32_t void_threshold) {
+    const size_t chunk = blockIdx.x;
+    const int sx = (int)(chunk % SX), sz = (int)((chunk / SX) % SZ), sy = (int)(chunk / ((size_t)SX * SZ));
+    for (int i = threadIdx.x; i < kChunkVoxels; i += blockDim.x) {
+        const long long gx = (long long)(cx_min + sx) * 32 + (i & 31), gz = (long long)(cz_min + sz) * 32 + ((i >> 5) & 31),
+                        gy = (long long)(cy_min + sy) * 32 + (i >> 10);
+        const uint64_t k = ((uint64_t)gx & 0x1FFFFF) | (((uint64_t)gy & 0x1FFFFF) << 21) | (((uint64_t)gz & 0x1FFFFF) << 42);
+        uint64_t z = (seed ^ k) + 0x9e3779b97f4a7c15ULL; // splitmix64 (bxw_terragen/src/math.rs:24-30)
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+        const uint64_t r = z ^ (z >> 31);
+        uint32_t datum = 0;
+        if ((r & 0xFF) >= void_threshold) {
+            const uint32_t id = 1u + (uint32_t)((r >> 8) % 7);
+            const uint32_t s = (uint32_t)(r >> 16) & 15u;
+            const uint32_t shape = s < 10 ? 0u : (s < 12 ? 1u : (s < 14 ? 2u : 3u));
+            const uint32_t orient = (uint32_t)((r >> 20) % 24);
+            datum = (id << 16) | (orient * 64u + shape);
+        }
+        blocks[chunk * kChunkVoxels + i] = datum;
+    }
+}
+
 } // namespace
+
+void launch_fill_synthetic(uint32_t *blocks, int SX, int SY, int SZ, int32_t cx_min, int32_t cy_min, int32_t cz_min, uint64_t seed,
+                           uint32_t void_threshold, cudaStream_t stream) {
+    fill_synthetic_kernel<<<(unsigned)((size_t)SX * SY * SZ), 256, 0, stream>>>(blocks, SX, SY, SZ, cx_min, cy_min, cz_min, seed, void_threshold);
+}
 
 void launch_halo_plane(uint32_t *blocks, int SX, int SY, int SZ, int sx, int lx, uint32_t *plane, int import, cudaStream_t stream) {
     dim3 grid((SZ * 32 + 127) / 128, SY * 32);

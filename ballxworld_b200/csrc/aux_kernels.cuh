@@ -1,0 +1,41 @@
+// aux_kernels.cuh — launchers of the kernels in aux_kernels.cu
+#pragma once
+#include "device_common.cuh"
+
+namespace bxw {
+
+void launch_halo_plane(uint32_t *blocks, int SX, int SY, int SZ, int sx, int lx, uint32_t *plane, int import, cudaStream_t stream);
+
+struct EditParams {
+    uint32_t *blocks;
+    int SX, SY, SZ;
+    int32_t x_min, y_min, z_min;     // world voxel coordinate of storage voxel (0,0,0)
+    const bxw_voxel_change *changes; // grouped by voxel, original order within a group
+    const uint32_t *run_start;       // [n_runs + 1]
+    uint32_t n_runs;
+    uint8_t *dirty;                  // interior chunk flags
+};
+void launch_apply_changes(const EditParams &p, cudaStream_t stream);
+void launch_dirty_list(uint8_t *dirty, uint32_t n, int nx, int nz, int SX, int SZ, uint32_t *work, uint32_t *work_span, uint32_t *count,
+                       int clear, cudaStream_t stream);
+
+// phase 0: per-chunk word counts -> offsets (n+1); phase 1: write words at offsets
+void launch_rle_compress(const uint32_t *dense, size_t n_chunks, uint32_t *len, uint64_t *offsets, uint32_t *out_words, int phase,
+                         cudaStream_t stream);
+void launch_rle_decompress(const uint32_t *words, const uint64_t *offsets, size_t n_chunks, uint32_t *out_dense, uint32_t *status,
+                           cudaStream_t stream);
+
+struct TerragenTables {
+    uint16_t perm[2048];
+    double gx[2048], gy[2048];
+    int32_t lat_x[32], lat_y[32];
+    double lat_dx[32], lat_dy[32];
+};
+void build_terragen_tables(uint64_t seed, TerragenTables &t);
+void launch_terragen_noise2(const TerragenTables *T, const double *xs, const double *ys, size_t n, double *out, cudaStream_t stream);
+
+// synthetic benchmark input: hashed random blocks incl. shapes/orientations
+void launch_fill_synthetic(uint32_t *blocks, int SX, int SY, int SZ, int32_t cx_min, int32_t cy_min, int32_t cz_min, uint64_t seed,
+                           uint32_t void_threshold, cudaStream_t stream);
+
+} // namespace bxw

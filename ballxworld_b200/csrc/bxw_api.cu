@@ -9,6 +9,9 @@
 #include <string>
 #include <vector>
 
+#include <algorithm>
+
+#include "aux_kernels.cuh"
 #include "device_common.cuh"
 
 using namespace bxw;
@@ -68,6 +71,12 @@ struct bxw_ctx {
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_m0 = nullptr, ev_m1 = nullptr;
     double mesh_ms = 0.0;
     uint64_t mesh_launches = 0;
+    // staging for host<->device codecs
+    void *io_a = nullptr, *io_b = nullptr, *io_c = nullptr;
+    size_t io_a_cap = 0, io_b_cap = 0, io_c_cap = 0;
+    TerragenTables *d_tg = nullptr;
+    bool tg_valid = false;
+    uint64_t tg_seed = 0;
 };
 
 namespace {
@@ -348,6 +357,47 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
     return fail(ctx, BXW_E_NOSPACE, "mesh arena sizing did not converge");
 }
 
+int ensure_io(bxw_ctx *ctx, size_t bytes_a, size_t bytes_b) {
+    if (bytes_a > ctx->io_a_cap) {
+        cudaFree(ctx->io_a);
+        ctx->io_a = nullptr;
+        ctx->io_a_cap = 0;
+        CK(cudaMalloc(&ctx->io_a, bytes_a));
+        ctx->io_a_cap = bytes_a;
+    }
+    if (bytes_b > ctx->io_b_cap) {
+        cudaFree(ctx->io_b);
+        ctx->io_b = nullptr;
+        ctx->io_b_cap = 0;
+        CK(cudaMalloc(&ctx->io_b, bytes_b));
+        ctx->io_b_cap = bytes_b;
+    }
+    return BXW_OK;
+}
+
+// host RLE words -> device dense chunks (decompress_rle, lib.rs:304-345)
+int rle_decode_into(bxw_ctx *ctx, const uint32_t *words, const uint64_t *offsets, size_t n, uint32_t *d_dense) {
+    const size_t nwords = offsets[n];
+    const size_t a_bytes = (nwords ? nwords : 1) * sizeof(uint32_t);
+    const size_t b_bytes = (n + 1) * sizeof(uint64_t) + n * sizeof(uint32_t);
+    int rc = ensure_io(ctx, a_bytes, b_bytes);
+    if (rc) return rc;
+    uint32_t *d_words = (uint32_t *)ctx->io_a;
+    uint64_t *d_offs = (uint64_t *)ctx->io_b;
+    uint32_t *d_status = (uint32_t *)(d_offs + n + 1);
+    CK(cudaMemcpyAsync(d_words, words, nwords * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_offs, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    launch_rle_decompress(d_words, d_offs, n, d_dense, d_status, ctx->stream);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    std::vector<uint32_t> st(n);
+    CK(cudaMemcpyAsync(st.data(), d_status, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < n; i++)
+        if (st[i]) return fail(ctx, BXW_E_BAD_RLE, "chunk %zu: RLE stream does not decode (RleDecompressError %u)", i, st[i]);
+    return BXW_OK;
+}
+
 int ensure_scratch(bxw_ctx *ctx) {
     if (ctx->scratch.live) return BXW_OK;
     return region_alloc(ctx, ctx->scratch, 0, 0, 0, 1, 1, 1);
@@ -414,6 +464,10 @@ void bxw_destroy(bxw_ctx *ctx) {
     cudaFree(ctx->d_color);
     cudaFree(ctx->d_tables);
     cudaFree(ctx->d_gen);
+    cudaFree(ctx->io_a);
+    cudaFree(ctx->io_b);
+    cudaFree(ctx->io_c);
+    cudaFree(ctx->d_tg);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
     if (ctx->ev_m0) cudaEventDestroy(ctx->ev_m0);
@@ -514,10 +568,25 @@ int bxw_mesh_chunk27(bxw_ctx *ctx, const uint32_t *const dense[27], bxw_mesh_spa
 }
 
 int bxw_mesh_chunk27_rle(bxw_ctx *ctx, const uint32_t *const rle[27], const size_t rle_len[27], bxw_mesh_span *counts) {
-    (void)rle;
-    (void)rle_len;
-    (void)counts;
-    return not_implemented(ctx, "bxw_mesh_chunk27_rle");
+    if (!ctx || !rle || !rle_len || !counts) return fail(ctx, BXW_E_INVALID, "null argument");
+    int rc = ensure_scratch(ctx);
+    if (rc) return rc;
+    Region &r = ctx->scratch;
+    // upload the 27 RLE streams back to back, decode on the device straight into the 3x3x3 scratch storage
+    std::vector<uint64_t> offs(28, 0);
+    for (int i = 0; i < 27; i++) {
+        if (!rle[i]) return fail(ctx, BXW_E_INVALID, "rle[%d] is null", i);
+        offs[i + 1] = offs[i] + rle_len[i];
+    }
+    std::vector<uint32_t> words(offs[27] ? offs[27] : 1);
+    for (int i = 0; i < 27; i++) std::memcpy(words.data() + offs[i], rle[i], rle_len[i] * sizeof(uint32_t));
+    rc = rle_decode_into(ctx, words.data(), offs.data(), 27, r.blocks);
+    if (rc) return rc;
+    rc = region_mesh(ctx, r, r.work, r.work_span, 1, false);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(counts, r.spans, sizeof(bxw_mesh_span), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BXW_OK;
 }
 
 int bxw_mesh_fetch(bxw_ctx *ctx, bxw_vertex *vertices, uint32_t *indices) {
@@ -549,8 +618,51 @@ int bxw_is_chunk_trivial(bxw_ctx *ctx, const uint32_t *rle, size_t rle_len, int 
 
 size_t bxw_rle_bound(size_t n_chunks) { return n_chunks * (size_t)(kChunkVoxels + kChunkVoxels / 2 + 1); }
 
-int bxw_rle_compress(bxw_ctx *ctx, const uint32_t *, size_t, uint32_t *, uint64_t *) { return not_implemented(ctx, "bxw_rle_compress"); }
-int bxw_rle_decompress(bxw_ctx *ctx, const uint32_t *, const uint64_t *, size_t, uint32_t *) { return not_implemented(ctx, "bxw_rle_decompress"); }
+int bxw_rle_compress(bxw_ctx *ctx, const uint32_t *dense, size_t n_chunks, uint32_t *out_words, uint64_t *out_offsets) {
+    if (!ctx || !dense || !out_words || !out_offsets || n_chunks == 0) return fail(ctx, BXW_E_INVALID, "null argument");
+    const size_t dense_bytes = n_chunks * kChunkVoxels * sizeof(uint32_t);
+    const size_t meta_bytes = (n_chunks + 1) * sizeof(uint64_t) + n_chunks * sizeof(uint32_t);
+    int rc = ensure_io(ctx, dense_bytes, meta_bytes);
+    if (rc) return rc;
+    uint32_t *d_dense = (uint32_t *)ctx->io_a;
+    uint64_t *d_offs = (uint64_t *)ctx->io_b;
+    uint32_t *d_len = (uint32_t *)(d_offs + n_chunks + 1);
+    CK(cudaMemcpyAsync(d_dense, dense, dense_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    launch_rle_compress(d_dense, n_chunks, d_len, d_offs, nullptr, 0, ctx->stream);
+    CK(cudaMemcpyAsync(out_offsets, d_offs, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const size_t nwords = out_offsets[n_chunks];
+    if (nwords * sizeof(uint32_t) > ctx->io_c_cap) {
+        cudaFree(ctx->io_c);
+        ctx->io_c = nullptr;
+        ctx->io_c_cap = 0;
+        CK(cudaMalloc(&ctx->io_c, nwords * sizeof(uint32_t)));
+        ctx->io_c_cap = nwords * sizeof(uint32_t);
+    }
+    launch_rle_compress(d_dense, n_chunks, d_len, d_offs, (uint32_t *)ctx->io_c, 1, ctx->stream);
+    ctx->launches += 3;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_words, ctx->io_c, nwords * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BXW_OK;
+}
+
+int bxw_rle_decompress(bxw_ctx *ctx, const uint32_t *words, const uint64_t *offsets, size_t n_chunks, uint32_t *out_dense) {
+    if (!ctx || !words || !offsets || !out_dense || n_chunks == 0) return fail(ctx, BXW_E_INVALID, "null argument");
+    const size_t dense_bytes = n_chunks * kChunkVoxels * sizeof(uint32_t);
+    if (dense_bytes > ctx->io_c_cap) {
+        cudaFree(ctx->io_c);
+        ctx->io_c = nullptr;
+        ctx->io_c_cap = 0;
+        CK(cudaMalloc(&ctx->io_c, dense_bytes));
+        ctx->io_c_cap = dense_bytes;
+    }
+    int rc = rle_decode_into(ctx, words, offsets, n_chunks, (uint32_t *)ctx->io_c);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out_dense, ctx->io_c, dense_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BXW_OK;
+}
 
 int bxw_region_create(bxw_ctx *ctx, int32_t cx0, int32_t cy0, int32_t cz0, uint32_t nx, uint32_t ny, uint32_t nz) {
     if (!ctx || nx == 0 || ny == 0 || nz == 0) return fail(ctx, BXW_E_INVALID, "bad region dims");
@@ -649,15 +761,102 @@ int bxw_region_mesh_fetch(bxw_ctx *ctx, bxw_vertex *vertices, uint64_t n_vertice
     return BXW_OK;
 }
 
-int bxw_region_apply_changes(bxw_ctx *ctx, const bxw_voxel_change *, uint32_t, uint32_t *) { return not_implemented(ctx, "bxw_region_apply_changes"); }
-int bxw_region_remesh_dirty(bxw_ctx *ctx, uint32_t *) { return not_implemented(ctx, "bxw_region_remesh_dirty"); }
+int bxw_region_apply_changes(bxw_ctx *ctx, const bxw_voxel_change *changes, uint32_t n, uint32_t *n_dirty) {
+    if (!ctx || !ctx->region.live || (n && !changes)) return fail(ctx, BXW_E_INVALID, "no region / null");
+    Region &r = ctx->region;
+    const int32_t x_min = (r.cx0 - 1) * 32, y_min = (r.cy0 - 1) * 32, z_min = (r.cz0 - 1) * 32;
+    // Keep the changes whose chunk is held by this region (the reference skips chunks that are not loaded,
+    // worldmgr.rs:324-326) and group them by voxel, preserving the caller's order inside a group: the reference
+    // replays a chunk's changes sequentially (generation.rs:52-57).
+    struct Keyed {
+        uint64_t key;
+        uint32_t idx;
+    };
+    std::vector<Keyed> keyed;
+    keyed.reserve(n);
+    for (uint32_t i = 0; i < n; i++) {
+        const int64_t gx = (int64_t)changes[i].x - x_min, gy = (int64_t)changes[i].y - y_min, gz = (int64_t)changes[i].z - z_min;
+        if (gx < 0 || gy < 0 || gz < 0 || gx >= (int64_t)r.SX * 32 || gy >= (int64_t)r.SY * 32 || gz >= (int64_t)r.SZ * 32) continue;
+        keyed.push_back({((uint64_t)gy * (uint64_t)(r.SZ * 32) + (uint64_t)gz) * (uint64_t)(r.SX * 32) + (uint64_t)gx, i});
+    }
+    std::stable_sort(keyed.begin(), keyed.end(), [](const Keyed &a, const Keyed &b) { return a.key < b.key; });
+    std::vector<bxw_voxel_change> sorted(keyed.size());
+    std::vector<uint32_t> runs;
+    for (size_t i = 0; i < keyed.size(); i++) {
+        sorted[i] = changes[keyed[i].idx];
+        if (i == 0 || keyed[i].key != keyed[i - 1].key) runs.push_back((uint32_t)i);
+    }
+    const uint32_t n_runs = (uint32_t)runs.size();
+    runs.push_back((uint32_t)keyed.size());
+    if (n_runs) {
+        int rc = ensure_io(ctx, sorted.size() * sizeof(bxw_voxel_change), runs.size() * sizeof(uint32_t));
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(ctx->io_a, sorted.data(), sorted.size() * sizeof(bxw_voxel_change), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->io_b, runs.data(), runs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        EditParams ep;
+        ep.blocks = r.blocks;
+        ep.SX = r.SX;
+        ep.SY = r.SY;
+        ep.SZ = r.SZ;
+        ep.x_min = x_min;
+        ep.y_min = y_min;
+        ep.z_min = z_min;
+        ep.changes = (const bxw_voxel_change *)ctx->io_a;
+        ep.run_start = (const uint32_t *)ctx->io_b;
+        ep.n_runs = n_runs;
+        ep.dirty = r.dirty;
+        launch_apply_changes(ep, ctx->stream);
+        ctx->launches += 1;
+    }
+    CK(cudaMemsetAsync(r.dirty_count, 0, sizeof(uint32_t), ctx->stream));
+    launch_dirty_list(r.dirty, r.n_work, (int)r.nx, (int)r.nz, r.SX, r.SZ, r.dirty_work, r.dirty_span, r.dirty_count, 0, ctx->stream);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    uint32_t nd = 0;
+    CK(cudaMemcpyAsync(&nd, r.dirty_count, sizeof nd, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream)); // also keeps `sorted` / `runs` alive until the copies are done
+    if (n_dirty) *n_dirty = nd;
+    return BXW_OK;
+}
+
+int bxw_region_remesh_dirty(bxw_ctx *ctx, uint32_t *n_remeshed) {
+    if (!ctx || !ctx->region.live) return fail(ctx, BXW_E_INVALID, "no region");
+    Region &r = ctx->region;
+    CK(cudaMemsetAsync(r.dirty_count, 0, sizeof(uint32_t), ctx->stream));
+    launch_dirty_list(r.dirty, r.n_work, (int)r.nx, (int)r.nz, r.SX, r.SZ, r.dirty_work, r.dirty_span, r.dirty_count, 1, ctx->stream);
+    ctx->launches += 1;
+    uint32_t nd = 0;
+    CK(cudaMemcpyAsync(&nd, r.dirty_count, sizeof nd, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n_remeshed) *n_remeshed = nd;
+    if (nd == 0) return BXW_OK;
+    // fresh arena space is appended; the old spans of these chunks become garbage until the next full mesh
+    return region_mesh(ctx, r, r.dirty_work, r.dirty_span, nd, true);
+}
 
 size_t bxw_region_halo_bytes(const bxw_ctx *ctx) {
     if (!ctx || !ctx->region.live) return 0;
     return (size_t)ctx->region.SZ * 32 * ctx->region.SY * 32 * sizeof(uint32_t);
 }
-int bxw_region_halo_export(bxw_ctx *ctx, int, void *) { return not_implemented(ctx, "bxw_region_halo_export"); }
-int bxw_region_halo_import(bxw_ctx *ctx, int, const void *) { return not_implemented(ctx, "bxw_region_halo_import"); }
+int bxw_region_halo_export(bxw_ctx *ctx, int face, void *dev_buf) {
+    if (!ctx || !ctx->region.live || !dev_buf || (face != 0 && face != 1)) return fail(ctx, BXW_E_INVALID, "bad halo export");
+    Region &r = ctx->region;
+    // the interior's own boundary plane: x- face = storage chunk column 1, local x 0; x+ face = column nx, local x 31
+    launch_halo_plane(r.blocks, r.SX, r.SY, r.SZ, face == 0 ? 1 : (int)r.nx, face == 0 ? 0 : 31, (uint32_t *)dev_buf, 0, ctx->stream);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    return BXW_OK;
+}
+
+int bxw_region_halo_import(bxw_ctx *ctx, int face, const void *dev_buf) {
+    if (!ctx || !ctx->region.live || !dev_buf || (face != 0 && face != 1)) return fail(ctx, BXW_E_INVALID, "bad halo import");
+    Region &r = ctx->region;
+    // into the shell: x- shell = column 0, local x 31; x+ shell = column nx+1, local x 0
+    launch_halo_plane(r.blocks, r.SX, r.SY, r.SZ, face == 0 ? 0 : (int)r.nx + 1, face == 0 ? 31 : 0, (uint32_t *)dev_buf, 1, ctx->stream);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    return BXW_OK;
+}
 
 int bxw_region_device_ptrs(bxw_ctx *ctx, void **blocks, void **vertices, void **indices) {
     if (!ctx || !ctx->region.live) return fail(ctx, BXW_E_INVALID, "no region");
@@ -667,7 +866,44 @@ int bxw_region_device_ptrs(bxw_ctx *ctx, void **blocks, void **vertices, void **
     return BXW_OK;
 }
 
-int bxw_terragen_noise2(bxw_ctx *ctx, uint64_t, const double *, const double *, size_t, double *) { return not_implemented(ctx, "bxw_terragen_noise2"); }
+int bxw_terragen_noise2(bxw_ctx *ctx, uint64_t seed, const double *xs, const double *ys, size_t n, double *out) {
+    if (!ctx || !xs || !ys || !out) return fail(ctx, BXW_E_INVALID, "null argument");
+    if (n == 0) return BXW_OK;
+    if (!ctx->tg_valid || ctx->tg_seed != seed) {
+        TerragenTables *t = new (std::nothrow) TerragenTables();
+        if (!t) return fail(ctx, BXW_E_NOMEM, "host alloc");
+        build_terragen_tables(seed, *t);
+        if (!ctx->d_tg && cudaMalloc(&ctx->d_tg, sizeof(TerragenTables)) != cudaSuccess) {
+            delete t;
+            return fail(ctx, BXW_E_CUDA, "cudaMalloc terragen tables");
+        }
+        cudaError_t e = cudaMemcpy(ctx->d_tg, t, sizeof(TerragenTables), cudaMemcpyHostToDevice);
+        delete t;
+        if (e != cudaSuccess) return fail(ctx, BXW_E_CUDA, "upload terragen tables");
+        ctx->tg_valid = true;
+        ctx->tg_seed = seed;
+    }
+    int rc = ensure_io(ctx, 2 * n * sizeof(double), n * sizeof(double));
+    if (rc) return rc;
+    double *dx = (double *)ctx->io_a, *dy = dx + n, *dout = (double *)ctx->io_b;
+    CK(cudaMemcpyAsync(dx, xs, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dy, ys, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    launch_terragen_noise2(ctx->d_tg, dx, dy, n, dout, ctx->stream);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, dout, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BXW_OK;
+}
+
+int bxw_region_fill_synthetic(bxw_ctx *ctx, uint64_t seed, uint32_t void_threshold) {
+    if (!ctx || !ctx->region.live) return fail(ctx, BXW_E_INVALID, "no region");
+    Region &r = ctx->region;
+    launch_fill_synthetic(r.blocks, r.SX, r.SY, r.SZ, r.cx0 - 1, r.cy0 - 1, r.cz0 - 1, seed, void_threshold, ctx->stream);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    return BXW_OK;
+}
 
 int bxw_timer_start(bxw_ctx *ctx) {
     if (!ctx) return BXW_E_INVALID;

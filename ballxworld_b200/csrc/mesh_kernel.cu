@@ -44,6 +44,8 @@ struct Smem {
     float ao_lut[8];
     uint32_t nbr[27 + 5];
     uint32_t warp_tv[NW], warp_ti[NW];
+    uint32_t solid[34 * 34];  // per (y',z') row: bit x set when voxel x (0..31) has a mesh (class != 0)
+    uint8_t solid_halo[34 * 34 + 4]; // bit0: x=-1 solid, bit1: x=32 solid
     unsigned long long vbase, ibase;
     uint32_t work_item;
     int emit;
@@ -120,68 +122,111 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
         }
         __syncthreads();
 
-        // ---------------- phase A: stage 34^3 class bytes ----------------
+        // ---------------- phase A: stage 34^3 class bytes + per-row solid bit planes ----------------
         uint32_t err = 0;
+        uint32_t shapes = 0; // saw a non-cube shape (class > 24)
         {
-            // 1156 (y',z') rows of 32 interior-x voxels: 8 lanes x uint4 per row, 4 rows per warp instruction
+            // 1156 (y',z') rows of 32 interior-x voxels: 8 lanes x uint4 per row, 4 rows per warp instruction.
+            // Terrain is mostly uniform: when all 128 voxels of a warp load are equal, classify once.
             constexpr int GROUPS = 1156 / 4; // 289
-            for (int g0 = warp; g0 < GROUPS; g0 += NW * 4) {
-                uint4 v[4];
-                int at[4];
+            constexpr int UNR = 8;
+            for (int g0 = warp; g0 < GROUPS; g0 += NW * UNR) {
+                uint4 v[UNR];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    int g = g0 + u * NW;
-                    at[u] = -1;
+                for (int u = 0; u < UNR; u++) {
+                    const int g = g0 + u * NW;
                     if (g < GROUPS) {
-                        int r = g * 4 + (lane >> 3);
-                        int yy = r / 34, zz = r - yy * 34;
-                        int ry = yy == 0 ? 0 : (yy <= 32 ? 1 : 2), rz = zz == 0 ? 0 : (zz <= 32 ? 1 : 2);
-                        int by = (yy - 1) & 31, bz = (zz - 1) & 31;
+                        const int r = g * 4 + (lane >> 3);
+                        const int yy = r / 34, zz = r - yy * 34;
+                        const int ry = yy == 0 ? 0 : (yy <= 32 ? 1 : 2), rz = zz == 0 ? 0 : (zz <= 32 ? 1 : 2);
+                        const int by = (yy - 1) & 31, bz = (zz - 1) & 31;
                         const uint32_t *src = p.blocks + (size_t)s.nbr[1 + 3 * rz + 9 * ry] * kChunkVoxels + by * 1024 + bz * 32 + (lane & 7) * 4;
                         v[u] = __ldg(reinterpret_cast<const uint4 *>(src));
-                        at[u] = yy * PLANE + zz * ROWB + (lane & 7) * 4;
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    if (at[u] >= 0) {
-                        uint32_t b = classify(v[u].x, p.reg, err) | (classify(v[u].y, p.reg, err) << 8) |
-                                     (classify(v[u].z, p.reg, err) << 16) | (classify(v[u].w, p.reg, err) << 24);
-                        *reinterpret_cast<uint32_t *>(&s.cls[at[u]]) = b;
+                for (int u = 0; u < UNR; u++) {
+                    const int g = g0 + u * NW; // warp-uniform
+                    if (g < GROUPS) {
+                        const int r = g * 4 + (lane >> 3);
+                        const int yy = r / 34, zz = r - yy * 34;
+                        const int at = yy * PLANE + zz * ROWB + (lane & 7) * 4;
+                        const uint32_t first = __shfl_sync(FULL, v[u].x, 0);
+                        const bool same = (v[u].x == first) & (v[u].y == first) & (v[u].z == first) & (v[u].w == first);
+                        uint32_t b, rowmask;
+                        if (__all_sync(FULL, same)) {
+                            const uint32_t c = classify(first, p.reg, err);
+                            b = c * 0x01010101u;
+                            rowmask = c ? 0xFFFFFFFFu : 0u;
+                            shapes |= (c > 24u);
+                        } else {
+                            const uint32_t c0 = classify(v[u].x, p.reg, err), c1 = classify(v[u].y, p.reg, err),
+                                           c2 = classify(v[u].z, p.reg, err), c3 = classify(v[u].w, p.reg, err);
+                            b = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
+                            shapes |= (c0 > 24u) | (c1 > 24u) | (c2 > 24u) | (c3 > 24u);
+                            uint32_t m = ((c0 != 0u) | ((c1 != 0u) << 1) | ((c2 != 0u) << 2) | ((c3 != 0u) << 3)) << ((lane & 7) * 4);
+                            m |= __shfl_xor_sync(FULL, m, 1);
+                            m |= __shfl_xor_sync(FULL, m, 2);
+                            m |= __shfl_xor_sync(FULL, m, 4);
+                            rowmask = m;
+                        }
+                        *reinterpret_cast<uint32_t *>(&s.cls[at]) = b;
+                        if ((lane & 7) == 0) s.solid[r] = rowmask;
                     }
                 }
             }
             // the two x-halo voxels of every row: x=-1 (chunk rx=0, local x 31) and x=32 (chunk rx=2, local x 0)
-            constexpr int HALO = 1156 * 2;
-            constexpr int HIT = (HALO + NT - 1) / NT; // 10
-            uint32_t hv[HIT];
+            constexpr int HIT = (1156 + NT - 1) / NT; // 5
+            uint32_t hv[HIT][2];
 #pragma unroll
             for (int k = 0; k < HIT; k++) {
-                int h = tid + k * NT;
-                hv[k] = 0;
-                if (h < HALO) {
-                    int r = h >> 1, side = h & 1;
-                    int yy = r / 34, zz = r - yy * 34;
-                    int ry = yy == 0 ? 0 : (yy <= 32 ? 1 : 2), rz = zz == 0 ? 0 : (zz <= 32 ? 1 : 2);
-                    int by = (yy - 1) & 31, bz = (zz - 1) & 31;
-                    const uint32_t *src = p.blocks + (size_t)s.nbr[(side ? 2 : 0) + 3 * rz + 9 * ry] * kChunkVoxels + by * 1024 + bz * 32 + (side ? 0 : 31);
-                    hv[k] = __ldg(src);
+                const int r = tid + k * NT;
+                hv[k][0] = hv[k][1] = 0;
+                if (r < 1156) {
+                    const int yy = r / 34, zz = r - yy * 34;
+                    const int ry = yy == 0 ? 0 : (yy <= 32 ? 1 : 2), rz = zz == 0 ? 0 : (zz <= 32 ? 1 : 2);
+                    const int by = (yy - 1) & 31, bz = (zz - 1) & 31;
+                    const size_t off = (size_t)by * 1024 + bz * 32;
+                    hv[k][0] = __ldg(p.blocks + (size_t)s.nbr[0 + 3 * rz + 9 * ry] * kChunkVoxels + off + 31);
+                    hv[k][1] = __ldg(p.blocks + (size_t)s.nbr[2 + 3 * rz + 9 * ry] * kChunkVoxels + off);
                 }
             }
 #pragma unroll
             for (int k = 0; k < HIT; k++) {
-                int h = tid + k * NT;
-                if (h < HALO) {
-                    int r = h >> 1, side = h & 1;
-                    int yy = r / 34, zz = r - yy * 34;
-                    s.cls[yy * PLANE + zz * ROWB + (side ? 32 : 33)] = (uint8_t)classify(hv[k], p.reg, err);
+                const int r = tid + k * NT;
+                if (r < 1156) {
+                    const int yy = r / 34, zz = r - yy * 34;
+                    const uint32_t cm = classify(hv[k][0], p.reg, err), cp = classify(hv[k][1], p.reg, err);
+                    shapes |= (cm > 24u) | (cp > 24u);
+                    s.cls[yy * PLANE + zz * ROWB + 33] = (uint8_t)cm;
+                    s.cls[yy * PLANE + zz * ROWB + 32] = (uint8_t)cp;
+                    s.solid_halo[r] = (uint8_t)((cm != 0u) | ((cp != 0u) << 1));
                 }
             }
         }
         if (err) atomicOr(&p.counters->flags, kFlagUnknownId);
-        __syncthreads();
+        const int has_shapes = __syncthreads_or((int)shapes);
 
         // ---------------- phase B: per-row counts ----------------
+        if (!has_shapes) {
+            // Cubes and void only: every meshed voxel clips and can be clipped on all six sides, so a side is visible
+            // iff the voxel is solid and its neighbour is not (voxmesh.rs:119). One thread per row, 34-bit words.
+            for (int row = tid; row < 1024; row += NT) {
+                const int y = row >> 5, z = row & 31;
+                const int r = (y + 1) * 34 + (z + 1);
+                auto word = [&](int rr) {
+                    const unsigned long long h = s.solid_halo[rr];
+                    return ((unsigned long long)s.solid[rr] << 1) | (h & 1ull) | ((h >> 1) << 33);
+                };
+                const unsigned long long C = word(r), M = 0x1FFFFFFFEull;
+                uint32_t nf = 0;
+                if (C & M) {
+                    nf = __popcll(C & ~(C << 1) & M) + __popcll(C & ~(C >> 1) & M) + __popcll(C & ~word(r - 34) & M) +
+                         __popcll(C & ~word(r + 34) & M) + __popcll(C & ~word(r - 1) & M) + __popcll(C & ~word(r + 1) & M);
+                }
+                s.rowcnt[row] = (nf * 4u) | ((nf * 6u) << 16);
+            }
+        } else
         for (int row = warp; row < 1024; row += NW) {
             const int y = row >> 5, z = row & 31;
             const int at = (y + 1) * PLANE + (z + 1) * ROWB + lane;

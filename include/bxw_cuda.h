@@ -128,6 +128,10 @@ int bxw_region_generate(bxw_ctx *ctx, uint64_t seed, int precision);
 int bxw_region_heightmap(bxw_ctx *ctx, int32_t *height, uint8_t *elevation, double *raw_height);
 int bxw_region_upload_chunk(bxw_ctx *ctx, int32_t lx, int32_t ly, int32_t lz, const uint32_t *blocks_yzx);
 int bxw_region_download_chunk(bxw_ctx *ctx, int32_t lx, int32_t ly, int32_t lz, uint32_t *blocks_yzx);
+/* Synthetic benchmark input (BASELINE.json configs[1], SURVEY.md section 8d cfg 2): every voxel (shell included) is a
+ * pure hash of its global position: splitmix64(seed ^ key) -> void if low byte < void_threshold, else a random id in
+ * 1..7 with a random shape (cube/slope/corner/inner corner) and one of the 24 orientations. */
+int bxw_region_fill_synthetic(bxw_ctx *ctx, uint64_t seed, uint32_t void_threshold);
 /* Mesh arena capacity (vertices / indices). Without a reservation bxw_region_mesh sizes it with a count pass. */
 int bxw_region_mesh_reserve(bxw_ctx *ctx, uint64_t max_vertices, uint64_t max_indices);
 /* Mesh every interior chunk (mesh_from_chunk semantics per chunk). Totals include alignment padding between
