@@ -5,60 +5,68 @@
 // voxmesh.rs:53-80; RleVoxelIterator::skip_until_index returns exactly blocks_yzx[idx]).
 //
 // One CTA meshes one chunk at a time:
-//   A  stage the chunk plus its 1-voxel halo (34^3) in shared memory as one CLASS BYTE per voxel
-//      (class = shape x orientation of the datum, 0 = no mesh); 16-byte coalesced loads of the u32 storage.
-//   B  per (y,z) row (one warp, lane = x): face visibility (voxmesh.rs:105-121) from the class bytes, packed
-//      per-row vertex/index counts by warp reduction.
+//   A  stage the chunk plus its 1-voxel halo (34^3) in shared memory as one CLASS BYTE per voxel (class = shape x
+//      orientation of the datum, 0 = no mesh) plus one 34-bit SOLID word per (y,z) row; 16-byte coalesced loads of
+//      the u32 storage; a warp whose 128 loaded voxels are all equal classifies once (terrain is mostly uniform).
+//   B  per-row vertex/index/face counts. Cubes-and-void chunks: one thread per row, visibility by bit operations
+//      on the solid words (voxmesh.rs:119 reduces to solid & ~neighbour-solid). Chunks containing slopes/corners:
+//      one warp per row, lane = x, the general orientation-aware test (voxmesh.rs:105-121).
 //   S  block-wide exclusive scan of the 1024 row counts = the reference's emission order (cells y,z,x-major,
 //      directions 0..5 minor, voxmesh.rs:94,104); one atomicAdd pair reserves the chunk's arena span.
-//   C  per non-empty row: cell-parallel face list -> face-parallel AO counts + index values -> slot-parallel
-//      vertex records staged in shared memory and copied out with fully coalesced 8-byte stores.
+//   C  emission in tiles of <=1024 faces: (C1) face records in emission order, (C2) face-parallel AO occluder counts
+//      and index values, (C3) vertex-slot-parallel vertex records staged in shared memory and copied out with fully
+//      coalesced 8-byte stores. All 256 threads work on faces/vertices, not on rows.
 #include "device_common.cuh"
 
 namespace bxw {
 namespace {
 
-constexpr int NW = 8;          // warps per CTA
-constexpr int NT = NW * 32;    // threads per CTA
-constexpr int ROWB = 36;       // bytes per (y,z) row of the class table: x=0..31, [32] = x=32, [33] = x=-1, 2 pad
-constexpr int PLANE = 34 * ROWB;
+constexpr int NW = 8;        // warps per CTA
+constexpr int NT = NW * 32;  // threads per CTA
+// class table: row (y',z') = 40 bytes: [3] = x=-1, [4..35] = x=0..31, [36] = x=32 (so x +- 1 is address +- 1)
+constexpr int ROWB = kClsRowBytes;
+constexpr int PLANE = kClsPlaneBytes;
+constexpr int XOFF = 4;
 constexpr int CLS_BYTES = 34 * PLANE;
 constexpr unsigned FULL = 0xFFFFFFFFu;
-
-struct WarpScratch {
-    uint32_t frecA[192]; // face record: x | dir<<5 | vstart<<8 | istart<<18 (row-relative starts)
-    uint32_t frecB[192]; // AO occluder counts of the face's vertices, 3 bits each
-    uint16_t frecC[192]; // block id
-    uint8_t s2f[768];    // vertex slot -> face
-    uint32_t istage[192];
-    uint2 vstage[160];   // 32 vertices x 40 B
-};
+constexpr int FC = 1024;     // faces per emission tile
+constexpr int VC = 4096;     // vertex slots per emission tile
+constexpr int REGC = 64;     // registry entries cached in shared memory
 
 struct Smem {
     uint8_t cls[CLS_BYTES];
-    uint32_t rowcnt[1024]; // V | I<<16 per row
-    uint32_t rowV[1024];   // exclusive prefix over rows (chunk-relative first vertex of the row)
-    uint32_t rowI[1024];
+    uint32_t rowV[1028];   // exclusive prefix over rows: first vertex of the row (chunk-relative); [1024] = total
+    uint32_t rowI[1028];
+    uint32_t rowF[1028];
+    uint32_t solid[34 * 34];         // per (y',z') row: bit x set when voxel x (0..31) has a mesh (class != 0)
+    uint8_t solid_halo[34 * 34 + 4]; // bit0: x=-1 solid, bit1: x=32 solid
     uint32_t ctab[kNumClasses + 3];
     uint32_t stab[kNumClasses * 6 + 2];
     float ao_lut[8];
+    float reg_color[REGC * 3];
+    float reg_texf[REGC * 6];
+    uint8_t reg_kind[256];
     uint32_t nbr[27 + 5];
-    uint32_t warp_tv[NW], warp_ti[NW];
-    uint32_t solid[34 * 34];  // per (y',z') row: bit x set when voxel x (0..31) has a mesh (class != 0)
-    uint8_t solid_halo[34 * 34 + 4]; // bit0: x=-1 solid, bit1: x=32 solid
+    uint32_t warp_tot[3][NW];
     unsigned long long vbase, ibase;
-    uint32_t work_item;
+    uint32_t work_item[2];
     int emit;
-    WarpScratch ws[NW];
+    // emission tile
+    uint32_t frecA[FC];   // row | x<<10 | dir<<15 | vstart<<18 (tile-relative first vertex)
+    uint32_t frecB[FC];   // AO occluder counts, 3 bits per vertex | istart<<18 (tile-relative first index)
+    uint16_t frecC[FC];   // block id
+    uint16_t s2f[VC];     // vertex slot -> face (tiles with non-quad sides only)
+    uint32_t istage[NT * 6];
+    uint2 vstage[NT * 5]; // 256 vertices x 40 B
 };
 
-__device__ __forceinline__ uint32_t classify(uint32_t d, const DeviceRegistry &reg, uint32_t &err) {
+__device__ __forceinline__ uint32_t classify(uint32_t d, const Smem &s, const DeviceRegistry &reg, uint32_t &err) {
     // voxmesh.rs:76-78 -> stdshapes.rs:51-72
-    uint32_t id = d >> 16;
-    uint32_t k = (id < reg.n) ? (uint32_t)__ldg(reg.kind + id) : 0u;
+    const uint32_t id = d >> 16;
+    const uint32_t k = id < 256u ? (uint32_t)s.reg_kind[id] : (id < reg.n ? (uint32_t)__ldg(reg.kind + id) : 0u);
     if (k == 0u) err = 1u;          // voxregistry.rs:141-143 would panic
     if (k != 2u) return 0u;         // VoxelMesh::None
-    uint32_t meta = d & 0xFFFFu;
+    const uint32_t meta = d & 0xFFFFu;
     uint32_t shape = meta & 63u;    // StdMeta::from_meta: meta % 64
     if (shape > 3u) shape = 0u;     // unknown shape -> cube (stdshapes.rs:59)
     uint32_t o = meta >> 6;         // meta / 64
@@ -66,19 +74,18 @@ __device__ __forceinline__ uint32_t classify(uint32_t d, const DeviceRegistry &r
     return 1u + shape * 24u + o;
 }
 
-// visibility of the 6 sides of the cell at byte `at` (lane = x) -- voxmesh.rs:104-121
-__device__ __forceinline__ uint32_t cell_visibility(const Smem &s, int at, int lane, uint32_t t) {
-    uint32_t ec = (t >> 6) & 63u, eu = (t >> 12) & 63u;
+// visibility of the 6 sides of the cell at byte `at` -- voxmesh.rs:104-121
+__device__ __forceinline__ uint32_t cell_visibility(const Smem &s, int at, uint32_t t) {
+    const uint32_t ec = (t >> 6) & 63u, eu = (t >> 12) & 63u;
     uint32_t vis = eu;
     if (ec) {
-        int xl = lane == 0 ? 33 - lane : -1; // x-1 lives at byte 33 for x == 0
-        uint32_t n0 = s.cls[at + xl], n1 = s.cls[at + 1];
-        uint32_t n2 = s.cls[at - PLANE], n3 = s.cls[at + PLANE];
-        uint32_t n4 = s.cls[at - ROWB], n5 = s.cls[at + ROWB];
+        const uint32_t n0 = s.cls[at - 1], n1 = s.cls[at + 1];
+        const uint32_t n2 = s.cls[at - PLANE], n3 = s.cls[at + PLANE];
+        const uint32_t n4 = s.cls[at - ROWB], n5 = s.cls[at + ROWB];
         // neighbour in world dir d must can_clip on its side facing us (dir d^1)
-        uint32_t blocked = ((s.ctab[n0] >> 1) & 1u) | (((s.ctab[n1] >> 0) & 1u) << 1) | (((s.ctab[n2] >> 3) & 1u) << 2) |
-                           (((s.ctab[n3] >> 2) & 1u) << 3) | (((s.ctab[n4] >> 5) & 1u) << 4) |
-                           (((s.ctab[n5] >> 4) & 1u) << 5);
+        const uint32_t blocked = ((s.ctab[n0] >> 1) & 1u) | (((s.ctab[n1] >> 0) & 1u) << 1) | (((s.ctab[n2] >> 3) & 1u) << 2) |
+                                 (((s.ctab[n3] >> 2) & 1u) << 3) | (((s.ctab[n4] >> 5) & 1u) << 4) |
+                                 (((s.ctab[n5] >> 4) & 1u) << 5);
         vis |= ec & ~blocked;
     }
     return vis;
@@ -86,48 +93,70 @@ __device__ __forceinline__ uint32_t cell_visibility(const Smem &s, int at, int l
 
 // vertices / indices / faces of a cell, packed V | I<<10 | F<<21
 __device__ __forceinline__ uint32_t cell_counts(uint32_t vis, uint32_t t) {
-    uint32_t codes = t >> 18;
+    const uint32_t codes = t >> 18;
     uint32_t v = 0, i = 0;
 #pragma unroll
     for (int d = 0; d < 6; d++) {
-        uint32_t code = (codes >> (2 * d)) & 3u;
-        bool on = (vis >> d) & 1u;
+        const uint32_t code = (codes >> (2 * d)) & 3u;
+        const bool on = (vis >> d) & 1u;
         v += on ? code + 2u + (code == 3u) : 0u;
         i += on ? (code == 1u ? 3u : 6u) : 0u;
     }
     return v | (i << 10) | ((uint32_t)__popc(vis) << 21);
 }
 
+// the 34-bit solid word of row rr (bit 0: x=-1, bits 1..32: x=0..31, bit 33: x=32)
+__device__ __forceinline__ unsigned long long solid_word(const Smem &s, int rr) {
+    const unsigned long long h = s.solid_halo[rr];
+    return ((unsigned long long)s.solid[rr] << 1) | (h & 1ull) | ((h >> 1) << 33);
+}
+
+// visible-side words of a cubes-and-void row: bit x+1 of out[d] = side d of cell x is visible
+__device__ __forceinline__ void row_visibility(const Smem &s, int y, int z, unsigned long long out[6]) {
+    const int r = (y + 1) * 34 + (z + 1);
+    const unsigned long long C = solid_word(s, r), M = 0x1FFFFFFFEull;
+    out[0] = C & ~(C << 1) & M;
+    out[1] = C & ~(C >> 1) & M;
+    out[2] = C & ~solid_word(s, r - 34) & M;
+    out[3] = C & ~solid_word(s, r + 34) & M;
+    out[4] = C & ~solid_word(s, r - 1) & M;
+    out[5] = C & ~solid_word(s, r + 1) & M;
+}
+
 __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem &s = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const MeshTables *T = p.tables;
 
-    for (int i = tid; i < kNumClasses; i += NT) s.ctab[i] = p.tables->ctab[i];
-    for (int i = tid; i < kNumClasses * 6; i += NT) s.stab[i] = (&p.tables->stab[0][0])[i];
-    if (tid < 8) s.ao_lut[tid] = p.tables->ao_lut[tid];
+    for (int i = tid; i < kNumClasses; i += NT) s.ctab[i] = T->ctab[i];
+    for (int i = tid; i < kNumClasses * 6; i += NT) s.stab[i] = (&T->stab[0][0])[i];
+    if (tid < 8) s.ao_lut[tid] = T->ao_lut[tid];
+    for (int i = tid; i < 256; i += NT) s.reg_kind[i] = (uint32_t)i < p.reg.n ? p.reg.kind[i] : (uint8_t)0;
+    for (int i = tid; i < REGC * 3; i += NT) s.reg_color[i] = (uint32_t)(i / 3) < p.reg.n ? p.reg.color[i] : 0.0f;
+    for (int i = tid; i < REGC * 6; i += NT) s.reg_texf[i] = (uint32_t)(i / 6) < p.reg.n ? p.reg.texf[i] : 0.0f;
+    if (tid == 0) s.work_item[0] = (uint32_t)atomicAdd(&p.counters->work_next, 1ull);
 
-    for (;;) {
+    for (uint32_t iter = 0;; iter++) {
         __syncthreads();
-        if (tid == 0) s.work_item = (uint32_t)atomicAdd(&p.counters->work_next, 1ull);
-        __syncthreads();
-        const uint32_t w = s.work_item;
+        const uint32_t w = s.work_item[iter & 1];
         if (w >= p.n_work) break;
+        // fetch the next work item now; its latency hides behind this chunk
+        if (tid == 0) s.work_item[(iter + 1) & 1] = (uint32_t)atomicAdd(&p.counters->work_next, 1ull);
         const uint32_t c0 = p.work[w];
         if (tid < 27) {
-            int sx = (int)(c0 % (uint32_t)p.SX), sz = (int)((c0 / (uint32_t)p.SX) % (uint32_t)p.SZ),
-                sy = (int)(c0 / (uint32_t)(p.SX * p.SZ));
-            int rx = tid % 3, rz = (tid / 3) % 3, ry = tid / 9;
+            const int sx = (int)(c0 % (uint32_t)p.SX), sz = (int)((c0 / (uint32_t)p.SX) % (uint32_t)p.SZ),
+                      sy = (int)(c0 / (uint32_t)(p.SX * p.SZ));
+            const int rx = tid % 3, rz = (tid / 3) % 3, ry = tid / 9;
             s.nbr[tid] = (uint32_t)((sx + rx - 1) + p.SX * ((sz + rz - 1) + p.SZ * (sy + ry - 1)));
         }
         __syncthreads();
 
-        // ---------------- phase A: stage 34^3 class bytes + per-row solid bit planes ----------------
+        // ---------------- phase A: stage 34^3 class bytes + per-row solid words ----------------
         uint32_t err = 0;
         uint32_t shapes = 0; // saw a non-cube shape (class > 24)
         {
             // 1156 (y',z') rows of 32 interior-x voxels: 8 lanes x uint4 per row, 4 rows per warp instruction.
-            // Terrain is mostly uniform: when all 128 voxels of a warp load are equal, classify once.
             constexpr int GROUPS = 1156 / 4; // 289
             constexpr int UNR = 8;
             for (int g0 = warp; g0 < GROUPS; g0 += NW * UNR) {
@@ -150,21 +179,21 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                     if (g < GROUPS) {
                         const int r = g * 4 + (lane >> 3);
                         const int yy = r / 34, zz = r - yy * 34;
-                        const int at = yy * PLANE + zz * ROWB + (lane & 7) * 4;
+                        const int at = yy * PLANE + zz * ROWB + XOFF + (lane & 7) * 4;
                         const uint32_t first = __shfl_sync(FULL, v[u].x, 0);
                         const bool same = (v[u].x == first) & (v[u].y == first) & (v[u].z == first) & (v[u].w == first);
                         uint32_t b, rowmask;
                         if (__all_sync(FULL, same)) {
-                            const uint32_t c = classify(first, p.reg, err);
+                            const uint32_t c = classify(first, s, p.reg, err);
                             b = c * 0x01010101u;
                             rowmask = c ? 0xFFFFFFFFu : 0u;
                             shapes |= (c > 24u);
                         } else {
-                            const uint32_t c0 = classify(v[u].x, p.reg, err), c1 = classify(v[u].y, p.reg, err),
-                                           c2 = classify(v[u].z, p.reg, err), c3 = classify(v[u].w, p.reg, err);
-                            b = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
-                            shapes |= (c0 > 24u) | (c1 > 24u) | (c2 > 24u) | (c3 > 24u);
-                            uint32_t m = ((c0 != 0u) | ((c1 != 0u) << 1) | ((c2 != 0u) << 2) | ((c3 != 0u) << 3)) << ((lane & 7) * 4);
+                            const uint32_t k0 = classify(v[u].x, s, p.reg, err), k1 = classify(v[u].y, s, p.reg, err),
+                                           k2 = classify(v[u].z, s, p.reg, err), k3 = classify(v[u].w, s, p.reg, err);
+                            b = k0 | (k1 << 8) | (k2 << 16) | (k3 << 24);
+                            shapes |= (k0 > 24u) | (k1 > 24u) | (k2 > 24u) | (k3 > 24u);
+                            uint32_t m = ((k0 != 0u) | ((k1 != 0u) << 1) | ((k2 != 0u) << 2) | ((k3 != 0u) << 3)) << ((lane & 7) * 4);
                             m |= __shfl_xor_sync(FULL, m, 1);
                             m |= __shfl_xor_sync(FULL, m, 2);
                             m |= __shfl_xor_sync(FULL, m, 4);
@@ -196,10 +225,10 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                 const int r = tid + k * NT;
                 if (r < 1156) {
                     const int yy = r / 34, zz = r - yy * 34;
-                    const uint32_t cm = classify(hv[k][0], p.reg, err), cp = classify(hv[k][1], p.reg, err);
+                    const uint32_t cm = classify(hv[k][0], s, p.reg, err), cp = classify(hv[k][1], s, p.reg, err);
                     shapes |= (cm > 24u) | (cp > 24u);
-                    s.cls[yy * PLANE + zz * ROWB + 33] = (uint8_t)cm;
-                    s.cls[yy * PLANE + zz * ROWB + 32] = (uint8_t)cp;
+                    s.cls[yy * PLANE + zz * ROWB + XOFF - 1] = (uint8_t)cm;
+                    s.cls[yy * PLANE + zz * ROWB + XOFF + 32] = (uint8_t)cp;
                     s.solid_halo[r] = (uint8_t)((cm != 0u) | ((cp != 0u) << 1));
                 }
             }
@@ -207,81 +236,78 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
         if (err) atomicOr(&p.counters->flags, kFlagUnknownId);
         const int has_shapes = __syncthreads_or((int)shapes);
 
-        // ---------------- phase B: per-row counts ----------------
+        // ---------------- phase B: per-row counts (packed V | I<<10 | F<<21 into rowV) ----------------
         if (!has_shapes) {
-            // Cubes and void only: every meshed voxel clips and can be clipped on all six sides, so a side is visible
-            // iff the voxel is solid and its neighbour is not (voxmesh.rs:119). One thread per row, 34-bit words.
             for (int row = tid; row < 1024; row += NT) {
+                unsigned long long vw[6];
+                row_visibility(s, row >> 5, row & 31, vw);
+                const uint32_t nf = __popcll(vw[0]) + __popcll(vw[1]) + __popcll(vw[2]) + __popcll(vw[3]) + __popcll(vw[4]) + __popcll(vw[5]);
+                s.rowV[row] = (nf * 4u) | ((nf * 6u) << 10) | (nf << 21);
+            }
+        } else {
+            for (int row = warp; row < 1024; row += NW) {
                 const int y = row >> 5, z = row & 31;
-                const int r = (y + 1) * 34 + (z + 1);
-                auto word = [&](int rr) {
-                    const unsigned long long h = s.solid_halo[rr];
-                    return ((unsigned long long)s.solid[rr] << 1) | (h & 1ull) | ((h >> 1) << 33);
-                };
-                const unsigned long long C = word(r), M = 0x1FFFFFFFEull;
-                uint32_t nf = 0;
-                if (C & M) {
-                    nf = __popcll(C & ~(C << 1) & M) + __popcll(C & ~(C >> 1) & M) + __popcll(C & ~word(r - 34) & M) +
-                         __popcll(C & ~word(r + 34) & M) + __popcll(C & ~word(r - 1) & M) + __popcll(C & ~word(r + 1) & M);
+                const int at = (y + 1) * PLANE + (z + 1) * ROWB + XOFF + lane;
+                const uint32_t c = s.cls[at];
+                uint32_t cnt = 0;
+                if (__any_sync(FULL, c != 0)) {
+                    const uint32_t t = s.ctab[c];
+                    cnt = __reduce_add_sync(FULL, cell_counts(cell_visibility(s, at, t), t));
                 }
-                s.rowcnt[row] = (nf * 4u) | ((nf * 6u) << 16);
+                if (lane == 0) s.rowV[row] = cnt;
             }
-        } else
-        for (int row = warp; row < 1024; row += NW) {
-            const int y = row >> 5, z = row & 31;
-            const int at = (y + 1) * PLANE + (z + 1) * ROWB + lane;
-            uint32_t c = s.cls[at];
-            uint32_t cnt = 0;
-            if (__any_sync(FULL, c != 0)) {
-                uint32_t t = s.ctab[c];
-                uint32_t vis = cell_visibility(s, at, lane, t);
-                uint32_t pk = cell_counts(vis, t);
-                cnt = (pk & 1023u) | (((pk >> 10) & 2047u) << 16);
-                cnt = __reduce_add_sync(FULL, cnt);
-            }
-            if (lane == 0) s.rowcnt[row] = cnt;
         }
         __syncthreads();
 
         // ---------------- scan of the 1024 row counts ----------------
         {
-            uint32_t v[4], i[4], tv = 0, ti = 0;
+            uint32_t v[4], i[4], f[4], tv = 0, ti = 0, tf = 0;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                uint32_t c = s.rowcnt[tid * 4 + k];
+                const uint32_t c = s.rowV[tid * 4 + k];
                 v[k] = tv;
                 i[k] = ti;
-                tv += c & 0xFFFFu;
-                ti += c >> 16;
+                f[k] = tf;
+                tv += c & 1023u;
+                ti += (c >> 10) & 2047u;
+                tf += c >> 21;
             }
-            uint32_t sv = tv, si = ti;
+            uint32_t sv = tv, si = ti, sf = tf;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                uint32_t a = __shfl_up_sync(FULL, sv, o), b = __shfl_up_sync(FULL, si, o);
+                const uint32_t a = __shfl_up_sync(FULL, sv, o), b = __shfl_up_sync(FULL, si, o), c = __shfl_up_sync(FULL, sf, o);
                 if (lane >= o) {
                     sv += a;
                     si += b;
+                    sf += c;
                 }
             }
             if (lane == 31) {
-                s.warp_tv[warp] = sv;
-                s.warp_ti[warp] = si;
+                s.warp_tot[0][warp] = sv;
+                s.warp_tot[1][warp] = si;
+                s.warp_tot[2][warp] = sf;
             }
             __syncthreads();
-            uint32_t bv = 0, bi = 0;
+            uint32_t bv = 0, bi = 0, bf = 0;
             for (int k = 0; k < warp; k++) {
-                bv += s.warp_tv[k];
-                bi += s.warp_ti[k];
+                bv += s.warp_tot[0][k];
+                bi += s.warp_tot[1][k];
+                bf += s.warp_tot[2][k];
             }
             bv += sv - tv;
             bi += si - ti;
+            bf += sf - tf;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 s.rowV[tid * 4 + k] = bv + v[k];
                 s.rowI[tid * 4 + k] = bi + i[k];
+                s.rowF[tid * 4 + k] = bf + f[k];
             }
             if (tid == NT - 1) {
                 const unsigned long long TV = bv + tv, TI = bi + ti;
+                s.rowV[1024] = bv + tv;
+                s.rowI[1024] = bi + ti;
+                s.rowF[1024] = bf + tf;
                 const unsigned long long padV = (TV + 3ull) & ~3ull, padI = (TI + 7ull) & ~7ull;
                 unsigned long long vb = 0, ib = 0;
                 int emit = 0;
@@ -307,129 +333,180 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
         __syncthreads();
         if (!s.emit) continue;
 
-        // ---------------- phase C: emit ----------------
-        WarpScratch &ws = s.ws[warp];
+        // ---------------- phase C: emit, tile by tile ----------------
         const uint32_t *center = p.blocks + (size_t)c0 * kChunkVoxels;
-        const MeshTables *T = p.tables;
-        for (int row = warp; row < 1024; row += NW) {
-            if (s.rowcnt[row] == 0) continue;
-            const int y = row >> 5, z = row & 31;
-            const int rowat = (y + 1) * PLANE + (z + 1) * ROWB;
-            // (1) cell-parallel: visibility, row-relative prefix, face records
-            uint32_t Vrow, Irow, Frow;
-            {
-                const int at = rowat + lane;
-                uint32_t c = s.cls[at];
-                uint32_t t = s.ctab[c];
-                uint32_t vis = c ? cell_visibility(s, at, lane, t) : 0u;
-                uint32_t pk = cell_counts(vis, t);
-                uint32_t incl = pk;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    uint32_t a = __shfl_up_sync(FULL, incl, o);
-                    if (lane >= o) incl += a;
-                }
-                uint32_t total = __shfl_sync(FULL, incl, 31);
-                Vrow = total & 1023u;
-                Irow = (total >> 10) & 2047u;
-                Frow = total >> 21;
-                uint32_t excl = incl - pk;
-                if (vis) {
-                    uint32_t vs = excl & 1023u, is = (excl >> 10) & 2047u, f = excl >> 21;
-                    uint32_t id = __ldg(center + row * 32 + lane) >> 16;
-                    uint32_t codes = t >> 18;
-#pragma unroll
-                    for (int d = 0; d < 6; d++) {
-                        if ((vis >> d) & 1u) {
-                            uint32_t code = (codes >> (2 * d)) & 3u;
-                            ws.frecA[f] = (uint32_t)lane | ((uint32_t)d << 5) | (vs << 8) | (is << 18);
-                            ws.frecC[f] = (uint16_t)id;
-                            f++;
-                            vs += code + 2u + (code == 3u);
-                            is += (code == 1u ? 3u : 6u);
-                        }
-                    }
-                }
+        bxw_vertex *const vout = p.varena + s.vbase;
+        uint32_t *const iout = p.iarena + s.ibase;
+        const bool quads_only = !has_shapes; // every side has 4 vertices / 6 indices
+        for (uint32_t r0 = 0; r0 < 1024;) {
+            // largest r1 with faces(r0..r1) <= FC and vertices(r0..r1) <= VC (a single row never exceeds 192 / 768)
+            uint32_t lo = r0 + 1, hi = 1024;
+            const uint32_t f0 = s.rowF[r0], v0 = s.rowV[r0], i0 = s.rowI[r0];
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi + 1) >> 1;
+                if (s.rowF[mid] - f0 <= (uint32_t)FC && s.rowV[mid] - v0 <= (uint32_t)VC) lo = mid;
+                else hi = mid - 1;
             }
-            __syncwarp();
-            // (2) face-parallel: AO occluder counts, slot map, index values
-            const unsigned long long ibase_row = s.ibase + s.rowI[row];
-            const uint32_t vrow0 = s.rowV[row];
-            for (uint32_t fb = 0; fb < Frow; fb += 32) {
-                const uint32_t f = fb + lane;
-                const uint32_t i0 = (ws.frecA[fb] >> 18) & 2047u;
-                if (f < Frow) {
-                    const uint32_t a = ws.frecA[f];
-                    const int x = a & 31u, d = (a >> 5) & 7u;
-                    const uint32_t vs = (a >> 8) & 1023u, is = (a >> 18) & 2047u;
-                    const uint32_t cx = s.cls[rowat + x];
-                    const uint32_t st = s.stab[cx * 6 + d];
-                    const uint32_t nv = (st >> 3) & 7u, ni = (st >> 6) & 7u;
-                    const unsigned long long *vt = &T->vtab[cx][d][0];
-                    uint32_t ks = 0;
-                    for (uint32_t j = 0; j < nv; j++) {
-                        const unsigned long long e = __ldg(vt + j);
-                        const uint32_t n = (uint32_t)(e >> 10) & 7u;
-                        uint32_t k = 0;
+            const uint32_t r1 = lo;
+            const uint32_t tileF = s.rowF[r1] - f0, tileV = s.rowV[r1] - v0, tileI = s.rowI[r1] - i0;
+            if (tileF == 0) {
+                r0 = r1;
+                continue;
+            }
+            // ---- C1: face records in emission order ----
+            if (quads_only) {
+                for (uint32_t row = r0 + tid; row < r1; row += NT) {
+                    uint32_t f = s.rowF[row] - f0;
+                    if (s.rowF[row + 1] - s.rowF[row] == 0) continue;
+                    unsigned long long vw[6];
+                    row_visibility(s, row >> 5, row & 31, vw);
+                    unsigned long long any = vw[0] | vw[1] | vw[2] | vw[3] | vw[4] | vw[5];
+                    while (any) {
+                        const int b = __ffsll((long long)any) - 1; // bit x+1
+                        any &= any - 1;
 #pragma unroll
-                        for (uint32_t q = 0; q < 5; q++) {
-                            if (q < n) {
-                                uint32_t c6 = (uint32_t)(e >> (13 + 6 * q)) & 63u;
-                                int dx = (int)(c6 & 3u) - 1, dy = (int)((c6 >> 2) & 3u) - 1, dz = (int)(c6 >> 4) - 1;
-                                int xi = x + dx;
-                                xi = xi < 0 ? 33 : xi;
-                                // shp.causes_ambient_occlusion (voxmesh.rs:133-136): every meshed shape does
-                                k += s.cls[rowat + dy * PLANE + dz * ROWB + xi] != 0;
+                        for (int d = 0; d < 6; d++) {
+                            if ((vw[d] >> b) & 1ull) {
+                                s.frecA[f] = row | ((uint32_t)(b - 1) << 10) | ((uint32_t)d << 15) | ((f * 4u) << 18);
+                                f++;
                             }
                         }
-                        ks |= k << (3 * j);
-                        ws.s2f[vs + j] = (uint8_t)f;
-                    }
-                    ws.frecB[f] = ks;
-                    const uint32_t rel = is - i0;
-                    const uint32_t v0 = vrow0 + vs; // voff = vbuf.len() (voxmesh.rs:123)
-                    if (nv == 4) { // QUAD_INDICES (stdshapes.rs:198)
-                        ws.istage[rel + 0] = v0;
-                        ws.istage[rel + 1] = v0 + 1;
-                        ws.istage[rel + 2] = v0 + 2;
-                        ws.istage[rel + 3] = v0 + 2;
-                        ws.istage[rel + 4] = v0 + 3;
-                        ws.istage[rel + 5] = v0;
-                    } else {
-                        for (uint32_t k = 0; k < ni; k++) ws.istage[rel + k] = v0 + k;
                     }
                 }
-                __syncwarp();
-                const uint32_t iend = (fb + 32 < Frow) ? ((ws.frecA[fb + 32] >> 18) & 2047u) : Irow;
-                for (uint32_t k = lane; k < iend - i0; k += 32) p.iarena[ibase_row + i0 + k] = ws.istage[k];
-                __syncwarp();
+            } else {
+                for (uint32_t row = r0 + warp; row < r1; row += NW) {
+                    if (s.rowF[row + 1] - s.rowF[row] == 0) continue;
+                    const int at = ((row >> 5) + 1) * PLANE + ((row & 31) + 1) * ROWB + XOFF + lane;
+                    const uint32_t c = s.cls[at];
+                    const uint32_t t = s.ctab[c];
+                    const uint32_t vis = c ? cell_visibility(s, at, t) : 0u;
+                    const uint32_t pk = cell_counts(vis, t);
+                    uint32_t incl = pk;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t a = __shfl_up_sync(FULL, incl, o);
+                        if (lane >= o) incl += a;
+                    }
+                    const uint32_t excl = incl - pk;
+                    if (vis) {
+                        uint32_t vs = s.rowV[row] - v0 + (excl & 1023u), is = s.rowI[row] - i0 + ((excl >> 10) & 2047u),
+                                 f = s.rowF[row] - f0 + (excl >> 21);
+                        const uint32_t codes = t >> 18;
+#pragma unroll
+                        for (int d = 0; d < 6; d++) {
+                            if ((vis >> d) & 1u) {
+                                const uint32_t code = (codes >> (2 * d)) & 3u;
+                                s.frecA[f] = row | ((uint32_t)lane << 10) | ((uint32_t)d << 15) | (vs << 18);
+                                s.frecB[f] = is << 18;
+                                f++;
+                                vs += code + 2u + (code == 3u);
+                                is += (code == 1u ? 3u : 6u);
+                            }
+                        }
+                    }
+                }
             }
-            // (3) slot-parallel: one vertex per lane, staged then copied out coalesced
-            bxw_vertex *vdst_row = p.varena + s.vbase + vrow0;
-            for (uint32_t vb = 0; vb < Vrow; vb += 32) {
-                const uint32_t sl = vb + lane;
-                if (sl < Vrow) {
-                    const uint32_t f = ws.s2f[sl];
-                    const uint32_t a = ws.frecA[f], ks = ws.frecB[f], id = ws.frecC[f];
-                    const int x = a & 31u, d = (a >> 5) & 7u;
-                    const uint32_t j = sl - ((a >> 8) & 1023u);
-                    const uint32_t cx = s.cls[rowat + x];
+            __syncthreads();
+            // ---- C2: face-parallel AO occluder counts (+ slot map and index values for non-quad tiles) ----
+            for (uint32_t fb = 0; fb < tileF; fb += NT) {
+                const uint32_t f = fb + tid;
+                uint32_t is = 0, nv = 0, ni = 0, vs = 0;
+                if (f < tileF) {
+                    const uint32_t a = s.frecA[f];
+                    const uint32_t row = a & 1023u, x = (a >> 10) & 31u, d = (a >> 15) & 7u;
+                    vs = a >> 18;
+                    const int at = ((row >> 5) + 1) * PLANE + ((row & 31) + 1) * ROWB + XOFF + (int)x;
+                    const uint32_t cx = s.cls[at];
+                    const uint32_t st = s.stab[cx * 6 + d];
+                    nv = (st >> 3) & 7u;
+                    ni = (st >> 6) & 7u;
+                    s.frecC[f] = (uint16_t)(__ldg(center + row * 32 + x) >> 16);
+                    const uint4 *ao = reinterpret_cast<const uint4 *>(&T->aotab[cx][d][0][0]);
+                    uint32_t ks = 0;
+                    for (uint32_t j = 0; j < nv; j++) {
+                        const uint4 e = __ldg(ao + j);
+                        const int n = (int)(short)(e.z >> 16);
+                        // shp.causes_ambient_occlusion (voxmesh.rs:133-136): every meshed shape does
+                        uint32_t k = (s.cls[at + (int)(short)(e.x & 0xFFFFu)] != 0) + (s.cls[at + (int)(short)(e.x >> 16)] != 0) +
+                                     (s.cls[at + (int)(short)(e.y & 0xFFFFu)] != 0);
+                        if (n > 3) k += s.cls[at + (int)(short)(e.y >> 16)] != 0;
+                        if (n > 4) k += s.cls[at + (int)(short)(e.z & 0xFFFFu)] != 0;
+                        ks |= k << (3 * j);
+                        if (!quads_only) s.s2f[vs + j] = (uint16_t)f;
+                    }
+                    if (quads_only) {
+                        s.frecB[f] = ks;
+                    } else {
+                        is = s.frecB[f] >> 18;
+                        s.frecB[f] = ks | (is << 18);
+                    }
+                }
+                if (!quads_only) {
+                    // index values of this batch of faces, staged then copied out coalesced
+                    __syncthreads(); // frecB/s2f of the batch complete; previous batch's istage reads done
+                    const uint32_t is_first = s.frecB[fb] >> 18;
+                    if (f < tileF) {
+                        const uint32_t rel = is - is_first;
+                        const uint32_t vq = v0 + vs; // voff = vbuf.len() (voxmesh.rs:123), chunk-relative
+                        if (nv == 4) { // QUAD_INDICES (stdshapes.rs:198)
+                            s.istage[rel + 0] = vq;
+                            s.istage[rel + 1] = vq + 1;
+                            s.istage[rel + 2] = vq + 2;
+                            s.istage[rel + 3] = vq + 2;
+                            s.istage[rel + 4] = vq + 3;
+                            s.istage[rel + 5] = vq;
+                        } else {
+                            for (uint32_t k = 0; k < ni; k++) s.istage[rel + k] = vq + k;
+                        }
+                    }
+                    __syncthreads();
+                    const uint32_t is_end = (fb + NT < tileF) ? (s.frecB[fb + NT] >> 18) : tileI;
+                    for (uint32_t k = tid; k < is_end - is_first; k += NT) iout[i0 + is_first + k] = s.istage[k];
+                }
+            }
+            if (quads_only) {
+                // indices of quad-only tiles follow arithmetically: face i/6, pattern [0,1,2,2,3,0]
+                for (uint32_t k = tid; k < tileI; k += NT) {
+                    const uint32_t f = k / 6u, q = k - f * 6u;
+                    iout[i0 + k] = v0 + f * 4u + ((0x032210u >> (4u * q)) & 15u);
+                }
+            }
+            __syncthreads();
+            // ---- C3: one vertex per thread, staged then copied out coalesced ----
+            for (uint32_t vb = 0; vb < tileV; vb += NT) {
+                const uint32_t sl = vb + tid;
+                if (sl < tileV) {
+                    const uint32_t f = quads_only ? (sl >> 2) : (uint32_t)s.s2f[sl];
+                    const uint32_t a = s.frecA[f], ks = s.frecB[f], id = s.frecC[f];
+                    const uint32_t row = a & 1023u, x = (a >> 10) & 31u, d = (a >> 15) & 7u;
+                    const uint32_t y = row >> 5, z = row & 31u;
+                    const uint32_t j = sl - (a >> 18);
+                    const uint32_t cx = s.cls[(y + 1) * PLANE + (z + 1) * ROWB + XOFF + x];
                     const uint32_t st = s.stab[cx * 6 + d];
                     const uint32_t ls = st & 7u, nv = (st >> 3) & 7u, signs = st >> 9;
                     const unsigned long long e = __ldg(&T->vtab[cx][d][j]);
                     // as_wxyz10 of (ipos + voffset + 0.5)/32 (voxmesh.rs:36-41,139-145,165): every vertex sits on a
                     // voxel corner, so each 10-bit field is 16 * corner coordinate; w = (1/32*2) as u32 = 0.
-                    const uint32_t px = (uint32_t)x + ((uint32_t)e & 1u), py = (uint32_t)y + ((uint32_t)(e >> 1) & 1u),
-                                   pz = (uint32_t)z + ((uint32_t)(e >> 2) & 1u);
+                    const uint32_t px = x + ((uint32_t)e & 1u), py = y + ((uint32_t)(e >> 1) & 1u), pz = z + ((uint32_t)(e >> 2) & 1u);
                     const uint32_t position = (((px * 16u) & 0x3FFu) << 20) | (((py * 16u) & 0x3FFu) << 10) | ((pz * 16u) & 0x3FFu);
-                    const float dc0 = __ldg(p.reg.color + id * 3), dc1 = __ldg(p.reg.color + id * 3 + 1),
-                                dc2 = __ldg(p.reg.color + id * 3 + 2);
+                    float dc0, dc1, dc2, texid;
+                    if (id < (uint32_t)REGC) {
+                        dc0 = s.reg_color[id * 3];
+                        dc1 = s.reg_color[id * 3 + 1];
+                        dc2 = s.reg_color[id * 3 + 2];
+                        texid = s.reg_texf[id * 6 + ls]; // texture of the LOCAL side (voxmesh.rs:146)
+                    } else {
+                        dc0 = __ldg(p.reg.color + id * 3);
+                        dc1 = __ldg(p.reg.color + id * 3 + 1);
+                        dc2 = __ldg(p.reg.color + id * 3 + 2);
+                        texid = __ldg(p.reg.texf + id * 6 + ls);
+                    }
                     const float ao = s.ao_lut[(ks >> (3 * j)) & 7u];
-                    const float c0 = __fmul_rn(dc0, ao), c1 = __fmul_rn(dc1, ao), c2 = __fmul_rn(dc2, ao);
+                    const float c0f = __fmul_rn(dc0, ao), c1f = __fmul_rn(dc1, ao), c2f = __fmul_rn(dc2, ao);
                     // as_rgba8 (voxmesh.rs:29-34); Rust's `as u32` saturates like cvt.rzi.u32.f32
-                    const uint32_t color = ((__float2uint_rz(__fmul_rn(c0, 255.0f)) & 0xFFu) << 24) |
-                                           ((__float2uint_rz(__fmul_rn(c1, 255.0f)) & 0xFFu) << 16) |
-                                           ((__float2uint_rz(__fmul_rn(c2, 255.0f)) & 0xFFu) << 8) | 0xFFu;
+                    const uint32_t color = ((__float2uint_rz(__fmul_rn(c0f, 255.0f)) & 0xFFu) << 24) |
+                                           ((__float2uint_rz(__fmul_rn(c1f, 255.0f)) & 0xFFu) << 16) |
+                                           ((__float2uint_rz(__fmul_rn(c2f, 255.0f)) & 0xFFu) << 8) | 0xFFu;
                     // barycentric_color_sum over the side's vertices in order (voxmesh.rs:124,153,172-174)
                     float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, b3 = 0.0f;
                     for (uint32_t jj = 0; jj < nv; jj++) {
@@ -441,21 +518,21 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                         b3 = __fadd_rn(b3, __fmul_rn(sg, 1.0f));
                     }
                     const float tu = (float)((uint32_t)(e >> 3) & 1u), tv = (float)((uint32_t)(e >> 4) & 1u);
-                    const float texid = __ldg(p.reg.texf + id * 6 + ls); // texture of the LOCAL side (voxmesh.rs:146)
-                    const uint32_t index = (uint32_t)(x + 32 * z + 1024 * y) | (((uint32_t)(e >> 5) & 7u) << 17);
-                    uint2 *o = &ws.vstage[lane * 5];
+                    const uint32_t index = (x + 32u * z + 1024u * y) | (((uint32_t)(e >> 5) & 7u) << 17);
+                    uint2 *o = &s.vstage[tid * 5];
                     o[0] = make_uint2(position, color);
                     o[1] = make_uint2(__float_as_uint(tu), __float_as_uint(tv));
                     o[2] = make_uint2(__float_as_uint(texid), index);
                     o[3] = make_uint2(__float_as_uint(b0), __float_as_uint(b1));
                     o[4] = make_uint2(__float_as_uint(b2), __float_as_uint(b3));
                 }
-                __syncwarp();
-                const uint32_t n2 = min(32u, Vrow - vb) * 5u;
-                uint2 *dst = reinterpret_cast<uint2 *>(vdst_row + vb);
-                for (uint32_t k = lane; k < n2; k += 32) dst[k] = ws.vstage[k];
-                __syncwarp();
+                __syncthreads();
+                const uint32_t n2 = min((uint32_t)NT, tileV - vb) * 5u;
+                uint2 *dst = reinterpret_cast<uint2 *>(vout + v0 + vb);
+                for (uint32_t k = tid; k < n2; k += NT) dst[k] = s.vstage[k];
+                __syncthreads();
             }
+            r0 = r1;
         }
     }
 }

@@ -227,8 +227,10 @@ void build_mesh_tables(MeshTables &t) {
                     if (lv.inormal.y == 0) samples[n++] = V3{ic.x, 0, ic.z};
                     if (lv.inormal.z == 0) samples[n++] = V3{ic.x, ic.y, 0};
                     e |= (unsigned long long)n << 10;
+                    t.aotab[cls][d][j][5] = (short)n;
                     for (int k = 0; k < n; k++) {
                         V3 a = rot(samples[k]);
+                        t.aotab[cls][d][j][k] = (short)(a.y * kClsPlaneBytes + a.z * kClsRowBytes + a.x);
                         unsigned long long code6 = (unsigned long long)(a.x + 1) | (unsigned long long)(a.y + 1) << 2 |
                                                    (unsigned long long)(a.z + 1) << 4;
                         e |= code6 << (13 + 6 * k);

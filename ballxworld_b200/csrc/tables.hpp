@@ -24,7 +24,14 @@ struct MeshTables {
     uint32_t stab[kNumClasses][6];
     unsigned long long vtab[kNumClasses][6][6];
     float ao_lut[8]; // ao after k occluding samples: sequential f32 multiplies by 0.88 (voxmesh.rs:27,129-137)
+    // aotab[class][d][j]: the AO samples of vtab[class][d][j] as byte offsets into the kernel's 34^3 class table
+    // (dy*plane + dz*row + dx), entries 0..4; entry 5 = sample count
+    alignas(16) short aotab[kNumClasses][6][6][8];
 };
+
+// shared-memory layout of the kernel's class table (bytes per (y,z) row / per y plane), baked into aotab
+constexpr int kClsRowBytes = 40;
+constexpr int kClsPlaneBytes = 34 * kClsRowBytes;
 
 void build_mesh_tables(MeshTables &t);
 
