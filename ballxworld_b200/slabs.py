@@ -1,0 +1,60 @@
+"""Multi-GPU decomposition of a region: contiguous slabs of chunk columns along x, one process per GPU.
+
+Generation is a pure function of (seed, position) and needs no communication; meshing needs the 1-voxel plane just
+outside each slab boundary. exchange_halos() moves those planes between x-neighbour ranks with
+torch.distributed point-to-point ops (NCCL over NVLink on GPUs; gloo in the CPU tests). There is no collective on
+the data path.
+"""
+from dataclasses import dataclass
+
+
+@dataclass(frozen=True)
+class Slab:
+    rank: int
+    world: int
+    x0: int  # first interior chunk column of this rank (region-relative)
+    nx: int  # interior chunk columns of this rank
+
+    @property
+    def has_lo(self):
+        return self.rank > 0
+
+    @property
+    def has_hi(self):
+        return self.rank < self.world - 1
+
+
+def slab_partition(total_nx, world, rank):
+    """Split total_nx chunk columns into `world` contiguous slabs, remainders to the lowest ranks."""
+    if not (0 <= rank < world) or total_nx < world:
+        raise ValueError("bad slab partition")
+    base, rem = divmod(total_nx, world)
+    nx = base + (1 if rank < rem else 0)
+    x0 = rank * base + min(rank, rem)
+    return Slab(rank, world, x0, nx)
+
+
+def exchange_halos(slab, dist, bufs, export_plane, import_plane):
+    """One halo exchange.
+
+    bufs: dict with tensors send_lo, send_hi, recv_lo, recv_hi (same shape/dtype/device).
+    export_plane(face, tensor): pack this rank's own boundary plane at face 0 (x-) / 1 (x+) into tensor.
+    import_plane(face, tensor): write a received plane into this rank's shell at that face.
+    The x- plane of rank r becomes the x+ shell of rank r-1 and vice versa.
+    """
+    ops = []
+    if slab.has_lo:
+        export_plane(0, bufs["send_lo"])
+        ops.append(dist.P2POp(dist.isend, bufs["send_lo"], slab.rank - 1))
+        ops.append(dist.P2POp(dist.irecv, bufs["recv_lo"], slab.rank - 1))
+    if slab.has_hi:
+        export_plane(1, bufs["send_hi"])
+        ops.append(dist.P2POp(dist.isend, bufs["send_hi"], slab.rank + 1))
+        ops.append(dist.P2POp(dist.irecv, bufs["recv_hi"], slab.rank + 1))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    if slab.has_lo:
+        import_plane(0, bufs["recv_lo"])
+    if slab.has_hi:
+        import_plane(1, bufs["recv_hi"])

@@ -185,22 +185,14 @@ def main():
         hb = ctx.region_halo_bytes()
         halo = {k: torch.empty(hb // 4, dtype=torch.int32, device="cuda") for k in ("send_lo", "send_hi", "recv_lo", "recv_hi")}
 
+    from ballxworld_b200.slabs import exchange_halos, slab_partition
+
+    slab_info = slab_partition(nx * world, world, rank)
+
     def exchange():
         """slab-boundary voxel planes to the x-neighbour ranks"""
-        ops = []
-        if rank > 0:
-            ctx.region_halo_export(0, halo["send_lo"].data_ptr())
-            ops += [dist.P2POp(dist.isend, halo["send_lo"], rank - 1), dist.P2POp(dist.irecv, halo["recv_lo"], rank - 1)]
-        if rank < world - 1:
-            ctx.region_halo_export(1, halo["send_hi"].data_ptr())
-            ops += [dist.P2POp(dist.isend, halo["send_hi"], rank + 1), dist.P2POp(dist.irecv, halo["recv_hi"], rank + 1)]
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        if rank > 0:
-            ctx.region_halo_import(0, halo["recv_lo"].data_ptr())
-        if rank < world - 1:
-            ctx.region_halo_import(1, halo["recv_hi"].data_ptr())
+        exchange_halos(slab_info, dist, halo, lambda f, t: ctx.region_halo_export(f, t.data_ptr()),
+                       lambda f, t: ctx.region_halo_import(f, t.data_ptr()))
 
     def step():
         region.generate(SEED, 64)
