@@ -9,15 +9,19 @@ namespace {
 // Halo planes. One x = const voxel plane over the whole storage extent in y and z (shell rows included so that
 // edges and corners travel too: AO samples diagonal neighbours, stdshapes.rs:131-152). Layout [gy][gz].
 // ------------------------------------------------------------------------------------------------------------
-__global__ void halo_plane_kernel(uint32_t *blocks, int SX, int SY, int SZ, int sx, int lx, uint32_t *plane, int import) {
+__global__ void halo_plane_kernel(uint32_t *blocks, uint32_t *xface, int SX, int SY, int SZ, int sx, int lx, uint32_t *plane, int import) {
     const int gz = blockIdx.x * blockDim.x + threadIdx.x;
     const int gy = blockIdx.y;
     if (gz >= SZ * 32) return;
     const int sy = gy >> 5, ly = gy & 31, sz = gz >> 5, lz = gz & 31;
     uint32_t *v = blocks + ((size_t)(sx + SX * (sz + SZ * sy))) * kChunkVoxels + lx + 32 * lz + 1024 * ly;
     uint32_t *p = plane + (size_t)gy * (SZ * 32) + gz;
-    if (import) *v = *p;
-    else *p = *v;
+    if (import) {
+        *v = *p;
+        xface[((size_t)(sx + SX * (sz + SZ * sy))) * 2048 + (lx ? 1024 : 0) + ly * 32 + lz] = *p; // lx is 0 or 31 here
+    } else {
+        *p = *v;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -40,6 +44,7 @@ __global__ void apply_changes_kernel(EditParams p) {
         if (cur == c.from) cur = c.to;
     }
     *v = cur;
+    if (lx == 0 || lx == 31) p.xface[((size_t)(sx + p.SX * (sz + p.SZ * sy))) * 2048 + (lx ? 1024 : 0) + ly * 32 + lz] = cur;
     auto mark = [&](int cx, int cy, int cz) { // interior chunks only carry meshes
         if (cx >= 1 && cx <= p.SX - 2 && cy >= 1 && cy <= p.SY - 2 && cz >= 1 && cz <= p.SZ - 2)
             p.dirty[(cx - 1) + (p.SX - 2) * ((cz - 1) + (p.SZ - 2) * (cy - 1))] = 1;
@@ -304,6 +309,17 @@ __global__ void terragen_noise2_kernel(const TerragenTables *T, const double *xs
     out[i] = value;
 }
 
+// x=0 / x=31 planes of a list of chunks (after uploads / RLE decodes): thread per (side, y, z)
+__global__ void xface_extract_kernel(const uint32_t *blocks, uint32_t *xface, const uint32_t *chunks, uint32_t first, uint32_t n) {
+    const uint32_t k = blockIdx.x;
+    if (k >= n) return;
+    const size_t c = chunks ? chunks[k] : (size_t)first + k;
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
+        const int side = i >> 10, y = (i >> 5) & 31, z = i & 31;
+        xface[c * 2048 + i] = blocks[c * kChunkVoxels + (side ? 31 : 0) + 32 * z + 1024 * y];
+    }
+}
+
 // Synthetic input of BASELINE config 2: every voxel is a pure function of its global position.
 __global__ void fill_synthetic_kernel(uint32_t *blocks, int SX, int SY, int SZ, int32_t cx_min, int32_t cy_min, int32_t cz_min,
                                       uint64_t seed, uint32_t void_threshold) {
@@ -331,14 +347,18 @@ __global__ void fill_synthetic_kernel(uint32_t *blocks, int SX, int SY, int SZ, 
 
 } // namespace
 
+void launch_xface_extract(const uint32_t *blocks, uint32_t *xface, const uint32_t *chunks, uint32_t first, uint32_t n, cudaStream_t stream) {
+    if (n) xface_extract_kernel<<<n, 256, 0, stream>>>(blocks, xface, chunks, first, n);
+}
+
 void launch_fill_synthetic(uint32_t *blocks, int SX, int SY, int SZ, int32_t cx_min, int32_t cy_min, int32_t cz_min, uint64_t seed,
                            uint32_t void_threshold, cudaStream_t stream) {
     fill_synthetic_kernel<<<(unsigned)((size_t)SX * SY * SZ), 256, 0, stream>>>(blocks, SX, SY, SZ, cx_min, cy_min, cz_min, seed, void_threshold);
 }
 
-void launch_halo_plane(uint32_t *blocks, int SX, int SY, int SZ, int sx, int lx, uint32_t *plane, int import, cudaStream_t stream) {
+void launch_halo_plane(uint32_t *blocks, uint32_t *xface, int SX, int SY, int SZ, int sx, int lx, uint32_t *plane, int import, cudaStream_t stream) {
     dim3 grid((SZ * 32 + 127) / 128, SY * 32);
-    halo_plane_kernel<<<grid, 128, 0, stream>>>(blocks, SX, SY, SZ, sx, lx, plane, import);
+    halo_plane_kernel<<<grid, 128, 0, stream>>>(blocks, xface, SX, SY, SZ, sx, lx, plane, import);
 }
 
 void launch_apply_changes(const EditParams &p, cudaStream_t stream) {

@@ -4,10 +4,11 @@
 
 namespace bxw {
 
-void launch_halo_plane(uint32_t *blocks, int SX, int SY, int SZ, int sx, int lx, uint32_t *plane, int import, cudaStream_t stream);
+void launch_halo_plane(uint32_t *blocks, uint32_t *xface, int SX, int SY, int SZ, int sx, int lx, uint32_t *plane, int import, cudaStream_t stream);
 
 struct EditParams {
     uint32_t *blocks;
+    uint32_t *xface;
     int SX, SY, SZ;
     int32_t x_min, y_min, z_min;     // world voxel coordinate of storage voxel (0,0,0)
     const bxw_voxel_change *changes; // grouped by voxel, original order within a group
@@ -33,6 +34,9 @@ struct TerragenTables {
 };
 void build_terragen_tables(uint64_t seed, TerragenTables &t);
 void launch_terragen_noise2(const TerragenTables *T, const double *xs, const double *ys, size_t n, double *out, cudaStream_t stream);
+
+// refresh the x-face planes of chunks[0..n) (or of chunks first..first+n when chunks == nullptr)
+void launch_xface_extract(const uint32_t *blocks, uint32_t *xface, const uint32_t *chunks, uint32_t first, uint32_t n, cudaStream_t stream);
 
 // synthetic benchmark input: hashed random blocks incl. shapes/orientations
 void launch_fill_synthetic(uint32_t *blocks, int SX, int SY, int SZ, int32_t cx_min, int32_t cy_min, int32_t cz_min, uint64_t seed,

@@ -24,6 +24,7 @@ struct Region {
     uint32_t nx = 0, ny = 0, nz = 0;   // interior dims
     int SX = 0, SY = 0, SZ = 0;        // storage dims (shell included)
     uint32_t *blocks = nullptr;
+    uint32_t *xface = nullptr; // [chunk][2][32][32]: x=0 / x=31 planes, maintained by every writer of `blocks`
     int32_t *hmap = nullptr;
     double *raw = nullptr;
     bool have_hmap = false;
@@ -158,6 +159,7 @@ int ensure_gen_tables(bxw_ctx *ctx, uint64_t seed) {
 
 void region_free(Region &r) {
     cudaFree(r.blocks);
+    cudaFree(r.xface);
     cudaFree(r.hmap);
     cudaFree(r.raw);
     cudaFree(r.cells);
@@ -190,6 +192,7 @@ int region_alloc(bxw_ctx *ctx, Region &r, int32_t cx0, int32_t cy0, int32_t cz0,
     if (nst >= (1ull << 32)) return fail(ctx, BXW_E_INVALID, "region too large");
     r.n_work = nx * ny * nz;
     CK(cudaMalloc(&r.blocks, nst * kChunkVoxels * sizeof(uint32_t)));
+    CK(cudaMalloc(&r.xface, nst * 2048 * sizeof(uint32_t)));
     CK(cudaMalloc(&r.hmap, (size_t)r.SX * 32 * r.SZ * 32 * sizeof(int32_t)));
     CK(cudaMalloc(&r.work, r.n_work * sizeof(uint32_t)));
     CK(cudaMalloc(&r.work_span, r.n_work * sizeof(uint32_t)));
@@ -258,6 +261,7 @@ int region_generate(bxw_ctx *ctx, Region &r, uint64_t seed, int precision, bool 
     fp.hmap = r.hmap;
     fp.W = W;
     fp.blocks = r.blocks;
+    fp.xface = r.xface;
     fp.SX = r.SX;
     fp.SY = r.SY;
     fp.SZ = r.SZ;
@@ -268,7 +272,7 @@ int region_generate(bxw_ctx *ctx, Region &r, uint64_t seed, int precision, bool 
     fp.id_stone = (uint32_t)ctx->gen_ids[3] << 16;
     fp.id_snow = (uint32_t)ctx->gen_ids[4] << 16;
     launch_fill_kernel(fp, ctx->stream);
-    ctx->launches += 3;
+    ctx->launches += 4;
     CK(cudaGetLastError());
     r.have_hmap = true;
     return BXW_OK;
@@ -299,6 +303,7 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
     if (!ctx->d_kind) return fail(ctx, BXW_E_NO_REGISTRY, "bxw_set_registry not called");
     MeshParams p;
     p.blocks = r.blocks;
+    p.xface = r.xface;
     p.SX = r.SX;
     p.SY = r.SY;
     p.SZ = r.SZ;
@@ -309,6 +314,7 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
     p.counters = r.counters;
     p.tables = ctx->d_tables;
     p.reg = dev_registry(ctx);
+    p.debug = getenv("BXW_DEBUG") ? atoi(getenv("BXW_DEBUG")) : 0;
     unsigned long long base_v = 0, base_i = 0;
     if (append) {
         CK(cudaMemcpyAsync(r.h_counters, r.counters, sizeof(MeshCounters), cudaMemcpyDeviceToHost, ctx->stream));
@@ -560,6 +566,8 @@ int bxw_mesh_chunk27(bxw_ctx *ctx, const uint32_t *const dense[27], bxw_mesh_spa
         // slot rx + 3 rz + 9 ry (voxmesh.rs:72) is exactly the 3x3x3 storage order sx + 3*(sz + 3*sy)
         CK(cudaMemcpyAsync(r.blocks + (size_t)i * kChunkVoxels, dense[i], kChunkVoxels * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     }
+    launch_xface_extract(r.blocks, r.xface, nullptr, 0, 27, ctx->stream);
+    ctx->launches += 1;
     rc = region_mesh(ctx, r, r.work, r.work_span, 1, false);
     if (rc) return rc;
     CK(cudaMemcpyAsync(counts, r.spans, sizeof(bxw_mesh_span), cudaMemcpyDeviceToHost, ctx->stream));
@@ -582,6 +590,8 @@ int bxw_mesh_chunk27_rle(bxw_ctx *ctx, const uint32_t *const rle[27], const size
     for (int i = 0; i < 27; i++) std::memcpy(words.data() + offs[i], rle[i], rle_len[i] * sizeof(uint32_t));
     rc = rle_decode_into(ctx, words.data(), offs.data(), 27, r.blocks);
     if (rc) return rc;
+    launch_xface_extract(r.blocks, r.xface, nullptr, 0, 27, ctx->stream);
+    ctx->launches += 1;
     rc = region_mesh(ctx, r, r.work, r.work_span, 1, false);
     if (rc) return rc;
     CK(cudaMemcpyAsync(counts, r.spans, sizeof(bxw_mesh_span), cudaMemcpyDeviceToHost, ctx->stream));
@@ -706,6 +716,8 @@ int bxw_region_upload_chunk(bxw_ctx *ctx, int32_t lx, int32_t ly, int32_t lz, co
     Region &r = ctx->region;
     if (!local_ok(r, lx, ly, lz)) return fail(ctx, BXW_E_INVALID, "chunk (%d,%d,%d) outside region+shell", lx, ly, lz);
     CK(cudaMemcpyAsync(r.blocks + storage_index(r, lx, ly, lz) * kChunkVoxels, blocks_yzx, kChunkVoxels * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    launch_xface_extract(r.blocks, r.xface, nullptr, (uint32_t)storage_index(r, lx, ly, lz), 1, ctx->stream);
+    ctx->launches += 1;
     CK(cudaStreamSynchronize(ctx->stream));
     return BXW_OK;
 }
@@ -729,7 +741,7 @@ int bxw_region_mesh_reserve(bxw_ctx *ctx, uint64_t max_vertices, uint64_t max_in
 int bxw_region_mesh(bxw_ctx *ctx, uint64_t *arena_vertices, uint64_t *arena_indices) {
     if (!ctx || !ctx->region.live) return fail(ctx, BXW_E_INVALID, "no region");
     Region &r = ctx->region;
-    int rc = region_mesh(ctx, r, r.work, r.work_span, r.n_work, false);
+    int rc = region_mesh(ctx, r, nullptr, nullptr, r.n_work, false); // implicit interior enumeration
     if (rc) return rc;
     CK(cudaMemsetAsync(r.dirty, 0, r.n_work, ctx->stream));
     if (arena_vertices) *arena_vertices = r.h_counters->v_alloc;
@@ -795,6 +807,7 @@ int bxw_region_apply_changes(bxw_ctx *ctx, const bxw_voxel_change *changes, uint
         CK(cudaMemcpyAsync(ctx->io_b, runs.data(), runs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
         EditParams ep;
         ep.blocks = r.blocks;
+        ep.xface = r.xface;
         ep.SX = r.SX;
         ep.SY = r.SY;
         ep.SZ = r.SZ;
@@ -842,7 +855,7 @@ int bxw_region_halo_export(bxw_ctx *ctx, int face, void *dev_buf) {
     if (!ctx || !ctx->region.live || !dev_buf || (face != 0 && face != 1)) return fail(ctx, BXW_E_INVALID, "bad halo export");
     Region &r = ctx->region;
     // the interior's own boundary plane: x- face = storage chunk column 1, local x 0; x+ face = column nx, local x 31
-    launch_halo_plane(r.blocks, r.SX, r.SY, r.SZ, face == 0 ? 1 : (int)r.nx, face == 0 ? 0 : 31, (uint32_t *)dev_buf, 0, ctx->stream);
+    launch_halo_plane(r.blocks, r.xface, r.SX, r.SY, r.SZ, face == 0 ? 1 : (int)r.nx, face == 0 ? 0 : 31, (uint32_t *)dev_buf, 0, ctx->stream);
     ctx->launches += 1;
     CK(cudaGetLastError());
     return BXW_OK;
@@ -852,7 +865,7 @@ int bxw_region_halo_import(bxw_ctx *ctx, int face, const void *dev_buf) {
     if (!ctx || !ctx->region.live || !dev_buf || (face != 0 && face != 1)) return fail(ctx, BXW_E_INVALID, "bad halo import");
     Region &r = ctx->region;
     // into the shell: x- shell = column 0, local x 31; x+ shell = column nx+1, local x 0
-    launch_halo_plane(r.blocks, r.SX, r.SY, r.SZ, face == 0 ? 0 : (int)r.nx + 1, face == 0 ? 31 : 0, (uint32_t *)dev_buf, 1, ctx->stream);
+    launch_halo_plane(r.blocks, r.xface, r.SX, r.SY, r.SZ, face == 0 ? 0 : (int)r.nx + 1, face == 0 ? 31 : 0, (uint32_t *)dev_buf, 1, ctx->stream);
     ctx->launches += 1;
     CK(cudaGetLastError());
     return BXW_OK;
@@ -900,7 +913,8 @@ int bxw_region_fill_synthetic(bxw_ctx *ctx, uint64_t seed, uint32_t void_thresho
     if (!ctx || !ctx->region.live) return fail(ctx, BXW_E_INVALID, "no region");
     Region &r = ctx->region;
     launch_fill_synthetic(r.blocks, r.SX, r.SY, r.SZ, r.cx0 - 1, r.cy0 - 1, r.cz0 - 1, seed, void_threshold, ctx->stream);
-    ctx->launches += 1;
+    launch_xface_extract(r.blocks, r.xface, nullptr, 0, (uint32_t)r.n_storage(), ctx->stream);
+    ctx->launches += 2;
     CK(cudaGetLastError());
     return BXW_OK;
 }

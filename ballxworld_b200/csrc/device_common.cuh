@@ -32,6 +32,7 @@ struct MeshCounters {
 
 struct MeshParams {
     const uint32_t *blocks; // region storage: chunk c at blocks + c*32768, voxel x + 32 z + 1024 y
+    const uint32_t *xface;  // per chunk the x=0 and x=31 voxel planes, [chunk][side][y][z] (2 x 4 KB): the mesher's x-halo source
     int SX, SY, SZ;         // storage dims in chunks (shell included); chunk index sx + SX*(sz + SZ*sy)
     const uint32_t *work;   // [n_work] storage chunk index of each chunk to mesh
     const uint32_t *work_span; // [n_work] span slot of each work item
@@ -44,6 +45,7 @@ struct MeshParams {
     const MeshTables *tables;
     DeviceRegistry reg;
     int count_only; // 1: fill spans' counts only (offsets = running totals), no vertex/index writes
+    int debug;      // experiment switches (BXW_DEBUG env var); 0 in production
 };
 
 void launch_mesh_kernel(const MeshParams &p, int sm_count, cudaStream_t stream);
@@ -78,6 +80,7 @@ struct FillParams {
     const int32_t *hmap; // [D][W]
     int32_t W;
     uint32_t *blocks;
+    uint32_t *xface;
     int SX, SY, SZ;
     int32_t cy_min;      // world chunk y of storage layer 0
     uint32_t id_void, id_grass, id_dirt, id_stone, id_snow; // already shifted datums (id << 16)

@@ -314,6 +314,28 @@ __global__ void __launch_bounds__(256) fill_kernel(FillParams p) {
     }
 }
 
+// The x=0 / x=31 voxel planes of every chunk, straight from the column parameters (same selection rule as fill_kernel).
+// One CTA per (sx, sz) chunk column, thread = (side, z); loops over all layers; coalesced 128-byte stores.
+__global__ void __launch_bounds__(64) fill_xface_kernel(FillParams p) {
+    const int sx = blockIdx.x, sz = blockIdx.y;
+    const int side = threadIdx.x >> 5, z = threadIdx.x & 31;
+    const int hm = __ldg(p.hmap + (size_t)(sz * 32 + z) * p.W + sx * 32 + (side ? 31 : 0));
+    const int h = hm >> 2, el = hm & 3;
+    for (int sy = 0; sy < p.SY; sy++) {
+        uint32_t *dst = p.xface + ((size_t)(sx + p.SX * (sz + p.SZ * sy))) * 2048 + side * 1024 + z;
+        const int ybase = (p.cy_min + sy) * 32;
+        for (int yc = 0; yc < 32; yc++) {
+            const int y = ybase + yc;
+            uint32_t v;
+            if (y == h) v = (el == 2 && y > 80) ? p.id_snow : p.id_grass;
+            else if (y < h - 5) v = p.id_stone;
+            else if (y < h) v = p.id_dirt;
+            else v = p.id_void;
+            dst[yc * 32] = v;
+        }
+    }
+}
+
 bool g_const_uploaded = false;
 void ensure_constants() {
     if (g_const_uploaded) return;
@@ -344,6 +366,7 @@ void launch_heightmap_kernel(const GenParams &p, int precision, cudaStream_t str
 void launch_fill_kernel(const FillParams &p, cudaStream_t stream) {
     dim3 grid(p.SX, p.SZ);
     fill_kernel<<<grid, 256, 0, stream>>>(p);
+    if (p.xface) fill_xface_kernel<<<grid, 64, 0, stream>>>(p);
 }
 
 } // namespace bxw

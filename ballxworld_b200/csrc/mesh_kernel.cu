@@ -143,7 +143,16 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
         if (w >= p.n_work) break;
         // fetch the next work item now; its latency hides behind this chunk
         if (tid == 0) s.work_item[(iter + 1) & 1] = (uint32_t)atomicAdd(&p.counters->work_next, 1ull);
-        const uint32_t c0 = p.work[w];
+        uint32_t c0, span_slot;
+        if (p.work) {
+            c0 = p.work[w];
+            span_slot = p.work_span[w];
+        } else { // the whole interior, enumerated x, z, y (no dependent global load)
+            const uint32_t nx = (uint32_t)p.SX - 2u, nz = (uint32_t)p.SZ - 2u;
+            const uint32_t ix = w % nx, iz = (w / nx) % nz, iy = w / (nx * nz);
+            c0 = (ix + 1u) + (uint32_t)p.SX * ((iz + 1u) + (uint32_t)p.SZ * (iy + 1u));
+            span_slot = w;
+        }
         if (tid < 27) {
             const int sx = (int)(c0 % (uint32_t)p.SX), sz = (int)((c0 / (uint32_t)p.SX) % (uint32_t)p.SZ),
                       sy = (int)(c0 / (uint32_t)(p.SX * p.SZ));
@@ -154,87 +163,145 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
 
         // ---------------- phase A: stage 34^3 class bytes + per-row solid words ----------------
         uint32_t err = 0;
-        uint32_t shapes = 0; // saw a non-cube shape (class > 24)
+        uint32_t shapes = 0;  // saw a non-cube shape (class > 24)
+        uint32_t mixed = 0;   // saw a voxel different from the chunk's first voxel
+        const uint32_t ref = __ldg(p.blocks + (size_t)c0 * kChunkVoxels); // every voxel equal to this one => trivial chunk
         {
-            // 1156 (y',z') rows of 32 interior-x voxels: 8 lanes x uint4 per row, 4 rows per warp instruction.
-            constexpr int GROUPS = 1156 / 4; // 289
-            constexpr int UNR = 8;
-            for (int g0 = warp; g0 < GROUPS; g0 += NW * UNR) {
-                uint4 v[UNR];
+            // main stream: warp w takes y' layers w, w+NW, ...; a layer is 34 rows of 32 voxels = 9 warp loads of
+            // 4 rows (8 lanes x uint4 per row; the 9th covers rows 32,33 with lanes 0..15).
+            uint32_t last_d = ref, last_c = classify(ref, s, p.reg, err);
+            const int q = lane & 7, zsub = lane >> 3;
+            for (int yy = warp; yy < 34; yy += NW) {
+                const int ry = yy == 0 ? 0 : (yy <= 32 ? 1 : 2), by = (yy - 1) & 31;
+                const uint32_t *b0 = p.blocks + (size_t)s.nbr[1 + 0 + 9 * ry] * kChunkVoxels + by * 1024 + 31 * 32 + q * 4; // zz = 0
+                const uint32_t *b1 = p.blocks + (size_t)s.nbr[1 + 3 + 9 * ry] * kChunkVoxels + by * 1024 + q * 4;           // zz = 1..32
+                const uint32_t *b2 = p.blocks + (size_t)s.nbr[1 + 6 + 9 * ry] * kChunkVoxels + by * 1024 + q * 4;           // zz = 33
+                uint4 v[9];
 #pragma unroll
-                for (int u = 0; u < UNR; u++) {
-                    const int g = g0 + u * NW;
-                    if (g < GROUPS) {
-                        const int r = g * 4 + (lane >> 3);
-                        const int yy = r / 34, zz = r - yy * 34;
-                        const int ry = yy == 0 ? 0 : (yy <= 32 ? 1 : 2), rz = zz == 0 ? 0 : (zz <= 32 ? 1 : 2);
-                        const int by = (yy - 1) & 31, bz = (zz - 1) & 31;
-                        const uint32_t *src = p.blocks + (size_t)s.nbr[1 + 3 * rz + 9 * ry] * kChunkVoxels + by * 1024 + bz * 32 + (lane & 7) * 4;
-                        v[u] = __ldg(reinterpret_cast<const uint4 *>(src));
-                    }
+                for (int j = 0; j < 9; j++) {
+                    const int zz = 4 * j + zsub;
+                    const uint32_t *src = zz == 0 ? b0 : (zz == 33 ? b2 : b1 + (zz - 1) * 32);
+                    if (zz < 34) v[j] = __ldg(reinterpret_cast<const uint4 *>(src));
+                    else v[j] = make_uint4(ref, ref, ref, ref);
                 }
+                // x-halo of this layer from the x-neighbour chunks' face planes ([chunk][side][y][z], coalesced):
+                // lane z holds the x=-1 / x=32 voxels of row zz = z+1; lanes 0..3 also hold the four corner rows
+                // (zz = 0 / 33) that live in the diagonal neighbours
+                const uint32_t hm = __ldg(p.xface + (size_t)s.nbr[0 + 3 + 9 * ry] * 2048 + 1024 + by * 32 + lane);
+                const uint32_t hp = __ldg(p.xface + (size_t)s.nbr[2 + 3 + 9 * ry] * 2048 + by * 32 + lane);
+                uint32_t he = 0;
+                if (lane < 4) {
+                    const int erx = (lane & 1) ? 2 : 0, erz = (lane & 2) ? 2 : 0;
+                    he = __ldg(p.xface + (size_t)s.nbr[erx + 3 * erz + 9 * ry] * 2048 + ((lane & 1) ? 0 : 1024) + by * 32 + ((lane & 2) ? 0 : 31));
+                }
+                // Whole-layer test first: 1088 voxels equal to one datum (the common case in terrain) costs one
+                // match + one vote for the layer instead of a shuffle/vote chain per 128-voxel group.
+                const uint32_t x0 = v[0].x;
+                bool ok = true;
 #pragma unroll
-                for (int u = 0; u < UNR; u++) {
-                    const int g = g0 + u * NW; // warp-uniform
-                    if (g < GROUPS) {
-                        const int r = g * 4 + (lane >> 3);
-                        const int yy = r / 34, zz = r - yy * 34;
-                        const int at = yy * PLANE + zz * ROWB + XOFF + (lane & 7) * 4;
-                        const uint32_t first = __shfl_sync(FULL, v[u].x, 0);
-                        const bool same = (v[u].x == first) & (v[u].y == first) & (v[u].z == first) & (v[u].w == first);
-                        uint32_t b, rowmask;
-                        if (__all_sync(FULL, same)) {
-                            const uint32_t c = classify(first, s, p.reg, err);
-                            b = c * 0x01010101u;
-                            rowmask = c ? 0xFFFFFFFFu : 0u;
-                            shapes |= (c > 24u);
-                        } else {
-                            const uint32_t k0 = classify(v[u].x, s, p.reg, err), k1 = classify(v[u].y, s, p.reg, err),
-                                           k2 = classify(v[u].z, s, p.reg, err), k3 = classify(v[u].w, s, p.reg, err);
-                            b = k0 | (k1 << 8) | (k2 << 16) | (k3 << 24);
-                            shapes |= (k0 > 24u) | (k1 > 24u) | (k2 > 24u) | (k3 > 24u);
-                            uint32_t m = ((k0 != 0u) | ((k1 != 0u) << 1) | ((k2 != 0u) << 2) | ((k3 != 0u) << 3)) << ((lane & 7) * 4);
-                            m |= __shfl_xor_sync(FULL, m, 1);
-                            m |= __shfl_xor_sync(FULL, m, 2);
-                            m |= __shfl_xor_sync(FULL, m, 4);
-                            rowmask = m;
+                for (int j = 0; j < 9; j++) {
+                    const uint32_t d = ((v[j].x ^ x0) | (v[j].y ^ x0)) | ((v[j].z ^ x0) | (v[j].w ^ x0));
+                    ok &= (d == 0u) | (4 * j + zsub >= 34);
+                }
+                ok &= (hm == x0) & (hp == x0) & ((he == x0) | (lane >= 4));
+                int same_x0;
+                __match_all_sync(FULL, x0, &same_x0);
+                if (__all_sync(FULL, ok) && same_x0) {
+                    if (x0 != last_d) {
+                        last_d = x0;
+                        last_c = classify(x0, s, p.reg, err);
+                    }
+                    mixed |= (x0 != ref);
+                    shapes |= (last_c > 24u);
+                    const uint32_t b = last_c * 0x01010101u, rowmask = last_c ? 0xFFFFFFFFu : 0u;
+#pragma unroll
+                    for (int j = 0; j < 9; j++) {
+                        const int zz = 4 * j + zsub;
+                        if (zz < 34) {
+                            *reinterpret_cast<uint32_t *>(&s.cls[yy * PLANE + zz * ROWB + XOFF + q * 4]) = b;
+                            if (q == 0) s.solid[yy * 34 + zz] = rowmask;
                         }
-                        *reinterpret_cast<uint32_t *>(&s.cls[at]) = b;
-                        if ((lane & 7) == 0) s.solid[r] = rowmask;
+                    }
+                    {
+                        uint8_t *row = &s.cls[yy * PLANE + (lane + 1) * ROWB + XOFF];
+                        row[-1] = (uint8_t)last_c;
+                        row[32] = (uint8_t)last_c;
+                        s.solid_halo[yy * 34 + lane + 1] = last_c ? 3 : 0;
+                        if (lane == 0 || lane == 2) {
+                            const int zz = lane ? 33 : 0;
+                            s.cls[yy * PLANE + zz * ROWB + XOFF - 1] = (uint8_t)last_c;
+                            s.cls[yy * PLANE + zz * ROWB + XOFF + 32] = (uint8_t)last_c;
+                            s.solid_halo[yy * 34 + zz] = last_c ? 3 : 0;
+                        }
+                    }
+                    continue;
+                }
+                {
+                    // general x-halo of this layer
+                    const uint32_t cm = classify(hm, s, p.reg, err), cp = classify(hp, s, p.reg, err);
+                    const uint32_t ce = lane < 4 ? classify(he, s, p.reg, err) : 0u;
+                    const uint32_t co = __shfl_xor_sync(FULL, ce, 1); // the other side of the same corner row
+                    mixed |= (hm != ref) | (hp != ref) | ((he != ref) & (lane < 4));
+                    shapes |= (cm > 24u) | (cp > 24u) | (ce > 24u);
+                    uint8_t *row = &s.cls[yy * PLANE + (lane + 1) * ROWB + XOFF];
+                    row[-1] = (uint8_t)cm;
+                    row[32] = (uint8_t)cp;
+                    s.solid_halo[yy * 34 + lane + 1] = (uint8_t)((cm != 0u) | ((cp != 0u) << 1));
+                    if (lane == 0 || lane == 2) {
+                        const int zz = lane ? 33 : 0;
+                        s.cls[yy * PLANE + zz * ROWB + XOFF - 1] = (uint8_t)ce;
+                        s.cls[yy * PLANE + zz * ROWB + XOFF + 32] = (uint8_t)co;
+                        s.solid_halo[yy * 34 + zz] = (uint8_t)((ce != 0u) | ((co != 0u) << 1));
                     }
                 }
-            }
-            // the two x-halo voxels of every row: x=-1 (chunk rx=0, local x 31) and x=32 (chunk rx=2, local x 0)
-            constexpr int HIT = (1156 + NT - 1) / NT; // 5
-            uint32_t hv[HIT][2];
 #pragma unroll
-            for (int k = 0; k < HIT; k++) {
-                const int r = tid + k * NT;
-                hv[k][0] = hv[k][1] = 0;
-                if (r < 1156) {
-                    const int yy = r / 34, zz = r - yy * 34;
-                    const int ry = yy == 0 ? 0 : (yy <= 32 ? 1 : 2), rz = zz == 0 ? 0 : (zz <= 32 ? 1 : 2);
-                    const int by = (yy - 1) & 31, bz = (zz - 1) & 31;
-                    const size_t off = (size_t)by * 1024 + bz * 32;
-                    hv[k][0] = __ldg(p.blocks + (size_t)s.nbr[0 + 3 * rz + 9 * ry] * kChunkVoxels + off + 31);
-                    hv[k][1] = __ldg(p.blocks + (size_t)s.nbr[2 + 3 * rz + 9 * ry] * kChunkVoxels + off);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < HIT; k++) {
-                const int r = tid + k * NT;
-                if (r < 1156) {
-                    const int yy = r / 34, zz = r - yy * 34;
-                    const uint32_t cm = classify(hv[k][0], s, p.reg, err), cp = classify(hv[k][1], s, p.reg, err);
-                    shapes |= (cm > 24u) | (cp > 24u);
-                    s.cls[yy * PLANE + zz * ROWB + XOFF - 1] = (uint8_t)cm;
-                    s.cls[yy * PLANE + zz * ROWB + XOFF + 32] = (uint8_t)cp;
-                    s.solid_halo[r] = (uint8_t)((cm != 0u) | ((cp != 0u) << 1));
+                for (int j = 0; j < 9; j++) {
+                    const int zz = 4 * j + zsub;
+                    const uint32_t first = __shfl_sync(FULL, v[j].x, 0);
+                    const uint32_t diff = ((v[j].x ^ first) | (v[j].y ^ first)) | ((v[j].z ^ first) | (v[j].w ^ first));
+                    uint32_t b, rowmask;
+                    if (__all_sync(FULL, diff == 0u || zz >= 34)) { // all 128 voxels equal: classify once (cached)
+                        if (first != last_d) {
+                            last_d = first;
+                            last_c = classify(first, s, p.reg, err);
+                        }
+                        mixed |= (first != ref);
+                        b = last_c * 0x01010101u;
+                        rowmask = last_c ? 0xFFFFFFFFu : 0u;
+                        shapes |= (last_c > 24u);
+                    } else {
+                        mixed = 1;
+                        const uint32_t k0 = classify(v[j].x, s, p.reg, err), k1 = classify(v[j].y, s, p.reg, err),
+                                       k2 = classify(v[j].z, s, p.reg, err), k3 = classify(v[j].w, s, p.reg, err);
+                        b = k0 | (k1 << 8) | (k2 << 16) | (k3 << 24);
+                        shapes |= (k0 > 24u) | (k1 > 24u) | (k2 > 24u) | (k3 > 24u);
+                        uint32_t m = ((k0 != 0u) | ((k1 != 0u) << 1) | ((k2 != 0u) << 2) | ((k3 != 0u) << 3)) << (q * 4);
+                        m |= __shfl_xor_sync(FULL, m, 1);
+                        m |= __shfl_xor_sync(FULL, m, 2);
+                        m |= __shfl_xor_sync(FULL, m, 4);
+                        rowmask = m;
+                    }
+                    if (zz < 34) {
+                        *reinterpret_cast<uint32_t *>(&s.cls[yy * PLANE + zz * ROWB + XOFF + q * 4]) = b;
+                        if (q == 0) s.solid[yy * 34 + zz] = rowmask;
+                    }
                 }
             }
         }
         if (err) atomicOr(&p.counters->flags, kFlagUnknownId);
-        const int has_shapes = __syncthreads_or((int)shapes);
+        const int flags = __syncthreads_or((int)(shapes | (mixed << 1)));
+        const int has_shapes = flags & 1;
+        if (flags == 0) {
+            // The whole 34^3 neighbourhood is one datum and it is void or a cube: every side is either absent or
+            // clipped by an identical neighbour (voxmesh.rs:100,119) -> empty mesh, nothing to count or emit.
+            if (tid == 0) {
+                bxw_mesh_span sp;
+                sp.v_off = sp.i_off = 0;
+                sp.v_count = sp.i_count = 0;
+                p.spans[span_slot] = sp;
+            }
+            continue;
+        }
 
         // ---------------- phase B: per-row counts (packed V | I<<10 | F<<21 into rowV) ----------------
         if (!has_shapes) {
@@ -324,7 +391,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                 sp.i_off = ib;
                 sp.v_count = (uint32_t)TV;
                 sp.i_count = (uint32_t)TI;
-                p.spans[p.work_span[w]] = sp;
+                p.spans[span_slot] = sp;
                 s.vbase = vb;
                 s.ibase = ib;
                 s.emit = emit;
