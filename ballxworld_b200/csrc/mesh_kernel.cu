@@ -50,6 +50,7 @@ struct Smem {
     uint32_t warp_tot[3][NW];
     unsigned long long vbase, ibase;
     uint32_t work_item[2];
+    uint32_t wref[NW];     // per-warp reference datum (trivial-chunk detection)
     int emit;
     // emission tile
     uint32_t frecA[FC];   // row | x<<10 | dir<<15 | vstart<<18 (tile-relative first vertex)
@@ -164,39 +165,106 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
         // ---------------- phase A: stage 34^3 class bytes + per-row solid words ----------------
         uint32_t err = 0;
         uint32_t shapes = 0;  // saw a non-cube shape (class > 24)
-        uint32_t mixed = 0;   // saw a voxel different from the chunk's first voxel
-        const uint32_t ref = __ldg(p.blocks + (size_t)c0 * kChunkVoxels); // every voxel equal to this one => trivial chunk
+        uint32_t mixed = 0;   // saw a voxel different from this warp's reference voxel
         {
-            // main stream: warp w takes y' layers w, w+NW, ...; a layer is 34 rows of 32 voxels = 9 warp loads of
-            // 4 rows (8 lanes x uint4 per row; the 9th covers rows 32,33 with lanes 0..15).
-            uint32_t last_d = ref, last_c = classify(ref, s, p.reg, err);
             const int q = lane & 7, zsub = lane >> 3;
-            for (int yy = warp; yy < 34; yy += NW) {
-                const int ry = yy == 0 ? 0 : (yy <= 32 ? 1 : 2), by = (yy - 1) & 31;
-                const uint32_t *b0 = p.blocks + (size_t)s.nbr[1 + 0 + 9 * ry] * kChunkVoxels + by * 1024 + 31 * 32 + q * 4; // zz = 0
-                const uint32_t *b1 = p.blocks + (size_t)s.nbr[1 + 3 + 9 * ry] * kChunkVoxels + by * 1024 + q * 4;           // zz = 1..32
-                const uint32_t *b2 = p.blocks + (size_t)s.nbr[1 + 6 + 9 * ry] * kChunkVoxels + by * 1024 + q * 4;           // zz = 33
-                uint4 v[9];
-#pragma unroll
-                for (int j = 0; j < 9; j++) {
-                    const int zz = 4 * j + zsub;
-                    const uint32_t *src = zz == 0 ? b0 : (zz == 33 ? b2 : b1 + (zz - 1) * 32);
-                    if (zz < 34) v[j] = __ldg(reinterpret_cast<const uint4 *>(src));
-                    else v[j] = make_uint4(ref, ref, ref, ref);
+            uint32_t last_d = 0, last_c = 0, wref = 0;
+            bool have_ref = false;
+            auto note_ref = [&](uint32_t x) { // first datum this warp sees: reference for trivial-chunk detection
+                if (!have_ref) {
+                    have_ref = true;
+                    wref = __shfl_sync(FULL, x, 0);
+                    last_d = wref;
+                    last_c = classify(wref, s, p.reg, err);
                 }
-                // x-halo of this layer from the x-neighbour chunks' face planes ([chunk][side][y][z], coalesced):
-                // lane z holds the x=-1 / x=32 voxels of row zz = z+1; lanes 0..3 also hold the four corner rows
-                // (zz = 0 / 33) that live in the diagonal neighbours
-                const uint32_t hm = __ldg(p.xface + (size_t)s.nbr[0 + 3 + 9 * ry] * 2048 + 1024 + by * 32 + lane);
-                const uint32_t hp = __ldg(p.xface + (size_t)s.nbr[2 + 3 + 9 * ry] * 2048 + by * 32 + lane);
-                uint32_t he = 0;
+            };
+            // source pointers of a layer's rows: zz = 0 / 1..32 / 33 live in the three z-column chunks at this ry
+            auto row_src = [&](int ry, int by, int zz) {
+                const int rz = zz == 0 ? 0 : (zz == 33 ? 2 : 1), bz = (zz - 1) & 31;
+                return p.blocks + (size_t)s.nbr[1 + 3 * rz + 9 * ry] * kChunkVoxels + by * 1024 + bz * 32 + q * 4;
+            };
+            // one 128-voxel group (4 rows x 32) of layer yy: class bytes + solid words
+            auto do_group = [&](int yy, int j, uint4 v) {
+                const int zz = 4 * j + zsub;
+                const uint32_t first = __shfl_sync(FULL, v.x, 0);
+                const uint32_t diff = ((v.x ^ first) | (v.y ^ first)) | ((v.z ^ first) | (v.w ^ first));
+                uint32_t b, rowmask;
+                if (__all_sync(FULL, diff == 0u || zz >= 34)) { // all 128 voxels equal: classify once (cached)
+                    if (first != last_d) {
+                        last_d = first;
+                        last_c = classify(first, s, p.reg, err);
+                    }
+                    mixed |= (first != wref);
+                    b = last_c * 0x01010101u;
+                    rowmask = last_c ? 0xFFFFFFFFu : 0u;
+                    shapes |= (last_c > 24u);
+                } else {
+                    mixed = 1;
+                    const bool valid = zz < 34;
+                    const uint32_t k0 = valid ? classify(v.x, s, p.reg, err) : 0u, k1 = valid ? classify(v.y, s, p.reg, err) : 0u,
+                                   k2 = valid ? classify(v.z, s, p.reg, err) : 0u, k3 = valid ? classify(v.w, s, p.reg, err) : 0u;
+                    b = k0 | (k1 << 8) | (k2 << 16) | (k3 << 24);
+                    shapes |= (k0 > 24u) | (k1 > 24u) | (k2 > 24u) | (k3 > 24u);
+                    uint32_t m = ((k0 != 0u) | ((k1 != 0u) << 1) | ((k2 != 0u) << 2) | ((k3 != 0u) << 3)) << (q * 4);
+                    m |= __shfl_xor_sync(FULL, m, 1);
+                    m |= __shfl_xor_sync(FULL, m, 2);
+                    m |= __shfl_xor_sync(FULL, m, 4);
+                    rowmask = m;
+                }
+                if (zz < 34) {
+                    *reinterpret_cast<uint32_t *>(&s.cls[yy * PLANE + zz * ROWB + XOFF + q * 4]) = b;
+                    if (q == 0) s.solid[yy * 34 + zz] = rowmask;
+                }
+            };
+            // x-halo of a layer from the x-neighbour chunks' face planes ([chunk][side][y][z], coalesced): lane z holds the
+            // x=-1 / x=32 voxels of row zz = z+1; lanes 0..3 also hold the four corner rows (zz = 0 / 33) of the diagonals
+            auto halo_load = [&](int ry, int by, uint32_t &hm, uint32_t &hp, uint32_t &he) {
+                hm = __ldg(p.xface + (size_t)s.nbr[0 + 3 + 9 * ry] * 2048 + 1024 + by * 32 + lane);
+                hp = __ldg(p.xface + (size_t)s.nbr[2 + 3 + 9 * ry] * 2048 + by * 32 + lane);
+                he = 0;
                 if (lane < 4) {
                     const int erx = (lane & 1) ? 2 : 0, erz = (lane & 2) ? 2 : 0;
                     he = __ldg(p.xface + (size_t)s.nbr[erx + 3 * erz + 9 * ry] * 2048 + ((lane & 1) ? 0 : 1024) + by * 32 + ((lane & 2) ? 0 : 31));
                 }
-                // Whole-layer test first: 1088 voxels equal to one datum (the common case in terrain) costs one
+            };
+            auto halo_store = [&](int yy, uint32_t cm, uint32_t cp, uint32_t ce, uint32_t co) {
+                uint8_t *row = &s.cls[yy * PLANE + (lane + 1) * ROWB + XOFF];
+                row[-1] = (uint8_t)cm;
+                row[32] = (uint8_t)cp;
+                s.solid_halo[yy * 34 + lane + 1] = (uint8_t)((cm != 0u) | ((cp != 0u) << 1));
+                if (lane == 0 || lane == 2) {
+                    const int zz = lane ? 33 : 0;
+                    s.cls[yy * PLANE + zz * ROWB + XOFF - 1] = (uint8_t)ce;
+                    s.cls[yy * PLANE + zz * ROWB + XOFF + 32] = (uint8_t)co;
+                    s.solid_halo[yy * 34 + zz] = (uint8_t)((ce != 0u) | ((co != 0u) << 1));
+                }
+            };
+            auto halo_general = [&](int yy, uint32_t hm, uint32_t hp, uint32_t he) {
+                const uint32_t cm = classify(hm, s, p.reg, err), cp = classify(hp, s, p.reg, err);
+                const uint32_t ce = lane < 4 ? classify(he, s, p.reg, err) : 0u;
+                const uint32_t co = __shfl_xor_sync(FULL, ce, 1); // the other side of the same corner row
+                mixed |= (hm != wref) | (hp != wref) | ((he != wref) & (lane < 4));
+                shapes |= (cm > 24u) | (cp > 24u) | (ce > 24u);
+                halo_store(yy, cm, cp, ce, co);
+            };
+
+            // layers 0..31: four whole layers per warp (9 warp loads of 4 rows: 8 lanes x uint4 per row, the 9th covers
+            // rows 32,33 with lanes 0..15)
+            for (int yy = warp; yy < 32; yy += NW) {
+                const int ry = yy == 0 ? 0 : 1, by = (yy - 1) & 31;
+                uint4 v[9];
+#pragma unroll
+                for (int j = 0; j < 9; j++) {
+                    const int zz = 4 * j + zsub;
+                    if (zz < 34) v[j] = __ldg(reinterpret_cast<const uint4 *>(row_src(ry, by, zz)));
+                    else v[j] = make_uint4(0, 0, 0, 0);
+                }
+                uint32_t hm, hp, he;
+                halo_load(ry, by, hm, hp, he);
+                // Whole-layer test first: 1088 + 68 voxels equal to one datum (the common case in terrain) costs one
                 // match + one vote for the layer instead of a shuffle/vote chain per 128-voxel group.
                 const uint32_t x0 = v[0].x;
+                note_ref(x0);
                 bool ok = true;
 #pragma unroll
                 for (int j = 0; j < 9; j++) {
@@ -211,7 +279,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                         last_d = x0;
                         last_c = classify(x0, s, p.reg, err);
                     }
-                    mixed |= (x0 != ref);
+                    mixed |= (x0 != wref);
                     shapes |= (last_c > 24u);
                     const uint32_t b = last_c * 0x01010101u, rowmask = last_c ? 0xFFFFFFFFu : 0u;
 #pragma unroll
@@ -222,76 +290,42 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                             if (q == 0) s.solid[yy * 34 + zz] = rowmask;
                         }
                     }
-                    {
-                        uint8_t *row = &s.cls[yy * PLANE + (lane + 1) * ROWB + XOFF];
-                        row[-1] = (uint8_t)last_c;
-                        row[32] = (uint8_t)last_c;
-                        s.solid_halo[yy * 34 + lane + 1] = last_c ? 3 : 0;
-                        if (lane == 0 || lane == 2) {
-                            const int zz = lane ? 33 : 0;
-                            s.cls[yy * PLANE + zz * ROWB + XOFF - 1] = (uint8_t)last_c;
-                            s.cls[yy * PLANE + zz * ROWB + XOFF + 32] = (uint8_t)last_c;
-                            s.solid_halo[yy * 34 + zz] = last_c ? 3 : 0;
-                        }
-                    }
+                    halo_store(yy, last_c, last_c, last_c, last_c);
                     continue;
                 }
-                {
-                    // general x-halo of this layer
-                    const uint32_t cm = classify(hm, s, p.reg, err), cp = classify(hp, s, p.reg, err);
-                    const uint32_t ce = lane < 4 ? classify(he, s, p.reg, err) : 0u;
-                    const uint32_t co = __shfl_xor_sync(FULL, ce, 1); // the other side of the same corner row
-                    mixed |= (hm != ref) | (hp != ref) | ((he != ref) & (lane < 4));
-                    shapes |= (cm > 24u) | (cp > 24u) | (ce > 24u);
-                    uint8_t *row = &s.cls[yy * PLANE + (lane + 1) * ROWB + XOFF];
-                    row[-1] = (uint8_t)cm;
-                    row[32] = (uint8_t)cp;
-                    s.solid_halo[yy * 34 + lane + 1] = (uint8_t)((cm != 0u) | ((cp != 0u) << 1));
-                    if (lane == 0 || lane == 2) {
-                        const int zz = lane ? 33 : 0;
-                        s.cls[yy * PLANE + zz * ROWB + XOFF - 1] = (uint8_t)ce;
-                        s.cls[yy * PLANE + zz * ROWB + XOFF + 32] = (uint8_t)co;
-                        s.solid_halo[yy * 34 + zz] = (uint8_t)((ce != 0u) | ((co != 0u) << 1));
-                    }
-                }
+                halo_general(yy, hm, hp, he);
 #pragma unroll
-                for (int j = 0; j < 9; j++) {
-                    const int zz = 4 * j + zsub;
-                    const uint32_t first = __shfl_sync(FULL, v[j].x, 0);
-                    const uint32_t diff = ((v[j].x ^ first) | (v[j].y ^ first)) | ((v[j].z ^ first) | (v[j].w ^ first));
-                    uint32_t b, rowmask;
-                    if (__all_sync(FULL, diff == 0u || zz >= 34)) { // all 128 voxels equal: classify once (cached)
-                        if (first != last_d) {
-                            last_d = first;
-                            last_c = classify(first, s, p.reg, err);
-                        }
-                        mixed |= (first != ref);
-                        b = last_c * 0x01010101u;
-                        rowmask = last_c ? 0xFFFFFFFFu : 0u;
-                        shapes |= (last_c > 24u);
-                    } else {
-                        mixed = 1;
-                        const uint32_t k0 = classify(v[j].x, s, p.reg, err), k1 = classify(v[j].y, s, p.reg, err),
-                                       k2 = classify(v[j].z, s, p.reg, err), k3 = classify(v[j].w, s, p.reg, err);
-                        b = k0 | (k1 << 8) | (k2 << 16) | (k3 << 24);
-                        shapes |= (k0 > 24u) | (k1 > 24u) | (k2 > 24u) | (k3 > 24u);
-                        uint32_t m = ((k0 != 0u) | ((k1 != 0u) << 1) | ((k2 != 0u) << 2) | ((k3 != 0u) << 3)) << (q * 4);
-                        m |= __shfl_xor_sync(FULL, m, 1);
-                        m |= __shfl_xor_sync(FULL, m, 2);
-                        m |= __shfl_xor_sync(FULL, m, 4);
-                        rowmask = m;
-                    }
-                    if (zz < 34) {
-                        *reinterpret_cast<uint32_t *>(&s.cls[yy * PLANE + zz * ROWB + XOFF + q * 4]) = b;
-                        if (q == 0) s.solid[yy * 34 + zz] = rowmask;
-                    }
-                }
+                for (int j = 0; j < 9; j++) do_group(yy, j, v[j]);
             }
+            // layers 32 and 33, split over all warps so nobody idles: warp w takes groups [j0, j1) of layer 32 + (w >> 2)
+            {
+                const int yy = 32 + (warp >> 2), part = warp & 3;
+                const int j0 = part == 0 ? 0 : 1 + 2 * part, j1 = part == 0 ? 3 : j0 + 2;
+                const int ry = yy <= 32 ? 1 : 2, by = (yy - 1) & 31;
+                uint4 v[3];
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const int j = j0 + k, zz = 4 * j + zsub;
+                    if (j < j1 && zz < 34) v[k] = __ldg(reinterpret_cast<const uint4 *>(row_src(ry, by, zz)));
+                    else v[k] = make_uint4(0, 0, 0, 0);
+                }
+                uint32_t hm = 0, hp = 0, he = 0;
+                if (part == 0) halo_load(ry, by, hm, hp, he);
+                note_ref(v[0].x);
+                if (part == 0) halo_general(yy, hm, hp, he);
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    if (j0 + k < j1) do_group(yy, j0 + k, v[k]);
+            }
+            if (lane == 0) s.wref[warp] = wref;
         }
         if (err) atomicOr(&p.counters->flags, kFlagUnknownId);
-        const int flags = __syncthreads_or((int)(shapes | (mixed << 1)));
-        const int has_shapes = flags & 1;
-        if (flags == 0) {
+        // (__syncthreads_or returns a truth value, not the OR of the operands: two reductions)
+        const int has_shapes = __syncthreads_or((int)shapes);
+        int any_mixed = __syncthreads_or((int)mixed);
+#pragma unroll
+        for (int k = 1; k < NW; k++) any_mixed |= (s.wref[k] != s.wref[0]); // did all warps see the same single datum?
+        if (!has_shapes && !any_mixed) {
             // The whole 34^3 neighbourhood is one datum and it is void or a cube: every side is either absent or
             // clipped by an identical neighbour (voxmesh.rs:100,119) -> empty mesh, nothing to count or emit.
             if (tid == 0) {
