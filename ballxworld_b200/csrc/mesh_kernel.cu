@@ -16,6 +16,8 @@
 //   C  emission in tiles of <=1024 faces: (C1) face records in emission order, (C2) face-parallel AO occluder counts
 //      and index values, (C3) vertex-slot-parallel vertex records staged in shared memory and copied out with fully
 //      coalesced 8-byte stores. All 256 threads work on faces/vertices, not on rows.
+#include <type_traits>
+
 #include "device_common.cuh"
 
 namespace bxw {
@@ -33,11 +35,30 @@ constexpr int FC = 1024;     // faces per emission tile
 constexpr int VC = 4096;     // vertex slots per emission tile
 constexpr int REGC = 64;     // registry entries cached in shared memory
 
-struct Smem {
-    uint8_t cls[CLS_BYTES];
+// phase-A staging: every warp streams its share of the 34^3 neighbourhood through a private cp.async ring.
+// One unit = a third of a y' layer: 3 warp copies of 4 rows (12 rows x 128 B) + (first third only) the layer's x-halo.
+constexpr int RSLOTS = 3;
+constexpr int RSLOT_BYTES = 3 * 512 + 128 + 128 + 16;
+
+struct Scratch { // phases B, S, C
     uint32_t rowV[1028];   // exclusive prefix over rows: first vertex of the row (chunk-relative); [1024] = total
     uint32_t rowI[1028];
     uint32_t rowF[1028];
+    // emission tile
+    uint32_t frecA[FC];   // row | x<<10 | dir<<15 | vstart<<18 (tile-relative first vertex)
+    uint32_t frecB[FC];   // AO occluder counts, 3 bits per vertex | istart<<18 (tile-relative first index)
+    uint16_t frecC[FC];   // block id
+    uint16_t s2f[VC];     // vertex slot -> face (tiles with non-quad sides only)
+    uint32_t istage[NT * 6];
+    uint2 vstage[NT * 5]; // 256 vertices x 40 B
+};
+
+struct Smem {
+    uint8_t cls[CLS_BYTES];
+    union {
+        Scratch sc;                                          // phases B, S, C
+        alignas(16) uint8_t ring[NW][RSLOTS][RSLOT_BYTES];   // phase A
+    };
     uint32_t solid[34 * 34];         // per (y',z') row: bit x set when voxel x (0..31) has a mesh (class != 0)
     uint8_t solid_halo[34 * 34 + 4]; // bit0: x=-1 solid, bit1: x=32 solid
     uint32_t ctab[kNumClasses + 3];
@@ -52,14 +73,19 @@ struct Smem {
     uint32_t work_item[2];
     uint32_t wref[NW];     // per-warp reference datum (trivial-chunk detection)
     int emit;
-    // emission tile
-    uint32_t frecA[FC];   // row | x<<10 | dir<<15 | vstart<<18 (tile-relative first vertex)
-    uint32_t frecB[FC];   // AO occluder counts, 3 bits per vertex | istart<<18 (tile-relative first index)
-    uint16_t frecC[FC];   // block id
-    uint16_t s2f[VC];     // vertex slot -> face (tiles with non-quad sides only)
-    uint32_t istage[NT * 6];
-    uint2 vstage[NT * 5]; // 256 vertices x 40 B
 };
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
 __device__ __forceinline__ uint32_t classify(uint32_t d, const Smem &s, const DeviceRegistry &reg, uint32_t &err) {
     // voxmesh.rs:76-78 -> stdshapes.rs:51-72
@@ -248,33 +274,72 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                 halo_store(yy, cm, cp, ce, co);
             };
 
-            // layers 0..31: four whole layers per warp (9 warp loads of 4 rows: 8 lanes x uint4 per row, the 9th covers
-            // rows 32,33 with lanes 0..15)
-            for (int yy = warp; yy < 32; yy += NW) {
-                const int ry = yy == 0 ? 0 : 1, by = (yy - 1) & 31;
-                uint4 v[9];
-#pragma unroll
-                for (int j = 0; j < 9; j++) {
-                    const int zz = 4 * j + zsub;
-                    if (zz < 34) v[j] = __ldg(reinterpret_cast<const uint4 *>(row_src(ry, by, zz)));
-                    else v[j] = make_uint4(0, 0, 0, 0);
+            // The 34 layers are cut into 102 units (layer, third); warp w takes units w, w+NW, ... and streams them through
+            // its private ring, two units (6 warp copies + halo) ahead of their use.
+            constexpr int N_UNITS = 34 * 3;
+            uint8_t *const ring = &s.ring[warp][0][0];
+            // rows of the chunk itself (yy 1..32, zz 1..32) come straight off this pointer; only the boundary rows look up
+            // a neighbour chunk
+            const uint32_t *const center_q = p.blocks + (size_t)c0 * kChunkVoxels + q * 4;
+            auto issue = [&](int g, int slot) {
+                if (g < N_UNITS) {
+                    const int yy = g / 3, part = g - yy * 3;
+                    uint8_t *dst = ring + slot * RSLOT_BYTES + lane * 16;
+                    const bool inner = (yy >= 1) & (yy <= 32);
+                    const int ry = yy == 0 ? 0 : (yy <= 32 ? 1 : 2), by = (yy - 1) & 31;
+                    const int zb = 12 * part + zsub; // zz of copy jj is zb + 4*jj
+                    const uint32_t *mid = (inner ? center_q : p.blocks + (size_t)s.nbr[1 + 3 + 9 * ry] * kChunkVoxels + q * 4) + by * 1024 + (zb - 1) * 32;
+                    if (part == 1) {
+                        cp_async16(dst, mid);
+                        cp_async16(dst + 512, mid + 128);
+                        cp_async16(dst + 1024, mid + 256);
+                    } else if (part == 0) {
+                        cp_async16(dst, zb == 0 ? row_src(ry, by, 0) : mid);
+                        cp_async16(dst + 512, mid + 128);
+                        cp_async16(dst + 1024, mid + 256);
+                        // x-halo of the layer from the x-neighbours' face planes (coalesced 128 B each) + 4 corner voxels
+                        uint8_t *hd = ring + slot * RSLOT_BYTES + 1536 + lane * 4;
+                        cp_async4(hd, p.xface + (size_t)s.nbr[0 + 3 + 9 * ry] * 2048 + 1024 + by * 32 + lane);
+                        cp_async4(hd + 128, p.xface + (size_t)s.nbr[2 + 3 + 9 * ry] * 2048 + by * 32 + lane);
+                        if (lane < 4) {
+                            const int erx = (lane & 1) ? 2 : 0, erz = (lane & 2) ? 2 : 0;
+                            cp_async4(hd + 256, p.xface + (size_t)s.nbr[erx + 3 * erz + 9 * ry] * 2048 + ((lane & 1) ? 0 : 1024) + by * 32 + ((lane & 2) ? 0 : 31));
+                        }
+                    } else {
+                        cp_async16(dst, mid);
+                        cp_async16(dst + 512, mid + 128);
+                        if (zb + 8 == 33) cp_async16(dst + 1024, row_src(ry, by, 33));
+                        else if (zb + 8 < 33) cp_async16(dst + 1024, mid + 256);
+                    }
                 }
-                uint32_t hm, hp, he;
-                halo_load(ry, by, hm, hp, he);
-                // Whole-layer test first: 1088 + 68 voxels equal to one datum (the common case in terrain) costs one
-                // match + one vote for the layer instead of a shuffle/vote chain per 128-voxel group.
-                const uint32_t x0 = v[0].x;
+                cp_async_commit();
+            };
+            // one unit: PART is a compile-time third so the row-validity tests fold away for the first two
+            auto process = [&](int yy, const uint8_t *src, auto part_tag) {
+                constexpr int PART = decltype(part_tag)::value;
+                uint4 v[3];
+#pragma unroll
+                for (int jj = 0; jj < 3; jj++) v[jj] = *reinterpret_cast<const uint4 *>(src + jj * 512 + lane * 16);
+                const bool last_valid = PART < 2 || zsub < 2; // rows 34, 35 of the last copy do not exist
+                if (PART == 2 && !last_valid) v[2] = make_uint4(0, 0, 0, 0);
+                uint32_t hm = 0, hp = 0, he = 0;
+                if (PART == 0) {
+                    hm = *reinterpret_cast<const uint32_t *>(src + 1536 + lane * 4);
+                    hp = *reinterpret_cast<const uint32_t *>(src + 1664 + lane * 4);
+                    if (lane < 4) he = *reinterpret_cast<const uint32_t *>(src + 1792 + lane * 4);
+                }
+                // whole-unit test first: 384 (+68) voxels equal to one datum (the common case in terrain) costs one match +
+                // one vote instead of a shuffle/vote chain per 128-voxel group
+                const uint32_t x0 = v[0].x; // rows of v[0] always exist
                 note_ref(x0);
-                bool ok = true;
-#pragma unroll
-                for (int j = 0; j < 9; j++) {
-                    const uint32_t d = ((v[j].x ^ x0) | (v[j].y ^ x0)) | ((v[j].z ^ x0) | (v[j].w ^ x0));
-                    ok &= (d == 0u) | (4 * j + zsub >= 34);
-                }
-                ok &= (hm == x0) & (hp == x0) & ((he == x0) | (lane >= 4));
+                uint32_t d = ((v[0].x ^ x0) | (v[0].y ^ x0)) | ((v[0].z ^ x0) | (v[0].w ^ x0));
+                d |= ((v[1].x ^ x0) | (v[1].y ^ x0)) | ((v[1].z ^ x0) | (v[1].w ^ x0));
+                const uint32_t d2 = ((v[2].x ^ x0) | (v[2].y ^ x0)) | ((v[2].z ^ x0) | (v[2].w ^ x0));
+                if (last_valid) d |= d2;
+                if (PART == 0) d |= (hm ^ x0) | (hp ^ x0) | (lane < 4 ? (he ^ x0) : 0u);
                 int same_x0;
                 __match_all_sync(FULL, x0, &same_x0);
-                if (__all_sync(FULL, ok) && same_x0) {
+                if (__all_sync(FULL, d == 0u) && same_x0) {
                     if (x0 != last_d) {
                         last_d = x0;
                         last_c = classify(x0, s, p.reg, err);
@@ -282,41 +347,41 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                     mixed |= (x0 != wref);
                     shapes |= (last_c > 24u);
                     const uint32_t b = last_c * 0x01010101u, rowmask = last_c ? 0xFFFFFFFFu : 0u;
-#pragma unroll
-                    for (int j = 0; j < 9; j++) {
-                        const int zz = 4 * j + zsub;
-                        if (zz < 34) {
-                            *reinterpret_cast<uint32_t *>(&s.cls[yy * PLANE + zz * ROWB + XOFF + q * 4]) = b;
-                            if (q == 0) s.solid[yy * 34 + zz] = rowmask;
-                        }
+                    uint8_t *cl = &s.cls[yy * PLANE + (12 * PART + zsub) * ROWB + XOFF + q * 4];
+                    uint32_t *so = &s.solid[yy * 34 + 12 * PART + zsub];
+                    *reinterpret_cast<uint32_t *>(cl) = b;
+                    *reinterpret_cast<uint32_t *>(cl + 4 * ROWB) = b;
+                    if (last_valid) *reinterpret_cast<uint32_t *>(cl + 8 * ROWB) = b;
+                    if (q == 0) {
+                        so[0] = rowmask;
+                        so[4] = rowmask;
+                        if (last_valid) so[8] = rowmask;
                     }
-                    halo_store(yy, last_c, last_c, last_c, last_c);
-                    continue;
+                    if (PART == 0) halo_store(yy, last_c, last_c, last_c, last_c);
+                    return;
                 }
-                halo_general(yy, hm, hp, he);
+                if (PART == 0) halo_general(yy, hm, hp, he);
 #pragma unroll
-                for (int j = 0; j < 9; j++) do_group(yy, j, v[j]);
+                for (int jj = 0; jj < 3; jj++) do_group(yy, 3 * PART + jj, v[jj]);
+            };
+            // The 34 layers are cut into 102 units (layer, third); warp w takes units w, w+NW, ... and streams them through
+            // its private ring, two units (6 warp copies + halo) ahead of their use.
+            issue(warp, 0);
+            issue(warp + NW, 1);
+            int slot = 0;
+            for (int g = warp; g < N_UNITS; g += NW) {
+                __syncwarp(); // every lane is done reading the slot that unit g+2*NW will overwrite
+                issue(g + 2 * NW, slot == 0 ? 2 : slot - 1);
+                cp_async_wait<2>();
+                __syncwarp(); // unit g's bytes, copied by all lanes, are visible to the warp
+                const int yy = g / 3, part = g - yy * 3;
+                const uint8_t *src = ring + slot * RSLOT_BYTES;
+                if (part == 0) process(yy, src, std::integral_constant<int, 0>());
+                else if (part == 1) process(yy, src, std::integral_constant<int, 1>());
+                else process(yy, src, std::integral_constant<int, 2>());
+                slot = slot == 2 ? 0 : slot + 1;
             }
-            // layers 32 and 33, split over all warps so nobody idles: warp w takes groups [j0, j1) of layer 32 + (w >> 2)
-            {
-                const int yy = 32 + (warp >> 2), part = warp & 3;
-                const int j0 = part == 0 ? 0 : 1 + 2 * part, j1 = part == 0 ? 3 : j0 + 2;
-                const int ry = yy <= 32 ? 1 : 2, by = (yy - 1) & 31;
-                uint4 v[3];
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    const int j = j0 + k, zz = 4 * j + zsub;
-                    if (j < j1 && zz < 34) v[k] = __ldg(reinterpret_cast<const uint4 *>(row_src(ry, by, zz)));
-                    else v[k] = make_uint4(0, 0, 0, 0);
-                }
-                uint32_t hm = 0, hp = 0, he = 0;
-                if (part == 0) halo_load(ry, by, hm, hp, he);
-                note_ref(v[0].x);
-                if (part == 0) halo_general(yy, hm, hp, he);
-#pragma unroll
-                for (int k = 0; k < 3; k++)
-                    if (j0 + k < j1) do_group(yy, j0 + k, v[k]);
-            }
+            cp_async_wait<0>();
             if (lane == 0) s.wref[warp] = wref;
         }
         if (err) atomicOr(&p.counters->flags, kFlagUnknownId);
@@ -343,7 +408,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                 unsigned long long vw[6];
                 row_visibility(s, row >> 5, row & 31, vw);
                 const uint32_t nf = __popcll(vw[0]) + __popcll(vw[1]) + __popcll(vw[2]) + __popcll(vw[3]) + __popcll(vw[4]) + __popcll(vw[5]);
-                s.rowV[row] = (nf * 4u) | ((nf * 6u) << 10) | (nf << 21);
+                s.sc.rowV[row] = (nf * 4u) | ((nf * 6u) << 10) | (nf << 21);
             }
         } else {
             for (int row = warp; row < 1024; row += NW) {
@@ -355,7 +420,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                     const uint32_t t = s.ctab[c];
                     cnt = __reduce_add_sync(FULL, cell_counts(cell_visibility(s, at, t), t));
                 }
-                if (lane == 0) s.rowV[row] = cnt;
+                if (lane == 0) s.sc.rowV[row] = cnt;
             }
         }
         __syncthreads();
@@ -365,7 +430,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
             uint32_t v[4], i[4], f[4], tv = 0, ti = 0, tf = 0;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const uint32_t c = s.rowV[tid * 4 + k];
+                const uint32_t c = s.sc.rowV[tid * 4 + k];
                 v[k] = tv;
                 i[k] = ti;
                 f[k] = tf;
@@ -400,15 +465,15 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
             bf += sf - tf;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                s.rowV[tid * 4 + k] = bv + v[k];
-                s.rowI[tid * 4 + k] = bi + i[k];
-                s.rowF[tid * 4 + k] = bf + f[k];
+                s.sc.rowV[tid * 4 + k] = bv + v[k];
+                s.sc.rowI[tid * 4 + k] = bi + i[k];
+                s.sc.rowF[tid * 4 + k] = bf + f[k];
             }
             if (tid == NT - 1) {
                 const unsigned long long TV = bv + tv, TI = bi + ti;
-                s.rowV[1024] = bv + tv;
-                s.rowI[1024] = bi + ti;
-                s.rowF[1024] = bf + tf;
+                s.sc.rowV[1024] = bv + tv;
+                s.sc.rowI[1024] = bi + ti;
+                s.sc.rowF[1024] = bf + tf;
                 const unsigned long long padV = (TV + 3ull) & ~3ull, padI = (TI + 7ull) & ~7ull;
                 unsigned long long vb = 0, ib = 0;
                 int emit = 0;
@@ -442,14 +507,14 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
         for (uint32_t r0 = 0; r0 < 1024;) {
             // largest r1 with faces(r0..r1) <= FC and vertices(r0..r1) <= VC (a single row never exceeds 192 / 768)
             uint32_t lo = r0 + 1, hi = 1024;
-            const uint32_t f0 = s.rowF[r0], v0 = s.rowV[r0], i0 = s.rowI[r0];
+            const uint32_t f0 = s.sc.rowF[r0], v0 = s.sc.rowV[r0], i0 = s.sc.rowI[r0];
             while (lo < hi) {
                 const uint32_t mid = (lo + hi + 1) >> 1;
-                if (s.rowF[mid] - f0 <= (uint32_t)FC && s.rowV[mid] - v0 <= (uint32_t)VC) lo = mid;
+                if (s.sc.rowF[mid] - f0 <= (uint32_t)FC && s.sc.rowV[mid] - v0 <= (uint32_t)VC) lo = mid;
                 else hi = mid - 1;
             }
             const uint32_t r1 = lo;
-            const uint32_t tileF = s.rowF[r1] - f0, tileV = s.rowV[r1] - v0, tileI = s.rowI[r1] - i0;
+            const uint32_t tileF = s.sc.rowF[r1] - f0, tileV = s.sc.rowV[r1] - v0, tileI = s.sc.rowI[r1] - i0;
             if (tileF == 0) {
                 r0 = r1;
                 continue;
@@ -457,8 +522,8 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
             // ---- C1: face records in emission order ----
             if (quads_only) {
                 for (uint32_t row = r0 + tid; row < r1; row += NT) {
-                    uint32_t f = s.rowF[row] - f0;
-                    if (s.rowF[row + 1] - s.rowF[row] == 0) continue;
+                    uint32_t f = s.sc.rowF[row] - f0;
+                    if (s.sc.rowF[row + 1] - s.sc.rowF[row] == 0) continue;
                     unsigned long long vw[6];
                     row_visibility(s, row >> 5, row & 31, vw);
                     unsigned long long any = vw[0] | vw[1] | vw[2] | vw[3] | vw[4] | vw[5];
@@ -468,7 +533,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
 #pragma unroll
                         for (int d = 0; d < 6; d++) {
                             if ((vw[d] >> b) & 1ull) {
-                                s.frecA[f] = row | ((uint32_t)(b - 1) << 10) | ((uint32_t)d << 15) | ((f * 4u) << 18);
+                                s.sc.frecA[f] = row | ((uint32_t)(b - 1) << 10) | ((uint32_t)d << 15) | ((f * 4u) << 18);
                                 f++;
                             }
                         }
@@ -476,7 +541,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                 }
             } else {
                 for (uint32_t row = r0 + warp; row < r1; row += NW) {
-                    if (s.rowF[row + 1] - s.rowF[row] == 0) continue;
+                    if (s.sc.rowF[row + 1] - s.sc.rowF[row] == 0) continue;
                     const int at = ((row >> 5) + 1) * PLANE + ((row & 31) + 1) * ROWB + XOFF + lane;
                     const uint32_t c = s.cls[at];
                     const uint32_t t = s.ctab[c];
@@ -490,15 +555,15 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                     }
                     const uint32_t excl = incl - pk;
                     if (vis) {
-                        uint32_t vs = s.rowV[row] - v0 + (excl & 1023u), is = s.rowI[row] - i0 + ((excl >> 10) & 2047u),
-                                 f = s.rowF[row] - f0 + (excl >> 21);
+                        uint32_t vs = s.sc.rowV[row] - v0 + (excl & 1023u), is = s.sc.rowI[row] - i0 + ((excl >> 10) & 2047u),
+                                 f = s.sc.rowF[row] - f0 + (excl >> 21);
                         const uint32_t codes = t >> 18;
 #pragma unroll
                         for (int d = 0; d < 6; d++) {
                             if ((vis >> d) & 1u) {
                                 const uint32_t code = (codes >> (2 * d)) & 3u;
-                                s.frecA[f] = row | ((uint32_t)lane << 10) | ((uint32_t)d << 15) | (vs << 18);
-                                s.frecB[f] = is << 18;
+                                s.sc.frecA[f] = row | ((uint32_t)lane << 10) | ((uint32_t)d << 15) | (vs << 18);
+                                s.sc.frecB[f] = is << 18;
                                 f++;
                                 vs += code + 2u + (code == 3u);
                                 is += (code == 1u ? 3u : 6u);
@@ -513,7 +578,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                 const uint32_t f = fb + tid;
                 uint32_t is = 0, nv = 0, ni = 0, vs = 0;
                 if (f < tileF) {
-                    const uint32_t a = s.frecA[f];
+                    const uint32_t a = s.sc.frecA[f];
                     const uint32_t row = a & 1023u, x = (a >> 10) & 31u, d = (a >> 15) & 7u;
                     vs = a >> 18;
                     const int at = ((row >> 5) + 1) * PLANE + ((row & 31) + 1) * ROWB + XOFF + (int)x;
@@ -521,7 +586,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                     const uint32_t st = s.stab[cx * 6 + d];
                     nv = (st >> 3) & 7u;
                     ni = (st >> 6) & 7u;
-                    s.frecC[f] = (uint16_t)(__ldg(center + row * 32 + x) >> 16);
+                    s.sc.frecC[f] = (uint16_t)(__ldg(center + row * 32 + x) >> 16);
                     const uint4 *ao = reinterpret_cast<const uint4 *>(&T->aotab[cx][d][0][0]);
                     uint32_t ks = 0;
                     for (uint32_t j = 0; j < nv; j++) {
@@ -533,36 +598,36 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                         if (n > 3) k += s.cls[at + (int)(short)(e.y >> 16)] != 0;
                         if (n > 4) k += s.cls[at + (int)(short)(e.z & 0xFFFFu)] != 0;
                         ks |= k << (3 * j);
-                        if (!quads_only) s.s2f[vs + j] = (uint16_t)f;
+                        if (!quads_only) s.sc.s2f[vs + j] = (uint16_t)f;
                     }
                     if (quads_only) {
-                        s.frecB[f] = ks;
+                        s.sc.frecB[f] = ks;
                     } else {
-                        is = s.frecB[f] >> 18;
-                        s.frecB[f] = ks | (is << 18);
+                        is = s.sc.frecB[f] >> 18;
+                        s.sc.frecB[f] = ks | (is << 18);
                     }
                 }
                 if (!quads_only) {
                     // index values of this batch of faces, staged then copied out coalesced
                     __syncthreads(); // frecB/s2f of the batch complete; previous batch's istage reads done
-                    const uint32_t is_first = s.frecB[fb] >> 18;
+                    const uint32_t is_first = s.sc.frecB[fb] >> 18;
                     if (f < tileF) {
                         const uint32_t rel = is - is_first;
                         const uint32_t vq = v0 + vs; // voff = vbuf.len() (voxmesh.rs:123), chunk-relative
                         if (nv == 4) { // QUAD_INDICES (stdshapes.rs:198)
-                            s.istage[rel + 0] = vq;
-                            s.istage[rel + 1] = vq + 1;
-                            s.istage[rel + 2] = vq + 2;
-                            s.istage[rel + 3] = vq + 2;
-                            s.istage[rel + 4] = vq + 3;
-                            s.istage[rel + 5] = vq;
+                            s.sc.istage[rel + 0] = vq;
+                            s.sc.istage[rel + 1] = vq + 1;
+                            s.sc.istage[rel + 2] = vq + 2;
+                            s.sc.istage[rel + 3] = vq + 2;
+                            s.sc.istage[rel + 4] = vq + 3;
+                            s.sc.istage[rel + 5] = vq;
                         } else {
-                            for (uint32_t k = 0; k < ni; k++) s.istage[rel + k] = vq + k;
+                            for (uint32_t k = 0; k < ni; k++) s.sc.istage[rel + k] = vq + k;
                         }
                     }
                     __syncthreads();
-                    const uint32_t is_end = (fb + NT < tileF) ? (s.frecB[fb + NT] >> 18) : tileI;
-                    for (uint32_t k = tid; k < is_end - is_first; k += NT) iout[i0 + is_first + k] = s.istage[k];
+                    const uint32_t is_end = (fb + NT < tileF) ? (s.sc.frecB[fb + NT] >> 18) : tileI;
+                    for (uint32_t k = tid; k < is_end - is_first; k += NT) iout[i0 + is_first + k] = s.sc.istage[k];
                 }
             }
             if (quads_only) {
@@ -577,8 +642,8 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
             for (uint32_t vb = 0; vb < tileV; vb += NT) {
                 const uint32_t sl = vb + tid;
                 if (sl < tileV) {
-                    const uint32_t f = quads_only ? (sl >> 2) : (uint32_t)s.s2f[sl];
-                    const uint32_t a = s.frecA[f], ks = s.frecB[f], id = s.frecC[f];
+                    const uint32_t f = quads_only ? (sl >> 2) : (uint32_t)s.sc.s2f[sl];
+                    const uint32_t a = s.sc.frecA[f], ks = s.sc.frecB[f], id = s.sc.frecC[f];
                     const uint32_t row = a & 1023u, x = (a >> 10) & 31u, d = (a >> 15) & 7u;
                     const uint32_t y = row >> 5, z = row & 31u;
                     const uint32_t j = sl - (a >> 18);
@@ -620,7 +685,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                     }
                     const float tu = (float)((uint32_t)(e >> 3) & 1u), tv = (float)((uint32_t)(e >> 4) & 1u);
                     const uint32_t index = (x + 32u * z + 1024u * y) | (((uint32_t)(e >> 5) & 7u) << 17);
-                    uint2 *o = &s.vstage[tid * 5];
+                    uint2 *o = &s.sc.vstage[tid * 5];
                     o[0] = make_uint2(position, color);
                     o[1] = make_uint2(__float_as_uint(tu), __float_as_uint(tv));
                     o[2] = make_uint2(__float_as_uint(texid), index);
@@ -630,7 +695,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                 __syncthreads();
                 const uint32_t n2 = min((uint32_t)NT, tileV - vb) * 5u;
                 uint2 *dst = reinterpret_cast<uint2 *>(vout + v0 + vb);
-                for (uint32_t k = tid; k < n2; k += NT) dst[k] = s.vstage[k];
+                for (uint32_t k = tid; k < n2; k += NT) dst[k] = s.sc.vstage[k];
                 __syncthreads();
             }
             r0 = r1;
