@@ -72,6 +72,7 @@ struct Smem {
     unsigned long long vbase, ibase;
     uint32_t work_item[2];
     uint32_t wref[NW];     // per-warp reference datum (trivial-chunk detection)
+    uint32_t wflags[NW];   // per-warp shapes | mixed<<1
     int emit;
 };
 
@@ -174,11 +175,24 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
         if (p.work) {
             c0 = p.work[w];
             span_slot = p.work_span[w];
-        } else { // the whole interior, enumerated x, z, y (no dependent global load)
-            const uint32_t nx = (uint32_t)p.SX - 2u, nz = (uint32_t)p.SZ - 2u;
-            const uint32_t ix = w % nx, iz = (w / nx) % nz, iy = w / (nx * nz);
+        } else {
+            // The whole interior without a work list (no dependent global load). Order: x-tiles of 8 columns; inside a
+            // tile z-rows, then the 8 columns, then the vertical stack fastest. Chunks whose halos overlap are then
+            // in flight on neighbouring CTAs at about the same time, so halo rows/planes hit L2 instead of HBM.
+            const uint32_t nx = (uint32_t)p.SX - 2u, ny = (uint32_t)p.SY - 2u, nz = (uint32_t)p.SZ - 2u;
+            if (p.debug & 8) {
+                const uint32_t ix = w % nx, iz = (w / nx) % nz, iy = w / (nx * nz);
+                c0 = (ix + 1u) + (uint32_t)p.SX * ((iz + 1u) + (uint32_t)p.SZ * (iy + 1u));
+                span_slot = w;
+            } else {
+            const uint32_t per_tile = 8u * ny * nz;
+            const uint32_t t = w / per_tile, rem = w - t * per_tile;
+            const uint32_t tw = min(8u, nx - 8u * t);
+            const uint32_t iz = rem / (tw * ny), r2 = rem - iz * tw * ny;
+            const uint32_t ix = 8u * t + r2 / ny, iy = r2 % ny;
             c0 = (ix + 1u) + (uint32_t)p.SX * ((iz + 1u) + (uint32_t)p.SZ * (iy + 1u));
-            span_slot = w;
+            span_slot = ix + nx * (iz + nz * iy);
+            }
         }
         if (tid < 27) {
             const int sx = (int)(c0 % (uint32_t)p.SX), sz = (int)((c0 / (uint32_t)p.SX) % (uint32_t)p.SZ),
@@ -364,32 +378,92 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
 #pragma unroll
                 for (int jj = 0; jj < 3; jj++) do_group(yy, 3 * PART + jj, v[jj]);
             };
-            // The 34 layers are cut into 102 units (layer, third); warp w takes units w, w+NW, ... and streams them through
-            // its private ring, two units (6 warp copies + halo) ahead of their use.
-            issue(warp, 0);
-            issue(warp + NW, 1);
-            int slot = 0;
-            for (int g = warp; g < N_UNITS; g += NW) {
-                __syncwarp(); // every lane is done reading the slot that unit g+2*NW will overwrite
-                issue(g + 2 * NW, slot == 0 ? 2 : slot - 1);
+            // Unit schedule. The 32 layers that belong to the chunk's own y range (yy = 1..32, neighbours all at ry = 1) are
+            // dealt 4 per warp: their addresses are per-chunk constant pointers + by*stride. The two outer layers (yy = 0, 33:
+            // the y-neighbour chunks) make 6 more units, one each for warps 0..5, issued through the generic path.
+            const uint32_t *const Zm = p.blocks + (size_t)s.nbr[1 + 0 + 9] * kChunkVoxels + 31 * 32 + q * 4; // z- neighbour, row z=31
+            const uint32_t *const Zp = p.blocks + (size_t)s.nbr[1 + 6 + 9] * kChunkVoxels + q * 4;           // z+ neighbour, row z=0
+            const uint32_t *const Xm = p.xface + (size_t)s.nbr[0 + 3 + 9] * 2048 + 1024 + lane;              // x- neighbour, its x=31 plane
+            const uint32_t *const Xp = p.xface + (size_t)s.nbr[2 + 3 + 9] * 2048 + lane;                     // x+ neighbour, its x=0 plane
+            const uint32_t *const Xc = p.xface + (size_t)s.nbr[((lane & 1) ? 2 : 0) + 3 * ((lane & 2) ? 2 : 0) + 9] * 2048 +
+                                       ((lane & 1) ? 0 : 1024) + ((lane & 2) ? 0 : 31); // corner rows (lanes 0..3)
+            auto issue_inner = [&](int by, int slot_, auto part_tag) {
+                constexpr int PART = decltype(part_tag)::value;
+                uint8_t *dst = ring + slot_ * RSLOT_BYTES + lane * 16;
+                const uint32_t *rowbase = center_q + by * 1024 + (12 * PART + zsub - 1) * 32; // row of copy 0 (zz - 1)
+                if (PART == 0) {
+                    cp_async16(dst, zsub == 0 ? Zm + by * 1024 : rowbase);
+                    cp_async16(dst + 512, rowbase + 128);
+                    cp_async16(dst + 1024, rowbase + 256);
+                    uint8_t *hd = ring + slot_ * RSLOT_BYTES + 1536 + lane * 4;
+                    cp_async4(hd, Xm + by * 32);
+                    cp_async4(hd + 128, Xp + by * 32);
+                    if (lane < 4) cp_async4(hd + 256, Xc + by * 32);
+                } else if (PART == 1) {
+                    cp_async16(dst, rowbase);
+                    cp_async16(dst + 512, rowbase + 128);
+                    cp_async16(dst + 1024, rowbase + 256);
+                } else {
+                    cp_async16(dst, rowbase);
+                    cp_async16(dst + 512, rowbase + 128);
+                    if (zsub == 0) cp_async16(dst + 1024, rowbase + 256);
+                    else if (zsub == 1) cp_async16(dst + 1024, Zp + by * 1024);
+                }
+                cp_async_commit();
+            };
+            const std::integral_constant<int, 0> P0;
+            const std::integral_constant<int, 1> P1;
+            const std::integral_constant<int, 2> P2;
+            const int tail_g = warp < 6 ? (warp < 3 ? 0 : 33) * 3 + warp % 3 : N_UNITS; // N_UNITS = none (empty commit)
+            issue_inner(warp, 0, P0);
+            issue_inner(warp, 1, P1);
+            for (int li = 0; li < 4; li++) {
+                const int by = warp + NW * li; // layer yy = by + 1
+                // unit (li, 0) in slot 0; meanwhile fetch (li, 2) into slot 2
+                __syncwarp();
+                issue_inner(by, 2, P2);
                 cp_async_wait<2>();
-                __syncwarp(); // unit g's bytes, copied by all lanes, are visible to the warp
-                const int yy = g / 3, part = g - yy * 3;
-                const uint8_t *src = ring + slot * RSLOT_BYTES;
-                if (part == 0) process(yy, src, std::integral_constant<int, 0>());
-                else if (part == 1) process(yy, src, std::integral_constant<int, 1>());
-                else process(yy, src, std::integral_constant<int, 2>());
-                slot = slot == 2 ? 0 : slot + 1;
+                __syncwarp();
+                process(by + 1, ring, P0);
+                // unit (li, 1) in slot 1; fetch (li + 1, 0) -- or this warp's outer-layer unit -- into slot 0
+                __syncwarp();
+                if (li < 3) issue_inner(by + NW, 0, P0);
+                else issue(tail_g, 0);
+                cp_async_wait<2>();
+                __syncwarp();
+                process(by + 1, ring + RSLOT_BYTES, P1);
+                // unit (li, 2) in slot 2; fetch (li + 1, 1) into slot 1
+                __syncwarp();
+                if (li < 3) issue_inner(by + NW, 1, P1);
+                else cp_async_commit();
+                cp_async_wait<2>();
+                __syncwarp();
+                process(by + 1, ring + 2 * RSLOT_BYTES, P2);
+            }
+            if (tail_g < N_UNITS) {
+                cp_async_wait<0>();
+                __syncwarp();
+                const int yy = tail_g / 3, part = tail_g - yy * 3;
+                if (part == 0) process(yy, ring, P0);
+                else if (part == 1) process(yy, ring, P1);
+                else process(yy, ring, P2);
             }
             cp_async_wait<0>();
             if (lane == 0) s.wref[warp] = wref;
         }
         if (err) atomicOr(&p.counters->flags, kFlagUnknownId);
-        // (__syncthreads_or returns a truth value, not the OR of the operands: two reductions)
-        const int has_shapes = __syncthreads_or((int)shapes);
-        int any_mixed = __syncthreads_or((int)mixed);
+        // one barrier for both flags: each warp publishes shapes | mixed<<1 (warp-reduced) next to its reference datum
+        {
+            const uint32_t wf = __reduce_or_sync(FULL, shapes | (mixed << 1));
+            if (lane == 0) s.wflags[warp] = wf;
+        }
+        __syncthreads();
+        int has_shapes = 0, any_mixed = 0;
 #pragma unroll
-        for (int k = 1; k < NW; k++) any_mixed |= (s.wref[k] != s.wref[0]); // did all warps see the same single datum?
+        for (int k = 0; k < NW; k++) {
+            has_shapes |= (int)(s.wflags[k] & 1u);
+            any_mixed |= (int)(s.wflags[k] >> 1) | (int)(s.wref[k] != s.wref[0]); // did all warps see the same single datum?
+        }
         if (!has_shapes && !any_mixed) {
             // The whole 34^3 neighbourhood is one datum and it is void or a cube: every side is either absent or
             // clipped by an identical neighbour (voxmesh.rs:100,119) -> empty mesh, nothing to count or emit.
