@@ -451,6 +451,10 @@ int bxw_create(int device, bxw_ctx **out) {
     MeshTables *t = new (std::nothrow) MeshTables();
     if (!t) return bail(BXW_E_NOMEM);
     build_mesh_tables(*t);
+    if (!t->aomask_ok) { // the popcount AO shortcut of the mesher relies on this
+        delete t;
+        return bail(BXW_E_INVALID);
+    }
     cudaError_t e = cudaMalloc(&ctx->d_tables, sizeof(MeshTables));
     if (e == cudaSuccess) e = cudaMemcpy(ctx->d_tables, t, sizeof(MeshTables), cudaMemcpyHostToDevice);
     delete t;

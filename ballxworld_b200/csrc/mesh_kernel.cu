@@ -31,8 +31,8 @@ constexpr int PLANE = kClsPlaneBytes;
 constexpr int XOFF = 4;
 constexpr int CLS_BYTES = 34 * PLANE;
 constexpr unsigned FULL = 0xFFFFFFFFu;
-constexpr int FC = 1024;     // faces per emission tile
-constexpr int VC = 4096;     // vertex slots per emission tile
+constexpr int FC = 512;      // faces per emission tile
+constexpr int VC = 2048;     // vertex slots per emission tile
 constexpr int REGC = 64;     // registry entries cached in shared memory
 
 // phase-A staging: every warp streams its share of the 34^3 neighbourhood through a private cp.async ring.
@@ -47,7 +47,10 @@ struct Scratch { // phases B, S, C
     // emission tile
     uint32_t frecA[FC];   // row | x<<10 | dir<<15 | vstart<<18 (tile-relative first vertex)
     uint32_t frecB[FC];   // AO occluder counts, 3 bits per vertex | istart<<18 (tile-relative first index)
-    uint16_t frecC[FC];   // block id
+    uint32_t frecC[FC];   // block id | class<<16
+    uint32_t frecE[FC];   // occupancy of the cell's 3x3x3 neighbourhood, bit (dy+1)*9 + (dz+1)*3 + (dx+1)
+    uint32_t frecT[FC];   // texture id of the side as f32 bits
+    float4 frecD[FC];     // barycentric_color_offset of the side
     uint16_t s2f[VC];     // vertex slot -> face (tiles with non-quad sides only)
     uint32_t istage[NT * 6];
     uint2 vstage[NT * 5]; // 256 vertices x 40 B
@@ -66,6 +69,7 @@ struct Smem {
     float ao_lut[8];
     float reg_color[REGC * 3];
     float reg_texf[REGC * 6];
+    uint32_t col_lut[REGC * 8]; // as_rgba8(debug_color * ao_k) per cached block id and occluder count k
     uint8_t reg_kind[256];
     uint32_t nbr[27 + 5];
     uint32_t warp_tot[3][NW];
@@ -139,6 +143,19 @@ __device__ __forceinline__ unsigned long long solid_word(const Smem &s, int rr) 
     return ((unsigned long long)s.solid[rr] << 1) | (h & 1ull) | ((h >> 1) << 33);
 }
 
+// occupancy (class != 0) of the 3x3x3 neighbourhood of cell (x, y, z), bit (dy+1)*9 + (dz+1)*3 + (dx+1)
+__device__ __forceinline__ uint32_t neighbourhood27(const Smem &s, int y, int z, int x) {
+    uint32_t nb = 0;
+#pragma unroll
+    for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+        for (int dz = 0; dz < 3; dz++) {
+            const unsigned long long w = solid_word(s, (y + dy) * 34 + (z + dz)); // rows y-1..y+1, z-1..z+1 (+1 halo offset)
+            nb |= ((uint32_t)(w >> x) & 7u) << (3 * (dy * 3 + dz)); // bit x of w is cell x-1
+        }
+    return nb;
+}
+
 // visible-side words of a cubes-and-void row: bit x+1 of out[d] = side d of cell x is visible
 __device__ __forceinline__ void row_visibility(const Smem &s, int y, int z, unsigned long long out[6]) {
     const int r = (y + 1) * 34 + (z + 1);
@@ -163,6 +180,17 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
     for (int i = tid; i < 256; i += NT) s.reg_kind[i] = (uint32_t)i < p.reg.n ? p.reg.kind[i] : (uint8_t)0;
     for (int i = tid; i < REGC * 3; i += NT) s.reg_color[i] = (uint32_t)(i / 3) < p.reg.n ? p.reg.color[i] : 0.0f;
     for (int i = tid; i < REGC * 6; i += NT) s.reg_texf[i] = (uint32_t)(i / 6) < p.reg.n ? p.reg.texf[i] : 0.0f;
+    for (int i = tid; i < REGC * 8; i += NT) {
+        const uint32_t id = (uint32_t)i >> 3;
+        uint32_t col = 0;
+        if (id < p.reg.n) { // as_rgba8 (voxmesh.rs:29-34,147-152); Rust's `as u32` saturates like cvt.rzi.u32.f32
+            const float ao = T->ao_lut[i & 7];
+            const float c0f = __fmul_rn(p.reg.color[id * 3], ao), c1f = __fmul_rn(p.reg.color[id * 3 + 1], ao), c2f = __fmul_rn(p.reg.color[id * 3 + 2], ao);
+            col = ((__float2uint_rz(__fmul_rn(c0f, 255.0f)) & 0xFFu) << 24) | ((__float2uint_rz(__fmul_rn(c1f, 255.0f)) & 0xFFu) << 16) |
+                  ((__float2uint_rz(__fmul_rn(c2f, 255.0f)) & 0xFFu) << 8) | 0xFFu;
+        }
+        s.col_lut[i] = col;
+    }
     if (tid == 0) s.work_item[0] = (uint32_t)atomicAdd(&p.counters->work_next, 1ull);
 
     for (uint32_t iter = 0;; iter++) {
@@ -628,6 +656,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                         if (lane >= o) incl += a;
                     }
                     const uint32_t excl = incl - pk;
+                    const uint32_t nb = neighbourhood27(s, (int)(row >> 5), (int)(row & 31), lane); // row words are warp-uniform loads
                     if (vis) {
                         uint32_t vs = s.sc.rowV[row] - v0 + (excl & 1023u), is = s.sc.rowI[row] - i0 + ((excl >> 10) & 2047u),
                                  f = s.sc.rowF[row] - f0 + (excl >> 21);
@@ -638,6 +667,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                                 const uint32_t code = (codes >> (2 * d)) & 3u;
                                 s.sc.frecA[f] = row | ((uint32_t)lane << 10) | ((uint32_t)d << 15) | (vs << 18);
                                 s.sc.frecB[f] = is << 18;
+                                s.sc.frecE[f] = nb;
                                 f++;
                                 vs += code + 2u + (code == 3u);
                                 is += (code == 1u ? 3u : 6u);
@@ -647,7 +677,8 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                 }
             }
             __syncthreads();
-            // ---- C2: face-parallel AO occluder counts (+ slot map and index values for non-quad tiles) ----
+            // ---- C2: face-parallel: AO occluder counts, barycentric colour offset, texture id (+ slot map and index
+            //      values for non-quad tiles) ----
             for (uint32_t fb = 0; fb < tileF; fb += NT) {
                 const uint32_t f = fb + tid;
                 uint32_t is = 0, nv = 0, ni = 0, vs = 0;
@@ -655,25 +686,44 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                     const uint32_t a = s.sc.frecA[f];
                     const uint32_t row = a & 1023u, x = (a >> 10) & 31u, d = (a >> 15) & 7u;
                     vs = a >> 18;
-                    const int at = ((row >> 5) + 1) * PLANE + ((row & 31) + 1) * ROWB + XOFF + (int)x;
-                    const uint32_t cx = s.cls[at];
+                    const uint32_t cx = s.cls[((row >> 5) + 1) * PLANE + ((row & 31) + 1) * ROWB + XOFF + (int)x];
                     const uint32_t st = s.stab[cx * 6 + d];
+                    const uint32_t ls = st & 7u, signs = st >> 9;
                     nv = (st >> 3) & 7u;
                     ni = (st >> 6) & 7u;
-                    s.sc.frecC[f] = (uint16_t)(__ldg(center + row * 32 + x) >> 16);
-                    const uint4 *ao = reinterpret_cast<const uint4 *>(&T->aotab[cx][d][0][0]);
+                    const uint32_t id = __ldg(center + row * 32 + x) >> 16;
+                    const uint32_t nb = quads_only ? neighbourhood27(s, (int)(row >> 5), (int)(row & 31), (int)x) : s.sc.frecE[f];
+                    float dc0, dc1, dc2, texid;
+                    if (id < (uint32_t)REGC) {
+                        dc0 = s.reg_color[id * 3];
+                        dc1 = s.reg_color[id * 3 + 1];
+                        dc2 = s.reg_color[id * 3 + 2];
+                        texid = s.reg_texf[id * 6 + ls]; // texture of the LOCAL side (voxmesh.rs:146)
+                    } else {
+                        dc0 = __ldg(p.reg.color + id * 3);
+                        dc1 = __ldg(p.reg.color + id * 3 + 1);
+                        dc2 = __ldg(p.reg.color + id * 3 + 2);
+                        texid = __ldg(p.reg.texf + id * 6 + ls);
+                    }
+                    // per vertex: number of occluding AO samples (voxmesh.rs:128-137; every meshed shape occludes) and the
+                    // in-order barycentric colour sum (voxmesh.rs:124,153,172-174)
                     uint32_t ks = 0;
+                    float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, b3 = 0.0f;
+                    const uint32_t *am = &T->aomask[cx][d][0];
                     for (uint32_t j = 0; j < nv; j++) {
-                        const uint4 e = __ldg(ao + j);
-                        const int n = (int)(short)(e.z >> 16);
-                        // shp.causes_ambient_occlusion (voxmesh.rs:133-136): every meshed shape does
-                        uint32_t k = (s.cls[at + (int)(short)(e.x & 0xFFFFu)] != 0) + (s.cls[at + (int)(short)(e.x >> 16)] != 0) +
-                                     (s.cls[at + (int)(short)(e.y & 0xFFFFu)] != 0);
-                        if (n > 3) k += s.cls[at + (int)(short)(e.y >> 16)] != 0;
-                        if (n > 4) k += s.cls[at + (int)(short)(e.z & 0xFFFFu)] != 0;
+                        const uint32_t k = __popc(nb & __ldg(am + j));
                         ks |= k << (3 * j);
+                        const float sg = (float)((int)((signs >> (2 * j)) & 3u) - 1);
+                        const float aj = s.ao_lut[k];
+                        b0 = __fadd_rn(b0, __fmul_rn(sg, __fmul_rn(dc0, aj)));
+                        b1 = __fadd_rn(b1, __fmul_rn(sg, __fmul_rn(dc1, aj)));
+                        b2 = __fadd_rn(b2, __fmul_rn(sg, __fmul_rn(dc2, aj)));
+                        b3 = __fadd_rn(b3, __fmul_rn(sg, 1.0f));
                         if (!quads_only) s.sc.s2f[vs + j] = (uint16_t)f;
                     }
+                    s.sc.frecC[f] = id | (cx << 16);
+                    s.sc.frecT[f] = __float_as_uint(texid);
+                    s.sc.frecD[f] = make_float4(b0, b1, b2, b3);
                     if (quads_only) {
                         s.sc.frecB[f] = ks;
                     } else {
@@ -712,66 +762,52 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                 }
             }
             __syncthreads();
-            // ---- C3: one vertex per thread, staged then copied out coalesced ----
+            // ---- C3: one vertex per thread from the face records; 40-byte records staged in shared memory and copied
+            //      out with fully coalesced 8-byte stores ----
             for (uint32_t vb = 0; vb < tileV; vb += NT) {
                 const uint32_t sl = vb + tid;
                 if (sl < tileV) {
                     const uint32_t f = quads_only ? (sl >> 2) : (uint32_t)s.sc.s2f[sl];
-                    const uint32_t a = s.sc.frecA[f], ks = s.sc.frecB[f], id = s.sc.frecC[f];
+                    const uint32_t a = s.sc.frecA[f], ks = s.sc.frecB[f], ic = s.sc.frecC[f];
                     const uint32_t row = a & 1023u, x = (a >> 10) & 31u, d = (a >> 15) & 7u;
                     const uint32_t y = row >> 5, z = row & 31u;
                     const uint32_t j = sl - (a >> 18);
-                    const uint32_t cx = s.cls[(y + 1) * PLANE + (z + 1) * ROWB + XOFF + x];
-                    const uint32_t st = s.stab[cx * 6 + d];
-                    const uint32_t ls = st & 7u, nv = (st >> 3) & 7u, signs = st >> 9;
+                    const uint32_t id = ic & 0xFFFFu, cx = ic >> 16;
                     const unsigned long long e = __ldg(&T->vtab[cx][d][j]);
                     // as_wxyz10 of (ipos + voffset + 0.5)/32 (voxmesh.rs:36-41,139-145,165): every vertex sits on a
                     // voxel corner, so each 10-bit field is 16 * corner coordinate; w = (1/32*2) as u32 = 0.
                     const uint32_t px = x + ((uint32_t)e & 1u), py = y + ((uint32_t)(e >> 1) & 1u), pz = z + ((uint32_t)(e >> 2) & 1u);
                     const uint32_t position = (((px * 16u) & 0x3FFu) << 20) | (((py * 16u) & 0x3FFu) << 10) | ((pz * 16u) & 0x3FFu);
-                    float dc0, dc1, dc2, texid;
+                    const uint32_t k = (ks >> (3 * j)) & 7u;
+                    uint32_t color;
                     if (id < (uint32_t)REGC) {
-                        dc0 = s.reg_color[id * 3];
-                        dc1 = s.reg_color[id * 3 + 1];
-                        dc2 = s.reg_color[id * 3 + 2];
-                        texid = s.reg_texf[id * 6 + ls]; // texture of the LOCAL side (voxmesh.rs:146)
+                        color = s.col_lut[id * 8 + k];
                     } else {
-                        dc0 = __ldg(p.reg.color + id * 3);
-                        dc1 = __ldg(p.reg.color + id * 3 + 1);
-                        dc2 = __ldg(p.reg.color + id * 3 + 2);
-                        texid = __ldg(p.reg.texf + id * 6 + ls);
+                        const float ao = s.ao_lut[k];
+                        const float c0f = __fmul_rn(__ldg(p.reg.color + id * 3), ao), c1f = __fmul_rn(__ldg(p.reg.color + id * 3 + 1), ao),
+                                    c2f = __fmul_rn(__ldg(p.reg.color + id * 3 + 2), ao);
+                        color = ((__float2uint_rz(__fmul_rn(c0f, 255.0f)) & 0xFFu) << 24) | ((__float2uint_rz(__fmul_rn(c1f, 255.0f)) & 0xFFu) << 16) |
+                                ((__float2uint_rz(__fmul_rn(c2f, 255.0f)) & 0xFFu) << 8) | 0xFFu;
                     }
-                    const float ao = s.ao_lut[(ks >> (3 * j)) & 7u];
-                    const float c0f = __fmul_rn(dc0, ao), c1f = __fmul_rn(dc1, ao), c2f = __fmul_rn(dc2, ao);
-                    // as_rgba8 (voxmesh.rs:29-34); Rust's `as u32` saturates like cvt.rzi.u32.f32
-                    const uint32_t color = ((__float2uint_rz(__fmul_rn(c0f, 255.0f)) & 0xFFu) << 24) |
-                                           ((__float2uint_rz(__fmul_rn(c1f, 255.0f)) & 0xFFu) << 16) |
-                                           ((__float2uint_rz(__fmul_rn(c2f, 255.0f)) & 0xFFu) << 8) | 0xFFu;
-                    // barycentric_color_sum over the side's vertices in order (voxmesh.rs:124,153,172-174)
-                    float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, b3 = 0.0f;
-                    for (uint32_t jj = 0; jj < nv; jj++) {
-                        const float sg = (float)((int)((signs >> (2 * jj)) & 3u) - 1);
-                        const float aj = s.ao_lut[(ks >> (3 * jj)) & 7u];
-                        b0 = __fadd_rn(b0, __fmul_rn(sg, __fmul_rn(dc0, aj)));
-                        b1 = __fadd_rn(b1, __fmul_rn(sg, __fmul_rn(dc1, aj)));
-                        b2 = __fadd_rn(b2, __fmul_rn(sg, __fmul_rn(dc2, aj)));
-                        b3 = __fadd_rn(b3, __fmul_rn(sg, 1.0f));
-                    }
+                    const float4 bsum = s.sc.frecD[f];
                     const float tu = (float)((uint32_t)(e >> 3) & 1u), tv = (float)((uint32_t)(e >> 4) & 1u);
                     const uint32_t index = (x + 32u * z + 1024u * y) | (((uint32_t)(e >> 5) & 7u) << 17);
-                    uint2 *o = &s.sc.vstage[tid * 5];
+                    uint2 *o = (p.debug & 16) ? reinterpret_cast<uint2 *>(vout + v0 + sl) : &s.sc.vstage[tid * 5];
                     o[0] = make_uint2(position, color);
                     o[1] = make_uint2(__float_as_uint(tu), __float_as_uint(tv));
-                    o[2] = make_uint2(__float_as_uint(texid), index);
-                    o[3] = make_uint2(__float_as_uint(b0), __float_as_uint(b1));
-                    o[4] = make_uint2(__float_as_uint(b2), __float_as_uint(b3));
+                    o[2] = make_uint2(s.sc.frecT[f], index);
+                    o[3] = make_uint2(__float_as_uint(bsum.x), __float_as_uint(bsum.y));
+                    o[4] = make_uint2(__float_as_uint(bsum.z), __float_as_uint(bsum.w));
                 }
-                __syncthreads();
-                const uint32_t n2 = min((uint32_t)NT, tileV - vb) * 5u;
-                uint2 *dst = reinterpret_cast<uint2 *>(vout + v0 + vb);
-                for (uint32_t k = tid; k < n2; k += NT) dst[k] = s.sc.vstage[k];
-                __syncthreads();
+                if (!(p.debug & 16)) {
+                    __syncthreads();
+                    const uint32_t n2 = min((uint32_t)NT, tileV - vb) * 5u;
+                    uint2 *dst = reinterpret_cast<uint2 *>(vout + v0 + vb);
+                    for (uint32_t k = tid; k < n2; k += NT) dst[k] = s.sc.vstage[k];
+                    __syncthreads();
+                }
             }
+            __syncthreads(); // the face records are rewritten by the next tile
             r0 = r1;
         }
     }

@@ -231,6 +231,9 @@ void build_mesh_tables(MeshTables &t) {
                     for (int k = 0; k < n; k++) {
                         V3 a = rot(samples[k]);
                         t.aotab[cls][d][j][k] = (short)(a.y * kClsPlaneBytes + a.z * kClsRowBytes + a.x);
+                        // NB: two samples of one vertex never coincide, so the popcount of the masked neighbourhood equals
+                        // the number of occluding samples
+                        t.aomask[cls][d][j] |= 1u << ((a.y + 1) * 9 + (a.z + 1) * 3 + (a.x + 1));
                         unsigned long long code6 = (unsigned long long)(a.x + 1) | (unsigned long long)(a.y + 1) << 2 |
                                                    (unsigned long long)(a.z + 1) << 4;
                         e |= code6 << (13 + 6 * k);
@@ -240,6 +243,11 @@ void build_mesh_tables(MeshTables &t) {
             }
             t.ctab[cls] = cc | ec << 6 | eu << 12 | codes << 18;
         }
+    t.aomask_ok = 1;
+    for (int cls = 1; cls < kNumClasses; cls++)
+        for (int d = 0; d < 6; d++)
+            for (int j = 0; j < (int)((t.stab[cls][d] >> 3) & 7u); j++)
+                if (__builtin_popcount(t.aomask[cls][d][j]) != t.aotab[cls][d][j][5]) t.aomask_ok = 0;
     float ao = 1.0f;
     for (int k = 0; k < 8; k++) {
         t.ao_lut[k] = ao;

@@ -27,6 +27,9 @@ struct MeshTables {
     // aotab[class][d][j]: the AO samples of vtab[class][d][j] as byte offsets into the kernel's 34^3 class table
     // (dy*plane + dz*row + dx), entries 0..4; entry 5 = sample count
     alignas(16) short aotab[kNumClasses][6][6][8];
+    // aomask[class][d][j]: the same AO samples as a mask over the 3x3x3 neighbourhood, bit (dy+1)*9 + (dz+1)*3 + (dx+1)
+    uint32_t aomask[kNumClasses][6][6];
+    uint32_t aomask_ok; // 1 when no vertex lists the same AO sample twice (so popcount == number of occluders)
 };
 
 // shared-memory layout of the kernel's class table (bytes per (y,z) row / per y plane), baked into aotab
