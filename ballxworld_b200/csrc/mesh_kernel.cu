@@ -31,8 +31,8 @@ constexpr int PLANE = kClsPlaneBytes;
 constexpr int XOFF = 4;
 constexpr int CLS_BYTES = 34 * PLANE;
 constexpr unsigned FULL = 0xFFFFFFFFu;
-constexpr int FC = 512;      // faces per emission tile
-constexpr int VC = 2048;     // vertex slots per emission tile
+constexpr int FC = 1024;     // faces per emission tile
+constexpr int VC = 4096;     // vertex slots per emission tile
 constexpr int REGC = 64;     // registry entries cached in shared memory
 
 // phase-A staging: every warp streams its share of the 34^3 neighbourhood through a private cp.async ring.
@@ -44,16 +44,15 @@ struct Scratch { // phases B, S, C
     uint32_t rowV[1028];   // exclusive prefix over rows: first vertex of the row (chunk-relative); [1024] = total
     uint32_t rowI[1028];
     uint32_t rowF[1028];
-    // emission tile
+    // emission tile: face records written by C1
     uint32_t frecA[FC];   // row | x<<10 | dir<<15 | vstart<<18 (tile-relative first vertex)
-    uint32_t frecB[FC];   // AO occluder counts, 3 bits per vertex | istart<<18 (tile-relative first index)
-    uint32_t frecC[FC];   // block id | class<<16
-    uint32_t frecE[FC];   // occupancy of the cell's 3x3x3 neighbourhood, bit (dy+1)*9 + (dz+1)*3 + (dx+1)
-    uint32_t frecT[FC];   // texture id of the side as f32 bits
-    float4 frecD[FC];     // barycentric_color_offset of the side
-    uint16_t s2f[VC];     // vertex slot -> face (tiles with non-quad sides only)
-    uint32_t istage[NT * 6];
-    uint2 vstage[NT * 5]; // 256 vertices x 40 B
+    uint32_t frecB[FC];   // tile-relative first index (tiles with non-quad sides)
+    uint32_t frecC[FC];   // block id | class<<16 (tiles with non-quad sides)
+    uint32_t frecE[FC];   // occupancy of the cell's 3x3x3 neighbourhood, bit (dy+1)*9 + (dz+1)*3 + (dx+1) (ditto)
+    // per-warp staging of one batch of 32 faces
+    uint8_t wsf[NW][192];        // vertex slot of the batch -> lane owning the face
+    uint32_t wistage[NW][192];   // index values of the batch
+    alignas(16) uint2 wvstage[NW][32 * 5]; // 32 vertices x 40 B
 };
 
 struct Smem {
@@ -70,6 +69,7 @@ struct Smem {
     float reg_color[REGC * 3];
     float reg_texf[REGC * 6];
     uint32_t col_lut[REGC * 8]; // as_rgba8(debug_color * ao_k) per cached block id and occluder count k
+    uint32_t aolut[8 * 27];     // AO sample mask per (vertex corner, AO normal code)
     uint8_t reg_kind[256];
     uint32_t nbr[27 + 5];
     uint32_t warp_tot[3][NW];
@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
     for (int i = tid; i < 256; i += NT) s.reg_kind[i] = (uint32_t)i < p.reg.n ? p.reg.kind[i] : (uint8_t)0;
     for (int i = tid; i < REGC * 3; i += NT) s.reg_color[i] = (uint32_t)(i / 3) < p.reg.n ? p.reg.color[i] : 0.0f;
     for (int i = tid; i < REGC * 6; i += NT) s.reg_texf[i] = (uint32_t)(i / 6) < p.reg.n ? p.reg.texf[i] : 0.0f;
+    for (int i = tid; i < 8 * 27; i += NT) s.aolut[i] = T->aolut[i];
     for (int i = tid; i < REGC * 8; i += NT) {
         const uint32_t id = (uint32_t)i >> 3;
         uint32_t col = 0;
@@ -657,6 +658,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                     }
                     const uint32_t excl = incl - pk;
                     const uint32_t nb = neighbourhood27(s, (int)(row >> 5), (int)(row & 31), lane); // row words are warp-uniform loads
+                    const uint32_t idc = (__ldg(center + row * 32 + lane) >> 16) | (c << 16); // block id | class, one coalesced row load
                     if (vis) {
                         uint32_t vs = s.sc.rowV[row] - v0 + (excl & 1023u), is = s.sc.rowI[row] - i0 + ((excl >> 10) & 2047u),
                                  f = s.sc.rowF[row] - f0 + (excl >> 21);
@@ -666,8 +668,9 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                             if ((vis >> d) & 1u) {
                                 const uint32_t code = (codes >> (2 * d)) & 3u;
                                 s.sc.frecA[f] = row | ((uint32_t)lane << 10) | ((uint32_t)d << 15) | (vs << 18);
-                                s.sc.frecB[f] = is << 18;
+                                s.sc.frecB[f] = is;
                                 s.sc.frecE[f] = nb;
+                                s.sc.frecC[f] = idc;
                                 f++;
                                 vs += code + 2u + (code == 3u);
                                 is += (code == 1u ? 3u : 6u);
@@ -677,22 +680,38 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                 }
             }
             __syncthreads();
-            // ---- C2: face-parallel: AO occluder counts, barycentric colour offset, texture id (+ slot map and index
-            //      values for non-quad tiles) ----
-            for (uint32_t fb = 0; fb < tileF; fb += NT) {
-                const uint32_t f = fb + tid;
-                uint32_t is = 0, nv = 0, ni = 0, vs = 0;
-                if (f < tileF) {
-                    const uint32_t a = s.sc.frecA[f];
+            // ---- C2+C3, fused per warp: a warp takes 32 consecutive faces of the tile, computes their per-face data in
+            //      registers (AO occluder counts, barycentric colour offset, texture id), stages their index values and
+            //      their vertices (32 at a time, face data fetched from the owning lane by shuffle) in its private
+            //      shared-memory slice and writes both out with coalesced stores. No block barrier inside a tile. ----
+            const uint32_t n_batches = (tileF + 31u) >> 5;
+            for (uint32_t bt = warp; bt < n_batches; bt += NW) {
+                const uint32_t f = bt * 32u + lane;
+                const bool act = f < tileF;
+                uint32_t a = 0, ic = 0, ks = 0, texbits = 0, nv = 0, ni = 0, vs = 0, is = 0;
+                float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, b3 = 0.0f;
+                if (act) {
+                    a = s.sc.frecA[f];
                     const uint32_t row = a & 1023u, x = (a >> 10) & 31u, d = (a >> 15) & 7u;
                     vs = a >> 18;
-                    const uint32_t cx = s.cls[((row >> 5) + 1) * PLANE + ((row & 31) + 1) * ROWB + XOFF + (int)x];
+                    uint32_t id, cx, nb;
+                    if (quads_only) {
+                        cx = s.cls[((row >> 5) + 1) * PLANE + ((row & 31) + 1) * ROWB + XOFF + (int)x];
+                        id = __ldg(center + row * 32 + x) >> 16;
+                        nb = neighbourhood27(s, (int)(row >> 5), (int)(row & 31), (int)x);
+                        is = f * 6u;
+                    } else { // recorded by C1
+                        const uint32_t icr = s.sc.frecC[f];
+                        id = icr & 0xFFFFu;
+                        cx = icr >> 16;
+                        nb = s.sc.frecE[f];
+                        is = s.sc.frecB[f];
+                    }
+                    ic = id | (cx << 16);
                     const uint32_t st = s.stab[cx * 6 + d];
                     const uint32_t ls = st & 7u, signs = st >> 9;
                     nv = (st >> 3) & 7u;
                     ni = (st >> 6) & 7u;
-                    const uint32_t id = __ldg(center + row * 32 + x) >> 16;
-                    const uint32_t nb = quads_only ? neighbourhood27(s, (int)(row >> 5), (int)(row & 31), (int)x) : s.sc.frecE[f];
                     float dc0, dc1, dc2, texid;
                     if (id < (uint32_t)REGC) {
                         dc0 = s.reg_color[id * 3];
@@ -705,13 +724,13 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                         dc2 = __ldg(p.reg.color + id * 3 + 2);
                         texid = __ldg(p.reg.texf + id * 6 + ls);
                     }
+                    texbits = __float_as_uint(texid);
                     // per vertex: number of occluding AO samples (voxmesh.rs:128-137; every meshed shape occludes) and the
                     // in-order barycentric colour sum (voxmesh.rs:124,153,172-174)
-                    uint32_t ks = 0;
-                    float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, b3 = 0.0f;
-                    const uint32_t *am = &T->aomask[cx][d][0];
+                    const uint16_t *vd = &T->vdesc[cx][d][0];
                     for (uint32_t j = 0; j < nv; j++) {
-                        const uint32_t k = __popc(nb & __ldg(am + j));
+                        const uint32_t desc = __ldg(vd + j);
+                        const uint32_t k = __popc(nb & s.aolut[(desc & 7u) * 27u + (desc >> 8)]);
                         ks |= k << (3 * j);
                         const float sg = (float)((int)((signs >> (2 * j)) & 3u) - 1);
                         const float aj = s.ao_lut[k];
@@ -719,92 +738,80 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                         b1 = __fadd_rn(b1, __fmul_rn(sg, __fmul_rn(dc1, aj)));
                         b2 = __fadd_rn(b2, __fmul_rn(sg, __fmul_rn(dc2, aj)));
                         b3 = __fadd_rn(b3, __fmul_rn(sg, 1.0f));
-                        if (!quads_only) s.sc.s2f[vs + j] = (uint16_t)f;
-                    }
-                    s.sc.frecC[f] = id | (cx << 16);
-                    s.sc.frecT[f] = __float_as_uint(texid);
-                    s.sc.frecD[f] = make_float4(b0, b1, b2, b3);
-                    if (quads_only) {
-                        s.sc.frecB[f] = ks;
-                    } else {
-                        is = s.sc.frecB[f] >> 18;
-                        s.sc.frecB[f] = ks | (is << 18);
                     }
                 }
-                if (!quads_only) {
-                    // index values of this batch of faces, staged then copied out coalesced
-                    __syncthreads(); // frecB/s2f of the batch complete; previous batch's istage reads done
-                    const uint32_t is_first = s.sc.frecB[fb] >> 18;
-                    if (f < tileF) {
-                        const uint32_t rel = is - is_first;
-                        const uint32_t vq = v0 + vs; // voff = vbuf.len() (voxmesh.rs:123), chunk-relative
-                        if (nv == 4) { // QUAD_INDICES (stdshapes.rs:198)
-                            s.sc.istage[rel + 0] = vq;
-                            s.sc.istage[rel + 1] = vq + 1;
-                            s.sc.istage[rel + 2] = vq + 2;
-                            s.sc.istage[rel + 3] = vq + 2;
-                            s.sc.istage[rel + 4] = vq + 3;
-                            s.sc.istage[rel + 5] = vq;
+                // vertex / index ranges of the batch (tile-relative)
+                const int last = (int)min(31u, tileF - 1u - bt * 32u);
+                const uint32_t vs0 = __shfl_sync(FULL, vs, 0), is0 = __shfl_sync(FULL, is, 0);
+                const uint32_t nbv = __shfl_sync(FULL, vs + nv, last) - vs0, nbi = __shfl_sync(FULL, is + ni, last) - is0;
+                if (act) {
+                    uint8_t *sf = &s.sc.wsf[warp][vs - vs0];
+                    for (uint32_t j = 0; j < nv; j++) sf[j] = (uint8_t)lane;
+                    uint32_t *ist = &s.sc.wistage[warp][is - is0];
+                    const uint32_t vq = v0 + vs; // voff = vbuf.len() (voxmesh.rs:123), chunk-relative
+                    if (nv == 4) { // QUAD_INDICES (stdshapes.rs:198)
+                        ist[0] = vq;
+                        ist[1] = vq + 1;
+                        ist[2] = vq + 2;
+                        ist[3] = vq + 2;
+                        ist[4] = vq + 3;
+                        ist[5] = vq;
+                    } else {
+                        for (uint32_t k = 0; k < ni; k++) ist[k] = vq + k;
+                    }
+                }
+                __syncwarp();
+                for (uint32_t k = lane; k < nbi; k += 32) iout[i0 + is0 + k] = s.sc.wistage[warp][k];
+                for (uint32_t sb = 0; sb < nbv; sb += 32) {
+                    const uint32_t sl = sb + lane;
+                    const bool actv = sl < nbv;
+                    const int fl = actv ? (int)s.sc.wsf[warp][sl] : 0;
+                    const uint32_t A = __shfl_sync(FULL, a, fl), KS = __shfl_sync(FULL, ks, fl), IC = __shfl_sync(FULL, ic, fl),
+                                   TB = __shfl_sync(FULL, texbits, fl);
+                    const float B0 = __shfl_sync(FULL, b0, fl), B1 = __shfl_sync(FULL, b1, fl), B2 = __shfl_sync(FULL, b2, fl),
+                                B3 = __shfl_sync(FULL, b3, fl);
+                    if (actv) {
+                        const uint32_t row = A & 1023u, x = (A >> 10) & 31u, d = (A >> 15) & 7u;
+                        const uint32_t y = row >> 5, z = row & 31u;
+                        const uint32_t j = vs0 + sl - (A >> 18);
+                        const uint32_t id = IC & 0xFFFFu, cx = IC >> 16;
+                        const uint32_t e = __ldg(&T->vdesc[cx][d][j]);
+                        // as_wxyz10 of (ipos + voffset + 0.5)/32 (voxmesh.rs:36-41,139-145,165): every vertex sits on a
+                        // voxel corner, so each 10-bit field is 16 * corner coordinate; w = (1/32*2) as u32 = 0.
+                        const uint32_t px = x + (e & 1u), py = y + ((e >> 1) & 1u), pz = z + ((e >> 2) & 1u);
+                        const uint32_t position = (((px * 16u) & 0x3FFu) << 20) | (((py * 16u) & 0x3FFu) << 10) | ((pz * 16u) & 0x3FFu);
+                        const uint32_t k = (KS >> (3 * j)) & 7u;
+                        uint32_t color;
+                        if (id < (uint32_t)REGC) {
+                            color = s.col_lut[id * 8 + k];
                         } else {
-                            for (uint32_t k = 0; k < ni; k++) s.sc.istage[rel + k] = vq + k;
+                            const float ao = s.ao_lut[k];
+                            const float c0f = __fmul_rn(__ldg(p.reg.color + id * 3), ao), c1f = __fmul_rn(__ldg(p.reg.color + id * 3 + 1), ao),
+                                        c2f = __fmul_rn(__ldg(p.reg.color + id * 3 + 2), ao);
+                            color = ((__float2uint_rz(__fmul_rn(c0f, 255.0f)) & 0xFFu) << 24) | ((__float2uint_rz(__fmul_rn(c1f, 255.0f)) & 0xFFu) << 16) |
+                                    ((__float2uint_rz(__fmul_rn(c2f, 255.0f)) & 0xFFu) << 8) | 0xFFu;
                         }
+                        const float tu = (float)((e >> 3) & 1u), tv = (float)((e >> 4) & 1u);
+                        const uint32_t index = (x + 32u * z + 1024u * y) | (((e >> 5) & 7u) << 17);
+                        uint2 *o = &s.sc.wvstage[warp][lane * 5];
+                        o[0] = make_uint2(position, color);
+                        o[1] = make_uint2(__float_as_uint(tu), __float_as_uint(tv));
+                        o[2] = make_uint2(TB, index);
+                        o[3] = make_uint2(__float_as_uint(B0), __float_as_uint(B1));
+                        o[4] = make_uint2(__float_as_uint(B2), __float_as_uint(B3));
                     }
-                    __syncthreads();
-                    const uint32_t is_end = (fb + NT < tileF) ? (s.sc.frecB[fb + NT] >> 18) : tileI;
-                    for (uint32_t k = tid; k < is_end - is_first; k += NT) iout[i0 + is_first + k] = s.sc.istage[k];
-                }
-            }
-            if (quads_only) {
-                // indices of quad-only tiles follow arithmetically: face i/6, pattern [0,1,2,2,3,0]
-                for (uint32_t k = tid; k < tileI; k += NT) {
-                    const uint32_t f = k / 6u, q = k - f * 6u;
-                    iout[i0 + k] = v0 + f * 4u + ((0x032210u >> (4u * q)) & 15u);
-                }
-            }
-            __syncthreads();
-            // ---- C3: one vertex per thread from the face records; 40-byte records staged in shared memory and copied
-            //      out with fully coalesced 8-byte stores ----
-            for (uint32_t vb = 0; vb < tileV; vb += NT) {
-                const uint32_t sl = vb + tid;
-                if (sl < tileV) {
-                    const uint32_t f = quads_only ? (sl >> 2) : (uint32_t)s.sc.s2f[sl];
-                    const uint32_t a = s.sc.frecA[f], ks = s.sc.frecB[f], ic = s.sc.frecC[f];
-                    const uint32_t row = a & 1023u, x = (a >> 10) & 31u, d = (a >> 15) & 7u;
-                    const uint32_t y = row >> 5, z = row & 31u;
-                    const uint32_t j = sl - (a >> 18);
-                    const uint32_t id = ic & 0xFFFFu, cx = ic >> 16;
-                    const unsigned long long e = __ldg(&T->vtab[cx][d][j]);
-                    // as_wxyz10 of (ipos + voffset + 0.5)/32 (voxmesh.rs:36-41,139-145,165): every vertex sits on a
-                    // voxel corner, so each 10-bit field is 16 * corner coordinate; w = (1/32*2) as u32 = 0.
-                    const uint32_t px = x + ((uint32_t)e & 1u), py = y + ((uint32_t)(e >> 1) & 1u), pz = z + ((uint32_t)(e >> 2) & 1u);
-                    const uint32_t position = (((px * 16u) & 0x3FFu) << 20) | (((py * 16u) & 0x3FFu) << 10) | ((pz * 16u) & 0x3FFu);
-                    const uint32_t k = (ks >> (3 * j)) & 7u;
-                    uint32_t color;
-                    if (id < (uint32_t)REGC) {
-                        color = s.col_lut[id * 8 + k];
+                    __syncwarp();
+                    const uint32_t n2 = min(32u, nbv - sb) * 5u; // 8-byte words to copy
+                    uint2 *dst = reinterpret_cast<uint2 *>(vout + v0 + vs0 + sb);
+                    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) { // even vertex offset: 16-byte copies
+                        const uint4 *src4 = reinterpret_cast<const uint4 *>(&s.sc.wvstage[warp][0]);
+                        uint4 *dst4 = reinterpret_cast<uint4 *>(dst);
+                        for (uint32_t k = lane; k < (n2 >> 1); k += 32) dst4[k] = src4[k];
+                        if ((n2 & 1u) && lane == 0) dst[n2 - 1] = s.sc.wvstage[warp][n2 - 1];
                     } else {
-                        const float ao = s.ao_lut[k];
-                        const float c0f = __fmul_rn(__ldg(p.reg.color + id * 3), ao), c1f = __fmul_rn(__ldg(p.reg.color + id * 3 + 1), ao),
-                                    c2f = __fmul_rn(__ldg(p.reg.color + id * 3 + 2), ao);
-                        color = ((__float2uint_rz(__fmul_rn(c0f, 255.0f)) & 0xFFu) << 24) | ((__float2uint_rz(__fmul_rn(c1f, 255.0f)) & 0xFFu) << 16) |
-                                ((__float2uint_rz(__fmul_rn(c2f, 255.0f)) & 0xFFu) << 8) | 0xFFu;
+                        for (uint32_t k = lane; k < n2; k += 32) dst[k] = s.sc.wvstage[warp][k];
                     }
-                    const float4 bsum = s.sc.frecD[f];
-                    const float tu = (float)((uint32_t)(e >> 3) & 1u), tv = (float)((uint32_t)(e >> 4) & 1u);
-                    const uint32_t index = (x + 32u * z + 1024u * y) | (((uint32_t)(e >> 5) & 7u) << 17);
-                    uint2 *o = (p.debug & 16) ? reinterpret_cast<uint2 *>(vout + v0 + sl) : &s.sc.vstage[tid * 5];
-                    o[0] = make_uint2(position, color);
-                    o[1] = make_uint2(__float_as_uint(tu), __float_as_uint(tv));
-                    o[2] = make_uint2(s.sc.frecT[f], index);
-                    o[3] = make_uint2(__float_as_uint(bsum.x), __float_as_uint(bsum.y));
-                    o[4] = make_uint2(__float_as_uint(bsum.z), __float_as_uint(bsum.w));
-                }
-                if (!(p.debug & 16)) {
-                    __syncthreads();
-                    const uint32_t n2 = min((uint32_t)NT, tileV - vb) * 5u;
-                    uint2 *dst = reinterpret_cast<uint2 *>(vout + v0 + vb);
-                    for (uint32_t k = tid; k < n2; k += NT) dst[k] = s.sc.vstage[k];
-                    __syncthreads();
+                    __syncwarp();
                 }
             }
             __syncthreads(); // the face records are rewritten by the next tile

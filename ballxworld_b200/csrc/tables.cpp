@@ -227,6 +227,10 @@ void build_mesh_tables(MeshTables &t) {
                     if (lv.inormal.y == 0) samples[n++] = V3{ic.x, 0, ic.z};
                     if (lv.inormal.z == 0) samples[n++] = V3{ic.x, ic.y, 0};
                     e |= (unsigned long long)n << 10;
+                    {
+                        V3 wn = rot(lv.inormal);
+                        t.vdesc[cls][d][j] = (uint16_t)((e & 0xFF) | (unsigned long long)((wn.x + 1) + 3 * (wn.y + 1) + 9 * (wn.z + 1)) << 8);
+                    }
                     t.aotab[cls][d][j][5] = (short)n;
                     for (int k = 0; k < n; k++) {
                         V3 a = rot(samples[k]);
@@ -243,7 +247,23 @@ void build_mesh_tables(MeshTables &t) {
             }
             t.ctab[cls] = cc | ec << 6 | eu << 12 | codes << 18;
         }
+    // aolut: corner_ao_set(corner, inormal) as a neighbourhood mask; the rule commutes with the 24 rotations
+    for (int cb = 0; cb < 8; cb++)
+        for (int nc = 0; nc < 27; nc++) {
+            const int cv[3] = {(cb & 1) ? 1 : -1, (cb & 2) ? 1 : -1, (cb & 4) ? 1 : -1};
+            const int nv[3] = {nc % 3 - 1, (nc / 3) % 3 - 1, nc / 9 - 1};
+            auto bit = [](int x, int y, int z) { return 1u << ((y + 1) * 9 + (z + 1) * 3 + (x + 1)); };
+            uint32_t m = bit(cv[0], cv[1], cv[2]) | bit(nv[0], nv[1], nv[2]);
+            if (nv[0] == 0) m |= bit(0, cv[1], cv[2]);
+            if (nv[1] == 0) m |= bit(cv[0], 0, cv[2]);
+            if (nv[2] == 0) m |= bit(cv[0], cv[1], 0);
+            t.aolut[cb * 27 + nc] = m;
+        }
     t.aomask_ok = 1;
+    for (int cls = 1; cls < kNumClasses; cls++)
+        for (int d = 0; d < 6; d++)
+            for (int j = 0; j < (int)((t.stab[cls][d] >> 3) & 7u); j++)
+                if (t.aolut[(t.vdesc[cls][d][j] & 7) * 27 + (t.vdesc[cls][d][j] >> 8)] != t.aomask[cls][d][j]) t.aomask_ok = 0;
     for (int cls = 1; cls < kNumClasses; cls++)
         for (int d = 0; d < 6; d++)
             for (int j = 0; j < (int)((t.stab[cls][d] >> 3) & 7u); j++)

@@ -29,6 +29,11 @@ struct MeshTables {
     alignas(16) short aotab[kNumClasses][6][6][8];
     // aomask[class][d][j]: the same AO samples as a mask over the 3x3x3 neighbourhood, bit (dy+1)*9 + (dz+1)*3 + (dx+1)
     uint32_t aomask[kNumClasses][6][6];
+    // compact per-vertex descriptor (what the emit phases read): bits 0-2 corner, 3 u, 4 v, 5-7 barycentric flags,
+    // 8-12 code of the world-space AO normal n: (n.x+1) + 3 (n.y+1) + 9 (n.z+1)
+    uint16_t vdesc[kNumClasses][6][6];
+    // AO sample mask over the 3x3x3 neighbourhood for (corner, normal code): corner_ao_set (stdshapes.rs:131-152)
+    uint32_t aolut[8 * 27];
     uint32_t aomask_ok; // 1 when no vertex lists the same AO sample twice (so popcount == number of occluders)
 };
 
