@@ -92,6 +92,7 @@ def load_library():
         "bxw_region_mesh_reserve": ([vp, C.c_uint64, C.c_uint64], C.c_int),
         "bxw_region_mesh": ([vp, u64p, u64p], C.c_int),
         "bxw_region_generate_and_mesh": ([vp, C.c_uint64, C.c_int, u64p, u64p], C.c_int),
+        "bxw_region_mesh_sphere": ([vp, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, u32p, u64p, u64p], C.c_int),
         "bxw_region_mesh_spans": ([vp, vp], C.c_int),
         "bxw_region_mesh_fetch": ([vp, vp, C.c_uint64, vp, C.c_uint64], C.c_int),
         "bxw_region_apply_changes": ([vp, vp, C.c_uint32, u32p], C.c_int),
@@ -285,6 +286,11 @@ class Context:
         v, i = C.c_uint64(), C.c_uint64()
         self._ck(self.L.bxw_region_generate_and_mesh(self.h, seed, precision, C.byref(v), C.byref(i)))
         return v.value, i.value
+
+    def region_mesh_sphere(self, anchor, radius):
+        n, v, i = C.c_uint32(), C.c_uint64(), C.c_uint64()
+        self._ck(self.L.bxw_region_mesh_sphere(self.h, anchor[0], anchor[1], anchor[2], radius, C.byref(n), C.byref(v), C.byref(i)))
+        return n.value, v.value, i.value
 
     def region_mesh_spans(self):
         nx, ny, nz = self.region_dims

@@ -759,6 +759,50 @@ int bxw_region_generate_and_mesh(bxw_ctx *ctx, uint64_t seed, int precision, uin
     return bxw_region_mesh(ctx, arena_vertices, arena_indices);
 }
 
+int bxw_region_mesh_sphere(bxw_ctx *ctx, int32_t ax, int32_t ay, int32_t az, uint32_t radius, uint32_t *n_meshed,
+                           uint64_t *arena_vertices, uint64_t *arena_indices) {
+    if (!ctx || !ctx->region.live) return fail(ctx, BXW_E_INVALID, "no region");
+    Region &r = ctx->region;
+    // iter_coords_to_load (worldmgr.rs:734-742): the cube -r..=r filtered by x^2+y^2+z^2 <= r^2; then nearest first
+    struct Item {
+        int64_t d2;
+        uint32_t chunk, span;
+    };
+    std::vector<Item> items;
+    const int64_t rr = (int64_t)radius * radius;
+    for (uint32_t iy = 0; iy < r.ny; iy++)
+        for (uint32_t iz = 0; iz < r.nz; iz++)
+            for (uint32_t ix = 0; ix < r.nx; ix++) {
+                const int64_t dx = (int64_t)r.cx0 + ix - ax, dy = (int64_t)r.cy0 + iy - ay, dz = (int64_t)r.cz0 + iz - az;
+                const int64_t d2 = dx * dx + dy * dy + dz * dz;
+                if (d2 <= rr)
+                    items.push_back({d2, (uint32_t)((ix + 1) + r.SX * ((iz + 1) + r.SZ * (iy + 1))), (uint32_t)(ix + r.nx * (iz + r.nz * iy))});
+            }
+    std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) { return a.d2 < b.d2; });
+    const uint32_t n = (uint32_t)items.size();
+    if (n_meshed) *n_meshed = n;
+    CK(cudaMemsetAsync(r.spans, 0, r.n_work * sizeof(bxw_mesh_span), ctx->stream));
+    if (n == 0) {
+        if (arena_vertices) *arena_vertices = 0;
+        if (arena_indices) *arena_indices = 0;
+        return BXW_OK;
+    }
+    std::vector<uint32_t> w(n), ws(n);
+    for (uint32_t i = 0; i < n; i++) {
+        w[i] = items[i].chunk;
+        ws[i] = items[i].span;
+    }
+    // the dirty work-list buffers double as the sphere list (both are at most n_work entries)
+    CK(cudaMemcpyAsync(r.dirty_work, w.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(r.dirty_span, ws.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int rc = region_mesh(ctx, r, r.dirty_work, r.dirty_span, n, false);
+    if (rc) return rc;
+    if (arena_vertices) *arena_vertices = r.h_counters->v_alloc;
+    if (arena_indices) *arena_indices = r.h_counters->i_alloc;
+    return BXW_OK;
+}
+
 int bxw_region_mesh_spans(bxw_ctx *ctx, bxw_mesh_span *spans) {
     if (!ctx || !ctx->region.live || !spans) return fail(ctx, BXW_E_INVALID, "no region / null");
     Region &r = ctx->region;

@@ -31,6 +31,13 @@ class Region:
         self.arena = self.ctx.region_mesh()
         return self.arena
 
+    def mesh_sphere(self, anchor, radius):
+        """Mesh the chunks within `radius` chunks of the load anchor (CLoadAnchor, worldmgr.rs:734-746), nearest first."""
+        self.registry.bind(self.ctx)
+        n, av, ai = self.ctx.region_mesh_sphere(anchor, radius)
+        self.arena = (av, ai)
+        return n
+
     def generate_and_mesh(self, seed=0, precision=64):
         self.registry.bind(self.ctx)
         self.ctx.set_gen_ids(*StdGenerator.resolve_ids(self.registry))

@@ -140,6 +140,12 @@ int bxw_region_mesh(bxw_ctx *ctx, uint64_t *arena_vertices, uint64_t *arena_indi
 /* Fused StdGenerator + mesher over the pristine region: blocks are written once and meshed from on-chip data. */
 int bxw_region_generate_and_mesh(bxw_ctx *ctx, uint64_t seed, int precision, uint64_t *arena_vertices,
                                  uint64_t *arena_indices);
+/* View-distance scheduling (World::recalculate_load_deltas, bxw_world/src/worldmgr.rs:633-746): mesh exactly the
+ * interior chunks inside the load-anchor sphere |c - anchor|^2 <= radius^2 (iter_coords_to_load, worldmgr.rs:734-742),
+ * nearest first (the reference sorts its deltas by distance); every other chunk's span is cleared.
+ * anchor is a world chunk position. n_meshed = chunks in the sphere that belong to this region. */
+int bxw_region_mesh_sphere(bxw_ctx *ctx, int32_t ax, int32_t ay, int32_t az, uint32_t radius, uint32_t *n_meshed,
+                           uint64_t *arena_vertices, uint64_t *arena_indices);
 /* spans: nx*ny*nz entries, chunk order x + nx*(z + nz*y). */
 int bxw_region_mesh_spans(bxw_ctx *ctx, bxw_mesh_span *spans);
 /* Copy arena extents [0,arena_vertices) / [0,arena_indices) to host (pinned memory recommended). */

@@ -230,3 +230,37 @@ def test_terragen_noise2_matches_oracle(ctx, oracle):
         want = np.array([L.bxo_tg_simplex_noise2(s, float(x), float(y)) for x, y in zip(xs, ys)])
         L.bxo_tg_simplex_free(s)
         assert got.tobytes() == want.tobytes(), f"seed {seed}: max abs diff {np.abs(got - want).max()}"
+
+
+def test_mesh_sphere_view_distance(ctx, oracle):
+    """bxw_region_mesh_sphere: the load-anchor sphere of worldmgr.rs:734-742, same meshes as the full-region pass."""
+    dims = (6, 3, 6)
+    origin = (8, 0, -3)
+    ctx.region_create(*origin, *dims)
+    ctx.region_generate(0, 64)
+    av, ai = ctx.region_mesh()
+    full_spans = ctx.region_mesh_spans()
+    FV, FI = ctx.region_mesh_fetch(av, ai)
+    anchor, radius = (10, 1, -1), 2
+    n, sv, si = ctx.region_mesh_sphere(anchor, radius)
+    spans = ctx.region_mesh_spans()
+    SV, SI = ctx.region_mesh_fetch(sv, si)
+    want = 0
+    for iy in range(dims[1]):
+        for iz in range(dims[2]):
+            for ix in range(dims[0]):
+                k = ix + dims[0] * (iz + dims[2] * iy)
+                d2 = (origin[0] + ix - anchor[0]) ** 2 + (origin[1] + iy - anchor[1]) ** 2 + (origin[2] + iz - anchor[2]) ** 2
+                s, f = spans[k], full_spans[k]
+                if d2 <= radius * radius:
+                    want += 1
+                    assert s["v_count"] == f["v_count"] and s["i_count"] == f["i_count"]
+                    a = SV[int(s["v_off"]): int(s["v_off"]) + int(s["v_count"])]
+                    b = FV[int(f["v_off"]): int(f["v_off"]) + int(f["v_count"])]
+                    assert a.tobytes() == b.tobytes()
+                    assert np.array_equal(SI[int(s["i_off"]): int(s["i_off"]) + int(s["i_count"])], FI[int(f["i_off"]): int(f["i_off"]) + int(f["i_count"])])
+                else:
+                    assert s["v_count"] == 0 and s["i_count"] == 0
+    assert n == want and want > 10
+    assert ctx.region_mesh_sphere((1000, 0, 0), 3)[0] == 0
+    ctx.region_destroy()
