@@ -314,7 +314,6 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
     p.counters = r.counters;
     p.tables = ctx->d_tables;
     p.reg = dev_registry(ctx);
-    p.debug = getenv("BXW_DEBUG") ? atoi(getenv("BXW_DEBUG")) : 0;
     unsigned long long base_v = 0, base_i = 0;
     if (append) {
         CK(cudaMemcpyAsync(r.h_counters, r.counters, sizeof(MeshCounters), cudaMemcpyDeviceToHost, ctx->stream));
@@ -416,8 +415,6 @@ size_t storage_index(const Region &r, int32_t lx, int32_t ly, int32_t lz) {
 bool local_ok(const Region &r, int32_t lx, int32_t ly, int32_t lz) {
     return lx >= -1 && ly >= -1 && lz >= -1 && lx <= (int32_t)r.nx && ly <= (int32_t)r.ny && lz <= (int32_t)r.nz;
 }
-
-int not_implemented(bxw_ctx *ctx, const char *what) { return fail(ctx, BXW_E_INVALID, "%s: not implemented in this build", what); }
 
 } // namespace
 

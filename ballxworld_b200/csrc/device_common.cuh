@@ -45,7 +45,6 @@ struct MeshParams {
     const MeshTables *tables;
     DeviceRegistry reg;
     int count_only; // 1: fill spans' counts only (offsets = running totals), no vertex/index writes
-    int debug;      // experiment switches (BXW_DEBUG env var); 0 in production
 };
 
 void launch_mesh_kernel(const MeshParams &p, int sm_count, cudaStream_t stream);

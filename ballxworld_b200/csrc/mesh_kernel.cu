@@ -4,18 +4,21 @@
 // GPU-resident dense block storage directly (the reference decodes 27 RLE streams into a 34^3 table first,
 // voxmesh.rs:53-80; RleVoxelIterator::skip_until_index returns exactly blocks_yzx[idx]).
 //
-// One CTA meshes one chunk at a time:
+// One CTA (256 threads, two per SM) meshes one chunk at a time:
 //   A  stage the chunk plus its 1-voxel halo (34^3) in shared memory as one CLASS BYTE per voxel (class = shape x
-//      orientation of the datum, 0 = no mesh) plus one 34-bit SOLID word per (y,z) row; 16-byte coalesced loads of
-//      the u32 storage; a warp whose 128 loaded voxels are all equal classifies once (terrain is mostly uniform).
+//      orientation of the datum, 0 = no mesh) plus one 34-bit SOLID word per (y,z) row. The rows stream through
+//      warp-private cp.async rings (16-byte copies, two units ahead); the x-halo comes from the neighbour chunks'
+//      x-face planes. A unit (384 voxels) that is one single datum costs one match + one vote (terrain is mostly
+//      uniform); a 34^3 neighbourhood that is one void/cube datum ends the chunk after one barrier.
 //   B  per-row vertex/index/face counts. Cubes-and-void chunks: one thread per row, visibility by bit operations
 //      on the solid words (voxmesh.rs:119 reduces to solid & ~neighbour-solid). Chunks containing slopes/corners:
 //      one warp per row, lane = x, the general orientation-aware test (voxmesh.rs:105-121).
 //   S  block-wide exclusive scan of the 1024 row counts = the reference's emission order (cells y,z,x-major,
 //      directions 0..5 minor, voxmesh.rs:94,104); one atomicAdd pair reserves the chunk's arena span.
-//   C  emission in tiles of <=1024 faces: (C1) face records in emission order, (C2) face-parallel AO occluder counts
-//      and index values, (C3) vertex-slot-parallel vertex records staged in shared memory and copied out with fully
-//      coalesced 8-byte stores. All 256 threads work on faces/vertices, not on rows.
+//   C  emission in tiles of <=1024 faces: (C1) face records in emission order; then, fused per warp and without block
+//      barriers, 32 faces at a time: per-face AO occluder counts (popcount of the cell's 3x3x3 occupancy under the
+//      vertex's sample mask), barycentric colour sums and texture ids in registers, index values and 40-byte vertex
+//      records staged in the warp's shared-memory slice and written out with coalesced 16-byte stores.
 #include <type_traits>
 
 #include "device_common.cuh"
@@ -209,11 +212,6 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
             // tile z-rows, then the 8 columns, then the vertical stack fastest. Chunks whose halos overlap are then
             // in flight on neighbouring CTAs at about the same time, so halo rows/planes hit L2 instead of HBM.
             const uint32_t nx = (uint32_t)p.SX - 2u, ny = (uint32_t)p.SY - 2u, nz = (uint32_t)p.SZ - 2u;
-            if (p.debug & 8) {
-                const uint32_t ix = w % nx, iz = (w / nx) % nz, iy = w / (nx * nz);
-                c0 = (ix + 1u) + (uint32_t)p.SX * ((iz + 1u) + (uint32_t)p.SZ * (iy + 1u));
-                span_slot = w;
-            } else {
             const uint32_t per_tile = 8u * ny * nz;
             const uint32_t t = w / per_tile, rem = w - t * per_tile;
             const uint32_t tw = min(8u, nx - 8u * t);
@@ -221,7 +219,6 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
             const uint32_t ix = 8u * t + r2 / ny, iy = r2 % ny;
             c0 = (ix + 1u) + (uint32_t)p.SX * ((iz + 1u) + (uint32_t)p.SZ * (iy + 1u));
             span_slot = ix + nx * (iz + nz * iy);
-            }
         }
         if (tid < 27) {
             const int sx = (int)(c0 % (uint32_t)p.SX), sz = (int)((c0 / (uint32_t)p.SX) % (uint32_t)p.SZ),
@@ -285,17 +282,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                     if (q == 0) s.solid[yy * 34 + zz] = rowmask;
                 }
             };
-            // x-halo of a layer from the x-neighbour chunks' face planes ([chunk][side][y][z], coalesced): lane z holds the
-            // x=-1 / x=32 voxels of row zz = z+1; lanes 0..3 also hold the four corner rows (zz = 0 / 33) of the diagonals
-            auto halo_load = [&](int ry, int by, uint32_t &hm, uint32_t &hp, uint32_t &he) {
-                hm = __ldg(p.xface + (size_t)s.nbr[0 + 3 + 9 * ry] * 2048 + 1024 + by * 32 + lane);
-                hp = __ldg(p.xface + (size_t)s.nbr[2 + 3 + 9 * ry] * 2048 + by * 32 + lane);
-                he = 0;
-                if (lane < 4) {
-                    const int erx = (lane & 1) ? 2 : 0, erz = (lane & 2) ? 2 : 0;
-                    he = __ldg(p.xface + (size_t)s.nbr[erx + 3 * erz + 9 * ry] * 2048 + ((lane & 1) ? 0 : 1024) + by * 32 + ((lane & 2) ? 0 : 31));
-                }
-            };
+            // x-halo class bytes / solid bits of a layer: lane z owns row zz = z+1, lanes 0 and 2 also the corner rows 0 / 33
             auto halo_store = [&](int yy, uint32_t cm, uint32_t cp, uint32_t ce, uint32_t co) {
                 uint8_t *row = &s.cls[yy * PLANE + (lane + 1) * ROWB + XOFF];
                 row[-1] = (uint8_t)cm;
@@ -617,7 +604,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                 else hi = mid - 1;
             }
             const uint32_t r1 = lo;
-            const uint32_t tileF = s.sc.rowF[r1] - f0, tileV = s.sc.rowV[r1] - v0, tileI = s.sc.rowI[r1] - i0;
+            const uint32_t tileF = s.sc.rowF[r1] - f0;
             if (tileF == 0) {
                 r0 = r1;
                 continue;

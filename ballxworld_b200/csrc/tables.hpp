@@ -16,7 +16,7 @@ constexpr int kNumClasses = 97;
 // ctab[class]: bits 0-5 CC (side facing world dir d can_clip), 6-11 EC (emits && can_be_clipped),
 //              12-17 EU (emits && !can_be_clipped), 18-29 per-dir vertex-count code (2 bits: 0 none,1 three,2 four,3 six)
 // stab[class][d]: bits 0-2 local side, 3-5 n_verts, 6-8 n_indices, 9-20 barycentric sign codes (2 bits/vertex: sign+1)
-// vtab[class][d][j] (64-bit):
+// vtab[class][d][j] (64-bit, host-side source of vdesc; the kernels read vdesc / aolut):
 //   bits 0-2 corner (x,y,z in {0,1}: vertex = cell + corner), 3 texcoord u, 4 texcoord v, 5-7 barycentric >0.1 flags (x,y,z),
 //   8-9 sign+1, 10-12 n_ao, 13+6k.. AO sample k: (dx+1) | (dy+1)<<2 | (dz+1)<<4
 struct MeshTables {
