@@ -98,29 +98,76 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *w
     return base + incl - v;
 }
 
-// words a run starting at voxel i contributes, given the dense data; run heads only
+// Each thread owns the run HEADS inside its 128-voxel segment. A run's length is the distance to the next head, which may
+// lie in a later segment: the first head of every segment goes to shared memory and a suffix-minimum gives each thread
+// the first head after its segment, so no thread ever walks a long run voxel by voxel.
 template <bool WRITE>
 __global__ void __launch_bounds__(RT) rle_compress_kernel(const uint32_t *dense, size_t n_chunks, const uint64_t *offsets,
                                                           uint32_t *out_words, uint32_t *out_len) {
     __shared__ uint32_t warp_tot[RT / 32];
+    __shared__ uint32_t first_head[RT + 1];
     const size_t c = blockIdx.x;
     if (c >= n_chunks) return;
     const uint32_t *d = dense + c * kChunkVoxels;
     const int t = threadIdx.x;
     const int b = t * RSEG;
-    // Each thread owns the run HEADS inside its segment; a run's length may extend past the segment.
-    // pass 1: count words for heads in this segment
-    uint32_t words = 0;
+    // pass 1: heads of this segment as a 128-bit mask; words they contribute
+    uint32_t hm[RSEG / 32];
     uint32_t prev = b ? d[b - 1] : 0;
-    for (int i = b; i < b + RSEG; i++) {
-        const uint32_t v = d[i];
-        const bool head = (i == 0) || (v != prev);
-        if (head) {
-            const bool longrun = (i + 1 < kChunkVoxels) && d[i + 1] == v;
-            words += longrun ? 3u : 1u;
+    uint32_t words = 0;
+#pragma unroll
+    for (int w = 0; w < RSEG / 32; w++) {
+        uint32_t m = 0;
+        for (int k = 0; k < 32; k++) {
+            const int i = b + w * 32 + k;
+            const uint32_t v = d[i];
+            const bool head = (i == 0) || (v != prev);
+            m |= (uint32_t)head << k;
+            prev = v;
         }
-        prev = v;
+        hm[w] = m;
     }
+    int fh = kChunkVoxels;
+#pragma unroll
+    for (int w = RSEG / 32 - 1; w >= 0; w--)
+        if (hm[w]) fh = b + w * 32 + __ffs(hm[w]) - 1;
+    first_head[t] = (uint32_t)fh;
+    if (t == 0) first_head[RT] = kChunkVoxels;
+    __syncthreads();
+    // first head strictly after this segment (suffix minimum; 256 entries, a short serial loop per thread is cheap
+    // because it stops at the first segment that has a head, which for run-heavy data is far but for those chunks
+    // there are few heads overall)
+    uint32_t next_after = kChunkVoxels;
+    for (int k = t + 1; k < RT; k++) {
+        if (first_head[k] < (uint32_t)kChunkVoxels) {
+            next_after = first_head[k];
+            break;
+        }
+    }
+    // run length of every head: distance to the next head (in this segment, else next_after)
+    auto for_each_head = [&](auto &&fn) {
+#pragma unroll
+        for (int w = 0; w < RSEG / 32; w++) {
+            uint32_t m = hm[w];
+            while (m) {
+                const int k = __ffs(m) - 1;
+                m &= m - 1;
+                const int i = b + w * 32 + k;
+                // next head after i
+                uint32_t nx = next_after;
+                uint32_t rest = m;
+                if (rest) nx = b + w * 32 + __ffs(rest) - 1;
+                else
+                    for (int w2 = w + 1; w2 < RSEG / 32; w2++)
+                        if (hm[w2]) {
+                            nx = b + w2 * 32 + __ffs(hm[w2]) - 1;
+                            break;
+                        }
+                fn(i, nx - (uint32_t)i);
+            }
+        }
+    };
+    for_each_head([&](int, uint32_t len) { words += len >= 2 ? 3u : 1u; });
     uint32_t total;
     uint32_t off = block_exclusive_scan(words, warp_tot, total);
     if (!WRITE) {
@@ -128,24 +175,14 @@ __global__ void __launch_bounds__(RT) rle_compress_kernel(const uint32_t *dense,
         return;
     }
     uint32_t *o = out_words + offsets[c];
-    prev = b ? d[b - 1] : 0;
-    for (int i = b; i < b + RSEG; i++) {
+    for_each_head([&](int i, uint32_t len) {
         const uint32_t v = d[i];
-        const bool head = (i == 0) || (v != prev);
-        if (head) {
-            int j = i + 1;
-            if (j < kChunkVoxels && d[j] == v) {
-                while (j < kChunkVoxels && d[j] == v) j++; // run length (may cross segments; long runs are rare per thread)
-                o[off] = v;
-                o[off + 1] = v;
-                o[off + 2] = (uint32_t)(j - i - 2);
-                off += 3;
-            } else {
-                o[off++] = v;
-            }
+        o[off++] = v;
+        if (len >= 2) { // [v, v, L-2] (lib.rs:263-294)
+            o[off++] = v;
+            o[off++] = len - 2;
         }
-        prev = v;
-    }
+    });
 }
 
 __global__ void offsets_scan_kernel(const uint32_t *len, size_t n, uint64_t *offsets) {
