@@ -299,7 +299,8 @@ int arena_resize(bxw_ctx *ctx, Region &r, unsigned long long v_cap, unsigned lon
 }
 
 // Runs the mesher over a work list. append=false restarts arena allocation at 0.
-int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *work_span, uint32_t n_work, bool append) {
+int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *work_span, uint32_t n_work, bool append,
+                bool from_hmap = false) {
     if (!ctx->d_kind) return fail(ctx, BXW_E_NO_REGISTRY, "bxw_set_registry not called");
     MeshParams p;
     p.blocks = r.blocks;
@@ -314,6 +315,19 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
     p.counters = r.counters;
     p.tables = ctx->d_tables;
     p.reg = dev_registry(ctx);
+    p.hmap = nullptr;
+    p.hmap_W = 0;
+    p.cy_min = 0;
+    p.gen_all_cubes = 0;
+    for (int i = 0; i < 5; i++) p.gen_datum[i] = 0;
+    if (from_hmap) { // fused generate+mesh: the region holds pristine StdGenerator terrain and its column parameters
+        p.hmap = r.hmap;
+        p.hmap_W = r.SX * 32;
+        p.cy_min = r.cy0 - 1;
+        for (int i = 0; i < 5; i++) p.gen_datum[i] = (uint32_t)ctx->gen_ids[i] << 16;
+        auto is_cube = [&](uint16_t id) { return id < ctx->reg_n && ctx->reg_host[id].present && ctx->reg_host[id].mesh_kind != 0; };
+        p.gen_all_cubes = is_cube(ctx->gen_ids[2]) && is_cube(ctx->gen_ids[3]);
+    }
     unsigned long long base_v = 0, base_i = 0;
     if (append) {
         CK(cudaMemcpyAsync(r.h_counters, r.counters, sizeof(MeshCounters), cudaMemcpyDeviceToHost, ctx->stream));
@@ -753,7 +767,15 @@ int bxw_region_mesh(bxw_ctx *ctx, uint64_t *arena_vertices, uint64_t *arena_indi
 int bxw_region_generate_and_mesh(bxw_ctx *ctx, uint64_t seed, int precision, uint64_t *arena_vertices, uint64_t *arena_indices) {
     int rc = bxw_region_generate(ctx, seed, precision);
     if (rc) return rc;
-    return bxw_region_mesh(ctx, arena_vertices, arena_indices);
+    // The blocks were just written from the column parameters and nothing has edited them: mesh from the height map
+    // (34x34 columns per chunk) instead of reading the voxels back.
+    Region &r = ctx->region;
+    rc = region_mesh(ctx, r, nullptr, nullptr, r.n_work, false, true);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(r.dirty, 0, r.n_work, ctx->stream));
+    if (arena_vertices) *arena_vertices = r.h_counters->v_alloc;
+    if (arena_indices) *arena_indices = r.h_counters->i_alloc;
+    return BXW_OK;
 }
 
 int bxw_region_mesh_sphere(bxw_ctx *ctx, int32_t ax, int32_t ay, int32_t az, uint32_t radius, uint32_t *n_meshed,

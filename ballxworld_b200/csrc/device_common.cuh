@@ -45,6 +45,11 @@ struct MeshParams {
     const MeshTables *tables;
     DeviceRegistry reg;
     int count_only; // 1: fill spans' counts only (offsets = running totals), no vertex/index writes
+    // fused generate+mesh (pristine StdGenerator terrain): derive the 34^3 table from the column parameters
+    const int32_t *hmap;   // nullptr = read the block storage
+    int32_t hmap_W, cy_min;
+    uint32_t gen_datum[5]; // void, grass, dirt, stone, snow_grass datums
+    int gen_all_cubes;     // dirt and stone both classify as cubes (1..24)
 };
 
 void launch_mesh_kernel(const MeshParams &p, int sm_count, cudaStream_t stream);

@@ -63,6 +63,10 @@ struct Smem {
     union {
         Scratch sc;                                          // phases B, S, C
         alignas(16) uint8_t ring[NW][RSLOTS][RSLOT_BYTES];   // phase A
+        struct {                                             // phase A of the fused generate+mesh path
+            int32_t hm[34 * 36];                             // packed column parameters (height*4 + elevation), [zz][xx]
+            int32_t red[2][NW];
+        } gen;
     };
     uint32_t solid[34 * 34];         // per (y',z') row: bit x set when voxel x (0..31) has a mesh (class != 0)
     uint8_t solid_halo[34 * 34 + 4]; // bit0: x=-1 solid, bit1: x=32 solid
@@ -80,6 +84,7 @@ struct Smem {
     uint32_t work_item[2];
     uint32_t wref[NW];     // per-warp reference datum (trivial-chunk detection)
     uint32_t wflags[NW];   // per-warp shapes | mixed<<1
+    uint32_t gen_cls[5];   // class of the five generator datums (void, grass, dirt, stone, snow_grass)
     int emit;
 };
 
@@ -195,6 +200,10 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
         }
         s.col_lut[i] = col;
     }
+    if (tid < 5) { // class of the generator's datums (meta 0): cube (class 1) when the block has a mesh, else 0
+        const uint32_t id = p.gen_datum[tid] >> 16;
+        s.gen_cls[tid] = (p.hmap && id < p.reg.n && p.reg.kind[id] == 2) ? 1u : 0u;
+    }
     if (tid == 0) s.work_item[0] = (uint32_t)atomicAdd(&p.counters->work_next, 1ull);
 
     for (uint32_t iter = 0;; iter++) {
@@ -232,7 +241,73 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
         uint32_t err = 0;
         uint32_t shapes = 0;  // saw a non-cube shape (class > 24)
         uint32_t mixed = 0;   // saw a voxel different from this warp's reference voxel
-        {
+        if (p.hmap) {
+            // Fused generate+mesh: the blocks of pristine terrain are a pure function of the column parameters
+            // (stdgen.rs:349-373), so the 34^3 table is derived from the 34x34 columns under the chunk instead of reading
+            // 148 KB of voxels back from HBM.
+            const int sx = (int)(c0 % (uint32_t)p.SX), sz = (int)((c0 / (uint32_t)p.SX) % (uint32_t)p.SZ), sy = (int)(c0 / (uint32_t)(p.SX * p.SZ));
+            const int y_lo = (p.cy_min + sy) * 32 - 1; // world y of layer yy = 0
+            int hmin = 0x7FFFFFFF, hmax = -0x7FFFFFFF;
+            for (int i = tid; i < 34 * 34; i += NT) {
+                const int zz = i / 34, xx = i - zz * 34;
+                const int v = __ldg(p.hmap + (size_t)(sz * 32 - 1 + zz) * p.hmap_W + sx * 32 - 1 + xx);
+                s.gen.hm[zz * 36 + xx] = v;
+                hmin = min(hmin, v >> 2);
+                hmax = max(hmax, v >> 2);
+            }
+            hmin = __reduce_min_sync(FULL, hmin);
+            hmax = __reduce_max_sync(FULL, hmax);
+            if (lane == 0) {
+                s.gen.red[0][warp] = hmin;
+                s.gen.red[1][warp] = hmax;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < NW; k++) {
+                hmin = min(hmin, s.gen.red[0][k]);
+                hmax = max(hmax, s.gen.red[1][k]);
+            }
+            const uint32_t c_void = s.gen_cls[0];
+            // all 34 layers above every column -> one void datum; all at or below every column's dirt/stone -> solid cubes
+            const bool all_void = y_lo > hmax;
+            const bool all_solid = (y_lo + 33 < hmin) && p.gen_all_cubes; // strictly below the surface layer: dirt / stone only
+            if ((all_void && c_void == 0u) || all_solid) {
+                mixed = 0;
+                shapes = 0;
+            } else {
+                mixed = 1;
+                // warp per z-row of columns, lane = x (lanes 0/1 also own the x = -1 / 32 halo columns); the column
+                // parameters stay in registers while the 34 layers are emitted
+                const uint32_t g0 = s.gen_cls[0], g1 = s.gen_cls[1], g2 = s.gen_cls[2], g3 = s.gen_cls[3], g4 = s.gen_cls[4];
+                auto cls_of = [&](int hv, int y) {
+                    const int h = hv >> 2, el = hv & 3;
+                    return (y == h) ? ((el == 2 && y > 80) ? g4 : g1) : (y < h - 5 ? g3 : (y < h ? g2 : g0));
+                };
+                for (int zz = warp; zz < 34; zz += NW) {
+                    const int hv = s.gen.hm[zz * 36 + lane + 1];
+                    const int hh = s.gen.hm[zz * 36 + (lane & 1 ? 33 : 0)]; // used by lanes 0 and 1
+#pragma unroll 2
+                    for (int yy = 0; yy < 34; yy++) {
+                        const int y = y_lo + yy;
+                        const uint32_t c = cls_of(hv, y);
+                        const uint32_t rowmask = __ballot_sync(FULL, c != 0u);
+                        shapes |= (c > 24u);
+                        s.cls[yy * PLANE + zz * ROWB + XOFF + lane] = (uint8_t)c;
+                        if (lane < 2) {
+                            const uint32_t ch = cls_of(hh, y);
+                            shapes |= (ch > 24u);
+                            s.cls[yy * PLANE + zz * ROWB + XOFF + (lane ? 32 : -1)] = (uint8_t)ch;
+                            const uint32_t other = __shfl_xor_sync(0x3u, ch, 1);
+                            if (lane == 0) {
+                                s.solid[yy * 34 + zz] = rowmask;
+                                s.solid_halo[yy * 34 + zz] = (uint8_t)((ch != 0u) | ((other != 0u) << 1));
+                            }
+                        }
+                    }
+                }
+            }
+            if (lane == 0) s.wref[warp] = 0;
+        } else {
             const int q = lane & 7, zsub = lane >> 3;
             uint32_t last_d = 0, last_c = 0, wref = 0;
             bool have_ref = false;

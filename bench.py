@@ -228,6 +228,19 @@ def main():
     ms = e0.elapsed_time(e1)
     launches = ctx.kernel_launches() - l0
     mesh_ms, mesh_launches = ctx.mesh_kernel_time_ms()
+    # ---------------- the library's fused generate+mesh (meshes pristine terrain from the column parameters) ----------------
+    fused_ms = None
+    if world == 1:
+        region.generate_and_mesh(SEED, 64)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(args.steps):
+            region.generate_and_mesh(SEED, 64)
+        f1.record(stream)
+        barrier()
+        fused_ms = f0.elapsed_time(f1) / args.steps
+
     # ---------------- end-to-end: public API, host buffers ----------------
     av, ai = arena
     hv = torch.empty(max(av, 1) * 40, dtype=torch.uint8, pin_memory=True)
@@ -288,6 +301,8 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": mesh_ms_per_launch,
                          "mesh_share_of_step": mesh_ms_per_launch / ms_per_step},
+            "fused_generate_and_mesh": None if fused_ms is None else {"ms_per_step": fused_ms, "value": n_chunks / (fused_ms / 1000.0), "unit": UNIT,
+                                                                      "note": "bxw_region_generate_and_mesh: blocks written once, meshed from the height map (what e2e calls)"},
             "mesh": {"vertices": tot_v_all, "indices": tot_i_all, "arena_vertices": av, "arena_indices": ai},
         }
         if args.slab:

@@ -75,3 +75,53 @@ def test_generate_then_mesh_matches_oracle(ctx, oracle):
                 total += len(wv)
     assert total > 0
     ctx.region_destroy()
+
+
+def test_fused_generate_and_mesh_equals_two_pass(ctx):
+    """bxw_region_generate_and_mesh meshes from the column parameters; it must equal generate + mesh-from-storage
+    chunk for chunk, including buried (all stone), sky (all void) and surface chunks, at negative coordinates."""
+    for origin, dims, seed in [((-4, -2, 3), (5, 6, 4), 0), ((20, 0, -9), (4, 5, 3), 0x13372137CAFE)]:
+        ctx.region_create(*origin, *dims)
+        av, ai = ctx.region_generate_and_mesh(seed, 64)
+        spans_f = ctx.region_mesh_spans()
+        Vf, If = ctx.region_mesh_fetch(av, ai)
+        ctx.region_generate(seed, 64)
+        av2, ai2 = ctx.region_mesh()
+        spans_t = ctx.region_mesh_spans()
+        Vt, It = ctx.region_mesh_fetch(av2, ai2)
+        assert np.array_equal(spans_f["v_count"], spans_t["v_count"]) and np.array_equal(spans_f["i_count"], spans_t["i_count"])
+        assert int(spans_t["v_count"].sum()) > 0 and int((spans_t["v_count"] == 0).sum()) > 0
+        for a, b in zip(spans_f, spans_t):
+            n, m = int(a["v_count"]), int(a["i_count"])
+            assert Vf[int(a["v_off"]): int(a["v_off"]) + n].tobytes() == Vt[int(b["v_off"]): int(b["v_off"]) + n].tobytes()
+            assert np.array_equal(If[int(a["i_off"]): int(a["i_off"]) + m], It[int(b["i_off"]): int(b["i_off"]) + m])
+        ctx.region_destroy()
+
+
+def test_fused_path_respects_a_registry_without_meshes(ctx):
+    """If a generator block has no mesh (VoxelMesh::None) the fused path must treat it as non-solid, like the mesher does."""
+    import ballxworld_b200 as bxw
+
+    reg = bxw.VoxelRegistry()
+    reg.register("core:grass", texture_mapping=(1,) * 6)
+    reg.register("core:snow_grass", texture_mapping=(2,) * 6)
+    reg.register("core:dirt", mesh="None")          # invisible dirt
+    reg.register("core:stone", texture_mapping=(4,) * 6)
+    reg.bind(ctx)
+    ctx.set_gen_ids(*bxw.StdGenerator.resolve_ids(reg))
+    ctx.region_create(9, 0, 0, 2, 2, 2)
+    av, ai = ctx.region_generate_and_mesh(0, 64)
+    sf = ctx.region_mesh_spans()
+    Vf, If = ctx.region_mesh_fetch(av, ai)
+    ctx.region_generate(0, 64)
+    av2, ai2 = ctx.region_mesh()
+    st = ctx.region_mesh_spans()
+    Vt, It = ctx.region_mesh_fetch(av2, ai2)
+    assert np.array_equal(sf["v_count"], st["v_count"]) and int(st["v_count"].sum()) > 0
+    for a, b in zip(sf, st):
+        n = int(a["v_count"])
+        assert Vf[int(a["v_off"]): int(a["v_off"]) + n].tobytes() == Vt[int(b["v_off"]): int(b["v_off"]) + n].tobytes()
+    ctx.region_destroy()
+    std = bxw.standard_registry()
+    std.bind(ctx)
+    ctx.set_gen_ids(*bxw.StdGenerator.resolve_ids(std))
