@@ -178,6 +178,7 @@ void region_free(Region &r) {
 }
 
 int region_alloc(bxw_ctx *ctx, Region &r, int32_t cx0, int32_t cy0, int32_t cz0, uint32_t nx, uint32_t ny, uint32_t nz) {
+    CK(cudaSetDevice(ctx->device));
     region_free(r);
     r.cx0 = cx0;
     r.cy0 = cy0;
@@ -224,6 +225,7 @@ int region_alloc(bxw_ctx *ctx, Region &r, int32_t cx0, int32_t cy0, int32_t cz0,
 }
 
 int region_generate(bxw_ctx *ctx, Region &r, uint64_t seed, int precision, bool want_raw) {
+    CK(cudaSetDevice(ctx->device));
     if (precision != 32 && precision != 64) return fail(ctx, BXW_E_INVALID, "precision must be 32 or 64");
     if (!ctx->have_gen_ids) return fail(ctx, BXW_E_NO_REGISTRY, "bxw_set_gen_ids not called");
     int rc = ensure_gen_tables(ctx, seed);
@@ -301,6 +303,7 @@ int arena_resize(bxw_ctx *ctx, Region &r, unsigned long long v_cap, unsigned lon
 // Runs the mesher over a work list. append=false restarts arena allocation at 0.
 int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *work_span, uint32_t n_work, bool append,
                 bool from_hmap = false) {
+    CK(cudaSetDevice(ctx->device));
     if (!ctx->d_kind) return fail(ctx, BXW_E_NO_REGISTRY, "bxw_set_registry not called");
     MeshParams p;
     p.blocks = r.blocks;

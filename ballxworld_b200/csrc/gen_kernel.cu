@@ -336,12 +336,14 @@ __global__ void __launch_bounds__(64) fill_xface_kernel(FillParams p) {
     }
 }
 
-bool g_const_uploaded = false;
+unsigned long long g_const_devices = 0; // bit d set: __constant__ tables uploaded on device d
 void ensure_constants() {
-    if (g_const_uploaded) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && (g_const_devices >> dev) & 1ull) return;
     cudaMemcpyToSymbol(c_lat_off, h_lat_off, sizeof h_lat_off);
     cudaMemcpyToSymbol(c_lat_pt, h_lat_pt, sizeof h_lat_pt);
-    g_const_uploaded = true;
+    if (dev < 64) g_const_devices |= 1ull << dev;
 }
 
 } // namespace

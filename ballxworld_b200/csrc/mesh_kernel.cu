@@ -54,8 +54,8 @@ struct Scratch { // phases B, S, C
     uint32_t frecE[FC];   // occupancy of the cell's 3x3x3 neighbourhood, bit (dy+1)*9 + (dz+1)*3 + (dx+1) (ditto)
     // per-warp staging of one batch of 32 faces
     uint8_t wsf[NW][192];        // vertex slot of the batch -> lane owning the face
-    uint32_t wistage[NW][192];   // index values of the batch
-    alignas(16) uint2 wvstage[NW][32 * 5]; // 32 vertices x 40 B
+    alignas(8) uint32_t wistage[NW][192];   // index values of the batch
+    alignas(16) uint2 wvstage[NW][32 * 5 + 2]; // 32 vertices x 40 B (+1 slot so the copy-out can be 16-byte aligned)
 };
 
 struct Smem {
@@ -811,22 +811,28 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                     for (uint32_t j = 0; j < nv; j++) sf[j] = (uint8_t)lane;
                     uint32_t *ist = &s.sc.wistage[warp][is - is0];
                     const uint32_t vq = v0 + vs; // voff = vbuf.len() (voxmesh.rs:123), chunk-relative
-                    if (nv == 4) { // QUAD_INDICES (stdshapes.rs:198)
-                        ist[0] = vq;
-                        ist[1] = vq + 1;
-                        ist[2] = vq + 2;
-                        ist[3] = vq + 2;
-                        ist[4] = vq + 3;
-                        ist[5] = vq;
-                    } else {
-                        for (uint32_t k = 0; k < ni; k++) ist[k] = vq + k;
-                    }
+                    // QUAD_INDICES [0,1,2,2,3,0] for quads (stdshapes.rs:198), 0..n-1 for the triangle lists
+                    const uint32_t pat = nv == 4 ? 0x032210u : 0x543210u;
+#pragma unroll
+                    for (uint32_t k = 0; k < 6; k++)
+                        if (k < ni) ist[k] = vq + ((pat >> (4 * k)) & 15u);
                 }
                 __syncwarp();
-                for (uint32_t k = lane; k < nbi; k += 32) iout[i0 + is0 + k] = s.sc.wistage[warp][k];
+                {
+                    uint32_t *idst = iout + i0 + is0;
+                    if ((reinterpret_cast<uintptr_t>(idst) & 7u) == 0) { // 8-byte copies
+                        const uint2 *src2 = reinterpret_cast<const uint2 *>(&s.sc.wistage[warp][0]);
+                        uint2 *dst2 = reinterpret_cast<uint2 *>(idst);
+                        for (uint32_t k = lane; k < (nbi >> 1); k += 32) dst2[k] = src2[k];
+                        if ((nbi & 1u) && lane == 0) idst[nbi - 1] = s.sc.wistage[warp][nbi - 1];
+                    } else {
+                        for (uint32_t k = lane; k < nbi; k += 32) idst[k] = s.sc.wistage[warp][k];
+                    }
+                }
                 for (uint32_t sb = 0; sb < nbv; sb += 32) {
                     const uint32_t sl = sb + lane;
                     const bool actv = sl < nbv;
+                    const uint32_t par = (v0 + vs0 + sb) & 1u; // odd vertex offset: stage 8 bytes later so 16-byte units line up
                     const int fl = actv ? (int)s.sc.wsf[warp][sl] : 0;
                     const uint32_t A = __shfl_sync(FULL, a, fl), KS = __shfl_sync(FULL, ks, fl), IC = __shfl_sync(FULL, ic, fl),
                                    TB = __shfl_sync(FULL, texbits, fl);
@@ -855,7 +861,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                         }
                         const float tu = (float)((e >> 3) & 1u), tv = (float)((e >> 4) & 1u);
                         const uint32_t index = (x + 32u * z + 1024u * y) | (((e >> 5) & 7u) << 17);
-                        uint2 *o = &s.sc.wvstage[warp][lane * 5];
+                        uint2 *o = &s.sc.wvstage[warp][par + lane * 5];
                         o[0] = make_uint2(position, color);
                         o[1] = make_uint2(__float_as_uint(tu), __float_as_uint(tv));
                         o[2] = make_uint2(TB, index);
@@ -863,16 +869,16 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                         o[4] = make_uint2(__float_as_uint(B2), __float_as_uint(B3));
                     }
                     __syncwarp();
-                    const uint32_t n2 = min(32u, nbv - sb) * 5u; // 8-byte words to copy
-                    uint2 *dst = reinterpret_cast<uint2 *>(vout + v0 + vs0 + sb);
-                    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) { // even vertex offset: 16-byte copies
-                        const uint4 *src4 = reinterpret_cast<const uint4 *>(&s.sc.wvstage[warp][0]);
-                        uint4 *dst4 = reinterpret_cast<uint4 *>(dst);
-                        for (uint32_t k = lane; k < (n2 >> 1); k += 32) dst4[k] = src4[k];
-                        if ((n2 & 1u) && lane == 0) dst[n2 - 1] = s.sc.wvstage[warp][n2 - 1];
-                    } else {
-                        for (uint32_t k = lane; k < n2; k += 32) dst[k] = s.sc.wvstage[warp][k];
+                    const uint32_t tot2 = par + min(32u, nbv - sb) * 5u; // 8-byte words staged, the first `par` of them unused
+                    uint2 *g2 = reinterpret_cast<uint2 *>(vout + v0 + vs0 + sb) - par; // 16-byte aligned
+                    const uint4 *src4 = reinterpret_cast<const uint4 *>(&s.sc.wvstage[warp][0]);
+                    uint4 *g4 = reinterpret_cast<uint4 *>(g2);
+                    for (uint32_t k = lane; k < (tot2 >> 1); k += 32) {
+                        const uint4 val = src4[k];
+                        if (k == 0 && par) g2[1] = make_uint2(val.z, val.w); // the first 8 bytes belong to the previous vertex
+                        else g4[k] = val;
                     }
+                    if ((tot2 & 1u) && lane == 0) g2[tot2 - 1] = s.sc.wvstage[warp][tot2 - 1];
                     __syncwarp();
                 }
             }
@@ -891,11 +897,8 @@ int mesh_kernel_max_ctas_per_sm() {
 }
 
 void launch_mesh_kernel(const MeshParams &p, int sm_count, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(mesh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-        attr_set = true;
-    }
+    // per device (a process may own contexts on several GPUs); cheap enough to repeat on every launch
+    cudaFuncSetAttribute(mesh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     int per_sm = mesh_kernel_max_ctas_per_sm();
     if (per_sm < 1) per_sm = 1;
     unsigned grid = (unsigned)(sm_count * per_sm);
