@@ -125,3 +125,37 @@ def test_fused_path_respects_a_registry_without_meshes(ctx):
     std = bxw.standard_registry()
     std.bind(ctx)
     ctx.set_gen_ids(*bxw.StdGenerator.resolve_ids(std))
+
+
+def test_far_coordinates_and_tiny_region(ctx, oracle):
+    """1x1x1 region far from the origin (large |x|, negative z): generator + mesher against the oracle."""
+    origin = (70000, 1, -65000)
+    ctx.region_create(*origin, 1, 1, 1)
+    av, ai = ctx.region_generate_and_mesh(0, 64)
+    g = oracle.StdGen(0)
+    d = [g.generate_chunk(origin[0] + dx, origin[1] + dy, origin[2] + dz) for dy in (-1, 0, 1) for dz in (-1, 0, 1) for dx in (-1, 0, 1)]
+    assert np.array_equal(ctx.region_download_chunk(0, 0, 0), d[13])
+    assert np.array_equal(ctx.region_download_chunk(-1, 1, 1), d[0 + 3 * 2 + 9 * 2])
+    wv, wi = oracle.mesh_from_dense27(oracle.OracleRegistry(), d)
+    s = ctx.region_mesh_spans()[0]
+    V, I = ctx.region_mesh_fetch(av, ai)
+    assert (int(s["v_count"]), int(s["i_count"])) == (len(wv), len(wi))
+    assert V[int(s["v_off"]): int(s["v_off"]) + len(wv)].tobytes() == wv.tobytes()
+    assert np.array_equal(I[int(s["i_off"]): int(s["i_off"]) + len(wi)], wi)
+    # per-chunk drop-in at the same place
+    assert np.array_equal(ctx.gen_chunk(0, *origin), d[13])
+    ctx.region_destroy()
+
+
+def test_fp32_variant_stays_close(ctx):
+    """precision=32 (north_star-literal FP32 noise): heights differ from f64 by at most one voxel on a tiny fraction of columns."""
+    ctx.region_create(0, 0, 0, 4, 1, 4)
+    ctx.region_generate(0, 64)
+    h64, e64 = ctx.region_heightmap()
+    ctx.region_generate(0, 32)
+    h32, e32 = ctx.region_heightmap()
+    diff = np.abs(h64.astype(np.int64) - h32)
+    assert diff.max() <= 1 and (diff != 0).mean() < 1e-3
+    assert (e64 != e32).mean() < 0.02
+    ctx.region_generate(0, 64)
+    ctx.region_destroy()
