@@ -88,6 +88,8 @@ def load_library():
         "bxw_region_heightmap": ([vp, vp, vp, vp], C.c_int),
         "bxw_region_upload_chunk": ([vp, C.c_int32, C.c_int32, C.c_int32, vp], C.c_int),
         "bxw_region_download_chunk": ([vp, C.c_int32, C.c_int32, C.c_int32, vp], C.c_int),
+        "bxw_region_export_rle": ([vp, vp, C.c_size_t, vp, C.c_size_t, vp], C.c_int),
+        "bxw_region_import_rle": ([vp, vp, C.c_size_t, vp, vp], C.c_int),
         "bxw_region_fill_synthetic": ([vp, C.c_uint64, C.c_uint32], C.c_int),
         "bxw_region_mesh_reserve": ([vp, C.c_uint64, C.c_uint64], C.c_int),
         "bxw_region_mesh": ([vp, u64p, u64p], C.c_int),
@@ -270,6 +272,24 @@ class Context:
         out = np.empty(32768, dtype=np.uint32)
         self._ck(self.L.bxw_region_download_chunk(self.h, lx, ly, lz, _ptr(out)))
         return out
+
+    def region_export_rle(self, lpos):
+        """lpos: (n, 3) local chunk coordinates -> (words, offsets[n+1]); the voxels never leave the device."""
+        lp = np.ascontiguousarray(lpos, dtype=np.int32).reshape(-1, 3)
+        n = lp.shape[0]
+        offs = np.empty(n + 1, dtype=np.uint64)
+        self._ck(self.L.bxw_region_export_rle(self.h, _ptr(lp), n, None, 0, _ptr(offs)))
+        words = np.empty(max(int(offs[n]), 1), dtype=np.uint32)
+        self._ck(self.L.bxw_region_export_rle(self.h, _ptr(lp), n, _ptr(words), words.size, _ptr(offs)))
+        return words[: int(offs[n])], offs
+
+    def region_import_rle(self, lpos, words, offsets):
+        lp = np.ascontiguousarray(lpos, dtype=np.int32).reshape(-1, 3)
+        w = _u32(words)
+        o = np.ascontiguousarray(offsets, dtype=np.uint64)
+        if o.size != lp.shape[0] + 1:
+            raise ValueError("offsets must have one more entry than lpos")
+        self._ck(self.L.bxw_region_import_rle(self.h, _ptr(lp), lp.shape[0], _ptr(w), _ptr(o)))
 
     def region_fill_synthetic(self, seed=1, void_threshold=128):
         self._ck(self.L.bxw_region_fill_synthetic(self.h, seed, void_threshold))

@@ -102,13 +102,13 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *w
 // lie in a later segment: the first head of every segment goes to shared memory and a suffix-minimum gives each thread
 // the first head after its segment, so no thread ever walks a long run voxel by voxel.
 template <bool WRITE>
-__global__ void __launch_bounds__(RT) rle_compress_kernel(const uint32_t *dense, size_t n_chunks, const uint64_t *offsets,
-                                                          uint32_t *out_words, uint32_t *out_len) {
+__global__ void __launch_bounds__(RT) rle_compress_kernel(const uint32_t *dense, const uint32_t *ids, size_t n_chunks,
+                                                          const uint64_t *offsets, uint32_t *out_words, uint32_t *out_len) {
     __shared__ uint32_t warp_tot[RT / 32];
     __shared__ uint32_t first_head[RT + 1];
     const size_t c = blockIdx.x;
     if (c >= n_chunks) return;
-    const uint32_t *d = dense + c * kChunkVoxels;
+    const uint32_t *d = dense + (ids ? (size_t)ids[c] : c) * kChunkVoxels;
     const int t = threadIdx.x;
     const int b = t * RSEG;
     // pass 1: heads of this segment as a 128-bit mask; words they contribute
@@ -408,14 +408,41 @@ void launch_dirty_list(uint8_t *dirty, uint32_t n, int nx, int nz, int SX, int S
     dirty_list_kernel<<<(n + 255) / 256, 256, 0, stream>>>(dirty, n, nx, nz, SX, SZ, work, work_span, count, clear);
 }
 
-void launch_rle_compress(const uint32_t *dense, size_t n_chunks, uint32_t *len, uint64_t *offsets, uint32_t *out_words, int phase,
-                         cudaStream_t stream) {
+void launch_rle_compress(const uint32_t *dense, const uint32_t *ids, size_t n_chunks, uint32_t *len, uint64_t *offsets,
+                         uint32_t *out_words, int phase, cudaStream_t stream) {
     if (phase == 0) {
-        rle_compress_kernel<false><<<(unsigned)n_chunks, RT, 0, stream>>>(dense, n_chunks, nullptr, nullptr, len);
+        rle_compress_kernel<false><<<(unsigned)n_chunks, RT, 0, stream>>>(dense, ids, n_chunks, nullptr, nullptr, len);
         offsets_scan_kernel<<<1, RT, 0, stream>>>(len, n_chunks, offsets);
     } else {
-        rle_compress_kernel<true><<<(unsigned)n_chunks, RT, 0, stream>>>(dense, n_chunks, offsets, out_words, nullptr);
+        rle_compress_kernel<true><<<(unsigned)n_chunks, RT, 0, stream>>>(dense, ids, n_chunks, offsets, out_words, nullptr);
     }
+}
+
+// Copy n decoded chunks into region storage at chunk indices ids[], refresh their x-face planes and mark every interior
+// chunk within one chunk of them dirty (their meshes read the new voxels).
+__global__ void chunk_scatter_kernel(const uint32_t *src, const uint32_t *ids, uint32_t *blocks, uint32_t *xface, int SX, int SY, int SZ,
+                                     uint8_t *dirty) {
+    const size_t k = blockIdx.x;
+    const size_t c = ids[k];
+    const uint4 *s = reinterpret_cast<const uint4 *>(src + k * kChunkVoxels);
+    uint4 *d = reinterpret_cast<uint4 *>(blocks + c * kChunkVoxels);
+    for (int i = threadIdx.x; i < kChunkVoxels / 4; i += blockDim.x) d[i] = s[i];
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
+        const int side = i >> 10, y = (i >> 5) & 31, z = i & 31;
+        xface[c * 2048 + i] = src[k * kChunkVoxels + (side ? 31 : 0) + 32 * z + 1024 * y];
+    }
+    if (dirty && threadIdx.x < 27) {
+        const int sx = (int)(c % SX), sz = (int)((c / SX) % SZ), sy = (int)(c / ((size_t)SX * SZ));
+        const int t = threadIdx.x;
+        const int cx = sx + t % 3 - 1, cz = sz + (t / 3) % 3 - 1, cy = sy + t / 9 - 1;
+        if (cx >= 1 && cx <= SX - 2 && cy >= 1 && cy <= SY - 2 && cz >= 1 && cz <= SZ - 2)
+            dirty[(cx - 1) + (SX - 2) * ((cz - 1) + (SZ - 2) * (cy - 1))] = 1;
+    }
+}
+
+void launch_chunk_scatter(const uint32_t *src, const uint32_t *ids, size_t n, uint32_t *blocks, uint32_t *xface, int SX, int SY, int SZ,
+                          uint8_t *dirty, cudaStream_t stream) {
+    if (n) chunk_scatter_kernel<<<(unsigned)n, 256, 0, stream>>>(src, ids, blocks, xface, SX, SY, SZ, dirty);
 }
 
 void launch_rle_decompress(const uint32_t *words, const uint64_t *offsets, size_t n_chunks, uint32_t *out_dense, uint32_t *status,

@@ -21,8 +21,11 @@ void launch_dirty_list(uint8_t *dirty, uint32_t n, int nx, int nz, int SX, int S
                        int clear, cudaStream_t stream);
 
 // phase 0: per-chunk word counts -> offsets (n+1); phase 1: write words at offsets
-void launch_rle_compress(const uint32_t *dense, size_t n_chunks, uint32_t *len, uint64_t *offsets, uint32_t *out_words, int phase,
-                         cudaStream_t stream);
+// ids (optional): chunk k is read from dense + ids[k]*32768 instead of dense + k*32768
+void launch_rle_compress(const uint32_t *dense, const uint32_t *ids, size_t n_chunks, uint32_t *len, uint64_t *offsets,
+                         uint32_t *out_words, int phase, cudaStream_t stream);
+void launch_chunk_scatter(const uint32_t *src, const uint32_t *ids, size_t n, uint32_t *blocks, uint32_t *xface, int SX, int SY, int SZ,
+                          uint8_t *dirty, cudaStream_t stream);
 void launch_rle_decompress(const uint32_t *words, const uint64_t *offsets, size_t n_chunks, uint32_t *out_dense, uint32_t *status,
                            cudaStream_t stream);
 

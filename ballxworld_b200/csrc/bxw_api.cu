@@ -314,6 +314,7 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
     p.work = work;
     p.work_span = work_span;
     p.n_work = n_work;
+    p.n_work_dev = nullptr;
     p.spans = r.spans;
     p.counters = r.counters;
     p.tables = ctx->d_tables;
@@ -330,6 +331,28 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
         for (int i = 0; i < 5; i++) p.gen_datum[i] = (uint32_t)ctx->gen_ids[i] << 16;
         auto is_cube = [&](uint16_t id) { return id < ctx->reg_n && ctx->reg_host[id].present && ctx->reg_host[id].mesh_kind != 0; };
         p.gen_all_cubes = is_cube(ctx->gen_ids[2]) && is_cube(ctx->gen_ids[3]);
+        if (!work) {
+            // whole interior: only chunks the surface passes through can have a mesh; list them on the device
+            CandidateParams c;
+            c.hmap = p.hmap;
+            c.hmap_W = p.hmap_W;
+            c.cy_min = p.cy_min;
+            c.SX = r.SX;
+            c.SY = r.SY;
+            c.SZ = r.SZ;
+            c.void_is_empty = !is_cube(ctx->gen_ids[0]);
+            c.gen_all_cubes = p.gen_all_cubes;
+            c.work = r.dirty_work;
+            c.work_span = r.dirty_span;
+            c.count = r.dirty_count;
+            c.spans = r.spans;
+            CK(cudaMemsetAsync(r.dirty_count, 0, sizeof(uint32_t), ctx->stream));
+            launch_hmap_candidates(c, ctx->stream);
+            ctx->launches += 1;
+            p.work = r.dirty_work;
+            p.work_span = r.dirty_span;
+            p.n_work_dev = r.dirty_count;
+        }
     }
     unsigned long long base_v = 0, base_i = 0;
     if (append) {
@@ -656,7 +679,7 @@ int bxw_rle_compress(bxw_ctx *ctx, const uint32_t *dense, size_t n_chunks, uint3
     uint64_t *d_offs = (uint64_t *)ctx->io_b;
     uint32_t *d_len = (uint32_t *)(d_offs + n_chunks + 1);
     CK(cudaMemcpyAsync(d_dense, dense, dense_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    launch_rle_compress(d_dense, n_chunks, d_len, d_offs, nullptr, 0, ctx->stream);
+    launch_rle_compress(d_dense, nullptr, n_chunks, d_len, d_offs, nullptr, 0, ctx->stream);
     CK(cudaMemcpyAsync(out_offsets, d_offs, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     const size_t nwords = out_offsets[n_chunks];
@@ -667,7 +690,7 @@ int bxw_rle_compress(bxw_ctx *ctx, const uint32_t *dense, size_t n_chunks, uint3
         CK(cudaMalloc(&ctx->io_c, nwords * sizeof(uint32_t)));
         ctx->io_c_cap = nwords * sizeof(uint32_t);
     }
-    launch_rle_compress(d_dense, n_chunks, d_len, d_offs, (uint32_t *)ctx->io_c, 1, ctx->stream);
+    launch_rle_compress(d_dense, nullptr, n_chunks, d_len, d_offs, (uint32_t *)ctx->io_c, 1, ctx->stream);
     ctx->launches += 3;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out_words, ctx->io_c, nwords * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -745,6 +768,84 @@ int bxw_region_download_chunk(bxw_ctx *ctx, int32_t lx, int32_t ly, int32_t lz, 
     Region &r = ctx->region;
     if (!local_ok(r, lx, ly, lz)) return fail(ctx, BXW_E_INVALID, "chunk (%d,%d,%d) outside region+shell", lx, ly, lz);
     CK(cudaMemcpyAsync(blocks_yzx, r.blocks + storage_index(r, lx, ly, lz) * kChunkVoxels, kChunkVoxels * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BXW_OK;
+}
+
+// local chunk coordinates -> storage chunk indices on the device (io_b tail); returns the device pointer
+static int upload_chunk_ids(bxw_ctx *ctx, const Region &r, const int32_t *lpos, size_t n, size_t b_prefix_bytes, uint32_t **d_ids) {
+    std::vector<uint32_t> ids(n);
+    for (size_t i = 0; i < n; i++) {
+        const int32_t lx = lpos[3 * i], ly = lpos[3 * i + 1], lz = lpos[3 * i + 2];
+        if (!local_ok(r, lx, ly, lz)) return fail(ctx, BXW_E_INVALID, "chunk (%d,%d,%d) outside region+shell", lx, ly, lz);
+        ids[i] = (uint32_t)storage_index(r, lx, ly, lz);
+    }
+    *d_ids = (uint32_t *)((char *)ctx->io_b + b_prefix_bytes);
+    CK(cudaMemcpyAsync(*d_ids, ids.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream)); // ids is a stack-owned staging vector
+    return BXW_OK;
+}
+
+static int ensure_io_c(bxw_ctx *ctx, size_t bytes) {
+    if (bytes > ctx->io_c_cap) {
+        cudaFree(ctx->io_c);
+        ctx->io_c = nullptr;
+        ctx->io_c_cap = 0;
+        CK(cudaMalloc(&ctx->io_c, bytes));
+        ctx->io_c_cap = bytes;
+    }
+    return BXW_OK;
+}
+
+int bxw_region_export_rle(bxw_ctx *ctx, const int32_t *lpos, size_t n_chunks, uint32_t *out_words, size_t cap_words,
+                          uint64_t *out_offsets) {
+    if (!ctx || !ctx->region.live || !lpos || !out_offsets || n_chunks == 0) return fail(ctx, BXW_E_INVALID, "no region / null argument");
+    Region &r = ctx->region;
+    const size_t meta_bytes = (n_chunks + 1) * sizeof(uint64_t) + n_chunks * sizeof(uint32_t);
+    int rc = ensure_io(ctx, 16, meta_bytes + n_chunks * sizeof(uint32_t));
+    if (rc) return rc;
+    uint64_t *d_offs = (uint64_t *)ctx->io_b;
+    uint32_t *d_len = (uint32_t *)(d_offs + n_chunks + 1);
+    uint32_t *d_ids = nullptr;
+    rc = upload_chunk_ids(ctx, r, lpos, n_chunks, meta_bytes, &d_ids);
+    if (rc) return rc;
+    launch_rle_compress(r.blocks, d_ids, n_chunks, d_len, d_offs, nullptr, 0, ctx->stream);
+    ctx->launches += 2;
+    CK(cudaMemcpyAsync(out_offsets, d_offs, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const size_t nwords = out_offsets[n_chunks];
+    if (!out_words) return BXW_OK; // size query
+    if (nwords > cap_words) return fail(ctx, BXW_E_NOSPACE, "RLE export needs %zu words, buffer holds %zu", nwords, cap_words);
+    rc = ensure_io_c(ctx, nwords * sizeof(uint32_t));
+    if (rc) return rc;
+    launch_rle_compress(r.blocks, d_ids, n_chunks, d_len, d_offs, (uint32_t *)ctx->io_c, 1, ctx->stream);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_words, ctx->io_c, nwords * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BXW_OK;
+}
+
+int bxw_region_import_rle(bxw_ctx *ctx, const int32_t *lpos, size_t n_chunks, const uint32_t *words, const uint64_t *offsets) {
+    if (!ctx || !ctx->region.live || !lpos || !words || !offsets || n_chunks == 0)
+        return fail(ctx, BXW_E_INVALID, "no region / null argument");
+    Region &r = ctx->region;
+    for (size_t i = 0; i < n_chunks; i++)
+        if (offsets[i + 1] < offsets[i]) return fail(ctx, BXW_E_INVALID, "offsets must be non-decreasing");
+    int rc = ensure_io_c(ctx, n_chunks * kChunkVoxels * sizeof(uint32_t));
+    if (rc) return rc;
+    // decode into scratch first: a stream that does not decode must leave the region untouched
+    rc = rle_decode_into(ctx, words, offsets, n_chunks, (uint32_t *)ctx->io_c);
+    if (rc) return rc;
+    const size_t meta_bytes = (n_chunks + 1) * sizeof(uint64_t) + n_chunks * sizeof(uint32_t);
+    rc = ensure_io(ctx, 16, meta_bytes + n_chunks * sizeof(uint32_t));
+    if (rc) return rc;
+    uint32_t *d_ids = nullptr;
+    rc = upload_chunk_ids(ctx, r, lpos, n_chunks, meta_bytes, &d_ids);
+    if (rc) return rc;
+    launch_chunk_scatter((const uint32_t *)ctx->io_c, d_ids, n_chunks, r.blocks, r.xface, r.SX, r.SY, r.SZ, r.dirty, ctx->stream);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
     return BXW_OK;
 }

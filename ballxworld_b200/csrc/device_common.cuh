@@ -36,7 +36,8 @@ struct MeshParams {
     int SX, SY, SZ;         // storage dims in chunks (shell included); chunk index sx + SX*(sz + SZ*sy)
     const uint32_t *work;   // [n_work] storage chunk index of each chunk to mesh
     const uint32_t *work_span; // [n_work] span slot of each work item
-    uint32_t n_work;
+    uint32_t n_work;           // upper bound of the list length (grid sizing)
+    const uint32_t *n_work_dev; // optional: the actual list length lives on the device (candidate list built by a kernel)
     bxw_mesh_span *spans;
     bxw_vertex *varena;
     uint32_t *iarena;
@@ -53,6 +54,18 @@ struct MeshParams {
 };
 
 void launch_mesh_kernel(const MeshParams &p, int sm_count, cudaStream_t stream);
+
+// Fused generate+mesh: list the interior chunks of pristine terrain that can have a mesh (the surface passes through
+// their 34^3 neighbourhood) and zero the spans of all others, from the height map alone.
+struct CandidateParams {
+    const int32_t *hmap;
+    int32_t hmap_W, cy_min;
+    int SX, SY, SZ;
+    int void_is_empty, gen_all_cubes;
+    uint32_t *work, *work_span, *count;
+    bxw_mesh_span *spans;
+};
+void launch_hmap_candidates(const CandidateParams &p, cudaStream_t stream);
 int mesh_kernel_max_ctas_per_sm();
 
 // generation -------------------------------------------------------------------------------------------------

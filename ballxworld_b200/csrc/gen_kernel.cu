@@ -42,8 +42,9 @@ __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a,
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
 
-// noise::SuperSimplex::get([x, y]) (f64)
-__device__ double super_simplex_2d(const uint8_t *__restrict__ perm, double px, double py) {
+// noise::SuperSimplex::get([x, y]) (f64). One copy per kernel (not inlined): the height map kernel calls it from 11 sites and
+// fully inlined it was 141 KB of SASS, more than half of its warp stalls were instruction-cache misses.
+__device__ __noinline__ double super_simplex_2d(const uint8_t *__restrict__ perm, double px, double py) {
     const double to_simplex_offset = dmul(dadd(px, py), kToSimplex);
     const double sx = dadd(px, to_simplex_offset), sy = dadd(py, to_simplex_offset);
     const double bxf = floor(sx), byf = floor(sy);
@@ -83,7 +84,7 @@ __device__ double super_simplex_2d(const uint8_t *__restrict__ perm, double px, 
 }
 
 // FP32 evaluation of the same noise (north_star-literal variant). Lattice decisions are taken in f32 too.
-__device__ float super_simplex_2d_f32(const uint8_t *__restrict__ perm, float px, float py) {
+__device__ __noinline__ float super_simplex_2d_f32(const uint8_t *__restrict__ perm, float px, float py) {
     const float to_simplex_offset = __fmul_rn(__fadd_rn(px, py), (float)kToSimplex);
     const float sx = __fadd_rn(px, to_simplex_offset), sy = __fadd_rn(py, to_simplex_offset);
     const float bxf = floorf(sx), byf = floorf(sy);
@@ -241,35 +242,37 @@ __global__ void __launch_bounds__(128) heightmap_kernel(GenParams p) {
             }
         }
     const double ec = elevation_noise<PREC>(T, x, z);
+    // stdgen.rs:222-243: <0.4 plains / <0.5 lerp plains-hills / <0.7 hills / <0.8 lerp hills-mountains / else mountains.
+    // Each biome height is evaluated at most once per column and at one call site.
+    const bool need_p = ec < 0.5, need_h = !(ec < 0.4) && ec < 0.8, need_m = !(ec < 0.7);
+    double ph = 0.0, hh = 0.0, mh = 0.0;
+    if (need_p) ph = plains_height<PREC>(T, x, z);
+    if (need_h) hh = hills_height<PREC>(T, x, z);
+    if (need_m) mh = mountains_height<PREC>(T, x, z);
     double height;
     if (ec < 0.4) {
-        height = plains_height<PREC>(T, x, z);
+        height = ph;
     } else if (ec < 0.5) {
         const double nlin = ddiv(dsub(ec, 0.4), 0.1);
         const double olin = dsub(1.0, nlin);
-        const double ph = plains_height<PREC>(T, x, z);
-        const double hh = hills_height<PREC>(T, x, z);
         height = dadd(dmul(olin, ph), dmul(nlin, hh));
     } else if (ec < 0.7) {
-        height = hills_height<PREC>(T, x, z);
+        height = hh;
     } else if (ec < 0.8) {
         const double nlin = ddiv(dsub(ec, 0.7), 0.1);
         const double olin = dsub(1.0, nlin);
-        const double hh = hills_height<PREC>(T, x, z);
-        const double mh = mountains_height<PREC>(T, x, z);
         height = dadd(dmul(olin, hh), dmul(nlin, mh));
     } else {
-        height = mountains_height<PREC>(T, x, z);
+        height = mh;
     }
-    int elevation;
+    int elevation; // stdgen.rs:245-267
     if (cec < 0.4) {
         elevation = 0;
-    } else if (cec < 0.5) {
-        elevation = noise_at<PREC>(T->perm[4], (double)x, (double)z) < 0.0 ? 0 : 1;
+    } else if (cec < 0.5 || (!(cec < 0.7) && cec < 0.8)) {
+        const int lo = cec < 0.5 ? 0 : 1;
+        elevation = noise_at<PREC>(T->perm[4], (double)x, (double)z) < 0.0 ? lo : lo + 1;
     } else if (cec < 0.7) {
         elevation = 1;
-    } else if (cec < 0.8) {
-        elevation = noise_at<PREC>(T->perm[4], (double)x, (double)z) < 0.0 ? 1 : 2;
     } else {
         elevation = 2;
     }

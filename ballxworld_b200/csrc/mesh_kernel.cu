@@ -205,11 +205,12 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
         s.gen_cls[tid] = (p.hmap && id < p.reg.n && p.reg.kind[id] == 2) ? 1u : 0u;
     }
     if (tid == 0) s.work_item[0] = (uint32_t)atomicAdd(&p.counters->work_next, 1ull);
+    const uint32_t n_work = p.n_work_dev ? __ldg(p.n_work_dev) : p.n_work;
 
     for (uint32_t iter = 0;; iter++) {
         __syncthreads();
         const uint32_t w = s.work_item[iter & 1];
-        if (w >= p.n_work) break;
+        if (w >= n_work) break;
         // fetch the next work item now; its latency hides behind this chunk
         if (tid == 0) s.work_item[(iter + 1) & 1] = (uint32_t)atomicAdd(&p.counters->work_next, 1ull);
         uint32_t c0, span_slot;
@@ -889,6 +890,46 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
 }
 
 } // namespace
+
+// One warp per interior (ix, iz) column of chunks: min / max surface height over the 34x34 columns under it, then the same
+// trivial test as the mesher's fused phase A for every chunk of the vertical stack.
+__global__ void __launch_bounds__(256) hmap_candidates_kernel(CandidateParams p) {
+    const int nx = p.SX - 2, ny = p.SY - 2, nz = p.SZ - 2;
+    const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (col >= nx * nz) return;
+    const int ix = col % nx, iz = col / nx;
+    int hmin = 0x7FFFFFFF, hmax = -0x7FFFFFFF;
+    for (int i = lane; i < 34 * 34; i += 32) {
+        const int zz = i / 34, xx = i - zz * 34;
+        const int v = __ldg(p.hmap + (size_t)((iz + 1) * 32 - 1 + zz) * p.hmap_W + (ix + 1) * 32 - 1 + xx) >> 2;
+        hmin = min(hmin, v);
+        hmax = max(hmax, v);
+    }
+    hmin = __reduce_min_sync(0xFFFFFFFFu, hmin);
+    hmax = __reduce_max_sync(0xFFFFFFFFu, hmax);
+    for (int iy = lane; iy < ny; iy += 32) {
+        const int y_lo = (p.cy_min + iy + 1) * 32 - 1;
+        const bool all_void = y_lo > hmax && p.void_is_empty;
+        const bool all_solid = (y_lo + 33 < hmin) && p.gen_all_cubes;
+        const uint32_t slot = (uint32_t)ix + (uint32_t)nx * ((uint32_t)iz + (uint32_t)nz * (uint32_t)iy);
+        if (all_void || all_solid) {
+            bxw_mesh_span sp;
+            sp.v_off = sp.i_off = 0;
+            sp.v_count = sp.i_count = 0;
+            p.spans[slot] = sp;
+        } else {
+            const uint32_t k = atomicAdd(p.count, 1u);
+            p.work[k] = (uint32_t)(ix + 1) + (uint32_t)p.SX * ((uint32_t)(iz + 1) + (uint32_t)p.SZ * (uint32_t)(iy + 1));
+            p.work_span[k] = slot;
+        }
+    }
+}
+
+void launch_hmap_candidates(const CandidateParams &p, cudaStream_t stream) {
+    const int cols = (p.SX - 2) * (p.SZ - 2);
+    hmap_candidates_kernel<<<(cols + 7) / 8, 256, 0, stream>>>(p);
+}
 
 int mesh_kernel_max_ctas_per_sm() {
     int n = 0;

@@ -62,6 +62,29 @@ class Region:
     def download_chunk(self, lx, ly, lz):
         return self.ctx.region_download_chunk(lx, ly, lz)
 
+    def get_data(self, lx, ly, lz):
+        """WorldBlocks::get_data (generation.rs:80-84): the chunk as a VChunk, compressed on the device."""
+        from .world import ChunkPosition, VChunk
+        words, _ = self.ctx.region_export_rle([(lx, ly, lz)])
+        o = self.ctx.region_origin
+        return VChunk(ChunkPosition(o[0] + lx, o[1] + ly, o[2] + lz), words.copy())
+
+    def serialize_data(self, lpos):
+        """WorldBlocks::serialize_data (generation.rs:158-166) for a batch: one little-endian save blob per chunk."""
+        words, offs = self.ctx.region_export_rle(lpos)
+        return [words[int(offs[i]):int(offs[i + 1])].astype("<u4").tobytes() for i in range(len(offs) - 1)]
+
+    def deserialize_data(self, lpos, blobs):
+        """WorldBlocks::deserialize_data (generation.rs:168-194) for a batch of save blobs; decoded on the device."""
+        for b in blobs:
+            if len(b) % 4:
+                raise ValueError("Invalid serialized data length")
+        arrs = [np.frombuffer(b, dtype="<u4").astype(np.uint32) for b in blobs]
+        offs = np.zeros(len(arrs) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum([a.size for a in arrs])
+        words = np.concatenate(arrs) if arrs else np.zeros(0, np.uint32)
+        self.ctx.region_import_rle(lpos, words, offs)
+
     def apply_voxel_changes(self, changes):
         """changes: iterable of (x, y, z, from, to) global block positions, applied in order (worldmgr.rs:312-357)."""
         ch = np.array([tuple(c) for c in changes], dtype=CHANGE_DTYPE) if not isinstance(changes, np.ndarray) else changes

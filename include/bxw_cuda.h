@@ -34,7 +34,7 @@ enum {
     BXW_E_CUDA = -2,       /* CUDA runtime error; see bxw_last_error */
     BXW_E_NOMEM = -3,      /* host or device allocation failed */
     BXW_E_UNKNOWN_ID = -4, /* a voxel's block id has no registry definition (reference panics: voxregistry.rs:141-143) */
-    BXW_E_NOSPACE = -5,    /* mesh arena too small and auto-grow disabled */
+    BXW_E_NOSPACE = -5,    /* caller buffer / mesh arena too small */
     BXW_E_BAD_RLE = -6,    /* RLE stream does not decode to 32768 voxels (lib.rs:296-302) */
     BXW_E_NO_REGISTRY = -7 /* registry / generator ids not set */
 };
@@ -128,6 +128,16 @@ int bxw_region_generate(bxw_ctx *ctx, uint64_t seed, int precision);
 int bxw_region_heightmap(bxw_ctx *ctx, int32_t *height, uint8_t *elevation, double *raw_height);
 int bxw_region_upload_chunk(bxw_ctx *ctx, int32_t lx, int32_t ly, int32_t lz, const uint32_t *blocks_yzx);
 int bxw_region_download_chunk(bxw_ctx *ctx, int32_t lx, int32_t ly, int32_t lz, uint32_t *blocks_yzx);
+/* WorldBlocks::get_data / serialize_data (bxw_world/src/generation.rs:80-84, 158-166) served from device storage:
+ * compress_rle (lib.rs:263-302) of the n_chunks region chunks lpos[3i..3i+2] = (lx,ly,lz) without moving their voxels to
+ * the host. out_offsets receives n_chunks+1 word offsets (the save blob of chunk i is words[offsets[i]..offsets[i+1]) as
+ * little-endian bytes). out_words == NULL is a size query; BXW_E_NOSPACE if cap_words < out_offsets[n_chunks]. */
+int bxw_region_export_rle(bxw_ctx *ctx, const int32_t *lpos, size_t n_chunks, uint32_t *out_words, size_t cap_words,
+                          uint64_t *out_offsets);
+/* WorldBlocks::deserialize_data (generation.rs:168-194): decode n_chunks RLE streams on the device into the region
+ * chunks lpos[], refresh derived planes and mark the chunks and their 26 neighbours dirty for bxw_region_remesh_dirty.
+ * A stream that does not decode returns BXW_E_BAD_RLE and leaves the region unchanged. */
+int bxw_region_import_rle(bxw_ctx *ctx, const int32_t *lpos, size_t n_chunks, const uint32_t *words, const uint64_t *offsets);
 /* Synthetic benchmark input (BASELINE.json configs[1], SURVEY.md section 8d cfg 2): every voxel (shell included) is a
  * pure hash of its global position: splitmix64(seed ^ key) -> void if low byte < void_threshold, else a random id in
  * 1..7 with a random shape (cube/slope/corner/inner corner) and one of the 24 orientations. */

@@ -264,3 +264,49 @@ def test_mesh_sphere_view_distance(ctx, oracle):
     assert n == want and want > 10
     assert ctx.region_mesh_sphere((1000, 0, 0), 3)[0] == 0
     ctx.region_destroy()
+
+
+def test_region_save_blobs_roundtrip(ctx, oracle):
+    """WorldBlocks::serialize_data / deserialize_data (generation.rs:158-194) served from device storage: export equals
+    the oracle's compress_rle of the same chunk, import decodes on the device, marks the 27-neighbourhood dirty and the
+    re-meshed result matches the oracle."""
+    import ballxworld_b200 as bxw
+
+    dims = (3, 2, 2)
+    origin = (9, 0, 0)
+    reg = bxw.Region(origin, dims, bxw.standard_registry(), ctx)
+    reg.generate(0)
+    reg.mesh()
+    chunks = _region_chunks(ctx, *dims)
+    lpos = [(-1, -1, -1), (0, 0, 0), (1, 1, 0), (2, 0, 1), (3, 2, 2), (1, 0, 1)]
+    words, offs = ctx.region_export_rle(lpos)
+    for i, k in enumerate(lpos):
+        assert np.array_equal(words[int(offs[i]):int(offs[i + 1])], oracle.compress_rle(chunks[k])), k
+    blobs = reg.serialize_data(lpos)
+    assert blobs[1] == oracle.compress_rle(chunks[(0, 0, 0)]).astype("<u4").tobytes()
+    vc = reg.get_data(1, 1, 0)
+    assert vc.position == bxw.ChunkPosition(10, 1, 0) and np.array_equal(vc.decompress(ctx).blocks_yzx, chunks[(1, 1, 0)])
+    # size query / capacity error
+    with pytest.raises(bxw.BxwError):
+        small = np.empty(2, np.uint32)
+        o = np.empty(len(lpos) + 1, np.uint64)
+        ctx._ck(ctx.L.bxw_region_export_rle(ctx.h, np.array(lpos, np.int32).ctypes.data, len(lpos), small.ctypes.data, 2, o.ctypes.data))
+
+    # import: swap two chunks' contents and load a hashed chunk into a third, all as save blobs
+    new = {(0, 0, 0): chunks[(2, 0, 1)], (2, 0, 1): chunks[(0, 0, 0)], (1, 0, 1): oracle.random_chunk(4, 5, 6)}
+    keys = list(new)
+    reg.deserialize_data(keys, [oracle.compress_rle(new[k]).astype("<u4").tobytes() for k in keys])
+    for k in keys:
+        chunks[k] = new[k]
+        assert np.array_equal(ctx.region_download_chunk(*k), new[k])
+    n = reg.remesh_dirty()
+    assert n == dims[0] * dims[1] * dims[2]      # every interior chunk is within one chunk of an imported one
+    _check_chunks_vs_oracle(ctx, oracle, chunks, dims, [(x, y, z) for x in range(3) for y in range(2) for z in range(2)])
+    # a stream that does not decode leaves the region untouched
+    with pytest.raises(bxw.BxwError):
+        ctx.region_import_rle([(0, 0, 0), (1, 0, 0)], np.array([1, 1, 32766, 0, 0, 5], np.uint32), np.array([0, 3, 6], np.uint64))
+    assert np.array_equal(ctx.region_download_chunk(0, 0, 0), new[(0, 0, 0)])
+    assert reg.remesh_dirty() == 0
+    with pytest.raises(ValueError):
+        reg.deserialize_data([(0, 0, 0)], [b"abc"])
+    ctx.region_destroy()
