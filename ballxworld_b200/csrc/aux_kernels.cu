@@ -9,7 +9,8 @@ namespace {
 // Halo planes. One x = const voxel plane over the whole storage extent in y and z (shell rows included so that
 // edges and corners travel too: AO samples diagonal neighbours, stdshapes.rs:131-152). Layout [gy][gz].
 // ------------------------------------------------------------------------------------------------------------
-__global__ void halo_plane_kernel(uint32_t *blocks, uint32_t *xface, int SX, int SY, int SZ, int sx, int lx, uint32_t *plane, int import) {
+__global__ void halo_plane_kernel(uint32_t *blocks, uint32_t *xface, unsigned long long *summary, int SX, int SY, int SZ, int sx, int lx,
+                                  uint32_t *plane, int import) {
     const int gz = blockIdx.x * blockDim.x + threadIdx.x;
     const int gy = blockIdx.y;
     if (gz >= SZ * 32) return;
@@ -19,6 +20,7 @@ __global__ void halo_plane_kernel(uint32_t *blocks, uint32_t *xface, int SX, int
     if (import) {
         *v = *p;
         xface[((size_t)(sx + SX * (sz + SZ * sy))) * 2048 + (lx ? 1024 : 0) + ly * 32 + lz] = *p; // lx is 0 or 31 here
+        if (summary && ly == 0 && lz == 0) summary[(size_t)(sx + SX * (sz + SZ * sy))] = 0; // no longer known uniform
     } else {
         *p = *v;
     }
@@ -38,12 +40,14 @@ __global__ void apply_changes_kernel(EditParams p) {
     const int gx = c0.x - p.x_min, gy = c0.y - p.y_min, gz = c0.z - p.z_min;
     const int sx = gx >> 5, sy = gy >> 5, sz = gz >> 5, lx = gx & 31, ly = gy & 31, lz = gz & 31;
     uint32_t *v = p.blocks + ((size_t)(sx + p.SX * (sz + p.SZ * sy))) * kChunkVoxels + lx + 32 * lz + 1024 * ly;
-    uint32_t cur = *v;
+    const uint32_t before = *v;
+    uint32_t cur = before;
     for (uint32_t k = b; k < e; k++) {
         const bxw_voxel_change c = p.changes[k];
         if (cur == c.from) cur = c.to;
     }
     *v = cur;
+    if (cur != before && p.summary) p.summary[(size_t)(sx + p.SX * (sz + p.SZ * sy))] = 0; // no longer known uniform
     if (lx == 0 || lx == 31) p.xface[((size_t)(sx + p.SX * (sz + p.SZ * sy))) * 2048 + (lx ? 1024 : 0) + ly * 32 + lz] = cur;
     auto mark = [&](int cx, int cy, int cz) { // interior chunks only carry meshes
         if (cx >= 1 && cx <= p.SX - 2 && cy >= 1 && cy <= p.SY - 2 && cz >= 1 && cz <= p.SZ - 2)
@@ -393,9 +397,10 @@ void launch_fill_synthetic(uint32_t *blocks, int SX, int SY, int SZ, int32_t cx_
     fill_synthetic_kernel<<<(unsigned)((size_t)SX * SY * SZ), 256, 0, stream>>>(blocks, SX, SY, SZ, cx_min, cy_min, cz_min, seed, void_threshold);
 }
 
-void launch_halo_plane(uint32_t *blocks, uint32_t *xface, int SX, int SY, int SZ, int sx, int lx, uint32_t *plane, int import, cudaStream_t stream) {
+void launch_halo_plane(uint32_t *blocks, uint32_t *xface, unsigned long long *summary, int SX, int SY, int SZ, int sx, int lx, uint32_t *plane,
+                       int import, cudaStream_t stream) {
     dim3 grid((SZ * 32 + 127) / 128, SY * 32);
-    halo_plane_kernel<<<grid, 128, 0, stream>>>(blocks, xface, SX, SY, SZ, sx, lx, plane, import);
+    halo_plane_kernel<<<grid, 128, 0, stream>>>(blocks, xface, summary, SX, SY, SZ, sx, lx, plane, import);
 }
 
 void launch_apply_changes(const EditParams &p, cudaStream_t stream) {
@@ -420,10 +425,11 @@ void launch_rle_compress(const uint32_t *dense, const uint32_t *ids, size_t n_ch
 
 // Copy n decoded chunks into region storage at chunk indices ids[], refresh their x-face planes and mark every interior
 // chunk within one chunk of them dirty (their meshes read the new voxels).
-__global__ void chunk_scatter_kernel(const uint32_t *src, const uint32_t *ids, uint32_t *blocks, uint32_t *xface, int SX, int SY, int SZ,
-                                     uint8_t *dirty) {
+__global__ void chunk_scatter_kernel(const uint32_t *src, const uint32_t *ids, uint32_t *blocks, uint32_t *xface,
+                                     unsigned long long *summary, int SX, int SY, int SZ, uint8_t *dirty) {
     const size_t k = blockIdx.x;
     const size_t c = ids[k];
+    if (summary && threadIdx.x == 0) summary[c] = 0; // no longer known uniform
     const uint4 *s = reinterpret_cast<const uint4 *>(src + k * kChunkVoxels);
     uint4 *d = reinterpret_cast<uint4 *>(blocks + c * kChunkVoxels);
     for (int i = threadIdx.x; i < kChunkVoxels / 4; i += blockDim.x) d[i] = s[i];
@@ -440,14 +446,132 @@ __global__ void chunk_scatter_kernel(const uint32_t *src, const uint32_t *ids, u
     }
 }
 
-void launch_chunk_scatter(const uint32_t *src, const uint32_t *ids, size_t n, uint32_t *blocks, uint32_t *xface, int SX, int SY, int SZ,
-                          uint8_t *dirty, cudaStream_t stream) {
-    if (n) chunk_scatter_kernel<<<(unsigned)n, 256, 0, stream>>>(src, ids, blocks, xface, SX, SY, SZ, dirty);
+void launch_chunk_scatter(const uint32_t *src, const uint32_t *ids, size_t n, uint32_t *blocks, uint32_t *xface,
+                          unsigned long long *summary, int SX, int SY, int SZ, uint8_t *dirty, cudaStream_t stream) {
+    if (n) chunk_scatter_kernel<<<(unsigned)n, 256, 0, stream>>>(src, ids, blocks, xface, summary, SX, SY, SZ, dirty);
 }
 
 void launch_rle_decompress(const uint32_t *words, const uint64_t *offsets, size_t n_chunks, uint32_t *out_dense, uint32_t *status,
                            cudaStream_t stream) {
     rle_decompress_kernel<<<(unsigned)n_chunks, RT, 0, stream>>>(words, offsets, n_chunks, out_dense, status);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Candidate list of a whole-interior mesh pass over storage (see StorageCandParams). Three small launches: keep flags +
+// per-block counts, a one-CTA scan of the counts, ordered compaction. Work index w enumerates the interior in the mesher's
+// tiled order (x-tiles of 8 columns; z-rows, columns, vertical stack fastest) so neighbouring chunks stay neighbours in time.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tiled_coords(uint32_t w, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t &ix, uint32_t &iy, uint32_t &iz) {
+    const uint32_t per_tile = 8u * ny * nz;
+    const uint32_t t = w / per_tile, rem = w - t * per_tile;
+    const uint32_t tw = min(8u, nx - 8u * t);
+    iz = rem / (tw * ny);
+    const uint32_t r2 = rem - iz * tw * ny;
+    ix = 8u * t + r2 / ny;
+    iy = r2 % ny;
+}
+
+__global__ void __launch_bounds__(256) cand_flags_kernel(StorageCandParams p, uint32_t n) {
+    const uint32_t w = blockIdx.x * 256u + threadIdx.x;
+    int keep = 0;
+    if (w < n) {
+        const uint32_t nx = (uint32_t)p.SX - 2u, ny = (uint32_t)p.SY - 2u, nz = (uint32_t)p.SZ - 2u;
+        uint32_t ix, iy, iz;
+        tiled_coords(w, nx, ny, nz, ix, iy, iz);
+        const size_t c0 = (ix + 1u) + (size_t)p.SX * ((iz + 1u) + (size_t)p.SZ * (iy + 1u));
+        const unsigned long long sc = p.summary[c0];
+        keep = 1;
+        if (sc & kUniformBit) {
+            const uint32_t d = (uint32_t)sc, id = d >> 16;
+            const uint32_t kind = id < p.reg.n ? p.reg.kind[id] : 0u; // 0 absent (the mesher reports it), 1 no mesh, 2 meshed
+            const uint32_t shape = d & 63u;
+            if (kind == 1u) {
+                keep = 0; // is_chunk_trivial (voxmesh.rs:16-25): nothing in this chunk emits a side
+            } else if (kind == 2u && (shape == 0u || shape > 3u)) {
+                // a chunk of cubes: empty mesh iff every neighbour is the same uniform datum (voxmesh.rs:119)
+                int same = 1;
+                for (int t = 0; t < 27; t++) {
+                    const int rx = t % 3 - 1, rz = (t / 3) % 3 - 1, ry = t / 9 - 1;
+                    const unsigned long long sn = p.summary[(size_t)((long long)c0 + rx + (long long)p.SX * (rz + (long long)p.SZ * ry))];
+                    same &= (sn == sc);
+                }
+                keep = !same;
+            }
+        }
+        p.keep[w] = (uint8_t)keep;
+    }
+    const int total = __syncthreads_count(keep);
+    if (threadIdx.x == 0) p.blk[blockIdx.x] = (uint32_t)total;
+}
+
+__global__ void __launch_bounds__(1024) cand_scan_kernel(uint32_t *blk, uint32_t n_blocks, uint32_t *count) {
+    // exclusive scan of the per-block counts in place (one CTA; n_blocks is n_work / 256)
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t carry, pass_total;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < n_blocks; base += 1024u) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n_blocks ? blk[i] : 0u;
+        uint32_t incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= (uint32_t)o) incl += t;
+        }
+        if (lane == 31u) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t wt = warp_tot[lane];
+            uint32_t wi = wt;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+                if (lane >= (uint32_t)o) wi += t;
+            }
+            warp_tot[lane] = wi - wt; // exclusive warp offsets
+            if (lane == 31u) pass_total = wi;
+        }
+        __syncthreads();
+        if (i < n_blocks) blk[i] = carry + warp_tot[warp] + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += pass_total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = carry;
+}
+
+__global__ void __launch_bounds__(256) cand_write_kernel(StorageCandParams p, uint32_t n) {
+    __shared__ uint32_t warp_tot[8];
+    const uint32_t w = blockIdx.x * 256u + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const int keep = w < n ? p.keep[w] : 0;
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    if (w >= n) return;
+    uint32_t off = p.blk[blockIdx.x] + __popc(bal & ((1u << lane) - 1u));
+    for (uint32_t k = 0; k < warp; k++) off += warp_tot[k];
+    const uint32_t nx = (uint32_t)p.SX - 2u, ny = (uint32_t)p.SY - 2u, nz = (uint32_t)p.SZ - 2u;
+    uint32_t ix, iy, iz;
+    tiled_coords(w, nx, ny, nz, ix, iy, iz);
+    const uint32_t slot = ix + nx * (iz + nz * iy);
+    if (keep) {
+        p.work[off] = (ix + 1u) + (uint32_t)p.SX * ((iz + 1u) + (uint32_t)p.SZ * (iy + 1u));
+        p.work_span[off] = slot;
+    } else {
+        bxw_mesh_span sp;
+        sp.v_off = sp.i_off = 0;
+        sp.v_count = sp.i_count = 0;
+        p.spans[slot] = sp;
+    }
+}
+
+void launch_storage_candidates(const StorageCandParams &p, cudaStream_t stream) {
+    const uint32_t n = (uint32_t)((p.SX - 2) * (p.SY - 2) * (p.SZ - 2));
+    const uint32_t nb = (n + 255u) / 256u;
+    cand_flags_kernel<<<nb, 256, 0, stream>>>(p, n);
+    cand_scan_kernel<<<1, 1024, 0, stream>>>(p.blk, nb, p.count);
+    cand_write_kernel<<<nb, 256, 0, stream>>>(p, n);
 }
 
 void launch_terragen_noise2(const TerragenTables *T, const double *xs, const double *ys, size_t n, double *out, cudaStream_t stream) {

@@ -4,11 +4,14 @@
 
 namespace bxw {
 
-void launch_halo_plane(uint32_t *blocks, uint32_t *xface, int SX, int SY, int SZ, int sx, int lx, uint32_t *plane, int import, cudaStream_t stream);
+// import also clears the summaries of the chunks it writes
+void launch_halo_plane(uint32_t *blocks, uint32_t *xface, unsigned long long *summary, int SX, int SY, int SZ, int sx, int lx, uint32_t *plane,
+                       int import, cudaStream_t stream);
 
 struct EditParams {
     uint32_t *blocks;
     uint32_t *xface;
+    unsigned long long *summary; // cleared for every chunk a change is applied to
     int SX, SY, SZ;
     int32_t x_min, y_min, z_min;     // world voxel coordinate of storage voxel (0,0,0)
     const bxw_voxel_change *changes; // grouped by voxel, original order within a group
@@ -24,8 +27,8 @@ void launch_dirty_list(uint8_t *dirty, uint32_t n, int nx, int nz, int SX, int S
 // ids (optional): chunk k is read from dense + ids[k]*32768 instead of dense + k*32768
 void launch_rle_compress(const uint32_t *dense, const uint32_t *ids, size_t n_chunks, uint32_t *len, uint64_t *offsets,
                          uint32_t *out_words, int phase, cudaStream_t stream);
-void launch_chunk_scatter(const uint32_t *src, const uint32_t *ids, size_t n, uint32_t *blocks, uint32_t *xface, int SX, int SY, int SZ,
-                          uint8_t *dirty, cudaStream_t stream);
+void launch_chunk_scatter(const uint32_t *src, const uint32_t *ids, size_t n, uint32_t *blocks, uint32_t *xface,
+                          unsigned long long *summary, int SX, int SY, int SZ, uint8_t *dirty, cudaStream_t stream);
 void launch_rle_decompress(const uint32_t *words, const uint64_t *offsets, size_t n_chunks, uint32_t *out_dense, uint32_t *status,
                            cudaStream_t stream);
 

@@ -41,6 +41,9 @@ struct Region {
     MeshCounters *h_counters = nullptr; // pinned
     uint8_t *dirty = nullptr;           // [n_work] interior dirty flags
     uint32_t *dirty_work = nullptr, *dirty_span = nullptr, *dirty_count = nullptr;
+    unsigned long long *summary = nullptr; // per storage chunk: kUniformBit | datum, or 0 (device_common.cuh)
+    uint8_t *cand_keep = nullptr;          // candidate-list scratch
+    uint32_t *cand_blk = nullptr;
     size_t n_storage() const { return (size_t)SX * SY * SZ; }
 };
 
@@ -173,6 +176,9 @@ void region_free(Region &r) {
     cudaFree(r.dirty_work);
     cudaFree(r.dirty_span);
     cudaFree(r.dirty_count);
+    cudaFree(r.summary);
+    cudaFree(r.cand_keep);
+    cudaFree(r.cand_blk);
     if (r.h_counters) cudaFreeHost(r.h_counters);
     r = Region();
 }
@@ -204,6 +210,10 @@ int region_alloc(bxw_ctx *ctx, Region &r, int32_t cx0, int32_t cy0, int32_t cz0,
     CK(cudaMalloc(&r.dirty_work, r.n_work * sizeof(uint32_t)));
     CK(cudaMalloc(&r.dirty_span, r.n_work * sizeof(uint32_t)));
     CK(cudaMalloc(&r.dirty_count, sizeof(uint32_t)));
+    CK(cudaMalloc(&r.summary, nst * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(r.summary, 0, nst * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMalloc(&r.cand_keep, r.n_work));
+    CK(cudaMalloc(&r.cand_blk, ((r.n_work + 255) / 256 + 1) * sizeof(uint32_t)));
     CK(cudaMemsetAsync(r.spans, 0, r.n_work * sizeof(bxw_mesh_span), ctx->stream));
     CK(cudaMemsetAsync(r.dirty, 0, r.n_work, ctx->stream));
     CK(cudaMemsetAsync(r.counters, 0, sizeof(MeshCounters), ctx->stream));
@@ -264,6 +274,7 @@ int region_generate(bxw_ctx *ctx, Region &r, uint64_t seed, int precision, bool 
     fp.W = W;
     fp.blocks = r.blocks;
     fp.xface = r.xface;
+    fp.summary = r.summary;
     fp.SX = r.SX;
     fp.SY = r.SY;
     fp.SZ = r.SZ;
@@ -353,6 +364,26 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
             p.work_span = r.dirty_span;
             p.n_work_dev = r.dirty_count;
         }
+    }
+    if (!from_hmap && !work) {
+        // whole interior from storage: drop the chunks whose summaries prove an empty mesh, keep the tiled order
+        StorageCandParams c;
+        c.summary = r.summary;
+        c.SX = r.SX;
+        c.SY = r.SY;
+        c.SZ = r.SZ;
+        c.reg = p.reg;
+        c.keep = r.cand_keep;
+        c.blk = r.cand_blk;
+        c.work = r.dirty_work;
+        c.work_span = r.dirty_span;
+        c.count = r.dirty_count;
+        c.spans = r.spans;
+        launch_storage_candidates(c, ctx->stream);
+        ctx->launches += 3;
+        p.work = r.dirty_work;
+        p.work_span = r.dirty_span;
+        p.n_work_dev = r.dirty_count;
     }
     unsigned long long base_v = 0, base_i = 0;
     if (append) {
@@ -602,6 +633,7 @@ int bxw_mesh_chunk27(bxw_ctx *ctx, const uint32_t *const dense[27], bxw_mesh_spa
     int rc = ensure_scratch(ctx);
     if (rc) return rc;
     Region &r = ctx->scratch;
+    CK(cudaMemsetAsync(r.summary, 0, r.n_storage() * sizeof(unsigned long long), ctx->stream));
     for (int i = 0; i < 27; i++) {
         if (!dense[i]) return fail(ctx, BXW_E_INVALID, "dense[%d] is null", i);
         // slot rx + 3 rz + 9 ry (voxmesh.rs:72) is exactly the 3x3x3 storage order sx + 3*(sz + 3*sy)
@@ -629,6 +661,7 @@ int bxw_mesh_chunk27_rle(bxw_ctx *ctx, const uint32_t *const rle[27], const size
     }
     std::vector<uint32_t> words(offs[27] ? offs[27] : 1);
     for (int i = 0; i < 27; i++) std::memcpy(words.data() + offs[i], rle[i], rle_len[i] * sizeof(uint32_t));
+    CK(cudaMemsetAsync(r.summary, 0, r.n_storage() * sizeof(unsigned long long), ctx->stream));
     rc = rle_decode_into(ctx, words.data(), offs.data(), 27, r.blocks);
     if (rc) return rc;
     launch_xface_extract(r.blocks, r.xface, nullptr, 0, 27, ctx->stream);
@@ -757,6 +790,7 @@ int bxw_region_upload_chunk(bxw_ctx *ctx, int32_t lx, int32_t ly, int32_t lz, co
     Region &r = ctx->region;
     if (!local_ok(r, lx, ly, lz)) return fail(ctx, BXW_E_INVALID, "chunk (%d,%d,%d) outside region+shell", lx, ly, lz);
     CK(cudaMemcpyAsync(r.blocks + storage_index(r, lx, ly, lz) * kChunkVoxels, blocks_yzx, kChunkVoxels * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(r.summary + storage_index(r, lx, ly, lz), 0, sizeof(unsigned long long), ctx->stream)); // no longer known uniform
     launch_xface_extract(r.blocks, r.xface, nullptr, (uint32_t)storage_index(r, lx, ly, lz), 1, ctx->stream);
     ctx->launches += 1;
     CK(cudaStreamSynchronize(ctx->stream));
@@ -843,7 +877,7 @@ int bxw_region_import_rle(bxw_ctx *ctx, const int32_t *lpos, size_t n_chunks, co
     uint32_t *d_ids = nullptr;
     rc = upload_chunk_ids(ctx, r, lpos, n_chunks, meta_bytes, &d_ids);
     if (rc) return rc;
-    launch_chunk_scatter((const uint32_t *)ctx->io_c, d_ids, n_chunks, r.blocks, r.xface, r.SX, r.SY, r.SZ, r.dirty, ctx->stream);
+    launch_chunk_scatter((const uint32_t *)ctx->io_c, d_ids, n_chunks, r.blocks, r.xface, r.summary, r.SX, r.SY, r.SZ, r.dirty, ctx->stream);
     ctx->launches += 1;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
@@ -979,6 +1013,7 @@ int bxw_region_apply_changes(bxw_ctx *ctx, const bxw_voxel_change *changes, uint
         EditParams ep;
         ep.blocks = r.blocks;
         ep.xface = r.xface;
+        ep.summary = r.summary;
         ep.SX = r.SX;
         ep.SY = r.SY;
         ep.SZ = r.SZ;
@@ -1026,7 +1061,7 @@ int bxw_region_halo_export(bxw_ctx *ctx, int face, void *dev_buf) {
     if (!ctx || !ctx->region.live || !dev_buf || (face != 0 && face != 1)) return fail(ctx, BXW_E_INVALID, "bad halo export");
     Region &r = ctx->region;
     // the interior's own boundary plane: x- face = storage chunk column 1, local x 0; x+ face = column nx, local x 31
-    launch_halo_plane(r.blocks, r.xface, r.SX, r.SY, r.SZ, face == 0 ? 1 : (int)r.nx, face == 0 ? 0 : 31, (uint32_t *)dev_buf, 0, ctx->stream);
+    launch_halo_plane(r.blocks, r.xface, nullptr, r.SX, r.SY, r.SZ, face == 0 ? 1 : (int)r.nx, face == 0 ? 0 : 31, (uint32_t *)dev_buf, 0, ctx->stream);
     ctx->launches += 1;
     CK(cudaGetLastError());
     return BXW_OK;
@@ -1036,7 +1071,7 @@ int bxw_region_halo_import(bxw_ctx *ctx, int face, const void *dev_buf) {
     if (!ctx || !ctx->region.live || !dev_buf || (face != 0 && face != 1)) return fail(ctx, BXW_E_INVALID, "bad halo import");
     Region &r = ctx->region;
     // into the shell: x- shell = column 0, local x 31; x+ shell = column nx+1, local x 0
-    launch_halo_plane(r.blocks, r.xface, r.SX, r.SY, r.SZ, face == 0 ? 0 : (int)r.nx + 1, face == 0 ? 31 : 0, (uint32_t *)dev_buf, 1, ctx->stream);
+    launch_halo_plane(r.blocks, r.xface, r.summary, r.SX, r.SY, r.SZ, face == 0 ? 0 : (int)r.nx + 1, face == 0 ? 31 : 0, (uint32_t *)dev_buf, 1, ctx->stream);
     ctx->launches += 1;
     CK(cudaGetLastError());
     return BXW_OK;
@@ -1083,6 +1118,7 @@ int bxw_terragen_noise2(bxw_ctx *ctx, uint64_t seed, const double *xs, const dou
 int bxw_region_fill_synthetic(bxw_ctx *ctx, uint64_t seed, uint32_t void_threshold) {
     if (!ctx || !ctx->region.live) return fail(ctx, BXW_E_INVALID, "no region");
     Region &r = ctx->region;
+    CK(cudaMemsetAsync(r.summary, 0, r.n_storage() * sizeof(unsigned long long), ctx->stream));
     launch_fill_synthetic(r.blocks, r.SX, r.SY, r.SZ, r.cx0 - 1, r.cy0 - 1, r.cz0 - 1, seed, void_threshold, ctx->stream);
     launch_xface_extract(r.blocks, r.xface, nullptr, 0, (uint32_t)r.n_storage(), ctx->stream);
     ctx->launches += 2;

@@ -66,6 +66,24 @@ struct CandidateParams {
     bxw_mesh_span *spans;
 };
 void launch_hmap_candidates(const CandidateParams &p, cudaStream_t stream);
+
+// Chunk summaries: the device-side analogue of a 3-word RLE chunk (lib.rs:263-302, voxmesh.rs:16-25). Every kernel that
+// writes voxels either proves the chunk uniform (the generator's fill) or clears the entry.
+constexpr unsigned long long kUniformBit = 1ull << 32;
+
+// Whole-interior meshing from storage: keep the chunks that can have a mesh, in the mesher's tiled processing order, and
+// zero the spans of the rest. A chunk is skipped when it is uniform and its block has no mesh (is_chunk_trivial), or when
+// it and its 26 neighbours are uniform with one cube datum (every side clipped by an identical neighbour).
+struct StorageCandParams {
+    const unsigned long long *summary;
+    int SX, SY, SZ;
+    DeviceRegistry reg;
+    uint8_t *keep;       // [n_work] scratch
+    uint32_t *blk;       // [ceil(n_work / 256) + 1] scratch: per-block keep counts -> exclusive offsets
+    uint32_t *work, *work_span, *count;
+    bxw_mesh_span *spans;
+};
+void launch_storage_candidates(const StorageCandParams &p, cudaStream_t stream);
 int mesh_kernel_max_ctas_per_sm();
 
 // generation -------------------------------------------------------------------------------------------------
@@ -98,6 +116,7 @@ struct FillParams {
     int32_t W;
     uint32_t *blocks;
     uint32_t *xface;
+    unsigned long long *summary; // per chunk: kUniformBit | datum when every voxel of the chunk holds that datum, else 0
     int SX, SY, SZ;
     int32_t cy_min;      // world chunk y of storage layer 0
     uint32_t id_void, id_grass, id_dirt, id_stone, id_snow; // already shifted datums (id << 16)

@@ -295,6 +295,29 @@ __global__ void __launch_bounds__(256) fill_kernel(FillParams p) {
     const int4 hm = __ldg(reinterpret_cast<const int4 *>(p.hmap + (size_t)(sz * 32 + zr) * p.W + sx * 32 + q * 4));
     const int hh[4] = {hm.x >> 2, hm.y >> 2, hm.z >> 2, hm.w >> 2};
     const int el[4] = {hm.x & 3, hm.y & 3, hm.z & 3, hm.w & 3};
+    if (p.summary) {
+        // chunk summaries of the stack: above every column -> all void; more than 5 below every column -> all stone
+        __shared__ int red[2][8];
+        int lo = min(min(hh[0], hh[1]), min(hh[2], hh[3])), hi = max(max(hh[0], hh[1]), max(hh[2], hh[3]));
+        lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+        hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+        if ((threadIdx.x & 31) == 0) {
+            red[0][threadIdx.x >> 5] = lo;
+            red[1][threadIdx.x >> 5] = hi;
+        }
+        __syncthreads();
+        for (int k = 0; k < 8; k++) {
+            lo = min(lo, red[0][k]);
+            hi = max(hi, red[1][k]);
+        }
+        for (int sy = threadIdx.x; sy < p.SY; sy += 256) {
+            const int ybase = (p.cy_min + sy) * 32;
+            unsigned long long sum = 0;
+            if (ybase > hi) sum = kUniformBit | p.id_void;
+            else if (ybase + 31 < lo - 5) sum = kUniformBit | p.id_stone;
+            p.summary[(size_t)(sx + p.SX * (sz + p.SZ * sy))] = sum;
+        }
+    }
     for (int sy = 0; sy < p.SY; sy++) {
         uint4 *dst = reinterpret_cast<uint4 *>(p.blocks + ((size_t)(sx + p.SX * (sz + p.SZ * sy))) * kChunkVoxels + zr * 32 + q * 4);
         const int ybase = (p.cy_min + sy) * 32;

@@ -310,3 +310,65 @@ def test_region_save_blobs_roundtrip(ctx, oracle):
     with pytest.raises(ValueError):
         reg.deserialize_data([(0, 0, 0)], [b"abc"])
     ctx.region_destroy()
+
+
+def _all_interior(dims):
+    return [(x, y, z) for x in range(dims[0]) for y in range(dims[1]) for z in range(dims[2])]
+
+
+def test_chunk_summaries_follow_every_writer(ctx, oracle):
+    """Whole-region meshing skips chunks whose summaries prove an empty mesh (uniform chunk without a mesh, or uniform
+    cubes surrounded by the same uniform cubes). Every kind of write into such a chunk must bring it back."""
+    import torch
+    import ballxworld_b200 as bxw
+
+    dims = (3, 5, 2)
+    origin = (9, -2, 0)
+    ctx.region_create(*origin, *dims)
+    ctx.region_generate(0, 64)
+    ctx.region_mesh()
+    chunks = _region_chunks(ctx, *dims)
+    sky = [k for k in _all_interior(dims) if not chunks[k].any()]
+    deep = [k for k in _all_interior(dims) if k[1] == 0]
+    assert sky and all(np.all(chunks[k] == chunks[deep[0]][0]) for k in deep)     # uniform void / uniform stone exist
+    _check_chunks_vs_oracle(ctx, oracle, chunks, dims, _all_interior(dims))
+    spans = ctx.region_mesh_spans()
+    assert all(int(spans[k[0] + dims[0] * (k[2] + dims[2] * k[1])]["v_count"]) == 0 for k in sky)
+    x0, y0, z0 = origin[0] * 32, origin[1] * 32, origin[2] * 32
+
+    def remesh_and_check():
+        ctx.region_mesh()
+        _check_chunks_vs_oracle(ctx, oracle, _region_chunks(ctx, *dims), dims, _all_interior(dims))
+        return ctx.region_mesh_spans()
+
+    # 1. edits strictly inside a sky chunk and inside a deep stone chunk
+    ks, kd = sky[0], (1, 0, 0)
+    stone = int(chunks[kd][0])
+    p_sky = (x0 + ks[0] * 32 + 7, y0 + ks[1] * 32 + 9, z0 + ks[2] * 32 + 11)
+    p_deep = (x0 + kd[0] * 32 + 16, y0 + kd[1] * 32 + 16, z0 + kd[2] * 32 + 16)
+    ctx.region_apply_changes(np.array([(*p_sky, 0, stone), (*p_deep, stone, 0)], dtype=bxw.CHANGE_DTYPE))
+    spans = remesh_and_check()
+    assert int(spans[ks[0] + dims[0] * (ks[2] + dims[2] * ks[1])]["v_count"]) == 24      # one free-standing cube
+    assert int(spans[kd[0] + dims[0] * (kd[2] + dims[2] * kd[1])]["v_count"]) == 24      # six walls of the hole
+    # 2. dense upload into another sky chunk
+    ku = sky[-1]
+    assert ku != ks
+    ctx.region_upload_chunk(*ku, oracle.random_chunk(3, 1, 4))
+    spans = remesh_and_check()
+    assert int(spans[ku[0] + dims[0] * (ku[2] + dims[2] * ku[1])]["v_count"]) > 0
+    # 3. save-blob import into a deep stone chunk
+    ki = (0, 0, 1)
+    ctx.region_import_rle([ki], oracle.compress_rle(oracle.random_chunk(8, 8, 8)), np.array([0, len(oracle.compress_rle(oracle.random_chunk(8, 8, 8)))], np.uint64))
+    spans = remesh_and_check()
+    assert int(spans[ki[0] + dims[0] * (ki[2] + dims[2] * ki[1])]["v_count"]) > 0
+    # 4. halo import: void replaces the x = 31 plane of the -x shell, so deep stone at ix = 0 grows -x faces
+    nb = ctx.region_halo_bytes()
+    ctx.region_halo_import(0, torch.zeros(nb // 4, dtype=torch.int32, device="cuda:0").data_ptr())
+    ctx.synchronize()
+    spans = remesh_and_check()
+    assert int(spans[0 + dims[0] * (0 + dims[2] * 0)]["v_count"]) >= 4 * 32 * 32
+    # 5. regenerating restores the summaries and the original meshes
+    ctx.region_generate(0, 64)
+    ctx.region_mesh()
+    _check_chunks_vs_oracle(ctx, oracle, chunks, dims, _all_interior(dims))
+    ctx.region_destroy()
