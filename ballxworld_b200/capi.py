@@ -107,6 +107,8 @@ def load_library():
         "bxw_timer_start": ([vp], C.c_int),
         "bxw_timer_stop_ms": ([vp, C.POINTER(C.c_float)], C.c_int),
         "bxw_mesh_kernel_time_ms": ([vp, C.POINTER(C.c_float), u64p, C.c_int], C.c_int),
+        "bxw_kernel_time_ms": ([vp, C.c_int, C.POINTER(C.c_float), u64p, C.c_int], C.c_int),
+        "bxw_region_mesh_candidates": ([vp, u32p, u32p], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(L, name)  # AttributeError = the library does not export what the header declares
@@ -372,3 +374,16 @@ class Context:
         ms, n = C.c_float(), C.c_uint64()
         self._ck(self.L.bxw_mesh_kernel_time_ms(self.h, C.byref(ms), C.byref(n), 1 if reset else 0))
         return ms.value, n.value
+
+    KERNEL_MESH, KERNEL_FILL, KERNEL_HEIGHTMAP = 0, 1, 2
+
+    def kernel_time_ms(self, which, reset=False):
+        ms, n = C.c_float(), C.c_uint64()
+        self._ck(self.L.bxw_kernel_time_ms(self.h, which, C.byref(ms), C.byref(n), 1 if reset else 0))
+        return ms.value, n.value
+
+    def region_mesh_candidates(self):
+        """(chunks meshed, interior chunks) of the last whole-region mesh pass"""
+        a, b = C.c_uint32(), C.c_uint32()
+        self._ck(self.L.bxw_region_mesh_candidates(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value

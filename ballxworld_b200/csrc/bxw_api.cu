@@ -73,8 +73,11 @@ struct bxw_ctx {
     Region scratch; // 3x3x3 storage behind the per-chunk drop-ins
     // timing
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_m0 = nullptr, ev_m1 = nullptr;
-    double mesh_ms = 0.0;
-    uint64_t mesh_launches = 0;
+    cudaEvent_t ev_g0 = nullptr, ev_g1 = nullptr, ev_g2 = nullptr; // before heightmap / before fill / after fill
+    bool gen_pending = false;                                     // ev_g* recorded, not yet read
+    double mesh_ms = 0.0, fill_ms = 0.0, hmap_ms = 0.0;
+    uint64_t mesh_launches = 0, fill_launches = 0, hmap_launches = 0;
+    uint32_t last_candidates = 0, last_candidates_of = 0;          // last whole-region mesh: chunks listed / interior chunks
     // staging for host<->device codecs
     void *io_a = nullptr, *io_b = nullptr, *io_c = nullptr;
     size_t io_a_cap = 0, io_b_cap = 0, io_c_cap = 0;
@@ -234,8 +237,27 @@ int region_alloc(bxw_ctx *ctx, Region &r, int32_t cx0, int32_t cy0, int32_t cz0,
     return BXW_OK;
 }
 
+// fold the event pair of the previous generation into the per-kernel totals (blocks until that generation finished)
+int flush_gen_timing(bxw_ctx *ctx) {
+    if (!ctx->gen_pending) return BXW_OK;
+    CK(cudaEventSynchronize(ctx->ev_g2));
+    float a = 0.f, b = 0.f;
+    CK(cudaEventElapsedTime(&a, ctx->ev_g0, ctx->ev_g1));
+    CK(cudaEventElapsedTime(&b, ctx->ev_g1, ctx->ev_g2));
+    ctx->hmap_ms += a;
+    ctx->fill_ms += b;
+    ctx->hmap_launches += 1;
+    ctx->fill_launches += 1;
+    ctx->gen_pending = false;
+    return BXW_OK;
+}
+
 int region_generate(bxw_ctx *ctx, Region &r, uint64_t seed, int precision, bool want_raw) {
     CK(cudaSetDevice(ctx->device));
+    {
+        int rc0 = flush_gen_timing(ctx);
+        if (rc0) return rc0;
+    }
     if (precision != 32 && precision != 64) return fail(ctx, BXW_E_INVALID, "precision must be 32 or 64");
     if (!ctx->have_gen_ids) return fail(ctx, BXW_E_NO_REGISTRY, "bxw_set_gen_ids not called");
     int rc = ensure_gen_tables(ctx, seed);
@@ -268,7 +290,9 @@ int region_generate(bxw_ctx *ctx, Region &r, uint64_t seed, int precision, bool 
     gp.tables = ctx->d_gen;
     gp.hmap = r.hmap;
     gp.raw = want_raw ? r.raw : nullptr;
+    CK(cudaEventRecord(ctx->ev_g0, ctx->stream));
     launch_heightmap_kernel(gp, precision, ctx->stream);
+    CK(cudaEventRecord(ctx->ev_g1, ctx->stream));
     FillParams fp;
     fp.hmap = r.hmap;
     fp.W = W;
@@ -285,6 +309,9 @@ int region_generate(bxw_ctx *ctx, Region &r, uint64_t seed, int precision, bool 
     fp.id_stone = (uint32_t)ctx->gen_ids[3] << 16;
     fp.id_snow = (uint32_t)ctx->gen_ids[4] << 16;
     launch_fill_kernel(fp, ctx->stream);
+    CK(cudaEventRecord(ctx->ev_g2, ctx->stream));
+    ctx->gen_pending = true;
+    launch_fill_xface_kernel(fp, ctx->stream);
     ctx->launches += 4;
     CK(cudaGetLastError());
     r.have_hmap = true;
@@ -428,6 +455,11 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
             if (rc) return rc;
             continue;
         }
+        if (p.n_work_dev) { // whole-region pass over a device-built candidate list: remember its length (statistics)
+            CK(cudaMemcpyAsync(&ctx->last_candidates, p.n_work_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            ctx->last_candidates_of = n_work;
+        }
         return BXW_OK;
     }
     return fail(ctx, BXW_E_NOSPACE, "mesh arena sizing did not converge");
@@ -514,7 +546,9 @@ int bxw_create(int device, bxw_ctx **out) {
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(BXW_E_CUDA);
     ctx->stream = ctx->own_stream;
     if (cudaEventCreate(&ctx->ev_a) != cudaSuccess || cudaEventCreate(&ctx->ev_b) != cudaSuccess ||
-        cudaEventCreate(&ctx->ev_m0) != cudaSuccess || cudaEventCreate(&ctx->ev_m1) != cudaSuccess)
+        cudaEventCreate(&ctx->ev_m0) != cudaSuccess || cudaEventCreate(&ctx->ev_m1) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev_g0) != cudaSuccess || cudaEventCreate(&ctx->ev_g1) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev_g2) != cudaSuccess)
         return bail(BXW_E_CUDA);
     MeshTables *t = new (std::nothrow) MeshTables();
     if (!t) return bail(BXW_E_NOMEM);
@@ -550,6 +584,9 @@ void bxw_destroy(bxw_ctx *ctx) {
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
     if (ctx->ev_m0) cudaEventDestroy(ctx->ev_m0);
     if (ctx->ev_m1) cudaEventDestroy(ctx->ev_m1);
+    if (ctx->ev_g0) cudaEventDestroy(ctx->ev_g0);
+    if (ctx->ev_g1) cudaEventDestroy(ctx->ev_g1);
+    if (ctx->ev_g2) cudaEventDestroy(ctx->ev_g2);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -1148,6 +1185,34 @@ int bxw_mesh_kernel_time_ms(bxw_ctx *ctx, float *ms, uint64_t *launches, int res
         ctx->mesh_ms = 0.0;
         ctx->mesh_launches = 0;
     }
+    return BXW_OK;
+}
+
+int bxw_kernel_time_ms(bxw_ctx *ctx, int which, float *ms, uint64_t *launches, int reset) {
+    if (!ctx) return BXW_E_INVALID;
+    int rc = flush_gen_timing(ctx);
+    if (rc) return rc;
+    double *acc;
+    uint64_t *cnt;
+    switch (which) {
+    case BXW_KERNEL_MESH: acc = &ctx->mesh_ms; cnt = &ctx->mesh_launches; break;
+    case BXW_KERNEL_FILL: acc = &ctx->fill_ms; cnt = &ctx->fill_launches; break;
+    case BXW_KERNEL_HEIGHTMAP: acc = &ctx->hmap_ms; cnt = &ctx->hmap_launches; break;
+    default: return fail(ctx, BXW_E_INVALID, "unknown kernel selector %d", which);
+    }
+    if (ms) *ms = (float)*acc;
+    if (launches) *launches = *cnt;
+    if (reset) {
+        *acc = 0.0;
+        *cnt = 0;
+    }
+    return BXW_OK;
+}
+
+int bxw_region_mesh_candidates(bxw_ctx *ctx, uint32_t *listed, uint32_t *interior) {
+    if (!ctx) return BXW_E_INVALID;
+    if (listed) *listed = ctx->last_candidates;
+    if (interior) *interior = ctx->last_candidates_of;
     return BXW_OK;
 }
 

@@ -122,5 +122,6 @@ struct FillParams {
     uint32_t id_void, id_grass, id_dirt, id_stone, id_snow; // already shifted datums (id << 16)
 };
 void launch_fill_kernel(const FillParams &p, cudaStream_t stream);
+void launch_fill_xface_kernel(const FillParams &p, cudaStream_t stream);
 
 } // namespace bxw

@@ -394,6 +394,10 @@ void launch_heightmap_kernel(const GenParams &p, int precision, cudaStream_t str
 void launch_fill_kernel(const FillParams &p, cudaStream_t stream) {
     dim3 grid(p.SX, p.SZ);
     fill_kernel<<<grid, 256, 0, stream>>>(p);
+}
+
+void launch_fill_xface_kernel(const FillParams &p, cudaStream_t stream) {
+    dim3 grid(p.SX, p.SZ);
     if (p.xface) fill_xface_kernel<<<grid, 64, 0, stream>>>(p);
 }
 

@@ -277,9 +277,24 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                 shapes = 0;
             } else {
                 mixed = 1;
-                // warp per z-row of columns, lane = x (lanes 0/1 also own the x = -1 / 32 halo columns); the column
-                // parameters stay in registers while the 34 layers are emitted
                 const uint32_t g0 = s.gen_cls[0], g1 = s.gen_cls[1], g2 = s.gen_cls[2], g3 = s.gen_cls[3], g4 = s.gen_cls[4];
+                // Layers above every column are all void, layers more than 5 below every column all stone: those are
+                // filled with one class word per 4 cells. Only the band in between looks at the columns.
+                const int yy_lo = max(0, min(34, (hmin - 5) - y_lo)); // first layer that can hold something else than stone
+                const int yy_hi = max(0, min(34, hmax - y_lo + 1));   // first layer that is void everywhere
+                for (int i = tid; i < 34 * 34; i += NT) {
+                    const int yy = i / 34, zz = i - yy * 34;
+                    if (yy >= yy_lo && yy < yy_hi) continue;
+                    const uint32_t c = yy < yy_lo ? g3 : g0;
+                    uint32_t *row = reinterpret_cast<uint32_t *>(&s.cls[yy * PLANE + zz * ROWB]);
+#pragma unroll
+                    for (int k = 0; k < ROWB / 4; k++) row[k] = c * 0x01010101u; // x = -1 .. 32 live at bytes XOFF-1 .. XOFF+32
+                    s.solid[yy * 34 + zz] = c ? 0xFFFFFFFFu : 0u;
+                    s.solid_halo[yy * 34 + zz] = c ? 3u : 0u;
+                    shapes |= (c > 24u);
+                }
+                // warp per z-row of columns, lane = x (lanes 0/1 also own the x = -1 / 32 halo columns); the column
+                // parameters stay in registers while the band's layers are emitted
                 auto cls_of = [&](int hv, int y) {
                     const int h = hv >> 2, el = hv & 3;
                     return (y == h) ? ((el == 2 && y > 80) ? g4 : g1) : (y < h - 5 ? g3 : (y < h ? g2 : g0));
@@ -288,7 +303,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                     const int hv = s.gen.hm[zz * 36 + lane + 1];
                     const int hh = s.gen.hm[zz * 36 + (lane & 1 ? 33 : 0)]; // used by lanes 0 and 1
 #pragma unroll 2
-                    for (int yy = 0; yy < 34; yy++) {
+                    for (int yy = yy_lo; yy < yy_hi; yy++) {
                         const int y = y_lo + yy;
                         const uint32_t c = cls_of(hv, y);
                         const uint32_t rowmask = __ballot_sync(FULL, c != 0u);

@@ -213,7 +213,8 @@ def main():
     tot_i = int(spans["i_count"].astype(np.uint64).sum())
 
     # ---------------- device-resident timing ----------------
-    ctx.mesh_kernel_time_ms(reset=True)
+    for k in (ctx.KERNEL_MESH, ctx.KERNEL_FILL, ctx.KERNEL_HEIGHTMAP):
+        ctx.kernel_time_ms(k, reset=True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -227,7 +228,10 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = ctx.kernel_launches() - l0
-    mesh_ms, mesh_launches = ctx.mesh_kernel_time_ms()
+    mesh_ms, mesh_launches = ctx.kernel_time_ms(ctx.KERNEL_MESH)
+    fill_ms, fill_launches = ctx.kernel_time_ms(ctx.KERNEL_FILL)
+    hmap_ms, hmap_launches = ctx.kernel_time_ms(ctx.KERNEL_HEIGHTMAP)
+    meshed_chunks, _ = ctx.region_mesh_candidates()
     # ---------------- the library's fused generate+mesh (meshes pristine terrain from the column parameters) ----------------
     fused_ms = None
     if world == 1:
@@ -278,17 +282,39 @@ def main():
         ms_per_step = ms / args.steps
         value = world * n_chunks / (ms_per_step / 1000.0)
         peak, peak_src = peaks()
-        # mesher roofline: algorithmic bytes = 131072 per chunk + 40 V + 4 I, this rank's launch
-        alg_bytes = n_chunks * 131072 + tot_v * 40 + tot_i * 4
-        mesh_ms_per_launch = mesh_ms / max(mesh_launches, 1)
-        achieved = alg_bytes / (mesh_ms_per_launch / 1000.0) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "mesh_traffic.json")
+        # Rooflines (DESIGN.md "Measurement"), this rank's launches, CUDA events inside the library.
+        #  mesh: algorithmic bytes = 131072 per interior chunk + 40 V + 4 I. Chunks proven empty from their summaries are
+        #        not read at all, so the figure can exceed the peak; `read_frac` is the same over the chunks actually read.
+        #  fill: algorithmic bytes = 131072 per chunk written (the region plus its 1-chunk shell).
+        traffic = {}
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                traffic = json.load(open(tp))
             except Exception:
-                traffic = None
+                traffic = {}
+
+        def roof(kernel, alg_bytes, ms_total, launches_, extra=None):
+            per = ms_total / max(launches_, 1)
+            ach = alg_bytes / (per / 1000.0) / 1e9 if per > 0 else 0.0
+            d = {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                 "traffic": (traffic.get(kernel) or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": per, "share_of_step": per / ms_per_step}
+            d.update(extra or {})
+            return d
+
+        sx, sy, sz = slab
+        storage_chunks = (sx + 2) * (sy + 2) * (sz + 2)
+        alg_mesh = n_chunks * 131072 + tot_v * 40 + tot_i * 4
+        read_bytes = meshed_chunks * 131072 + tot_v * 40 + tot_i * 4
+        mesh_per = mesh_ms / max(mesh_launches, 1)
+        roof_mesh = roof("mesh_kernel", alg_mesh, mesh_ms, mesh_launches,
+                         {"chunks_meshed": meshed_chunks, "chunks_skipped_by_summary": n_chunks - meshed_chunks,
+                          "read_frac": (read_bytes / (mesh_per / 1000.0) / 1e9 / peak) if mesh_per > 0 else None})
+        roof_fill = roof("fill_kernel", storage_chunks * 131072, fill_ms, fill_launches, {"chunks_written": storage_chunks})
+        dominant = roof_fill if roof_fill["ms_per_launch"] >= roof_mesh["ms_per_launch"] else roof_mesh
+        heightmap = {"kernel": "heightmap_kernel", "bound": "fp64 issue", "ms_per_launch": hmap_ms / max(hmap_launches, 1),
+                     "columns": (sx + 2) * 32 * (sz + 2) * 32}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -297,10 +323,7 @@ def main():
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_all,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "mesh_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": mesh_ms_per_launch,
-                         "mesh_share_of_step": mesh_ms_per_launch / ms_per_step},
+            "roofline": dominant, "roofline_mesh": roof_mesh, "roofline_fill": roof_fill, "heightmap": heightmap,
             "fused_generate_and_mesh": None if fused_ms is None else {"ms_per_step": fused_ms, "value": n_chunks / (fused_ms / 1000.0), "unit": UNIT,
                                                                       "note": "bxw_region_generate_and_mesh: blocks written once, meshed from the height map (what e2e calls)"},
             "mesh": {"vertices": tot_v_all, "indices": tot_i_all, "arena_vertices": av, "arena_indices": ai},
