@@ -74,7 +74,7 @@ struct bxw_ctx {
     // timing
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_m0 = nullptr, ev_m1 = nullptr;
     cudaEvent_t ev_g0 = nullptr, ev_g1 = nullptr, ev_g2 = nullptr; // before heightmap / before fill / after fill
-    bool gen_pending = false;                                     // ev_g* recorded, not yet read
+    bool gen_pending = false, gen_pending_fused = false;          // ev_g* recorded, not yet read
     double mesh_ms = 0.0, fill_ms = 0.0, hmap_ms = 0.0;
     uint64_t mesh_launches = 0, fill_launches = 0, hmap_launches = 0;
     uint32_t last_candidates = 0, last_candidates_of = 0;          // last whole-region mesh: chunks listed / interior chunks
@@ -244,10 +244,12 @@ int flush_gen_timing(bxw_ctx *ctx) {
     float a = 0.f, b = 0.f;
     CK(cudaEventElapsedTime(&a, ctx->ev_g0, ctx->ev_g1));
     CK(cudaEventElapsedTime(&b, ctx->ev_g1, ctx->ev_g2));
-    ctx->hmap_ms += a;
     ctx->fill_ms += b;
-    ctx->hmap_launches += 1;
     ctx->fill_launches += 1;
+    if (!ctx->gen_pending_fused) { // otherwise the column parameters were computed inside the fill kernel
+        ctx->hmap_ms += a;
+        ctx->hmap_launches += 1;
+    }
     ctx->gen_pending = false;
     return BXW_OK;
 }
@@ -290,8 +292,11 @@ int region_generate(bxw_ctx *ctx, Region &r, uint64_t seed, int precision, bool 
     gp.tables = ctx->d_gen;
     gp.hmap = r.hmap;
     gp.raw = want_raw ? r.raw : nullptr;
+    // want_raw (bxw_region_heightmap's f64 output) keeps the stand-alone height map kernel; otherwise the fill kernel
+    // computes the column parameters itself
+    const bool fused_gen = !want_raw;
     CK(cudaEventRecord(ctx->ev_g0, ctx->stream));
-    launch_heightmap_kernel(gp, precision, ctx->stream);
+    if (!fused_gen) launch_heightmap_kernel(gp, precision, ctx->stream);
     CK(cudaEventRecord(ctx->ev_g1, ctx->stream));
     FillParams fp;
     fp.hmap = r.hmap;
@@ -308,11 +313,13 @@ int region_generate(bxw_ctx *ctx, Region &r, uint64_t seed, int precision, bool 
     fp.id_dirt = (uint32_t)ctx->gen_ids[2] << 16;
     fp.id_stone = (uint32_t)ctx->gen_ids[3] << 16;
     fp.id_snow = (uint32_t)ctx->gen_ids[4] << 16;
-    launch_fill_kernel(fp, ctx->stream);
+    if (fused_gen) launch_gen_fill_kernel(fp, gp, precision, ctx->stream);
+    else launch_fill_kernel(fp, ctx->stream);
     CK(cudaEventRecord(ctx->ev_g2, ctx->stream));
     ctx->gen_pending = true;
+    ctx->gen_pending_fused = fused_gen;
     launch_fill_xface_kernel(fp, ctx->stream);
-    ctx->launches += 4;
+    ctx->launches += fused_gen ? 3 : 4;
     CK(cudaGetLastError());
     r.have_hmap = true;
     return BXW_OK;

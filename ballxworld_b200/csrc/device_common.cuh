@@ -123,5 +123,7 @@ struct FillParams {
 };
 void launch_fill_kernel(const FillParams &p, cudaStream_t stream);
 void launch_fill_xface_kernel(const FillParams &p, cudaStream_t stream);
+// height map + block selection in one kernel (g.hmap is written, g.raw is ignored)
+void launch_gen_fill_kernel(const FillParams &p, const GenParams &g, int precision, cudaStream_t stream);
 
 } // namespace bxw

@@ -213,12 +213,9 @@ __global__ void cellpoints_kernel(uint64_t seed, int32_t cell_x0, int32_t cell_z
     }
 }
 
-// CellGen::calc_voxel_params (stdgen.rs:215-276): one thread per column
+// CellGen::calc_voxel_params (stdgen.rs:215-276) of column (ix, iz) of the height map: returns height*4 + elevation class
 template <int PREC>
-__global__ void __launch_bounds__(128) heightmap_kernel(GenParams p) {
-    const int ix = blockIdx.x * blockDim.x + threadIdx.x;
-    const int iz = blockIdx.y;
-    if (ix >= p.W) return;
+__device__ __forceinline__ int32_t column_params(const GenParams &p, int ix, int iz, double *raw_out) {
     const int32_t x = p.x0 + ix, z = p.z0 + iz;
     const GenTables *T = p.tables;
 
@@ -283,16 +280,41 @@ __global__ void __launch_bounds__(128) heightmap_kernel(GenParams p) {
     else if (r >= 536870911.0) h = 536870911; // packed into 30 bits below; the terrain never approaches this
     else if (r <= -536870912.0) h = -536870912;
     else h = (int32_t)r;
-    p.hmap[(size_t)iz * p.W + ix] = h * 4 + elevation;
-    if (p.raw) p.raw[(size_t)iz * p.W + ix] = height;
+    if (raw_out) *raw_out = height;
+    return h * 4 + elevation;
 }
+
+// one thread per column
+template <int PREC>
+__global__ void __launch_bounds__(128) heightmap_kernel(GenParams p) {
+    const int ix = blockIdx.x * blockDim.x + threadIdx.x;
+    const int iz = blockIdx.y;
+    if (ix >= p.W) return;
+    double raw;
+    p.hmap[(size_t)iz * p.W + ix] = column_params<PREC>(p, ix, iz, &raw);
+    if (p.raw) p.raw[(size_t)iz * p.W + ix] = raw;
+}
+
 
 // StdGenerator::generate_chunk block selection (stdgen.rs:349-373) for a vertical stack of chunks.
 // CTA = one (sx,sz) chunk column; thread = 4 consecutive x of one z row; loops over all layers.
-__global__ void __launch_bounds__(256) fill_kernel(FillParams p) {
+// GEN = 0: column parameters come from the height map. GEN = 32 / 64: the CTA first computes the parameters of its 32x32
+// columns itself (4 per thread, FP32 / f64 noise) and stores them to the height map, then writes the stack: CTAs in their
+// FP64 phase share an SM with CTAs in their store phase, which hides the height map behind the HBM writes.
+template <int GEN>
+__global__ void __launch_bounds__(256, 4) fill_kernel(FillParams p, GenParams g) {
     const int sx = blockIdx.x, sz = blockIdx.y;
     const int q = threadIdx.x & 7, zr = threadIdx.x >> 3;
-    const int4 hm = __ldg(reinterpret_cast<const int4 *>(p.hmap + (size_t)(sz * 32 + zr) * p.W + sx * 32 + q * 4));
+    int4 hm;
+    if (GEN == 0) {
+        hm = __ldg(reinterpret_cast<const int4 *>(p.hmap + (size_t)(sz * 32 + zr) * p.W + sx * 32 + q * 4));
+    } else {
+        int hv[4];
+#pragma unroll 1
+        for (int k = 0; k < 4; k++) hv[k] = column_params<(GEN == 0 ? 64 : GEN)>(g, sx * 32 + q * 4 + k, sz * 32 + zr, nullptr);
+        hm = make_int4(hv[0], hv[1], hv[2], hv[3]);
+        *reinterpret_cast<int4 *>(g.hmap + (size_t)(sz * 32 + zr) * p.W + sx * 32 + q * 4) = hm;
+    }
     const int hh[4] = {hm.x >> 2, hm.y >> 2, hm.z >> 2, hm.w >> 2};
     const int el[4] = {hm.x & 3, hm.y & 3, hm.z & 3, hm.w & 3};
     if (p.summary) {
@@ -393,7 +415,14 @@ void launch_heightmap_kernel(const GenParams &p, int precision, cudaStream_t str
 
 void launch_fill_kernel(const FillParams &p, cudaStream_t stream) {
     dim3 grid(p.SX, p.SZ);
-    fill_kernel<<<grid, 256, 0, stream>>>(p);
+    fill_kernel<0><<<grid, 256, 0, stream>>>(p, GenParams{});
+}
+
+void launch_gen_fill_kernel(const FillParams &p, const GenParams &g, int precision, cudaStream_t stream) {
+    ensure_constants();
+    dim3 grid(p.SX, p.SZ);
+    if (precision == 32) fill_kernel<32><<<grid, 256, 0, stream>>>(p, g);
+    else fill_kernel<64><<<grid, 256, 0, stream>>>(p, g);
 }
 
 void launch_fill_xface_kernel(const FillParams &p, cudaStream_t stream) {
