@@ -167,6 +167,12 @@ class Context:
 
     # ---- context ----
     def set_stream(self, cuda_stream_ptr):
+        """Launch on an externally owned cudaStream_t; None = back to the context's own stream. The legacy default
+        stream (handle 0, e.g. torch.cuda.current_stream() before any torch.cuda.set_stream) cannot be expressed through
+        the ABI's NULL-means-own convention: create a torch.cuda.Stream(), make it current and pass its handle, so that
+        torch / NCCL work and the library's kernels are ordered on one stream."""
+        if cuda_stream_ptr is not None and int(cuda_stream_ptr) == 0:
+            raise ValueError("stream handle 0 (legacy default stream): pass a torch.cuda.Stream().cuda_stream, or None")
         self._ck(self.L.bxw_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
 
     def synchronize(self):

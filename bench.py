@@ -174,7 +174,9 @@ def main():
     slab = tuple(int(x) for x in args.slab.split(",")) if args.slab else SLAB
     nx, ny, nz = slab
     ctx = bxw.Context(local)
-    stream = torch.cuda.current_stream()
+    # one explicit stream for everything: the library's kernels, torch's events and NCCL's ordering all hang off it
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     reg = bxw.standard_registry()
     region = bxw.Region((rank * nx, 0, 0), (nx, ny, nz), reg, ctx=ctx)

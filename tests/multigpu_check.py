@@ -26,7 +26,9 @@ def main():
     ny, nz, per = 2, 2, 3
     slab = slab_partition(per * world, world, rank)
     ctx = bxw.Context(local)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)  # NCCL orders its sends / receives against the current stream
+    ctx.set_stream(stream.cuda_stream)
     reg = bxw.standard_registry()
     reg.bind(ctx)
     ctx.region_create(slab.x0, 0, 0, slab.nx, ny, nz)
@@ -58,6 +60,39 @@ def main():
                 gi = I[int(s["i_off"]): int(s["i_off"]) + int(s["i_count"])]
                 if gv.tobytes() != wv.tobytes() or not np.array_equal(gi, wi):
                     bad += 1
+                    print(f"rank {rank}: hashed-block chunk {(ix, iy, iz)} differs: {len(gv)} vs {len(wv)} vertices", flush=True)
+    ctx.region_destroy()
+
+    # Generated terrain with chunk summaries in play: deep uniform stone and sky are skipped without being read, so the
+    # shell the neighbour rank fills in through the halo import must invalidate what the generator recorded there.
+    ny2, oy = 4, -2
+    ctx.set_gen_ids(*bxw.StdGenerator.resolve_ids(reg))
+    ctx.region_create(9 + slab.x0, oy, 0, slab.nx, ny2, nz)
+    ctx.region_generate(0, 64)
+    for ly in range(-1, ny2 + 1):
+        for lz in range(-1, nz + 1):
+            if slab.has_lo:
+                ctx.region_upload_chunk(-1, ly, lz, zero)
+            if slab.has_hi:
+                ctx.region_upload_chunk(slab.nx, ly, lz, zero)
+    exchange_halos(slab, dist, bufs2 := {k: torch.empty(ctx.region_halo_bytes() // 4, dtype=torch.int32, device="cuda")
+                                         for k in ("send_lo", "send_hi", "recv_lo", "recv_hi")},
+                   lambda f, t: ctx.region_halo_export(f, t.data_ptr()), lambda f, t: ctx.region_halo_import(f, t.data_ptr()))
+    av, ai = ctx.region_mesh()
+    spans = ctx.region_mesh_spans()
+    V, I = ctx.region_mesh_fetch(av, ai)
+    g = O.StdGen(0)
+    for ix in sorted({0, slab.nx - 1}):
+        for iy in range(ny2):
+            for iz in range(nz):
+                d = [g.generate_chunk(9 + slab.x0 + ix + dx, oy + iy + dy, iz + dz) for dy in (-1, 0, 1) for dz in (-1, 0, 1) for dx in (-1, 0, 1)]
+                wv, wi = O.mesh_from_dense27(oreg, d)
+                s = spans[ix + slab.nx * (iz + nz * iy)]
+                gv = V[int(s["v_off"]): int(s["v_off"]) + int(s["v_count"])]
+                gi = I[int(s["i_off"]): int(s["i_off"]) + int(s["i_count"])]
+                if gv.tobytes() != wv.tobytes() or not np.array_equal(gi, wi):
+                    bad += 1
+                    print(f"rank {rank}: terrain chunk {(ix, iy, iz)} differs: {len(gv)} vs {len(wv)} vertices", flush=True)
     t = torch.tensor([bad], device="cuda")
     dist.all_reduce(t)
     if rank == 0:
