@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "csrc", "libbxw_cuda.so")
+_LIB_PATH = os.environ.get("BXW_CUDA_LIB") or os.path.join(_HERE, "csrc", "libbxw_cuda.so")  # override: profiling builds
 
 VERTEX_DTYPE = np.dtype(
     [
@@ -109,6 +109,7 @@ def load_library():
         "bxw_mesh_kernel_time_ms": ([vp, C.POINTER(C.c_float), u64p, C.c_int], C.c_int),
         "bxw_kernel_time_ms": ([vp, C.c_int, C.POINTER(C.c_float), u64p, C.c_int], C.c_int),
         "bxw_region_mesh_candidates": ([vp, u32p, u32p], C.c_int),
+        "bxw_debug_phase_cycles": ([vp, u64p], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(L, name)  # AttributeError = the library does not export what the header declares
@@ -387,6 +388,11 @@ class Context:
         ms, n = C.c_float(), C.c_uint64()
         self._ck(self.L.bxw_kernel_time_ms(self.h, which, C.byref(ms), C.byref(n), 1 if reset else 0))
         return ms.value, n.value
+
+    def debug_phase_cycles(self):
+        out = (C.c_uint64 * 12)()
+        self._ck(self.L.bxw_debug_phase_cycles(self.h, out))
+        return list(out)
 
     def region_mesh_candidates(self):
         """(chunks meshed, interior chunks) of the last whole-region mesh pass"""

@@ -432,6 +432,7 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
         init.i_alloc = base_i;
         init.flags = 0;
         init.work_next = 0;
+        for (int k = 0; k < 12; k++) init.phase[k] = 0;
         *r.h_counters = init;
         CK(cudaMemcpyAsync(r.counters, r.h_counters, sizeof(MeshCounters), cudaMemcpyHostToDevice, ctx->stream));
         const bool count_only = (r.varena == nullptr);
@@ -1213,6 +1214,12 @@ int bxw_kernel_time_ms(bxw_ctx *ctx, int which, float *ms, uint64_t *launches, i
         *acc = 0.0;
         *cnt = 0;
     }
+    return BXW_OK;
+}
+
+int bxw_debug_phase_cycles(bxw_ctx *ctx, uint64_t out[12]) {
+    if (!ctx || !ctx->region.live || !out) return BXW_E_INVALID;
+    for (int k = 0; k < 12; k++) out[k] = ctx->region.h_counters->phase[k];
     return BXW_OK;
 }
 

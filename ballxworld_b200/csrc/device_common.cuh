@@ -28,6 +28,9 @@ struct MeshCounters {
     unsigned long long i_alloc; // next free index slot
     unsigned long long flags;
     unsigned long long work_next; // dynamic work-list cursor
+    // -DBXW_PHASE_TIMING builds only: SM cycles of CTA thread 0 summed over chunks: [0] work fetch + neighbour table,
+    // [1] phase A, [2] phases B + scan + allocation, [3] phase C, [4] chunks that reached phase C, [5] chunks
+    unsigned long long phase[12]; // [6] tile setup, [7] C1, [8] warp 0's batches, [9] tile-end barrier wait
 };
 
 struct MeshParams {

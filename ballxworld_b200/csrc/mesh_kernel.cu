@@ -77,6 +77,7 @@ struct Smem {
     float reg_texf[REGC * 6];
     uint32_t col_lut[REGC * 8]; // as_rgba8(debug_color * ao_k) per cached block id and occluder count k
     uint32_t aolut[8 * 27];     // AO sample mask per (vertex corner, AO normal code)
+    uint16_t vdesc_cube[25 * 36]; // vertex descriptors of classes 0..24 (void + the 24 cube orientations): most faces anywhere
     uint8_t reg_kind[256];
     uint32_t nbr[27 + 5];
     uint32_t warp_tot[3][NW];
@@ -176,6 +177,14 @@ __device__ __forceinline__ void row_visibility(const Smem &s, int y, int z, unsi
     out[5] = C & ~solid_word(s, r + 1) & M;
 }
 
+#ifdef BXW_PHASE_TIMING
+#define PHASE_MARK(var) const long long var = clock64()
+#define PHASE_ADD(slot, a, b) do { if (tid == 0) atomicAdd(&p.counters->phase[slot], (unsigned long long)((b) - (a))); } while (0)
+#else
+#define PHASE_MARK(var)
+#define PHASE_ADD(slot, a, b)
+#endif
+
 __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem &s = *reinterpret_cast<Smem *>(smem_raw);
@@ -189,6 +198,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
     for (int i = tid; i < REGC * 3; i += NT) s.reg_color[i] = (uint32_t)(i / 3) < p.reg.n ? p.reg.color[i] : 0.0f;
     for (int i = tid; i < REGC * 6; i += NT) s.reg_texf[i] = (uint32_t)(i / 6) < p.reg.n ? p.reg.texf[i] : 0.0f;
     for (int i = tid; i < 8 * 27; i += NT) s.aolut[i] = T->aolut[i];
+    for (int i = tid; i < 25 * 36; i += NT) s.vdesc_cube[i] = (&T->vdesc[0][0][0])[i];
     for (int i = tid; i < REGC * 8; i += NT) {
         const uint32_t id = (uint32_t)i >> 3;
         uint32_t col = 0;
@@ -211,6 +221,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
         __syncthreads();
         const uint32_t w = s.work_item[iter & 1];
         if (w >= n_work) break;
+        PHASE_MARK(t_fetch);
         // fetch the next work item now; its latency hides behind this chunk
         if (tid == 0) s.work_item[(iter + 1) & 1] = (uint32_t)atomicAdd(&p.counters->work_next, 1ull);
         uint32_t c0, span_slot;
@@ -238,6 +249,9 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
         }
         __syncthreads();
 
+        PHASE_MARK(t_a0);
+        PHASE_ADD(0, t_fetch, t_a0);
+        PHASE_ADD(5, 0, 1);
         // ---------------- phase A: stage 34^3 class bytes + per-row solid words ----------------
         uint32_t err = 0;
         uint32_t shapes = 0;  // saw a non-cube shape (class > 24)
@@ -565,6 +579,8 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
             if (lane == 0) s.wflags[warp] = wf;
         }
         __syncthreads();
+        PHASE_MARK(t_a1);
+        PHASE_ADD(1, t_a0, t_a1);
         int has_shapes = 0, any_mixed = 0;
 #pragma unroll
         for (int k = 0; k < NW; k++) {
@@ -678,7 +694,10 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
             }
         }
         __syncthreads();
+        PHASE_MARK(t_b1);
+        PHASE_ADD(2, t_a1, t_b1);
         if (!s.emit) continue;
+        PHASE_ADD(4, 0, 1);
 
         // ---------------- phase C: emit, tile by tile ----------------
         const uint32_t *center = p.blocks + (size_t)c0 * kChunkVoxels;
@@ -686,6 +705,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
         uint32_t *const iout = p.iarena + s.ibase;
         const bool quads_only = !has_shapes; // every side has 4 vertices / 6 indices
         for (uint32_t r0 = 0; r0 < 1024;) {
+            PHASE_MARK(t_t0);
             // largest r1 with faces(r0..r1) <= FC and vertices(r0..r1) <= VC (a single row never exceeds 192 / 768)
             uint32_t lo = r0 + 1, hi = 1024;
             const uint32_t f0 = s.sc.rowF[r0], v0 = s.sc.rowV[r0], i0 = s.sc.rowI[r0];
@@ -700,8 +720,11 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                 r0 = r1;
                 continue;
             }
+            PHASE_MARK(t_t1);
+            PHASE_ADD(6, t_t0, t_t1);
             // ---- C1: face records in emission order ----
             if (quads_only) {
+                // thread per row (a surface chunk has a few hundred rows with ~3 faces each: a warp per row would idle 29 lanes)
                 for (uint32_t row = r0 + tid; row < r1; row += NT) {
                     uint32_t f = s.sc.rowF[row] - f0;
                     if (s.sc.rowF[row + 1] - s.sc.rowF[row] == 0) continue;
@@ -758,12 +781,15 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                 }
             }
             __syncthreads();
+            PHASE_MARK(t_t2);
+            PHASE_ADD(7, t_t1, t_t2);
             // ---- C2+C3, fused per warp: a warp takes 32 consecutive faces of the tile, computes their per-face data in
             //      registers (AO occluder counts, barycentric colour offset, texture id), stages their index values and
             //      their vertices (32 at a time, face data fetched from the owning lane by shuffle) in its private
             //      shared-memory slice and writes both out with coalesced stores. No block barrier inside a tile. ----
             const uint32_t n_batches = (tileF + 31u) >> 5;
             for (uint32_t bt = warp; bt < n_batches; bt += NW) {
+                PHASE_MARK(t_b_0);
                 const uint32_t f = bt * 32u + lane;
                 const bool act = f < tileF;
                 uint32_t a = 0, ic = 0, ks = 0, texbits = 0, nv = 0, ni = 0, vs = 0, is = 0;
@@ -805,9 +831,13 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                     texbits = __float_as_uint(texid);
                     // per vertex: number of occluding AO samples (voxmesh.rs:128-137; every meshed shape occludes) and the
                     // in-order barycentric colour sum (voxmesh.rs:124,153,172-174)
+                    const bool cube = cx <= 24u;
                     const uint16_t *vd = &T->vdesc[cx][d][0];
-                    for (uint32_t j = 0; j < nv; j++) {
-                        const uint32_t desc = __ldg(vd + j);
+                    const uint16_t *vds = &s.vdesc_cube[(cube ? cx : 0u) * 36u + d * 6u];
+#pragma unroll
+                    for (uint32_t j = 0; j < 6; j++) {
+                        if (j >= nv) break;
+                        const uint32_t desc = cube ? (uint32_t)vds[j] : (uint32_t)__ldg(vd + j);
                         const uint32_t k = __popc(nb & s.aolut[(desc & 7u) * 27u + (desc >> 8)]);
                         ks |= k << (3 * j);
                         const float sg = (float)((int)((signs >> (2 * j)) & 3u) - 1);
@@ -818,6 +848,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                         b3 = __fadd_rn(b3, __fmul_rn(sg, 1.0f));
                     }
                 }
+                PHASE_MARK(t_b_c2);
                 // vertex / index ranges of the batch (tile-relative)
                 const int last = (int)min(31u, tileF - 1u - bt * 32u);
                 const uint32_t vs0 = __shfl_sync(FULL, vs, 0), is0 = __shfl_sync(FULL, is, 0);
@@ -845,6 +876,9 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                         for (uint32_t k = lane; k < nbi; k += 32) idst[k] = s.sc.wistage[warp][k];
                     }
                 }
+                PHASE_MARK(t_b_ix);
+                PHASE_ADD(10, t_b_0, t_b_c2);
+                PHASE_ADD(11, t_b_c2, t_b_ix);
                 for (uint32_t sb = 0; sb < nbv; sb += 32) {
                     const uint32_t sl = sb + lane;
                     const bool actv = sl < nbv;
@@ -859,7 +893,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                         const uint32_t y = row >> 5, z = row & 31u;
                         const uint32_t j = vs0 + sl - (A >> 18);
                         const uint32_t id = IC & 0xFFFFu, cx = IC >> 16;
-                        const uint32_t e = __ldg(&T->vdesc[cx][d][j]);
+                        const uint32_t e = cx <= 24u ? (uint32_t)s.vdesc_cube[cx * 36u + d * 6u + j] : (uint32_t)__ldg(&T->vdesc[cx][d][j]);
                         // as_wxyz10 of (ipos + voffset + 0.5)/32 (voxmesh.rs:36-41,139-145,165): every vertex sits on a
                         // voxel corner, so each 10-bit field is 16 * corner coordinate; w = (1/32*2) as u32 = 0.
                         const uint32_t px = x + (e & 1u), py = y + ((e >> 1) & 1u), pz = z + ((e >> 2) & 1u);
@@ -898,9 +932,15 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                     __syncwarp();
                 }
             }
+            PHASE_MARK(t_t3);
+            PHASE_ADD(8, t_t2, t_t3);
             __syncthreads(); // the face records are rewritten by the next tile
+            PHASE_MARK(t_t4);
+            PHASE_ADD(9, t_t3, t_t4);
             r0 = r1;
         }
+        PHASE_MARK(t_c1);
+        PHASE_ADD(3, t_b1, t_c1);
     }
 }
 
