@@ -70,6 +70,7 @@ def load_library():
         "bxw_destroy": ([vp], None),
         "bxw_last_error": ([vp], C.c_char_p),
         "bxw_set_stream": ([vp, vp], C.c_int),
+        "bxw_set_option": ([vp, C.c_int, C.c_int], C.c_int),
         "bxw_synchronize": ([vp], C.c_int),
         "bxw_kernel_launches": ([vp], C.c_uint64),
         "bxw_set_registry": ([vp, C.POINTER(BlockDef), C.c_uint32], C.c_int),
@@ -175,6 +176,11 @@ class Context:
         if cuda_stream_ptr is not None and int(cuda_stream_ptr) == 0:
             raise ValueError("stream handle 0 (legacy default stream): pass a torch.cuda.Stream().cuda_stream, or None")
         self._ck(self.L.bxw_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    OPT_CHUNK_SUMMARIES = 0
+
+    def set_option(self, option, value):
+        self._ck(self.L.bxw_set_option(self.h, option, int(value)))
 
     def synchronize(self):
         self._ck(self.L.bxw_synchronize(self.h))

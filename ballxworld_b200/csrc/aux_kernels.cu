@@ -20,7 +20,11 @@ __global__ void halo_plane_kernel(uint32_t *blocks, uint32_t *xface, unsigned lo
     if (import) {
         *v = *p;
         xface[((size_t)(sx + SX * (sz + SZ * sy))) * 2048 + (lx ? 1024 : 0) + ly * 32 + lz] = *p; // lx is 0 or 31 here
-        if (summary && ly == 0 && lz == 0) summary[(size_t)(sx + SX * (sz + SZ * sy))] = 0; // no longer known uniform
+        if (summary) { // the chunk stays known-uniform only if every imported voxel equals its uniform datum
+            const size_t c = (size_t)(sx + SX * (sz + SZ * sy));
+            const unsigned long long sm = summary[c];
+            if ((sm & kUniformBit) && (uint32_t)sm != *p) summary[c] = 0;
+        }
     } else {
         *p = *v;
     }

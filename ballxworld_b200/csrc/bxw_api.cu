@@ -77,6 +77,7 @@ struct bxw_ctx {
     bool gen_pending = false, gen_pending_fused = false;          // ev_g* recorded, not yet read
     double mesh_ms = 0.0, fill_ms = 0.0, hmap_ms = 0.0;
     uint64_t mesh_launches = 0, fill_launches = 0, hmap_launches = 0;
+    bool use_summaries = true;                                     // BXW_OPT_CHUNK_SUMMARIES
     uint32_t last_candidates = 0, last_candidates_of = 0;          // last whole-region mesh: chunks listed / interior chunks
     // staging for host<->device codecs
     void *io_a = nullptr, *io_b = nullptr, *io_c = nullptr;
@@ -399,7 +400,7 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
             p.n_work_dev = r.dirty_count;
         }
     }
-    if (!from_hmap && !work) {
+    if (!from_hmap && !work && ctx->use_summaries) {
         // whole interior from storage: drop the chunks whose summaries prove an empty mesh, keep the tiled order
         StorageCandParams c;
         c.summary = r.summary;
@@ -466,6 +467,9 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
         if (p.n_work_dev) { // whole-region pass over a device-built candidate list: remember its length (statistics)
             CK(cudaMemcpyAsync(&ctx->last_candidates, p.n_work_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
+            ctx->last_candidates_of = n_work;
+        } else if (!work) { // whole region without a candidate list: everything was read
+            ctx->last_candidates = n_work;
             ctx->last_candidates_of = n_work;
         }
         return BXW_OK;
@@ -606,6 +610,15 @@ int bxw_set_stream(bxw_ctx *ctx, void *cuda_stream) {
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
     return BXW_OK;
+}
+
+int bxw_set_option(bxw_ctx *ctx, int option, int value) {
+    if (!ctx) return BXW_E_INVALID;
+    if (option == BXW_OPT_CHUNK_SUMMARIES) {
+        ctx->use_summaries = value != 0;
+        return BXW_OK;
+    }
+    return fail(ctx, BXW_E_INVALID, "unknown option %d", option);
 }
 
 int bxw_synchronize(bxw_ctx *ctx) {

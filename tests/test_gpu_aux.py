@@ -334,6 +334,13 @@ def test_chunk_summaries_follow_every_writer(ctx, oracle):
     _check_chunks_vs_oracle(ctx, oracle, chunks, dims, _all_interior(dims))
     spans = ctx.region_mesh_spans()
     assert all(int(spans[k[0] + dims[0] * (k[2] + dims[2] * k[1])]["v_count"]) == 0 for k in sky)
+    listed, interior = ctx.region_mesh_candidates()
+    assert interior == len(_all_interior(dims)) and 0 < listed <= interior - len(sky)
+    ctx.set_option(ctx.OPT_CHUNK_SUMMARIES, 0)            # every chunk read: same meshes
+    ctx.region_mesh()
+    assert ctx.region_mesh_candidates() == (interior, interior)
+    _check_chunks_vs_oracle(ctx, oracle, chunks, dims, _all_interior(dims))
+    ctx.set_option(ctx.OPT_CHUNK_SUMMARIES, 1)
     x0, y0, z0 = origin[0] * 32, origin[1] * 32, origin[2] * 32
 
     def remesh_and_check():
