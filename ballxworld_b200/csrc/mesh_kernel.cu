@@ -52,10 +52,8 @@ struct Scratch { // phases B, S, C
     uint32_t frecB[FC];   // tile-relative first index (tiles with non-quad sides)
     uint32_t frecC[FC];   // block id | class<<16 (tiles with non-quad sides)
     uint32_t frecE[FC];   // occupancy of the cell's 3x3x3 neighbourhood, bit (dy+1)*9 + (dz+1)*3 + (dx+1) (ditto)
-    // per-warp staging of one batch of 32 faces
-    uint8_t wsf[NW][192];        // vertex slot of the batch -> lane owning the face
-    alignas(8) uint32_t wistage[NW][192];   // index values of the batch
-    alignas(16) uint2 wvstage[NW][32 * 5 + 2]; // 32 vertices x 40 B (+1 slot so the copy-out can be 16-byte aligned)
+    // per-warp transpose buffer: 16 quads (or up to 64 vertices of mixed sides), then the batch's indices
+    alignas(16) uint4 wstage[NW][160];
 };
 
 struct Smem {
@@ -783,26 +781,32 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
             __syncthreads();
             PHASE_MARK(t_t2);
             PHASE_ADD(7, t_t1, t_t2);
-            // ---- C2+C3, fused per warp: a warp takes 32 consecutive faces of the tile, computes their per-face data in
-            //      registers (AO occluder counts, barycentric colour offset, texture id), stages their index values and
-            //      their vertices (32 at a time, face data fetched from the owning lane by shuffle) in its private
-            //      shared-memory slice and writes both out with coalesced stores. No block barrier inside a tile. ----
+            // ---- C2+C3: lane = face. The lane computes its face's data in registers once (AO occluder counts, barycentric
+            //      colour sum, texture id, the words of its 3..6 vertices); the warp then transposes through its private
+            //      shared-memory slice -- 16 quads (2560 B) at a time in cube chunks, 8 mixed sides at a time otherwise,
+            //      finally the batch's indices -- so that the arena is written with coalesced vector stores.
+            //      No block barrier inside a tile. ----
             const uint32_t n_batches = (tileF + 31u) >> 5;
             for (uint32_t bt = warp; bt < n_batches; bt += NW) {
                 PHASE_MARK(t_b_0);
                 const uint32_t f = bt * 32u + lane;
-                const bool act = f < tileF;
-                uint32_t a = 0, ic = 0, ks = 0, texbits = 0, nv = 0, ni = 0, vs = 0, is = 0;
-                float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, b3 = 0.0f;
+                const uint32_t nbf = min(32u, tileF - bt * 32u); // faces in this batch
+                const bool act = lane < nbf;
+                uint32_t vs = 0, is = 0, nv = 0, ni = 0, texbits = 0, cell = 0;
+                uint32_t fb0 = 0, fb1 = 0, fb2 = 0, fb3 = 0;
+                uint32_t w_pos[6], w_col[6], w_uvi[6]; // w_uvi: u | v<<1 | barycentric flags<<2
+#pragma unroll
+                for (int j = 0; j < 6; j++) w_pos[j] = w_col[j] = w_uvi[j] = 0;
                 if (act) {
-                    a = s.sc.frecA[f];
+                    const uint32_t a = s.sc.frecA[f];
                     const uint32_t row = a & 1023u, x = (a >> 10) & 31u, d = (a >> 15) & 7u;
                     vs = a >> 18;
+                    const uint32_t y = row >> 5, z = row & 31u;
                     uint32_t id, cx, nb;
                     if (quads_only) {
-                        cx = s.cls[((row >> 5) + 1) * PLANE + ((row & 31) + 1) * ROWB + XOFF + (int)x];
+                        cx = s.cls[(y + 1) * PLANE + (z + 1) * ROWB + XOFF + (int)x];
                         id = __ldg(center + row * 32 + x) >> 16;
-                        nb = neighbourhood27(s, (int)(row >> 5), (int)(row & 31), (int)x);
+                        nb = neighbourhood27(s, (int)y, (int)z, (int)x);
                         is = f * 6u;
                     } else { // recorded by C1
                         const uint32_t icr = s.sc.frecC[f];
@@ -811,13 +815,13 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                         nb = s.sc.frecE[f];
                         is = s.sc.frecB[f];
                     }
-                    ic = id | (cx << 16);
                     const uint32_t st = s.stab[cx * 6 + d];
                     const uint32_t ls = st & 7u, signs = st >> 9;
                     nv = (st >> 3) & 7u;
                     ni = (st >> 6) & 7u;
                     float dc0, dc1, dc2, texid;
-                    if (id < (uint32_t)REGC) {
+                    const bool small_id = id < (uint32_t)REGC;
+                    if (small_id) {
                         dc0 = s.reg_color[id * 3];
                         dc1 = s.reg_color[id * 3 + 1];
                         dc2 = s.reg_color[id * 3 + 2];
@@ -829,106 +833,131 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                         texid = __ldg(p.reg.texf + id * 6 + ls);
                     }
                     texbits = __float_as_uint(texid);
-                    // per vertex: number of occluding AO samples (voxmesh.rs:128-137; every meshed shape occludes) and the
-                    // in-order barycentric colour sum (voxmesh.rs:124,153,172-174)
+                    cell = x + 32u * z + 1024u * y;
+                    // per vertex: descriptor, number of occluding AO samples (voxmesh.rs:128-137; every meshed shape
+                    // occludes), colour, and the in-order barycentric colour sum (voxmesh.rs:124,153,172-174).
+                    // as_wxyz10 of (ipos + voffset + 0.5)/32 (voxmesh.rs:36-41,139-145,165): every vertex sits on a voxel
+                    // corner, so each 10-bit field is 16 * corner coordinate; w = (1/32*2) as u32 = 0.
                     const bool cube = cx <= 24u;
                     const uint16_t *vd = &T->vdesc[cx][d][0];
                     const uint16_t *vds = &s.vdesc_cube[(cube ? cx : 0u) * 36u + d * 6u];
+                    float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, b3 = 0.0f;
 #pragma unroll
                     for (uint32_t j = 0; j < 6; j++) {
-                        if (j >= nv) break;
-                        const uint32_t desc = cube ? (uint32_t)vds[j] : (uint32_t)__ldg(vd + j);
-                        const uint32_t k = __popc(nb & s.aolut[(desc & 7u) * 27u + (desc >> 8)]);
-                        ks |= k << (3 * j);
-                        const float sg = (float)((int)((signs >> (2 * j)) & 3u) - 1);
-                        const float aj = s.ao_lut[k];
-                        b0 = __fadd_rn(b0, __fmul_rn(sg, __fmul_rn(dc0, aj)));
-                        b1 = __fadd_rn(b1, __fmul_rn(sg, __fmul_rn(dc1, aj)));
-                        b2 = __fadd_rn(b2, __fmul_rn(sg, __fmul_rn(dc2, aj)));
-                        b3 = __fadd_rn(b3, __fmul_rn(sg, 1.0f));
+                        if (j < nv) {
+                            const uint32_t e = cube ? (uint32_t)vds[j] : (uint32_t)__ldg(vd + j);
+                            const uint32_t k = __popc(nb & s.aolut[(e & 7u) * 27u + (e >> 8)]);
+                            const float sg = (float)((int)((signs >> (2 * j)) & 3u) - 1);
+                            const float aj = s.ao_lut[k];
+                            b0 = __fadd_rn(b0, __fmul_rn(sg, __fmul_rn(dc0, aj)));
+                            b1 = __fadd_rn(b1, __fmul_rn(sg, __fmul_rn(dc1, aj)));
+                            b2 = __fadd_rn(b2, __fmul_rn(sg, __fmul_rn(dc2, aj)));
+                            b3 = __fadd_rn(b3, __fmul_rn(sg, 1.0f));
+                            const uint32_t px = x + (e & 1u), py = y + ((e >> 1) & 1u), pz = z + ((e >> 2) & 1u);
+                            w_pos[j] = (((px * 16u) & 0x3FFu) << 20) | (((py * 16u) & 0x3FFu) << 10) | ((pz * 16u) & 0x3FFu);
+                            if (small_id) {
+                                w_col[j] = s.col_lut[id * 8 + k];
+                            } else {
+                                const float c0f = __fmul_rn(dc0, aj), c1f = __fmul_rn(dc1, aj), c2f = __fmul_rn(dc2, aj);
+                                w_col[j] = ((__float2uint_rz(__fmul_rn(c0f, 255.0f)) & 0xFFu) << 24) | ((__float2uint_rz(__fmul_rn(c1f, 255.0f)) & 0xFFu) << 16) |
+                                           ((__float2uint_rz(__fmul_rn(c2f, 255.0f)) & 0xFFu) << 8) | 0xFFu;
+                            }
+                            w_uvi[j] = (e >> 3) & 31u;
+                        }
                     }
+                    fb0 = __float_as_uint(b0);
+                    fb1 = __float_as_uint(b1);
+                    fb2 = __float_as_uint(b2);
+                    fb3 = __float_as_uint(b3);
                 }
                 PHASE_MARK(t_b_c2);
-                // vertex / index ranges of the batch (tile-relative)
-                const int last = (int)min(31u, tileF - 1u - bt * 32u);
-                const uint32_t vs0 = __shfl_sync(FULL, vs, 0), is0 = __shfl_sync(FULL, is, 0);
-                const uint32_t nbv = __shfl_sync(FULL, vs + nv, last) - vs0, nbi = __shfl_sync(FULL, is + ni, last) - is0;
-                if (act) {
-                    uint8_t *sf = &s.sc.wsf[warp][vs - vs0];
-                    for (uint32_t j = 0; j < nv; j++) sf[j] = (uint8_t)lane;
-                    uint32_t *ist = &s.sc.wistage[warp][is - is0];
-                    const uint32_t vq = v0 + vs; // voff = vbuf.len() (voxmesh.rs:123), chunk-relative
-                    // QUAD_INDICES [0,1,2,2,3,0] for quads (stdshapes.rs:198), 0..n-1 for the triangle lists
-                    const uint32_t pat = nv == 4 ? 0x032210u : 0x543210u;
-#pragma unroll
-                    for (uint32_t k = 0; k < 6; k++)
-                        if (k < ni) ist[k] = vq + ((pat >> (4 * k)) & 15u);
-                }
-                __syncwarp();
-                {
-                    uint32_t *idst = iout + i0 + is0;
-                    if ((reinterpret_cast<uintptr_t>(idst) & 7u) == 0) { // 8-byte copies
-                        const uint2 *src2 = reinterpret_cast<const uint2 *>(&s.sc.wistage[warp][0]);
-                        uint2 *dst2 = reinterpret_cast<uint2 *>(idst);
-                        for (uint32_t k = lane; k < (nbi >> 1); k += 32) dst2[k] = src2[k];
-                        if ((nbi & 1u) && lane == 0) idst[nbi - 1] = s.sc.wistage[warp][nbi - 1];
-                    } else {
-                        for (uint32_t k = lane; k < nbi; k += 32) idst[k] = s.sc.wistage[warp][k];
-                    }
-                }
-                PHASE_MARK(t_b_ix);
                 PHASE_ADD(10, t_b_0, t_b_c2);
-                PHASE_ADD(11, t_b_c2, t_b_ix);
-                for (uint32_t sb = 0; sb < nbv; sb += 32) {
-                    const uint32_t sl = sb + lane;
-                    const bool actv = sl < nbv;
-                    const uint32_t par = (v0 + vs0 + sb) & 1u; // odd vertex offset: stage 8 bytes later so 16-byte units line up
-                    const int fl = actv ? (int)s.sc.wsf[warp][sl] : 0;
-                    const uint32_t A = __shfl_sync(FULL, a, fl), KS = __shfl_sync(FULL, ks, fl), IC = __shfl_sync(FULL, ic, fl),
-                                   TB = __shfl_sync(FULL, texbits, fl);
-                    const float B0 = __shfl_sync(FULL, b0, fl), B1 = __shfl_sync(FULL, b1, fl), B2 = __shfl_sync(FULL, b2, fl),
-                                B3 = __shfl_sync(FULL, b3, fl);
-                    if (actv) {
-                        const uint32_t row = A & 1023u, x = (A >> 10) & 31u, d = (A >> 15) & 7u;
-                        const uint32_t y = row >> 5, z = row & 31u;
-                        const uint32_t j = vs0 + sl - (A >> 18);
-                        const uint32_t id = IC & 0xFFFFu, cx = IC >> 16;
-                        const uint32_t e = cx <= 24u ? (uint32_t)s.vdesc_cube[cx * 36u + d * 6u + j] : (uint32_t)__ldg(&T->vdesc[cx][d][j]);
-                        // as_wxyz10 of (ipos + voffset + 0.5)/32 (voxmesh.rs:36-41,139-145,165): every vertex sits on a
-                        // voxel corner, so each 10-bit field is 16 * corner coordinate; w = (1/32*2) as u32 = 0.
-                        const uint32_t px = x + (e & 1u), py = y + ((e >> 1) & 1u), pz = z + ((e >> 2) & 1u);
-                        const uint32_t position = (((px * 16u) & 0x3FFu) << 20) | (((py * 16u) & 0x3FFu) << 10) | ((pz * 16u) & 0x3FFu);
-                        const uint32_t k = (KS >> (3 * j)) & 7u;
-                        uint32_t color;
-                        if (id < (uint32_t)REGC) {
-                            color = s.col_lut[id * 8 + k];
-                        } else {
-                            const float ao = s.ao_lut[k];
-                            const float c0f = __fmul_rn(__ldg(p.reg.color + id * 3), ao), c1f = __fmul_rn(__ldg(p.reg.color + id * 3 + 1), ao),
-                                        c2f = __fmul_rn(__ldg(p.reg.color + id * 3 + 2), ao);
-                            color = ((__float2uint_rz(__fmul_rn(c0f, 255.0f)) & 0xFFu) << 24) | ((__float2uint_rz(__fmul_rn(c1f, 255.0f)) & 0xFFu) << 16) |
-                                    ((__float2uint_rz(__fmul_rn(c2f, 255.0f)) & 0xFFu) << 8) | 0xFFu;
+                // record: position, color, texcoord (u, v, texture id), index | barycentric flags, barycentric_color_offset[4]
+                // (voxrender.rs:39-49)
+                auto tu = [&](int j) { return (w_uvi[j] & 1u) ? 0x3F800000u : 0u; };
+                auto tv = [&](int j) { return (w_uvi[j] & 2u) ? 0x3F800000u : 0u; };
+                auto ix = [&](int j) { return cell | ((w_uvi[j] >> 2) << 17); };
+                uint4 *const stg = &s.sc.wstage[warp][0];
+                const uint32_t vq = v0 + vs; // voff = vbuf.len() (voxmesh.rs:123), chunk-relative
+                if (quads_only) {
+                    // every side is a quad: the batch's vertices start at v0 + bt*128, 16-byte aligned
+#pragma unroll
+                    for (uint32_t h = 0; h < 2; h++) {
+                        if (act && (lane >> 4) == h) {
+                            uint4 *o = stg + (lane & 15u) * 10u;
+                            o[0] = make_uint4(w_pos[0], w_col[0], tu(0), tv(0));
+                            o[1] = make_uint4(texbits, ix(0), fb0, fb1);
+                            o[2] = make_uint4(fb2, fb3, w_pos[1], w_col[1]);
+                            o[3] = make_uint4(tu(1), tv(1), texbits, ix(1));
+                            o[4] = make_uint4(fb0, fb1, fb2, fb3);
+                            o[5] = make_uint4(w_pos[2], w_col[2], tu(2), tv(2));
+                            o[6] = make_uint4(texbits, ix(2), fb0, fb1);
+                            o[7] = make_uint4(fb2, fb3, w_pos[3], w_col[3]);
+                            o[8] = make_uint4(tu(3), tv(3), texbits, ix(3));
+                            o[9] = make_uint4(fb0, fb1, fb2, fb3);
                         }
-                        const float tu = (float)((e >> 3) & 1u), tv = (float)((e >> 4) & 1u);
-                        const uint32_t index = (x + 32u * z + 1024u * y) | (((e >> 5) & 7u) << 17);
-                        uint2 *o = &s.sc.wvstage[warp][par + lane * 5];
-                        o[0] = make_uint2(position, color);
-                        o[1] = make_uint2(__float_as_uint(tu), __float_as_uint(tv));
-                        o[2] = make_uint2(TB, index);
-                        o[3] = make_uint2(__float_as_uint(B0), __float_as_uint(B1));
-                        o[4] = make_uint2(__float_as_uint(B2), __float_as_uint(B3));
+                        __syncwarp();
+                        const uint32_t nfh = nbf > 16u * h ? min(16u, nbf - 16u * h) : 0u;
+                        uint4 *g = reinterpret_cast<uint4 *>(vout + v0 + bt * 128u + h * 64u);
+                        for (uint32_t k = lane; k < nfh * 10u; k += 32) g[k] = stg[k];
+                        __syncwarp();
+                    }
+                    // indices: QUAD_INDICES [0,1,2,2,3,0] (stdshapes.rs:198); 6 per side, the batch starts 8-byte aligned
+                    if (act) {
+                        uint2 *o2 = reinterpret_cast<uint2 *>(stg) + lane * 3u;
+                        o2[0] = make_uint2(vq, vq + 1u);
+                        o2[1] = make_uint2(vq + 2u, vq + 2u);
+                        o2[2] = make_uint2(vq + 3u, vq);
                     }
                     __syncwarp();
-                    const uint32_t tot2 = par + min(32u, nbv - sb) * 5u; // 8-byte words staged, the first `par` of them unused
-                    uint2 *g2 = reinterpret_cast<uint2 *>(vout + v0 + vs0 + sb) - par; // 16-byte aligned
-                    const uint4 *src4 = reinterpret_cast<const uint4 *>(&s.sc.wvstage[warp][0]);
-                    uint4 *g4 = reinterpret_cast<uint4 *>(g2);
-                    for (uint32_t k = lane; k < (tot2 >> 1); k += 32) {
-                        const uint4 val = src4[k];
-                        if (k == 0 && par) g2[1] = make_uint2(val.z, val.w); // the first 8 bytes belong to the previous vertex
-                        else g4[k] = val;
+                    {
+                        uint2 *g2 = reinterpret_cast<uint2 *>(iout + i0 + bt * 192u);
+                        const uint2 *src2 = reinterpret_cast<const uint2 *>(stg);
+                        for (uint32_t k = lane; k < nbf * 3u; k += 32) g2[k] = src2[k];
                     }
-                    if ((tot2 & 1u) && lane == 0) g2[tot2 - 1] = s.sc.wvstage[warp][tot2 - 1];
+                    __syncwarp();
+                } else {
+                    // mixed sides (3, 4 or 6 vertices): 8 faces (<= 48 vertices) per pass, 8-byte granularity
+                    uint2 *const st2 = reinterpret_cast<uint2 *>(stg);
+#pragma unroll 1
+                    for (uint32_t g8 = 0; g8 < 4; g8++) {
+                        if (g8 * 8u >= nbf) break;
+                        const int first = (int)(g8 * 8u), last = (int)min(g8 * 8u + 7u, nbf - 1u);
+                        const uint32_t vb = __shfl_sync(FULL, vs, first);
+                        const uint32_t ve = __shfl_sync(FULL, vs + nv, last);
+                        if (act && (lane >> 3) == g8) {
+                            uint2 *o = st2 + (vs - vb) * 5u;
+#pragma unroll
+                            for (uint32_t j = 0; j < 6; j++) {
+                                if (j < nv) {
+                                    o[j * 5 + 0] = make_uint2(w_pos[j], w_col[j]);
+                                    o[j * 5 + 1] = make_uint2(tu(j), tv(j));
+                                    o[j * 5 + 2] = make_uint2(texbits, ix(j));
+                                    o[j * 5 + 3] = make_uint2(fb0, fb1);
+                                    o[j * 5 + 4] = make_uint2(fb2, fb3);
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        uint2 *g2 = reinterpret_cast<uint2 *>(vout + v0 + vb);
+                        for (uint32_t k = lane; k < (ve - vb) * 5u; k += 32) g2[k] = st2[k];
+                        __syncwarp();
+                    }
+                    // indices: [0,1,2,2,3,0] for quads, 0..n-1 for the triangle lists (stdshapes.rs:198)
+                    const uint32_t ib = __shfl_sync(FULL, is, 0);
+                    const uint32_t ie = __shfl_sync(FULL, is + ni, (int)nbf - 1);
+                    uint32_t *sti = reinterpret_cast<uint32_t *>(stg);
+                    if (act) {
+                        const uint32_t pat = nv == 4 ? 0x032210u : 0x543210u;
+#pragma unroll
+                        for (uint32_t k = 0; k < 6; k++)
+                            if (k < ni) sti[is - ib + k] = vq + ((pat >> (4 * k)) & 15u);
+                    }
+                    __syncwarp();
+                    {
+                        uint32_t *gi = iout + i0 + ib;
+                        for (uint32_t k = lane; k < ie - ib; k += 32) gi[k] = sti[k];
+                    }
                     __syncwarp();
                 }
             }
@@ -985,6 +1014,9 @@ void launch_hmap_candidates(const CandidateParams &p, cudaStream_t stream) {
     const int cols = (p.SX - 2) * (p.SZ - 2);
     hmap_candidates_kernel<<<(cols + 7) / 8, 256, 0, stream>>>(p);
 }
+
+// two CTAs per SM: 228 KB of shared memory per SM, 1 KB reserved per CTA
+static_assert(sizeof(Smem) <= 113 * 1024 - 512, "mesh_kernel's shared memory no longer fits twice on an SM");
 
 int mesh_kernel_max_ctas_per_sm() {
     int n = 0;
