@@ -36,6 +36,8 @@ struct Region {
     bxw_vertex *varena = nullptr;
     uint32_t *iarena = nullptr;
     unsigned long long v_cap = 0, i_cap = 0;
+    uint32_t *frec = nullptr;          // face records between mesh_kernel and emit_kernel (kFaceWords arrays of f_cap)
+    unsigned long long f_cap = 0;
     bool reserved = false;
     MeshCounters *counters = nullptr;
     MeshCounters *h_counters = nullptr; // pinned
@@ -175,6 +177,7 @@ void region_free(Region &r) {
     cudaFree(r.spans);
     cudaFree(r.varena);
     cudaFree(r.iarena);
+    cudaFree(r.frec);
     cudaFree(r.counters);
     cudaFree(r.dirty);
     cudaFree(r.dirty_work);
@@ -346,6 +349,18 @@ int arena_resize(bxw_ctx *ctx, Region &r, unsigned long long v_cap, unsigned lon
     return BXW_OK;
 }
 
+// the face records are transient (one mesh pass), so growing never copies
+int faces_resize(bxw_ctx *ctx, Region &r, unsigned long long f_cap) {
+    if (f_cap <= r.f_cap) return BXW_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(r.frec);
+    r.frec = nullptr;
+    r.f_cap = 0;
+    CK(cudaMalloc(&r.frec, f_cap * kFaceWords * sizeof(uint32_t)));
+    r.f_cap = f_cap;
+    return BXW_OK;
+}
+
 // Runs the mesher over a work list. append=false restarts arena allocation at 0.
 int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *work_span, uint32_t n_work, bool append,
                 bool from_hmap = false) {
@@ -433,6 +448,7 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
         init.i_alloc = base_i;
         init.flags = 0;
         init.work_next = 0;
+        init.f_alloc = 0;
         for (int k = 0; k < 12; k++) init.phase[k] = 0;
         *r.h_counters = init;
         CK(cudaMemcpyAsync(r.counters, r.h_counters, sizeof(MeshCounters), cudaMemcpyHostToDevice, ctx->stream));
@@ -441,11 +457,17 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
         p.iarena = r.iarena;
         p.v_cap = r.v_cap;
         p.i_cap = r.i_cap;
+        p.frec = r.frec;
+        p.f_cap = r.f_cap;
         p.count_only = count_only ? 1 : 0;
         CK(cudaEventRecord(ctx->ev_m0, ctx->stream));
         launch_mesh_kernel(p, ctx->sm_count, ctx->stream);
-        CK(cudaEventRecord(ctx->ev_m1, ctx->stream));
         ctx->launches += 1;
+        if (!count_only) { // vertices and indices of the recorded sides (returns at once if a chunk did not fit)
+            launch_emit_kernel(p, ctx->sm_count, ctx->stream);
+            ctx->launches += 1;
+        }
+        CK(cudaEventRecord(ctx->ev_m1, ctx->stream));
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(r.h_counters, r.counters, sizeof(MeshCounters), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -461,6 +483,9 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
         if (count_only || (r.h_counters->flags & kFlagArenaOverflow)) {
             // size the arena from the measured need (+ slack so small edits can append) and run again
             int rc = arena_resize(ctx, r, need_v + need_v / 8 + 4096, need_i + need_i / 8 + 8192, base_v, base_i);
+            if (rc) return rc;
+            const unsigned long long need_f = r.h_counters->f_alloc;
+            rc = faces_resize(ctx, r, need_f + need_f / 8 + 4096);
             if (rc) return rc;
             continue;
         }
@@ -945,6 +970,7 @@ int bxw_region_import_rle(bxw_ctx *ctx, const int32_t *lpos, size_t n_chunks, co
 int bxw_region_mesh_reserve(bxw_ctx *ctx, uint64_t max_vertices, uint64_t max_indices) {
     if (!ctx || !ctx->region.live) return fail(ctx, BXW_E_INVALID, "no region");
     int rc = arena_resize(ctx, ctx->region, max_vertices, max_indices, 0, 0);
+    if (rc == BXW_OK) rc = faces_resize(ctx, ctx->region, max_vertices / 3 + 4096); // a side has at least 3 vertices
     if (rc == BXW_OK) ctx->region.reserved = true;
     return rc;
 }

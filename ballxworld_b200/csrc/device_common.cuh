@@ -28,6 +28,7 @@ struct MeshCounters {
     unsigned long long i_alloc; // next free index slot
     unsigned long long flags;
     unsigned long long work_next; // dynamic work-list cursor
+    unsigned long long f_alloc;   // next free face-record slot (a chunk takes a multiple of 32)
     // -DBXW_PHASE_TIMING builds only: SM cycles of CTA thread 0 summed over chunks: [0] work fetch + neighbour table,
     // [1] phase A, [2] phases B + scan + allocation, [3] phase C, [4] chunks that reached phase C, [5] chunks
     unsigned long long phase[12]; // [6] tile setup, [7] C1, [8] warp 0's batches, [9] tile-end barrier wait
@@ -45,6 +46,10 @@ struct MeshParams {
     bxw_vertex *varena;
     uint32_t *iarena;
     unsigned long long v_cap, i_cap;
+    // face records between mesh_kernel (stage, cull, count, order) and emit_kernel (vertex / index construction): five
+    // word arrays of f_cap entries, record k of a chunk at its face base + k. See kFaceWords below.
+    uint32_t *frec;
+    unsigned long long f_cap;
     MeshCounters *counters;
     const MeshTables *tables;
     DeviceRegistry reg;
@@ -57,6 +62,17 @@ struct MeshParams {
 };
 
 void launch_mesh_kernel(const MeshParams &p, int sm_count, cudaStream_t stream);
+
+// Face record (SoA, word w of record k at frec[w * f_cap + k]):
+//   0: row (y*32+z, 10 bits) | x << 10 | world dir << 15 | class << 18; 0xFFFFFFFF = padding (no face)
+//   1: first vertex of the side, chunk-relative (20 bits) | (block id & 0xFFF) << 20
+//   2: first index of the side, chunk-relative (21 bits) | (block id >> 12) << 21
+//   3: occupancy of the cell's 3x3x3 neighbourhood, bit (dy+1)*9 + (dz+1)*3 + (dx+1)
+//   4: span slot of the chunk (where its arena offsets are)
+constexpr int kFaceWords = 5;
+constexpr uint32_t kFacePad = 0xFFFFFFFFu;
+// Second half of mesh_from_chunk (voxmesh.rs:122-177): builds the vertices and indices of every recorded side.
+void launch_emit_kernel(const MeshParams &p, int sm_count, cudaStream_t stream);
 
 // Fused generate+mesh: list the interior chunks of pristine terrain that can have a mesh (the surface passes through
 // their 34^3 neighbourhood) and zero the spans of all others, from the height map alone.

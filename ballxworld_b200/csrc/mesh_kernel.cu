@@ -36,7 +36,6 @@ constexpr int CLS_BYTES = 34 * PLANE;
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int FC = 1024;     // faces per emission tile
 constexpr int VC = 4096;     // vertex slots per emission tile
-constexpr int REGC = 64;     // registry entries cached in shared memory
 
 // phase-A staging: every warp streams its share of the 34^3 neighbourhood through a private cp.async ring.
 // One unit = a third of a y' layer: 3 warp copies of 4 rows (12 rows x 128 B) + (first third only) the layer's x-halo.
@@ -52,8 +51,6 @@ struct Scratch { // phases B, S, C
     uint32_t frecB[FC];   // tile-relative first index (tiles with non-quad sides)
     uint32_t frecC[FC];   // block id | class<<16 (tiles with non-quad sides)
     uint32_t frecE[FC];   // occupancy of the cell's 3x3x3 neighbourhood, bit (dy+1)*9 + (dz+1)*3 + (dx+1) (ditto)
-    // per-warp transpose buffer: 16 quads (or up to 64 vertices of mixed sides), then the batch's indices
-    alignas(16) uint4 wstage[NW][160];
 };
 
 struct Smem {
@@ -69,17 +66,10 @@ struct Smem {
     uint32_t solid[34 * 34];         // per (y',z') row: bit x set when voxel x (0..31) has a mesh (class != 0)
     uint8_t solid_halo[34 * 34 + 4]; // bit0: x=-1 solid, bit1: x=32 solid
     uint32_t ctab[kNumClasses + 3];
-    uint32_t stab[kNumClasses * 6 + 2];
-    float ao_lut[8];
-    float reg_color[REGC * 3];
-    float reg_texf[REGC * 6];
-    uint32_t col_lut[REGC * 8]; // as_rgba8(debug_color * ao_k) per cached block id and occluder count k
-    uint32_t aolut[8 * 27];     // AO sample mask per (vertex corner, AO normal code)
-    uint16_t vdesc_cube[25 * 36]; // vertex descriptors of classes 0..24 (void + the 24 cube orientations): most faces anywhere
     uint8_t reg_kind[256];
     uint32_t nbr[27 + 5];
     uint32_t warp_tot[3][NW];
-    unsigned long long vbase, ibase;
+    unsigned long long vbase, ibase, fbase;
     uint32_t work_item[2];
     uint32_t wref[NW];     // per-warp reference datum (trivial-chunk detection)
     uint32_t wflags[NW];   // per-warp shapes | mixed<<1
@@ -190,24 +180,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
     const MeshTables *T = p.tables;
 
     for (int i = tid; i < kNumClasses; i += NT) s.ctab[i] = T->ctab[i];
-    for (int i = tid; i < kNumClasses * 6; i += NT) s.stab[i] = (&T->stab[0][0])[i];
-    if (tid < 8) s.ao_lut[tid] = T->ao_lut[tid];
     for (int i = tid; i < 256; i += NT) s.reg_kind[i] = (uint32_t)i < p.reg.n ? p.reg.kind[i] : (uint8_t)0;
-    for (int i = tid; i < REGC * 3; i += NT) s.reg_color[i] = (uint32_t)(i / 3) < p.reg.n ? p.reg.color[i] : 0.0f;
-    for (int i = tid; i < REGC * 6; i += NT) s.reg_texf[i] = (uint32_t)(i / 6) < p.reg.n ? p.reg.texf[i] : 0.0f;
-    for (int i = tid; i < 8 * 27; i += NT) s.aolut[i] = T->aolut[i];
-    for (int i = tid; i < 25 * 36; i += NT) s.vdesc_cube[i] = (&T->vdesc[0][0][0])[i];
-    for (int i = tid; i < REGC * 8; i += NT) {
-        const uint32_t id = (uint32_t)i >> 3;
-        uint32_t col = 0;
-        if (id < p.reg.n) { // as_rgba8 (voxmesh.rs:29-34,147-152); Rust's `as u32` saturates like cvt.rzi.u32.f32
-            const float ao = T->ao_lut[i & 7];
-            const float c0f = __fmul_rn(p.reg.color[id * 3], ao), c1f = __fmul_rn(p.reg.color[id * 3 + 1], ao), c2f = __fmul_rn(p.reg.color[id * 3 + 2], ao);
-            col = ((__float2uint_rz(__fmul_rn(c0f, 255.0f)) & 0xFFu) << 24) | ((__float2uint_rz(__fmul_rn(c1f, 255.0f)) & 0xFFu) << 16) |
-                  ((__float2uint_rz(__fmul_rn(c2f, 255.0f)) & 0xFFu) << 8) | 0xFFu;
-        }
-        s.col_lut[i] = col;
-    }
     if (tid < 5) { // class of the generator's datums (meta 0): cube (class 1) when the block has a mesh, else 0
         const uint32_t id = p.gen_datum[tid] >> 16;
         s.gen_cls[tid] = (p.hmap && id < p.reg.n && p.reg.kind[id] == 2) ? 1u : 0u;
@@ -670,13 +643,15 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                 s.sc.rowI[1024] = bi + ti;
                 s.sc.rowF[1024] = bf + tf;
                 const unsigned long long padV = (TV + 3ull) & ~3ull, padI = (TI + 7ull) & ~7ull;
-                unsigned long long vb = 0, ib = 0;
+                const unsigned long long padF = ((unsigned long long)(bf + tf) + 31ull) & ~31ull; // emit_kernel: a warp never straddles chunks
+                unsigned long long vb = 0, ib = 0, fb = 0;
                 int emit = 0;
                 if (TV | TI) {
                     vb = atomicAdd(&p.counters->v_alloc, padV);
                     ib = atomicAdd(&p.counters->i_alloc, padI);
+                    fb = atomicAdd(&p.counters->f_alloc, padF);
                     if (!p.count_only) {
-                        if (vb + padV <= p.v_cap && ib + padI <= p.i_cap) emit = 1;
+                        if (vb + padV <= p.v_cap && ib + padI <= p.i_cap && fb + padF <= p.f_cap) emit = 1;
                         else atomicOr(&p.counters->flags, kFlagArenaOverflow);
                     }
                 }
@@ -688,6 +663,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                 p.spans[span_slot] = sp;
                 s.vbase = vb;
                 s.ibase = ib;
+                s.fbase = fb;
                 s.emit = emit;
             }
         }
@@ -697,10 +673,9 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
         if (!s.emit) continue;
         PHASE_ADD(4, 0, 1);
 
-        // ---------------- phase C: emit, tile by tile ----------------
+        // ---------------- phase C: the chunk's face records, in emission order, tile by tile ----------------
         const uint32_t *center = p.blocks + (size_t)c0 * kChunkVoxels;
-        bxw_vertex *const vout = p.varena + s.vbase;
-        uint32_t *const iout = p.iarena + s.ibase;
+        const unsigned long long fbase = s.fbase;
         const bool quads_only = !has_shapes; // every side has 4 vertices / 6 indices
         for (uint32_t r0 = 0; r0 < 1024;) {
             PHASE_MARK(t_t0);
@@ -781,185 +756,30 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
             __syncthreads();
             PHASE_MARK(t_t2);
             PHASE_ADD(7, t_t1, t_t2);
-            // ---- C2+C3: lane = face. The lane computes its face's data in registers once (AO occluder counts, barycentric
-            //      colour sum, texture id, the words of its 3..6 vertices); the warp then transposes through its private
-            //      shared-memory slice -- 16 quads (2560 B) at a time in cube chunks, 8 mixed sides at a time otherwise,
-            //      finally the batch's indices -- so that the arena is written with coalesced vector stores.
-            //      No block barrier inside a tile. ----
-            const uint32_t n_batches = (tileF + 31u) >> 5;
-            for (uint32_t bt = warp; bt < n_batches; bt += NW) {
-                PHASE_MARK(t_b_0);
-                const uint32_t f = bt * 32u + lane;
-                const uint32_t nbf = min(32u, tileF - bt * 32u); // faces in this batch
-                const bool act = lane < nbf;
-                uint32_t vs = 0, is = 0, nv = 0, ni = 0, texbits = 0, cell = 0;
-                uint32_t fb0 = 0, fb1 = 0, fb2 = 0, fb3 = 0;
-                uint32_t w_pos[6], w_col[6], w_uvi[6]; // w_uvi: u | v<<1 | barycentric flags<<2
-#pragma unroll
-                for (int j = 0; j < 6; j++) w_pos[j] = w_col[j] = w_uvi[j] = 0;
-                if (act) {
-                    const uint32_t a = s.sc.frecA[f];
-                    const uint32_t row = a & 1023u, x = (a >> 10) & 31u, d = (a >> 15) & 7u;
-                    vs = a >> 18;
-                    const uint32_t y = row >> 5, z = row & 31u;
-                    uint32_t id, cx, nb;
-                    if (quads_only) {
-                        cx = s.cls[(y + 1) * PLANE + (z + 1) * ROWB + XOFF + (int)x];
-                        id = __ldg(center + row * 32 + x) >> 16;
-                        nb = neighbourhood27(s, (int)y, (int)z, (int)x);
-                        is = f * 6u;
-                    } else { // recorded by C1
-                        const uint32_t icr = s.sc.frecC[f];
-                        id = icr & 0xFFFFu;
-                        cx = icr >> 16;
-                        nb = s.sc.frecE[f];
-                        is = s.sc.frecB[f];
-                    }
-                    const uint32_t st = s.stab[cx * 6 + d];
-                    const uint32_t ls = st & 7u, signs = st >> 9;
-                    nv = (st >> 3) & 7u;
-                    ni = (st >> 6) & 7u;
-                    float dc0, dc1, dc2, texid;
-                    const bool small_id = id < (uint32_t)REGC;
-                    if (small_id) {
-                        dc0 = s.reg_color[id * 3];
-                        dc1 = s.reg_color[id * 3 + 1];
-                        dc2 = s.reg_color[id * 3 + 2];
-                        texid = s.reg_texf[id * 6 + ls]; // texture of the LOCAL side (voxmesh.rs:146)
-                    } else {
-                        dc0 = __ldg(p.reg.color + id * 3);
-                        dc1 = __ldg(p.reg.color + id * 3 + 1);
-                        dc2 = __ldg(p.reg.color + id * 3 + 2);
-                        texid = __ldg(p.reg.texf + id * 6 + ls);
-                    }
-                    texbits = __float_as_uint(texid);
-                    cell = x + 32u * z + 1024u * y;
-                    // per vertex: descriptor, number of occluding AO samples (voxmesh.rs:128-137; every meshed shape
-                    // occludes), colour, and the in-order barycentric colour sum (voxmesh.rs:124,153,172-174).
-                    // as_wxyz10 of (ipos + voffset + 0.5)/32 (voxmesh.rs:36-41,139-145,165): every vertex sits on a voxel
-                    // corner, so each 10-bit field is 16 * corner coordinate; w = (1/32*2) as u32 = 0.
-                    const bool cube = cx <= 24u;
-                    const uint16_t *vd = &T->vdesc[cx][d][0];
-                    const uint16_t *vds = &s.vdesc_cube[(cube ? cx : 0u) * 36u + d * 6u];
-                    float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, b3 = 0.0f;
-#pragma unroll
-                    for (uint32_t j = 0; j < 6; j++) {
-                        if (j < nv) {
-                            const uint32_t e = cube ? (uint32_t)vds[j] : (uint32_t)__ldg(vd + j);
-                            const uint32_t k = __popc(nb & s.aolut[(e & 7u) * 27u + (e >> 8)]);
-                            const float sg = (float)((int)((signs >> (2 * j)) & 3u) - 1);
-                            const float aj = s.ao_lut[k];
-                            b0 = __fadd_rn(b0, __fmul_rn(sg, __fmul_rn(dc0, aj)));
-                            b1 = __fadd_rn(b1, __fmul_rn(sg, __fmul_rn(dc1, aj)));
-                            b2 = __fadd_rn(b2, __fmul_rn(sg, __fmul_rn(dc2, aj)));
-                            b3 = __fadd_rn(b3, __fmul_rn(sg, 1.0f));
-                            const uint32_t px = x + (e & 1u), py = y + ((e >> 1) & 1u), pz = z + ((e >> 2) & 1u);
-                            w_pos[j] = (((px * 16u) & 0x3FFu) << 20) | (((py * 16u) & 0x3FFu) << 10) | ((pz * 16u) & 0x3FFu);
-                            if (small_id) {
-                                w_col[j] = s.col_lut[id * 8 + k];
-                            } else {
-                                const float c0f = __fmul_rn(dc0, aj), c1f = __fmul_rn(dc1, aj), c2f = __fmul_rn(dc2, aj);
-                                w_col[j] = ((__float2uint_rz(__fmul_rn(c0f, 255.0f)) & 0xFFu) << 24) | ((__float2uint_rz(__fmul_rn(c1f, 255.0f)) & 0xFFu) << 16) |
-                                           ((__float2uint_rz(__fmul_rn(c2f, 255.0f)) & 0xFFu) << 8) | 0xFFu;
-                            }
-                            w_uvi[j] = (e >> 3) & 31u;
-                        }
-                    }
-                    fb0 = __float_as_uint(b0);
-                    fb1 = __float_as_uint(b1);
-                    fb2 = __float_as_uint(b2);
-                    fb3 = __float_as_uint(b3);
-                }
-                PHASE_MARK(t_b_c2);
-                PHASE_ADD(10, t_b_0, t_b_c2);
-                // record: position, color, texcoord (u, v, texture id), index | barycentric flags, barycentric_color_offset[4]
-                // (voxrender.rs:39-49)
-                auto tu = [&](int j) { return (w_uvi[j] & 1u) ? 0x3F800000u : 0u; };
-                auto tv = [&](int j) { return (w_uvi[j] & 2u) ? 0x3F800000u : 0u; };
-                auto ix = [&](int j) { return cell | ((w_uvi[j] >> 2) << 17); };
-                uint4 *const stg = &s.sc.wstage[warp][0];
-                const uint32_t vq = v0 + vs; // voff = vbuf.len() (voxmesh.rs:123), chunk-relative
+            // ---- C2: complete the records and hand them to emit_kernel (coalesced: thread = face) ----
+            for (uint32_t f = tid; f < tileF; f += NT) {
+                const uint32_t a = s.sc.frecA[f];
+                const uint32_t row = a & 1023u, x = (a >> 10) & 31u;
+                const uint32_t y = row >> 5, z = row & 31u;
+                uint32_t id, cx, nb, is;
                 if (quads_only) {
-                    // every side is a quad: the batch's vertices start at v0 + bt*128, 16-byte aligned
-#pragma unroll
-                    for (uint32_t h = 0; h < 2; h++) {
-                        if (act && (lane >> 4) == h) {
-                            uint4 *o = stg + (lane & 15u) * 10u;
-                            o[0] = make_uint4(w_pos[0], w_col[0], tu(0), tv(0));
-                            o[1] = make_uint4(texbits, ix(0), fb0, fb1);
-                            o[2] = make_uint4(fb2, fb3, w_pos[1], w_col[1]);
-                            o[3] = make_uint4(tu(1), tv(1), texbits, ix(1));
-                            o[4] = make_uint4(fb0, fb1, fb2, fb3);
-                            o[5] = make_uint4(w_pos[2], w_col[2], tu(2), tv(2));
-                            o[6] = make_uint4(texbits, ix(2), fb0, fb1);
-                            o[7] = make_uint4(fb2, fb3, w_pos[3], w_col[3]);
-                            o[8] = make_uint4(tu(3), tv(3), texbits, ix(3));
-                            o[9] = make_uint4(fb0, fb1, fb2, fb3);
-                        }
-                        __syncwarp();
-                        const uint32_t nfh = nbf > 16u * h ? min(16u, nbf - 16u * h) : 0u;
-                        uint4 *g = reinterpret_cast<uint4 *>(vout + v0 + bt * 128u + h * 64u);
-                        for (uint32_t k = lane; k < nfh * 10u; k += 32) g[k] = stg[k];
-                        __syncwarp();
-                    }
-                    // indices: QUAD_INDICES [0,1,2,2,3,0] (stdshapes.rs:198); 6 per side, the batch starts 8-byte aligned
-                    if (act) {
-                        uint2 *o2 = reinterpret_cast<uint2 *>(stg) + lane * 3u;
-                        o2[0] = make_uint2(vq, vq + 1u);
-                        o2[1] = make_uint2(vq + 2u, vq + 2u);
-                        o2[2] = make_uint2(vq + 3u, vq);
-                    }
-                    __syncwarp();
-                    {
-                        uint2 *g2 = reinterpret_cast<uint2 *>(iout + i0 + bt * 192u);
-                        const uint2 *src2 = reinterpret_cast<const uint2 *>(stg);
-                        for (uint32_t k = lane; k < nbf * 3u; k += 32) g2[k] = src2[k];
-                    }
-                    __syncwarp();
-                } else {
-                    // mixed sides (3, 4 or 6 vertices): 8 faces (<= 48 vertices) per pass, 8-byte granularity
-                    uint2 *const st2 = reinterpret_cast<uint2 *>(stg);
-#pragma unroll 1
-                    for (uint32_t g8 = 0; g8 < 4; g8++) {
-                        if (g8 * 8u >= nbf) break;
-                        const int first = (int)(g8 * 8u), last = (int)min(g8 * 8u + 7u, nbf - 1u);
-                        const uint32_t vb = __shfl_sync(FULL, vs, first);
-                        const uint32_t ve = __shfl_sync(FULL, vs + nv, last);
-                        if (act && (lane >> 3) == g8) {
-                            uint2 *o = st2 + (vs - vb) * 5u;
-#pragma unroll
-                            for (uint32_t j = 0; j < 6; j++) {
-                                if (j < nv) {
-                                    o[j * 5 + 0] = make_uint2(w_pos[j], w_col[j]);
-                                    o[j * 5 + 1] = make_uint2(tu(j), tv(j));
-                                    o[j * 5 + 2] = make_uint2(texbits, ix(j));
-                                    o[j * 5 + 3] = make_uint2(fb0, fb1);
-                                    o[j * 5 + 4] = make_uint2(fb2, fb3);
-                                }
-                            }
-                        }
-                        __syncwarp();
-                        uint2 *g2 = reinterpret_cast<uint2 *>(vout + v0 + vb);
-                        for (uint32_t k = lane; k < (ve - vb) * 5u; k += 32) g2[k] = st2[k];
-                        __syncwarp();
-                    }
-                    // indices: [0,1,2,2,3,0] for quads, 0..n-1 for the triangle lists (stdshapes.rs:198)
-                    const uint32_t ib = __shfl_sync(FULL, is, 0);
-                    const uint32_t ie = __shfl_sync(FULL, is + ni, (int)nbf - 1);
-                    uint32_t *sti = reinterpret_cast<uint32_t *>(stg);
-                    if (act) {
-                        const uint32_t pat = nv == 4 ? 0x032210u : 0x543210u;
-#pragma unroll
-                        for (uint32_t k = 0; k < 6; k++)
-                            if (k < ni) sti[is - ib + k] = vq + ((pat >> (4 * k)) & 15u);
-                    }
-                    __syncwarp();
-                    {
-                        uint32_t *gi = iout + i0 + ib;
-                        for (uint32_t k = lane; k < ie - ib; k += 32) gi[k] = sti[k];
-                    }
-                    __syncwarp();
+                    cx = s.cls[(y + 1) * PLANE + (z + 1) * ROWB + XOFF + (int)x];
+                    id = __ldg(center + row * 32 + x) >> 16; // an L2 hit: phase A just streamed the chunk
+                    nb = neighbourhood27(s, (int)y, (int)z, (int)x);
+                    is = f * 6u;
+                } else { // recorded by C1
+                    const uint32_t icr = s.sc.frecC[f];
+                    id = icr & 0xFFFFu;
+                    cx = icr >> 16;
+                    nb = s.sc.frecE[f];
+                    is = s.sc.frecB[f];
                 }
+                const unsigned long long g = fbase + f0 + f;
+                p.frec[g] = (a & 0x3FFFFu) | (cx << 18);
+                p.frec[p.f_cap + g] = (v0 + (a >> 18)) | ((id & 0xFFFu) << 20);
+                p.frec[2 * p.f_cap + g] = (i0 + is) | ((id >> 12) << 21);
+                p.frec[3 * p.f_cap + g] = nb;
+                p.frec[4 * p.f_cap + g] = span_slot;
             }
             PHASE_MARK(t_t3);
             PHASE_ADD(8, t_t2, t_t3);
@@ -967,6 +787,11 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
             PHASE_MARK(t_t4);
             PHASE_ADD(9, t_t3, t_t4);
             r0 = r1;
+        }
+        {
+            const uint32_t TF = s.sc.rowF[1024];
+            const uint32_t padF = (TF + 31u) & ~31u;
+            if (tid < padF - TF) p.frec[fbase + TF + tid] = kFacePad;
         }
         PHASE_MARK(t_c1);
         PHASE_ADD(3, t_b1, t_c1);
