@@ -92,20 +92,31 @@ __global__ void __launch_bounds__(ENT, 4) emit_kernel(MeshParams p) {
     uint2 *const st2 = reinterpret_cast<uint2 *>(stg);
     uint32_t *const stw = reinterpret_cast<uint32_t *>(stg);
 
-    for (unsigned long long b = (unsigned long long)blockIdx.x * ENW + warp; b < n_batches; b += (unsigned long long)gridDim.x * ENW) {
-        const unsigned long long g = b * 32ull + lane;
-        const uint32_t r0 = __ldg(p.frec + g);
+    // the five record words of the warp's next batch are loaded one batch ahead
+    const unsigned long long bstep = (unsigned long long)gridDim.x * ENW;
+    uint32_t q0 = kFacePad, q1 = 0, q2 = 0, q3 = 0, q4 = 0;
+    auto fetch = [&](unsigned long long bb) {
+        if (bb < n_batches) {
+            const unsigned long long gg = bb * 32ull + lane;
+            q0 = __ldg(p.frec + gg);
+            q1 = __ldg(p.frec + p.f_cap + gg);
+            q2 = __ldg(p.frec + 2 * p.f_cap + gg);
+            q3 = __ldg(p.frec + 3 * p.f_cap + gg);
+            q4 = __ldg(p.frec + 4 * p.f_cap + gg);
+        }
+    };
+    fetch((unsigned long long)blockIdx.x * ENW + warp);
+    for (unsigned long long b = (unsigned long long)blockIdx.x * ENW + warp; b < n_batches; b += bstep) {
+        const uint32_t r0 = q0, r1 = q1, r2 = q2, nb = q3, slot = q4; // padding records carry garbage in words 1..4: unused
+        fetch(b + bstep);
         const bool act = r0 != kFacePad;          // padding only ever follows the faces of a chunk
         const uint32_t nbf = __popc(__ballot_sync(FULL, act));
-        uint32_t vq = 0, iq = 0, nv = 0, ni = 0, texbits = 0, cell = 0, slot = 0, st = 0, nb = 0, id = 0;
+        uint32_t vq = 0, iq = 0, nv = 0, ni = 0, texbits = 0, cell = 0, st = 0, id = 0;
         uint32_t fb0 = 0, fb1 = 0, fb2 = 0, fb3 = 0;
         uint32_t w_pos[6], w_col[6], w_uvi[6]; // w_uvi: u | v<<1 | barycentric flags<<2
 #pragma unroll
         for (int j = 0; j < 6; j++) w_pos[j] = w_col[j] = w_uvi[j] = 0;
         if (act) {
-            const uint32_t r1 = __ldg(p.frec + p.f_cap + g), r2 = __ldg(p.frec + 2 * p.f_cap + g);
-            nb = __ldg(p.frec + 3 * p.f_cap + g);
-            slot = __ldg(p.frec + 4 * p.f_cap + g);
             vq = r1 & 0xFFFFFu;
             iq = r2 & 0x1FFFFFu;
             id = (r1 >> 20) | ((r2 >> 21) << 12);
