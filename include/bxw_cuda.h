@@ -196,7 +196,7 @@ int bxw_kernel_time_ms(bxw_ctx *ctx, int which, float *ms, uint64_t *launches, i
 int bxw_region_mesh_candidates(bxw_ctx *ctx, uint32_t *listed, uint32_t *interior);
 /* Profiling builds (-DBXW_PHASE_TIMING) only, zeros otherwise: SM cycles per mesher phase of the last region mesh launch,
  * summed over chunks: fetch, phase A, phases B+scan, phase C, chunks that emitted, chunks, then phase C split into tile
- * setup, face records, warp 0's emission batches, tile-end barrier wait (2 spare). */
+ * setup, face ordering, record hand-off, tile-end barrier wait (2 spare). */
 int bxw_debug_phase_cycles(bxw_ctx *ctx, uint64_t out[12]);
 
 #ifdef __cplusplus

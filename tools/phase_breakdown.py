@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Per-phase SM cycles of the mesher on the bench terrain (needs the profiling build:
+"""Per-phase SM cycles of mesh_kernel (stage / count / order / face records; emit_kernel is a separate launch) on the bench terrain (needs the profiling build:
 `python -m ballxworld_b200.build --phase-timing` and BXW_CUDA_LIB=ballxworld_b200/csrc/libbxw_cuda_phase.so)."""
 import argparse
 import os
@@ -16,8 +16,8 @@ def show(tag, ph, mhz=1965.0):
     print(f"{tag}: chunks {chunks} (emitting {emitted}); per chunk: fetch {fetch / max(chunks, 1) / mhz:.2f} us, "
           f"A {a / max(chunks, 1) / mhz:.2f} us, B+scan {b / max(chunks, 1) / mhz:.2f} us, C {c / max(emitted, 1) / mhz:.2f} us "
           f"(shares {100 * fetch / tot:.0f}/{100 * a / tot:.0f}/{100 * b / tot:.0f}/{100 * c / tot:.0f} %); "
-          f"C split per emitting chunk: tile setup {ph[6] / max(emitted, 1) / mhz:.2f}, face records {ph[7] / max(emitted, 1) / mhz:.2f}, "
-          f"warp-0 batches {ph[8] / max(emitted, 1) / mhz:.2f} (per-face part {ph[10] / max(emitted, 1) / mhz:.2f}, indices {ph[11] / max(emitted, 1) / mhz:.2f}), end barrier {ph[9] / max(emitted, 1) / mhz:.2f} us")
+          f"C split per emitting chunk: tile setup {ph[6] / max(emitted, 1) / mhz:.2f}, face order {ph[7] / max(emitted, 1) / mhz:.2f}, "
+          f"record hand-off {ph[8] / max(emitted, 1) / mhz:.2f}, end barrier {ph[9] / max(emitted, 1) / mhz:.2f} us")
 
 
 def main():
