@@ -43,21 +43,16 @@ __device__ __forceinline__ void warp_copy_out(uint32_t *dst, const uint32_t *sta
     const uint32_t total = misal + n, nfull = total >> 2;
     const uint4 *s4 = reinterpret_cast<const uint4 *>(stage16);
     uint4 *d4 = reinterpret_cast<uint4 *>(d0);
-    for (uint32_t k = lane; k < nfull; k += 32) {
-        const uint4 v = s4[k];
-        if (k == 0 && misal) { // the first unit starts with `misal` words that belong to the previous side
-            if (misal <= 1) d0[1] = v.y;
-            if (misal <= 2) d0[2] = v.z;
-            d0[3] = v.w;
-        } else {
-            d4[k] = v;
-        }
+    // unit 0 may start with `misal` words that belong to the previous side: lanes 1..3 write its own words one by one
+    if (misal) {
+        if (lane >= misal && lane < 4u && lane < total) d0[lane] = stage16[lane];
+    } else if (lane == 0 && nfull) {
+        d4[0] = s4[0];
     }
-    const uint32_t rem = total & 3u; // tail words (when nfull == 0 the head words are here as well)
-    if (lane < rem) {
-        const uint32_t w = nfull * 4u + lane;
-        if (w >= misal) d0[w] = stage16[w];
-    }
+#pragma unroll 2
+    for (uint32_t k = lane + 1u; k < nfull; k += 32) d4[k] = s4[k];
+    const uint32_t rem = total & 3u; // tail words of the last, partial unit
+    if (lane < rem && (nfull || !misal)) d0[nfull * 4u + lane] = stage16[nfull * 4u + lane]; // (a short misaligned run was all head)
 }
 
 __global__ void __launch_bounds__(ENT, 4) emit_kernel(MeshParams p) {
