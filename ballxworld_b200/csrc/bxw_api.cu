@@ -36,7 +36,8 @@ struct Region {
     bxw_vertex *varena = nullptr;
     uint32_t *iarena = nullptr;
     unsigned long long v_cap = 0, i_cap = 0;
-    uint32_t *frec = nullptr;          // face records between mesh_kernel and emit_kernel (kFaceWords arrays of f_cap)
+    uint4 *frec = nullptr;             // face records between mesh_kernel and emit_kernel (device_common.cuh)
+    uint32_t *fslot = nullptr;         // span slot per 32 records
     unsigned long long f_cap = 0;
     bool reserved = false;
     MeshCounters *counters = nullptr;
@@ -178,6 +179,7 @@ void region_free(Region &r) {
     cudaFree(r.varena);
     cudaFree(r.iarena);
     cudaFree(r.frec);
+    cudaFree(r.fslot);
     cudaFree(r.counters);
     cudaFree(r.dirty);
     cudaFree(r.dirty_work);
@@ -354,9 +356,13 @@ int faces_resize(bxw_ctx *ctx, Region &r, unsigned long long f_cap) {
     if (f_cap <= r.f_cap) return BXW_OK;
     CK(cudaStreamSynchronize(ctx->stream));
     cudaFree(r.frec);
+    cudaFree(r.fslot);
     r.frec = nullptr;
+    r.fslot = nullptr;
     r.f_cap = 0;
-    CK(cudaMalloc(&r.frec, f_cap * kFaceWords * sizeof(uint32_t)));
+    f_cap = (f_cap + 31ull) & ~31ull;
+    CK(cudaMalloc(&r.frec, f_cap * sizeof(uint4)));
+    CK(cudaMalloc(&r.fslot, (f_cap / 32) * sizeof(uint32_t)));
     r.f_cap = f_cap;
     return BXW_OK;
 }
@@ -458,6 +464,7 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
         p.v_cap = r.v_cap;
         p.i_cap = r.i_cap;
         p.frec = r.frec;
+        p.fslot = r.fslot;
         p.f_cap = r.f_cap;
         p.count_only = count_only ? 1 : 0;
         CK(cudaEventRecord(ctx->ev_m0, ctx->stream));

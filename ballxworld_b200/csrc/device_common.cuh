@@ -46,9 +46,10 @@ struct MeshParams {
     bxw_vertex *varena;
     uint32_t *iarena;
     unsigned long long v_cap, i_cap;
-    // face records between mesh_kernel (stage, cull, count, order) and emit_kernel (vertex / index construction): five
-    // word arrays of f_cap entries, record k of a chunk at its face base + k. See kFaceWords below.
-    uint32_t *frec;
+    // face records between mesh_kernel (stage, cull, count, order) and emit_kernel (vertex / index construction): f_cap
+    // records + f_cap / 32 span slots, see kFacePad below
+    uint4 *frec;
+    uint32_t *fslot;
     unsigned long long f_cap;
     MeshCounters *counters;
     const MeshTables *tables;
@@ -63,13 +64,12 @@ struct MeshParams {
 
 void launch_mesh_kernel(const MeshParams &p, int sm_count, cudaStream_t stream);
 
-// Face record (SoA, word w of record k at frec[w * f_cap + k]):
-//   0: row (y*32+z, 10 bits) | x << 10 | world dir << 15 | class << 18; 0xFFFFFFFF = padding (no face)
-//   1: first vertex of the side, chunk-relative (20 bits) | (block id & 0xFFF) << 20
-//   2: first index of the side, chunk-relative (21 bits) | (block id >> 12) << 21
-//   3: occupancy of the cell's 3x3x3 neighbourhood, bit (dy+1)*9 + (dz+1)*3 + (dx+1)
-//   4: span slot of the chunk (where its arena offsets are)
-constexpr int kFaceWords = 5;
+// Face record: one uint4 per visible side, frec[k], in the reference's emission order; every chunk's records start on a
+// multiple of 32 and are padded to one, and fslot[k / 32] holds the chunk's span slot (where its arena offsets are).
+//   x: row (y*32+z, 10 bits) | x << 10 | world dir << 15 | class << 18; 0xFFFFFFFF = padding (no face)
+//   y: first vertex of the side, chunk-relative (20 bits) | (block id & 0xFFF) << 20
+//   z: first index of the side, chunk-relative (21 bits) | (block id >> 12) << 21
+//   w: occupancy of the cell's 3x3x3 neighbourhood, bit (dy+1)*9 + (dz+1)*3 + (dx+1)
 constexpr uint32_t kFacePad = 0xFFFFFFFFu;
 // Second half of mesh_from_chunk (voxmesh.rs:122-177): builds the vertices and indices of every recorded side.
 void launch_emit_kernel(const MeshParams &p, int sm_count, cudaStream_t stream);

@@ -4,7 +4,7 @@
 // mesh_kernel needs ~110 KB of shared memory per CTA (the 34^3 class table) and therefore runs 16 warps per SM, too few to
 // hide the dependent table lookups of vertex construction. Here the work is one face per lane with no large shared state,
 // so many warps are resident. Input: the face records mesh_kernel wrote in the reference's emission order
-// (device_common.cuh: kFaceWords); every chunk's records start on a multiple of 32, so the 32 faces of a warp belong to one
+// (device_common.cuh: kFacePad); every chunk's records start on a multiple of 32, so the 32 faces of a warp belong to one
 // chunk and their vertices / indices form one contiguous run of its arena span. The warp transposes that run through its
 // private shared-memory slice and writes it with coalesced 16-byte stores.
 //
@@ -87,22 +87,19 @@ __global__ void __launch_bounds__(ENT, 4) emit_kernel(MeshParams p) {
     uint2 *const st2 = reinterpret_cast<uint2 *>(stg);
     uint32_t *const stw = reinterpret_cast<uint32_t *>(stg);
 
-    // the five record words of the warp's next batch are loaded one batch ahead
+    // the records of the warp's next batch (one 16-byte load per lane + the batch's span slot) are loaded one batch ahead
     const unsigned long long bstep = (unsigned long long)gridDim.x * ENW;
-    uint32_t q0 = kFacePad, q1 = 0, q2 = 0, q3 = 0, q4 = 0;
+    uint4 q = make_uint4(kFacePad, 0u, 0u, 0u);
+    uint32_t qslot = 0;
     auto fetch = [&](unsigned long long bb) {
         if (bb < n_batches) {
-            const unsigned long long gg = bb * 32ull + lane;
-            q0 = __ldg(p.frec + gg);
-            q1 = __ldg(p.frec + p.f_cap + gg);
-            q2 = __ldg(p.frec + 2 * p.f_cap + gg);
-            q3 = __ldg(p.frec + 3 * p.f_cap + gg);
-            q4 = __ldg(p.frec + 4 * p.f_cap + gg);
+            q = __ldg(p.frec + bb * 32ull + lane);
+            qslot = __ldg(p.fslot + bb);
         }
     };
     fetch((unsigned long long)blockIdx.x * ENW + warp);
     for (unsigned long long b = (unsigned long long)blockIdx.x * ENW + warp; b < n_batches; b += bstep) {
-        const uint32_t r0 = q0, r1 = q1, r2 = q2, nb = q3, slot = q4; // padding records carry garbage in words 1..4: unused
+        const uint32_t r0 = q.x, r1 = q.y, r2 = q.z, nb = q.w, slot0 = qslot;
         fetch(b + bstep);
         const bool act = r0 != kFacePad;          // padding only ever follows the faces of a chunk
         const uint32_t nbf = __popc(__ballot_sync(FULL, act));
@@ -181,8 +178,7 @@ __global__ void __launch_bounds__(ENT, 4) emit_kernel(MeshParams p) {
         } else {
             if (act) face(std::integral_constant<uint32_t, 6>());
         }
-        // the chunk's arena span (lane 0 always holds a face)
-        const uint32_t slot0 = __shfl_sync(FULL, slot, 0);
+        // the chunk's arena span
         const unsigned long long v_off = p.spans[slot0].v_off, i_off = p.spans[slot0].i_off;
         bxw_vertex *const vout = p.varena + v_off;
         uint32_t *const iout = p.iarena + i_off;

@@ -774,12 +774,8 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                     nb = s.sc.frecE[f];
                     is = s.sc.frecB[f];
                 }
-                const unsigned long long g = fbase + f0 + f;
-                p.frec[g] = (a & 0x3FFFFu) | (cx << 18);
-                p.frec[p.f_cap + g] = (v0 + (a >> 18)) | ((id & 0xFFFu) << 20);
-                p.frec[2 * p.f_cap + g] = (i0 + is) | ((id >> 12) << 21);
-                p.frec[3 * p.f_cap + g] = nb;
-                p.frec[4 * p.f_cap + g] = span_slot;
+                p.frec[fbase + f0 + f] = make_uint4((a & 0x3FFFFu) | (cx << 18), (v0 + (a >> 18)) | ((id & 0xFFFu) << 20),
+                                                    (i0 + is) | ((id >> 12) << 21), nb);
             }
             PHASE_MARK(t_t3);
             PHASE_ADD(8, t_t2, t_t3);
@@ -791,7 +787,8 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
         {
             const uint32_t TF = s.sc.rowF[1024];
             const uint32_t padF = (TF + 31u) & ~31u;
-            if (tid < padF - TF) p.frec[fbase + TF + tid] = kFacePad;
+            if (tid < padF - TF) p.frec[fbase + TF + tid] = make_uint4(kFacePad, 0u, 0u, 0u);
+            for (uint32_t t = tid; t < (padF >> 5); t += NT) p.fslot[(fbase >> 5) + t] = span_slot;
         }
         PHASE_MARK(t_c1);
         PHASE_ADD(3, t_b1, t_c1);
