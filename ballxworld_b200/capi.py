@@ -98,6 +98,8 @@ def load_library():
         "bxw_region_mesh_sphere": ([vp, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, u32p, u64p, u64p], C.c_int),
         "bxw_region_mesh_spans": ([vp, vp], C.c_int),
         "bxw_region_mesh_fetch": ([vp, vp, C.c_uint64, vp, C.c_uint64], C.c_int),
+        "bxw_region_mesh_fetch_async": ([vp, vp, C.c_uint64, vp, C.c_uint64], C.c_int),
+        "bxw_region_fetch_wait": ([vp], C.c_int),
         "bxw_region_apply_changes": ([vp, vp, C.c_uint32, u32p], C.c_int),
         "bxw_region_remesh_dirty": ([vp, u32p], C.c_int),
         "bxw_region_halo_bytes": ([vp], C.c_size_t),
@@ -341,6 +343,12 @@ class Context:
 
     def region_mesh_fetch_ptr(self, vptr, n_vertices, iptr, n_indices):
         self._ck(self.L.bxw_region_mesh_fetch(self.h, C.c_void_p(vptr), n_vertices, C.c_void_p(iptr), n_indices))
+
+    def region_mesh_fetch_async_ptr(self, vptr, n_vertices, iptr, n_indices):
+        self._ck(self.L.bxw_region_mesh_fetch_async(self.h, C.c_void_p(vptr), n_vertices, C.c_void_p(iptr), n_indices))
+
+    def region_fetch_wait(self):
+        self._ck(self.L.bxw_region_fetch_wait(self.h))
 
     def region_apply_changes(self, changes):
         ch = np.ascontiguousarray(changes, dtype=CHANGE_DTYPE)

@@ -77,6 +77,9 @@ struct bxw_ctx {
     // timing
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_m0 = nullptr, ev_m1 = nullptr;
     cudaEvent_t ev_g0 = nullptr, ev_g1 = nullptr, ev_g2 = nullptr; // before heightmap / before fill / after fill
+    cudaStream_t copy_stream = nullptr;                            // bxw_region_mesh_fetch_async
+    cudaEvent_t ev_mesh_done = nullptr, ev_copy_done = nullptr;
+    bool copy_pending = false;                                     // ev_copy_done recorded and not yet waited for
     bool gen_pending = false, gen_pending_fused = false;          // ev_g* recorded, not yet read
     double mesh_ms = 0.0, fill_ms = 0.0, hmap_ms = 0.0;
     uint64_t mesh_launches = 0, fill_launches = 0, hmap_launches = 0;
@@ -194,6 +197,8 @@ void region_free(Region &r) {
 
 int region_alloc(bxw_ctx *ctx, Region &r, int32_t cx0, int32_t cy0, int32_t cz0, uint32_t nx, uint32_t ny, uint32_t nz) {
     CK(cudaSetDevice(ctx->device));
+    if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream)); // an asynchronous fetch may still read the old arena
+    ctx->copy_pending = false;
     region_free(r);
     r.cx0 = cx0;
     r.cy0 = cy0;
@@ -335,6 +340,10 @@ int arena_resize(bxw_ctx *ctx, Region &r, unsigned long long v_cap, unsigned lon
                  unsigned long long keep_i) {
     bxw_vertex *nv = nullptr;
     uint32_t *ni = nullptr;
+    if (ctx->copy_pending) { // an asynchronous fetch may still be reading the arena that is about to be freed
+        CK(cudaEventSynchronize(ctx->ev_copy_done));
+        ctx->copy_pending = false;
+    }
     if (v_cap < 64) v_cap = 64;
     if (i_cap < 64) i_cap = 64;
     CK(cudaMalloc(&nv, v_cap * sizeof(bxw_vertex)));
@@ -471,6 +480,8 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
         launch_mesh_kernel(p, ctx->sm_count, ctx->stream);
         ctx->launches += 1;
         if (!count_only) { // vertices and indices of the recorded sides (returns at once if a chunk did not fit)
+            // the arena is rewritten from here on: an asynchronous fetch of the previous meshes has to be through
+            if (ctx->copy_pending) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done, 0));
             launch_emit_kernel(p, ctx->sm_count, ctx->stream);
             ctx->launches += 1;
         }
@@ -592,7 +603,10 @@ int bxw_create(int device, bxw_ctx **out) {
     if (cudaEventCreate(&ctx->ev_a) != cudaSuccess || cudaEventCreate(&ctx->ev_b) != cudaSuccess ||
         cudaEventCreate(&ctx->ev_m0) != cudaSuccess || cudaEventCreate(&ctx->ev_m1) != cudaSuccess ||
         cudaEventCreate(&ctx->ev_g0) != cudaSuccess || cudaEventCreate(&ctx->ev_g1) != cudaSuccess ||
-        cudaEventCreate(&ctx->ev_g2) != cudaSuccess)
+        cudaEventCreate(&ctx->ev_g2) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_mesh_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_copy_done, cudaEventDisableTiming) != cudaSuccess)
         return bail(BXW_E_CUDA);
     MeshTables *t = new (std::nothrow) MeshTables();
     if (!t) return bail(BXW_E_NOMEM);
@@ -613,6 +627,7 @@ void bxw_destroy(bxw_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     region_free(ctx->region);
     region_free(ctx->scratch);
     cudaFree(ctx->d_kind);
@@ -631,6 +646,12 @@ void bxw_destroy(bxw_ctx *ctx) {
     if (ctx->ev_g0) cudaEventDestroy(ctx->ev_g0);
     if (ctx->ev_g1) cudaEventDestroy(ctx->ev_g1);
     if (ctx->ev_g2) cudaEventDestroy(ctx->ev_g2);
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
+    }
+    if (ctx->ev_mesh_done) cudaEventDestroy(ctx->ev_mesh_done);
+    if (ctx->ev_copy_done) cudaEventDestroy(ctx->ev_copy_done);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -846,6 +867,8 @@ int bxw_region_create(bxw_ctx *ctx, int32_t cx0, int32_t cy0, int32_t cz0, uint3
 int bxw_region_destroy(bxw_ctx *ctx) {
     if (!ctx) return BXW_E_INVALID;
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));
+    ctx->copy_pending = false;
     region_free(ctx->region);
     return BXW_OK;
 }
@@ -1066,6 +1089,29 @@ int bxw_region_mesh_fetch(bxw_ctx *ctx, bxw_vertex *vertices, uint64_t n_vertice
     if (n_vertices && vertices) CK(cudaMemcpyAsync(vertices, r.varena, n_vertices * sizeof(bxw_vertex), cudaMemcpyDeviceToHost, ctx->stream));
     if (n_indices && indices) CK(cudaMemcpyAsync(indices, r.iarena, n_indices * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return BXW_OK;
+}
+
+int bxw_region_mesh_fetch_async(bxw_ctx *ctx, bxw_vertex *vertices, uint64_t n_vertices, uint32_t *indices, uint64_t n_indices) {
+    if (!ctx || !ctx->region.live) return fail(ctx, BXW_E_INVALID, "no region");
+    Region &r = ctx->region;
+    if (n_vertices > r.v_cap || n_indices > r.i_cap) return fail(ctx, BXW_E_INVALID, "fetch exceeds arena");
+    CK(cudaEventRecord(ctx->ev_mesh_done, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_mesh_done, 0));
+    if (n_vertices && vertices)
+        CK(cudaMemcpyAsync(vertices, r.varena, n_vertices * sizeof(bxw_vertex), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if (n_indices && indices) CK(cudaMemcpyAsync(indices, r.iarena, n_indices * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->ev_copy_done, ctx->copy_stream));
+    ctx->copy_pending = true;
+    return BXW_OK;
+}
+
+int bxw_region_fetch_wait(bxw_ctx *ctx) {
+    if (!ctx) return BXW_E_INVALID;
+    if (ctx->copy_pending) {
+        CK(cudaEventSynchronize(ctx->ev_copy_done));
+        ctx->copy_pending = false;
+    }
     return BXW_OK;
 }
 

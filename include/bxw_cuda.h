@@ -165,6 +165,11 @@ int bxw_region_mesh_spans(bxw_ctx *ctx, bxw_mesh_span *spans);
 /* Copy arena extents [0,arena_vertices) / [0,arena_indices) to host (pinned memory recommended). */
 int bxw_region_mesh_fetch(bxw_ctx *ctx, bxw_vertex *vertices, uint64_t n_vertices, uint32_t *indices,
                           uint64_t n_indices);
+/* The same copy on the context's copy stream, returning at once: the next generate / mesh pass overlaps the transfer (only
+ * the kernel that rewrites the arena waits for it). The host buffers (pinned) are valid after bxw_region_fetch_wait. */
+int bxw_region_mesh_fetch_async(bxw_ctx *ctx, bxw_vertex *vertices, uint64_t n_vertices, uint32_t *indices,
+                                uint64_t n_indices);
+int bxw_region_fetch_wait(bxw_ctx *ctx);
 /* World::apply_voxel_changes (worldmgr.rs:312-357): CAS each change in order, mark touching_chunks
  * (lib.rs:110-135) dirty. n_dirty = interior chunks now dirty. */
 int bxw_region_apply_changes(bxw_ctx *ctx, const bxw_voxel_change *changes, uint32_t n, uint32_t *n_dirty);

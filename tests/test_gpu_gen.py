@@ -159,3 +159,24 @@ def test_fp32_variant_stays_close(ctx):
     assert (e64 != e32).mean() < 0.02
     ctx.region_generate(0, 64)
     ctx.region_destroy()
+
+
+def test_async_fetch_overlaps_the_next_pass_safely(ctx):
+    """bxw_region_mesh_fetch_async returns at once; a following generate + mesh (another seed, so the arena content changes)
+    must not disturb the copy: the kernel that rewrites the arena waits for it."""
+    import torch
+    from ballxworld_b200.capi import VERTEX_DTYPE
+
+    ctx.region_create(6, -1, 2, 12, 6, 12)
+    av, ai = ctx.region_generate_and_mesh(0, 64)
+    V0, I0 = ctx.region_mesh_fetch(av, ai)                       # synchronous copy = ground truth
+    hv = torch.zeros(av * 40, dtype=torch.uint8, pin_memory=True)
+    hi = torch.zeros(ai, dtype=torch.int32, pin_memory=True)
+    ctx.region_mesh_fetch_async_ptr(hv.data_ptr(), av, hi.data_ptr(), ai)
+    av2, ai2 = ctx.region_generate_and_mesh(0x13372137CAFE, 64)  # rewrites blocks, spans and the arena
+    ctx.region_fetch_wait()
+    assert hv.numpy().tobytes() == V0.tobytes() and np.array_equal(hi.numpy().view(np.uint32), I0)
+    V1, _ = ctx.region_mesh_fetch(av2, ai2)
+    assert (av2, ai2) != (av, ai) or V1.tobytes() != V0.tobytes()   # the second pass really produced something else
+    ctx.region_fetch_wait()                                       # idempotent
+    ctx.region_destroy()
