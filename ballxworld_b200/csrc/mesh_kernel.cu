@@ -39,7 +39,7 @@ constexpr int VC = 4096;     // vertex slots per emission tile
 
 // phase-A staging: every warp streams its share of the 34^3 neighbourhood through a private cp.async ring.
 // One unit = a third of a y' layer: 3 warp copies of 4 rows (12 rows x 128 B) + (first third only) the layer's x-halo.
-constexpr int RSLOTS = 3;
+constexpr int RSLOTS = 4;
 constexpr int RSLOT_BYTES = 3 * 512 + 128 + 128 + 16;
 
 struct Scratch { // phases B, S, C
@@ -507,30 +507,35 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
             const std::integral_constant<int, 1> P1;
             const std::integral_constant<int, 2> P2;
             const int tail_g = warp < 6 ? (warp < 3 ? 0 : 33) * 3 + warp % 3 : N_UNITS; // N_UNITS = none (empty commit)
+            // The warp's 12 inner units u = 3 li + part (and then its outer unit, u = 12) go through slot u & 3, three units
+            // ahead of their use.
             issue_inner(warp, 0, P0);
             issue_inner(warp, 1, P1);
+            issue_inner(warp, 2, P2);
             for (int li = 0; li < 4; li++) {
                 const int by = warp + NW * li; // layer yy = by + 1
-                // unit (li, 0) in slot 0; meanwhile fetch (li, 2) into slot 2
+                const int u0 = 3 * li;
+                // unit (li, 0); meanwhile fetch (li + 1, 0) -- or this warp's outer-layer unit
                 __syncwarp();
-                issue_inner(by, 2, P2);
-                cp_async_wait<2>();
-                __syncwarp();
-                process(by + 1, ring, P0);
-                // unit (li, 1) in slot 1; fetch (li + 1, 0) -- or this warp's outer-layer unit -- into slot 0
-                __syncwarp();
-                if (li < 3) issue_inner(by + NW, 0, P0);
+                if (li < 3) issue_inner(by + NW, (u0 + 3) & 3, P0);
                 else issue(tail_g, 0);
-                cp_async_wait<2>();
+                cp_async_wait<3>();
                 __syncwarp();
-                process(by + 1, ring + RSLOT_BYTES, P1);
-                // unit (li, 2) in slot 2; fetch (li + 1, 1) into slot 1
+                process(by + 1, ring + (u0 & 3) * RSLOT_BYTES, P0);
+                // unit (li, 1); fetch (li + 1, 1)
                 __syncwarp();
-                if (li < 3) issue_inner(by + NW, 1, P1);
+                if (li < 3) issue_inner(by + NW, (u0 + 4) & 3, P1);
                 else cp_async_commit();
-                cp_async_wait<2>();
+                cp_async_wait<3>();
                 __syncwarp();
-                process(by + 1, ring + 2 * RSLOT_BYTES, P2);
+                process(by + 1, ring + ((u0 + 1) & 3) * RSLOT_BYTES, P1);
+                // unit (li, 2); fetch (li + 1, 2)
+                __syncwarp();
+                if (li < 3) issue_inner(by + NW, (u0 + 5) & 3, P2);
+                else cp_async_commit();
+                cp_async_wait<3>();
+                __syncwarp();
+                process(by + 1, ring + ((u0 + 2) & 3) * RSLOT_BYTES, P2);
             }
             if (tail_g < N_UNITS) {
                 cp_async_wait<0>();
