@@ -93,6 +93,51 @@ def main():
                 if gv.tobytes() != wv.tobytes() or not np.array_equal(gi, wi):
                     bad += 1
                     print(f"rank {rank}: terrain chunk {(ix, iy, iz)} differs: {len(gv)} vs {len(wv)} vertices", flush=True)
+    # Edits across the slab boundaries (SURVEY.md section 8d cfg 5): every rank receives the same global change list and applies
+    # what falls inside its own storage box, shell included -- so a change in rank r's last voxel column also lands in rank
+    # r+1's shell plane and dirties rank r+1's first chunk column, with no further exchange.
+    world_chunks = {}
+
+    def chunk_of(cx, cy, cz):
+        if (cx, cy, cz) not in world_chunks:
+            world_chunks[(cx, cy, cz)] = g.generate_chunk(cx, cy, cz).copy()
+        return world_chunks[(cx, cy, cz)]
+
+    def voxel(x, y, z):
+        return chunk_of(x >> 5, y >> 5, z >> 5), (x & 31) + 32 * (z & 31) + 1024 * (y & 31)
+
+    changes = []
+    stone = O.STANDARD_GEN_IDS[3] << 16
+    for r in range(world - 1):
+        bx = (9 + slab_partition(per * world, world, r).x0 + slab_partition(per * world, world, r).nx) * 32  # first voxel column of rank r+1
+        for x in (bx - 1, bx):
+            for z in (5, 31, 32):
+                h = g.params(x, z).height
+                for (y, to) in ((h, 0), (h + 2, stone)):            # dig out the surface block, float a stone block above it
+                    c, k = voxel(x, y, z)
+                    changes.append((x, y, z, int(c[k]), to))
+                    c[k] = to
+    nd = ctx.region_apply_changes(np.array(changes, dtype=bxw.CHANGE_DTYPE))
+    n_re = ctx.region_remesh_dirty()
+    spans = ctx.region_mesh_spans()
+    av = int((spans["v_off"] + spans["v_count"]).max())
+    ai = int((spans["i_off"] + spans["i_count"]).max())
+    V, I = ctx.region_mesh_fetch(av, ai)
+    edited_seen = 0
+    for ix in sorted({0, slab.nx - 1}):
+        for iy in range(ny2):
+            for iz in range(nz):
+                d = [chunk_of(9 + slab.x0 + ix + dx, oy + iy + dy, iz + dz) for dy in (-1, 0, 1) for dz in (-1, 0, 1) for dx in (-1, 0, 1)]
+                wv, wi = O.mesh_from_dense27(oreg, d)
+                s = spans[ix + slab.nx * (iz + nz * iy)]
+                gv = V[int(s["v_off"]): int(s["v_off"]) + int(s["v_count"])]
+                gi = I[int(s["i_off"]): int(s["i_off"]) + int(s["i_count"])]
+                if gv.tobytes() != wv.tobytes() or not np.array_equal(gi, wi):
+                    bad += 1
+                    print(f"rank {rank}: edited terrain chunk {(ix, iy, iz)} differs: {len(gv)} vs {len(wv)} vertices", flush=True)
+    if world > 1 and (nd == 0 or n_re != nd):
+        bad += 1
+        print(f"rank {rank}: edits dirtied {nd} chunks, re-meshed {n_re}", flush=True)
     t = torch.tensor([bad], device="cuda")
     dist.all_reduce(t)
     if rank == 0:
