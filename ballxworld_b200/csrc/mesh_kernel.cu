@@ -1,24 +1,27 @@
-// mesh_kernel.cu — the chunk mesher as one persistent sm_100a kernel.
+// mesh_kernel.cu — first half of the chunk mesher: everything that needs the 34^3 neighbourhood on chip.
 //
-// Semantics: src/client/render/voxmesh.rs:45-190 (mesh_from_chunk) for every chunk of a work list, reading the
-// GPU-resident dense block storage directly (the reference decodes 27 RLE streams into a 34^3 table first,
-// voxmesh.rs:53-80; RleVoxelIterator::skip_until_index returns exactly blocks_yzx[idx]).
+// Semantics: src/client/render/voxmesh.rs:45-121 (mesh_from_chunk up to the culling decision, plus the emission ORDER) for
+// every chunk of a work list, reading the GPU-resident dense block storage directly (the reference decodes 27 RLE streams
+// into a 34^3 table first, voxmesh.rs:53-80; RleVoxelIterator::skip_until_index returns exactly blocks_yzx[idx]).
+// Output: per chunk its arena span (vertex / index counts and offsets) and one face record per visible side in the
+// reference's emission order; emit_kernel.cu turns the records into vertices and indices (voxmesh.rs:122-177).
 //
-// One CTA (256 threads, two per SM) meshes one chunk at a time:
+// One persistent CTA (256 threads, two per SM) takes one chunk at a time:
 //   A  stage the chunk plus its 1-voxel halo (34^3) in shared memory as one CLASS BYTE per voxel (class = shape x
 //      orientation of the datum, 0 = no mesh) plus one 34-bit SOLID word per (y,z) row. The rows stream through
-//      warp-private cp.async rings (16-byte copies, two units ahead); the x-halo comes from the neighbour chunks'
+//      warp-private cp.async rings (16-byte copies, three units ahead); the x-halo comes from the neighbour chunks'
 //      x-face planes. A unit (384 voxels) that is one single datum costs one match + one vote (terrain is mostly
-//      uniform); a 34^3 neighbourhood that is one void/cube datum ends the chunk after one barrier.
+//      uniform); a 34^3 neighbourhood that is one void/cube datum ends the chunk after one barrier. In height-map mode
+//      (bxw_region_generate_and_mesh) the table is derived from the 34x34 column parameters instead of reading voxels.
 //   B  per-row vertex/index/face counts. Cubes-and-void chunks: one thread per row, visibility by bit operations
 //      on the solid words (voxmesh.rs:119 reduces to solid & ~neighbour-solid). Chunks containing slopes/corners:
 //      one warp per row, lane = x, the general orientation-aware test (voxmesh.rs:105-121).
 //   S  block-wide exclusive scan of the 1024 row counts = the reference's emission order (cells y,z,x-major,
-//      directions 0..5 minor, voxmesh.rs:94,104); one atomicAdd pair reserves the chunk's arena span.
-//   C  emission in tiles of <=1024 faces: (C1) face records in emission order; then, fused per warp and without block
-//      barriers, 32 faces at a time: per-face AO occluder counts (popcount of the cell's 3x3x3 occupancy under the
-//      vertex's sample mask), barycentric colour sums and texture ids in registers, index values and 40-byte vertex
-//      records staged in the warp's shared-memory slice and written out with coalesced 16-byte stores.
+//      directions 0..5 minor, voxmesh.rs:94,104); one atomicAdd triple reserves the chunk's vertex span, index span and
+//      face records.
+//   C  face records in tiles of <=1024 sides: (C1) the sides in emission order with their first vertex / index; (C2) thread per
+//      side: class, block id, the 27-bit occupancy of the cell's 3x3x3 neighbourhood (all the AO test needs,
+//      voxmesh.rs:128-137), written as one uint4 (device_common.cuh).
 #include <type_traits>
 
 #include "device_common.cuh"
@@ -34,8 +37,8 @@ constexpr int PLANE = kClsPlaneBytes;
 constexpr int XOFF = 4;
 constexpr int CLS_BYTES = 34 * PLANE;
 constexpr unsigned FULL = 0xFFFFFFFFu;
-constexpr int FC = 1024;     // faces per emission tile
-constexpr int VC = 4096;     // vertex slots per emission tile
+constexpr int FC = 1024;     // sides per record tile
+constexpr int VC = 4096;     // vertices per record tile (the tile-relative first vertex has 14 bits)
 
 // phase-A staging: every warp streams its share of the 34^3 neighbourhood through a private cp.async ring.
 // One unit = a third of a y' layer: 3 warp copies of 4 rows (12 rows x 128 B) + (first third only) the layer's x-halo.
@@ -46,7 +49,7 @@ struct Scratch { // phases B, S, C
     uint32_t rowV[1028];   // exclusive prefix over rows: first vertex of the row (chunk-relative); [1024] = total
     uint32_t rowI[1028];
     uint32_t rowF[1028];
-    // emission tile: face records written by C1
+    // record tile: written by C1
     uint32_t frecA[FC];   // row | x<<10 | dir<<15 | vstart<<18 (tile-relative first vertex)
     uint32_t frecB[FC];   // tile-relative first index (tiles with non-quad sides)
     uint32_t frecC[FC];   // block id | class<<16 (tiles with non-quad sides)
