@@ -180,6 +180,7 @@ class Context:
         self._ck(self.L.bxw_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
 
     OPT_CHUNK_SUMMARIES = 0
+    OPT_MESH_FROM_HEIGHT_MAP = 1
 
     def set_option(self, option, value):
         self._ck(self.L.bxw_set_option(self.h, option, int(value)))

@@ -23,7 +23,7 @@ __global__ void halo_plane_kernel(uint32_t *blocks, uint32_t *xface, unsigned lo
         if (summary) { // the chunk stays known-uniform only if every imported voxel equals its uniform datum
             const size_t c = (size_t)(sx + SX * (sz + SZ * sy));
             const unsigned long long sm = summary[c];
-            if ((sm & kUniformBit) && (uint32_t)sm != *p) summary[c] = 0;
+            if (sm && (!(sm & kUniformBit) || (uint32_t)sm != *p)) summary[c] = 0; // (also drops the solid-terrain bits)
         }
     } else {
         *p = *v;
@@ -501,6 +501,12 @@ __global__ void __launch_bounds__(256) cand_flags_kernel(StorageCandParams p, ui
                 }
                 keep = !same;
             }
+        }
+        if (keep && p.solids_are_cubes && ((sc >> kSolidShift) & 1ull)) {
+            // solid terrain throughout: no side is visible iff each of the six neighbours shows a solid plane
+            auto plane = [&](long long off, int d) { return (int)((p.summary[(size_t)((long long)c0 + off)] >> (kSolidShift + 1 + d)) & 1ull); };
+            const long long sxs = 1, szs = p.SX, sys = (long long)p.SX * p.SZ;
+            keep = !(plane(-sxs, 1) & plane(sxs, 0) & plane(-sys, 3) & plane(sys, 2) & plane(-szs, 5) & plane(szs, 4));
         }
         p.keep[w] = (uint8_t)keep;
     }

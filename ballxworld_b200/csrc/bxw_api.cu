@@ -44,7 +44,8 @@ struct Region {
     MeshCounters *h_counters = nullptr; // pinned
     uint8_t *dirty = nullptr;           // [n_work] interior dirty flags
     uint32_t *dirty_work = nullptr, *dirty_span = nullptr, *dirty_count = nullptr;
-    unsigned long long *summary = nullptr; // per storage chunk: kUniformBit | datum, or 0 (device_common.cuh)
+    unsigned long long *summary = nullptr; // per storage chunk: kUniformBit | datum, solid-terrain bits, or 0 (device_common.cuh)
+    uint16_t fill_ids[5] = {0, 0, 0, 0, 0}; // generator block ids of the last fill (what the solid-terrain bits refer to)
     uint8_t *cand_keep = nullptr;          // candidate-list scratch
     uint32_t *cand_blk = nullptr;
     size_t n_storage() const { return (size_t)SX * SY * SZ; }
@@ -84,6 +85,7 @@ struct bxw_ctx {
     double mesh_ms = 0.0, fill_ms = 0.0, hmap_ms = 0.0;
     uint64_t mesh_launches = 0, fill_launches = 0, hmap_launches = 0;
     bool use_summaries = true;                                     // BXW_OPT_CHUNK_SUMMARIES
+    bool mesh_from_hmap = false;                                   // BXW_OPT_MESH_FROM_HEIGHT_MAP
     uint32_t last_candidates = 0, last_candidates_of = 0;          // last whole-region mesh: chunks listed / interior chunks
     // staging for host<->device codecs
     void *io_a = nullptr, *io_b = nullptr, *io_c = nullptr;
@@ -315,6 +317,7 @@ int region_generate(bxw_ctx *ctx, Region &r, uint64_t seed, int precision, bool 
     fp.blocks = r.blocks;
     fp.xface = r.xface;
     fp.summary = r.summary;
+    for (int i = 0; i < 5; i++) r.fill_ids[i] = ctx->gen_ids[i];
     fp.SX = r.SX;
     fp.SY = r.SY;
     fp.SZ = r.SZ;
@@ -406,7 +409,7 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
         p.cy_min = r.cy0 - 1;
         for (int i = 0; i < 5; i++) p.gen_datum[i] = (uint32_t)ctx->gen_ids[i] << 16;
         auto is_cube = [&](uint16_t id) { return id < ctx->reg_n && ctx->reg_host[id].present && ctx->reg_host[id].mesh_kind != 0; };
-        p.gen_all_cubes = is_cube(ctx->gen_ids[2]) && is_cube(ctx->gen_ids[3]);
+        p.gen_all_cubes = is_cube(ctx->gen_ids[1]) && is_cube(ctx->gen_ids[2]) && is_cube(ctx->gen_ids[3]) && is_cube(ctx->gen_ids[4]);
         if (!work) {
             // whole interior: only chunks the surface passes through can have a mesh; list them on the device
             CandidateParams c;
@@ -434,6 +437,11 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
         // whole interior from storage: drop the chunks whose summaries prove an empty mesh, keep the tiled order
         StorageCandParams c;
         c.summary = r.summary;
+        {
+            // solid terrain = grass, dirt, stone, snow grass of the last fill: do they all mesh as cubes today?
+            auto cube = [&](uint16_t id) { return id < ctx->reg_n && ctx->reg_host[id].present && ctx->reg_host[id].mesh_kind != 0; };
+            c.solids_are_cubes = cube(r.fill_ids[1]) && cube(r.fill_ids[2]) && cube(r.fill_ids[3]) && cube(r.fill_ids[4]);
+        }
         c.SX = r.SX;
         c.SY = r.SY;
         c.SZ = r.SZ;
@@ -669,6 +677,10 @@ int bxw_set_option(bxw_ctx *ctx, int option, int value) {
     if (!ctx) return BXW_E_INVALID;
     if (option == BXW_OPT_CHUNK_SUMMARIES) {
         ctx->use_summaries = value != 0;
+        return BXW_OK;
+    }
+    if (option == BXW_OPT_MESH_FROM_HEIGHT_MAP) {
+        ctx->mesh_from_hmap = value != 0;
         return BXW_OK;
     }
     return fail(ctx, BXW_E_INVALID, "unknown option %d", option);
@@ -1019,10 +1031,12 @@ int bxw_region_mesh(bxw_ctx *ctx, uint64_t *arena_vertices, uint64_t *arena_indi
 int bxw_region_generate_and_mesh(bxw_ctx *ctx, uint64_t seed, int precision, uint64_t *arena_vertices, uint64_t *arena_indices) {
     int rc = bxw_region_generate(ctx, seed, precision);
     if (rc) return rc;
-    // The blocks were just written from the column parameters and nothing has edited them: mesh from the height map
-    // (34x34 columns per chunk) instead of reading the voxels back.
+    // The blocks were just written from the column parameters and nothing has edited them, so the mesher may derive its
+    // class table from the height map (34x34 columns per chunk) instead of reading the voxels back
+    // (BXW_OPT_MESH_FROM_HEIGHT_MAP). With chunk summaries the voxel path only reads the chunks near the surface and is the
+    // faster of the two on B200, so it is the default.
     Region &r = ctx->region;
-    rc = region_mesh(ctx, r, nullptr, nullptr, r.n_work, false, true);
+    rc = region_mesh(ctx, r, nullptr, nullptr, r.n_work, false, ctx->mesh_from_hmap);
     if (rc) return rc;
     CK(cudaMemsetAsync(r.dirty, 0, r.n_work, ctx->stream));
     if (arena_vertices) *arena_vertices = r.h_counters->v_alloc;

@@ -59,7 +59,7 @@ struct MeshParams {
     const int32_t *hmap;   // nullptr = read the block storage
     int32_t hmap_W, cy_min;
     uint32_t gen_datum[5]; // void, grass, dirt, stone, snow_grass datums
-    int gen_all_cubes;     // dirt and stone both classify as cubes (1..24)
+    int gen_all_cubes;     // grass, dirt, stone and snow grass all classify as cubes (1..24)
 };
 
 void launch_mesh_kernel(const MeshParams &p, int sm_count, cudaStream_t stream);
@@ -89,12 +89,18 @@ void launch_hmap_candidates(const CandidateParams &p, cudaStream_t stream);
 // Chunk summaries: the device-side analogue of a 3-word RLE chunk (lib.rs:263-302, voxmesh.rs:16-25). Every kernel that
 // writes voxels either proves the chunk uniform (the generator's fill) or clears the entry.
 constexpr unsigned long long kUniformBit = 1ull << 32;
+// Bits 33..39 (generator only): every voxel of the chunk (bit 33) / of its boundary plane towards world dir d (bit 34 + d,
+// d = -x +x -y +y -z +z) lies at or below the terrain surface, i.e. is grass, snow grass, dirt or stone. A chunk that is
+// solid throughout and faces a solid plane on all six sides has no visible side when those four blocks are cubes.
+constexpr int kSolidShift = 33;
 
 // Whole-interior meshing from storage: keep the chunks that can have a mesh, in the mesher's tiled processing order, and
 // zero the spans of the rest. A chunk is skipped when it is uniform and its block has no mesh (is_chunk_trivial), or when
-// it and its 26 neighbours are uniform with one cube datum (every side clipped by an identical neighbour).
+// it and its 26 neighbours are uniform with one cube datum (every side clipped by an identical neighbour), or when it is
+// solid generator terrain facing solid planes on all six sides (solids_are_cubes: the four terrain blocks mesh as cubes).
 struct StorageCandParams {
     const unsigned long long *summary;
+    int solids_are_cubes;
     int SX, SY, SZ;
     DeviceRegistry reg;
     uint8_t *keep;       // [n_work] scratch

@@ -318,26 +318,46 @@ __global__ void __launch_bounds__(256, 4) fill_kernel(FillParams p, GenParams g)
     const int hh[4] = {hm.x >> 2, hm.y >> 2, hm.z >> 2, hm.w >> 2};
     const int el[4] = {hm.x & 3, hm.y & 3, hm.z & 3, hm.w & 3};
     if (p.summary) {
-        // chunk summaries of the stack: above every column -> all void; more than 5 below every column -> all stone
-        __shared__ int red[2][8];
+        // chunk summaries of the stack: above every column -> all void; more than 5 below every column -> all stone; at or below
+        // every column (of the chunk / of one of its four side planes) -> solid terrain (device_common.cuh: kSolidShift)
+        __shared__ int red[6][8];
+        const int big = 0x7FFFFFFF;
         int lo = min(min(hh[0], hh[1]), min(hh[2], hh[3])), hi = max(max(hh[0], hh[1]), max(hh[2], hh[3]));
+        int lx0 = q == 0 ? hh[0] : big, lx1 = q == 7 ? hh[3] : big;
+        int lz0 = zr == 0 ? lo : big, lz1 = zr == 31 ? lo : big;
         lo = __reduce_min_sync(0xFFFFFFFFu, lo);
         hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+        lx0 = __reduce_min_sync(0xFFFFFFFFu, lx0);
+        lx1 = __reduce_min_sync(0xFFFFFFFFu, lx1);
+        lz0 = __reduce_min_sync(0xFFFFFFFFu, lz0);
+        lz1 = __reduce_min_sync(0xFFFFFFFFu, lz1);
         if ((threadIdx.x & 31) == 0) {
-            red[0][threadIdx.x >> 5] = lo;
-            red[1][threadIdx.x >> 5] = hi;
+            const int w = threadIdx.x >> 5;
+            red[0][w] = lo;
+            red[1][w] = hi;
+            red[2][w] = lx0;
+            red[3][w] = lx1;
+            red[4][w] = lz0;
+            red[5][w] = lz1;
         }
         __syncthreads();
         for (int k = 0; k < 8; k++) {
             lo = min(lo, red[0][k]);
             hi = max(hi, red[1][k]);
+            lx0 = min(lx0, red[2][k]);
+            lx1 = min(lx1, red[3][k]);
+            lz0 = min(lz0, red[4][k]);
+            lz1 = min(lz1, red[5][k]);
         }
         for (int sy = threadIdx.x; sy < p.SY; sy += 256) {
-            const int ybase = (p.cy_min + sy) * 32;
+            const int ybase = (p.cy_min + sy) * 32, ytop = ybase + 31;
             unsigned long long sum = 0;
             if (ybase > hi) sum = kUniformBit | p.id_void;
-            else if (ybase + 31 < lo - 5) sum = kUniformBit | p.id_stone;
-            p.summary[(size_t)(sx + p.SX * (sz + p.SZ * sy))] = sum;
+            else if (ytop < lo - 5) sum = kUniformBit | p.id_stone;
+            // a voxel at height y of a column with surface h is grass / snow grass / dirt / stone iff y <= h
+            const unsigned solid = (ytop <= lo ? 1u : 0u) | (ytop <= lx0 ? 2u : 0u) | (ytop <= lx1 ? 4u : 0u) | (ybase <= lo ? 8u : 0u) |
+                                   (ytop <= lo ? 16u : 0u) | (ytop <= lz0 ? 32u : 0u) | (ytop <= lz1 ? 64u : 0u);
+            p.summary[(size_t)(sx + p.SX * (sz + p.SZ * sy))] = sum | ((unsigned long long)solid << kSolidShift);
         }
     }
     for (int sy = 0; sy < p.SY; sy++) {

@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
             const uint32_t c_void = s.gen_cls[0];
             // all 34 layers above every column -> one void datum; all at or below every column's dirt/stone -> solid cubes
             const bool all_void = y_lo > hmax;
-            const bool all_solid = (y_lo + 33 < hmin) && p.gen_all_cubes; // strictly below the surface layer: dirt / stone only
+            const bool all_solid = (y_lo + 33 <= hmin) && p.gen_all_cubes; // every voxel at or below its column's surface: terrain cubes only
             if ((all_void && c_void == 0u) || all_solid) {
                 mixed = 0;
                 shapes = 0;
@@ -825,7 +825,7 @@ __global__ void __launch_bounds__(256) hmap_candidates_kernel(CandidateParams p)
     for (int iy = lane; iy < ny; iy += 32) {
         const int y_lo = (p.cy_min + iy + 1) * 32 - 1;
         const bool all_void = y_lo > hmax && p.void_is_empty;
-        const bool all_solid = (y_lo + 33 < hmin) && p.gen_all_cubes;
+        const bool all_solid = (y_lo + 33 <= hmin) && p.gen_all_cubes;
         const uint32_t slot = (uint32_t)ix + (uint32_t)nx * ((uint32_t)iz + (uint32_t)nz * (uint32_t)iy);
         if (all_void || all_solid) {
             bxw_mesh_span sp;

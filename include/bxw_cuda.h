@@ -80,8 +80,10 @@ const char *bxw_last_error(const bxw_ctx *ctx);
 /* Launch all work on an externally owned cudaStream_t (e.g. torch's current stream); NULL = the context's own. */
 int bxw_set_stream(bxw_ctx *ctx, void *cuda_stream);
 /* Tuning switches. BXW_OPT_CHUNK_SUMMARIES (default 1): whole-region mesh passes consult the per-chunk uniformity
- * summaries and skip chunks proven empty; 0 = read and mesh every chunk (same output; used to measure the streaming rate). */
-enum { BXW_OPT_CHUNK_SUMMARIES = 0 };
+ * summaries and skip chunks proven empty; 0 = read and mesh every chunk (same output; used to measure the streaming rate).
+ * BXW_OPT_MESH_FROM_HEIGHT_MAP (default 0): bxw_region_generate_and_mesh derives the mesher's class table from the column
+ * parameters instead of reading the freshly written voxels (same output). */
+enum { BXW_OPT_CHUNK_SUMMARIES = 0, BXW_OPT_MESH_FROM_HEIGHT_MAP = 1 };
 int bxw_set_option(bxw_ctx *ctx, int option, int value);
 int bxw_synchronize(bxw_ctx *ctx);
 /* Number of this library's kernels launched since creation (bench.py's gpu_launches evidence). */

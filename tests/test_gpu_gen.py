@@ -43,13 +43,17 @@ def test_region_generate_matches_oracle(ctx, oracle):
     ctx.region_destroy()
 
 
-def test_generate_then_mesh_matches_oracle(ctx, oracle):
-    """cfg 1 slice: generated terrain meshed on the device equals oracle generate + oracle mesh."""
+@pytest.mark.parametrize("from_height_map", [0, 1])
+def test_generate_then_mesh_matches_oracle(ctx, oracle, from_height_map):
+    """cfg 1 slice: generated terrain meshed on the device equals oracle generate + oracle mesh, both when the mesher reads the
+    voxels back and when it derives its class table from the column parameters."""
     seed = 0
     nx, ny, nz = 3, 3, 2
     origin = (9, 0, 0)
     ctx.region_create(*origin, nx, ny, nz)
+    ctx.set_option(ctx.OPT_MESH_FROM_HEIGHT_MAP, from_height_map)
     av, ai = ctx.region_generate_and_mesh(seed, 64)
+    ctx.set_option(ctx.OPT_MESH_FROM_HEIGHT_MAP, 0)
     spans = ctx.region_mesh_spans()
     V, I = ctx.region_mesh_fetch(av, ai)
     g = oracle.StdGen(seed)
@@ -82,7 +86,9 @@ def test_fused_generate_and_mesh_equals_two_pass(ctx):
     chunk for chunk, including buried (all stone), sky (all void) and surface chunks, at negative coordinates."""
     for origin, dims, seed in [((-4, -2, 3), (5, 6, 4), 0), ((20, 0, -9), (4, 5, 3), 0x13372137CAFE)]:
         ctx.region_create(*origin, *dims)
+        ctx.set_option(ctx.OPT_MESH_FROM_HEIGHT_MAP, 1)
         av, ai = ctx.region_generate_and_mesh(seed, 64)
+        ctx.set_option(ctx.OPT_MESH_FROM_HEIGHT_MAP, 0)
         spans_f = ctx.region_mesh_spans()
         Vf, If = ctx.region_mesh_fetch(av, ai)
         ctx.region_generate(seed, 64)
@@ -110,7 +116,9 @@ def test_fused_path_respects_a_registry_without_meshes(ctx):
     reg.bind(ctx)
     ctx.set_gen_ids(*bxw.StdGenerator.resolve_ids(reg))
     ctx.region_create(9, 0, 0, 2, 2, 2)
+    ctx.set_option(ctx.OPT_MESH_FROM_HEIGHT_MAP, 1)
     av, ai = ctx.region_generate_and_mesh(0, 64)
+    ctx.set_option(ctx.OPT_MESH_FROM_HEIGHT_MAP, 0)
     sf = ctx.region_mesh_spans()
     Vf, If = ctx.region_mesh_fetch(av, ai)
     ctx.region_generate(0, 64)
