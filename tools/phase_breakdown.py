@@ -32,9 +32,11 @@ def main():
     for _ in range(2):
         region.mesh()
     show("storage (candidate list)", ctx.debug_phase_cycles())
+    ctx.set_option(ctx.OPT_MESH_FROM_HEIGHT_MAP, 1)
     for _ in range(2):
         region.generate_and_mesh(0)
-    show("fused (height map)", ctx.debug_phase_cycles())
+    ctx.set_option(ctx.OPT_MESH_FROM_HEIGHT_MAP, 0)
+    show("height-map mode", ctx.debug_phase_cycles())
     ctx.region_fill_synthetic(1, 128)
     ctx.region_destroy()
     ctx.region_create(0, 0, 0, 12, 12, 12)
