@@ -140,3 +140,41 @@ def test_region_mesh_matches_oracle(ctx, oracle):
     # download returns what was uploaded
     assert np.array_equal(ctx.region_download_chunk(0, 0, 0), chunks[(0, 0, 0)])
     ctx.region_destroy()
+
+
+def test_large_and_sparse_block_ids(ctx, oracle):
+    """Block ids beyond the tables cached on chip (>= 64 for colours / textures, >= 256 for the mesh kind) and beyond 12 bits
+    (the face record splits the id over two words), in a registry with holes."""
+    import ballxworld_b200 as bxw
+
+    n = 6000
+    rng = np.random.default_rng(11)
+    defs = (oracle.BlockDef * n)()
+    used = [3, 63, 64, 70, 255, 256, 300, 4095, 4096, 4100, 5999]
+    defs[0].present, defs[0].mesh_kind = 1, 0                      # void
+    for i in used:
+        defs[i].present, defs[i].mesh_kind = 1, 1
+        for k in range(3):
+            defs[i].debug_color[k] = float(rng.random())
+        for k in range(6):
+            defs[i].tex[k] = int(rng.integers(0, 92))
+    defs[300].mesh_kind = 0                                        # a registered block without a mesh
+    oreg = oracle.OracleRegistry(defs)
+    ctx.set_registry(oracle.defs_to_numpy(defs))
+    ctx._bound_registry = None
+    try:
+        chunks = []
+        for c in range(27):
+            r = rng.integers(0, 1 << 30, 32768)
+            ids = np.array(used, dtype=np.uint32)[r % len(used)]
+            shape = np.where((r >> 8) % 4 == 0, (r >> 10) % 4, 0).astype(np.uint32)
+            orient = ((r >> 12) % 24).astype(np.uint32)
+            d = (ids << 16) | (orient * 64 + shape)
+            d[(r >> 20) % 3 == 0] = 0
+            chunks.append(d.astype(np.uint32))
+        wv, wi = oracle.mesh_from_dense27(oreg, chunks)
+        gv, gi = ctx.mesh_chunk27(chunks)
+        assert len(wv) > 50000
+        assert gv.tobytes() == wv.tobytes() and np.array_equal(gi, wi)
+    finally:
+        bxw.standard_registry().bind(ctx)
