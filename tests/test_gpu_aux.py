@@ -379,3 +379,38 @@ def test_chunk_summaries_follow_every_writer(ctx, oracle):
     ctx.region_mesh()
     _check_chunks_vs_oracle(ctx, oracle, chunks, dims, _all_interior(dims))
     ctx.region_destroy()
+
+
+def test_arena_reserve_and_regrowth(ctx, oracle):
+    """bxw_region_mesh_reserve with room to spare, then with arenas far too small: the pass notices (vertex, index or
+    face-record space), grows them and produces the same meshes; appended re-meshes after edits grow the arena too."""
+    import ballxworld_b200 as bxw
+
+    dims = (3, 2, 3)
+    ctx.region_create(0, 0, 0, *dims)
+    ctx.region_fill_synthetic(7, 140)
+    av0, ai0 = ctx.region_mesh()
+    spans0 = ctx.region_mesh_spans().copy()
+    chunks = _region_chunks(ctx, *dims)
+    ctx.region_destroy()
+    for cap_v, cap_i in ((av0 * 2, ai0 * 2), (1024, 1024), (av0 // 2, ai0 * 2)):
+        ctx.region_create(0, 0, 0, *dims)
+        ctx.region_fill_synthetic(7, 140)
+        ctx.region_mesh_reserve(cap_v, cap_i)
+        av, ai = ctx.region_mesh()
+        spans = ctx.region_mesh_spans()
+        assert np.array_equal(spans["v_count"], spans0["v_count"]) and np.array_equal(spans["i_count"], spans0["i_count"])
+        _check_chunks_vs_oracle(ctx, oracle, chunks, dims, [(0, 0, 0), (2, 1, 2), (1, 0, 1)])
+        # fill a free-standing void pocket... rather: carve a block out of the middle chunk and append its re-mesh several times
+        x, y, z = 32 + 5, 9, 32 + 7
+        cur = int(chunks[(1, 0, 1)][(x & 31) + 32 * (z & 31) + 1024 * y])
+        for k in range(6):
+            nxt = (5 << 16) if cur == 0 else 0
+            ctx.region_apply_changes(np.array([(x, y, z, cur, nxt)], dtype=bxw.CHANGE_DTYPE))
+            assert ctx.region_remesh_dirty() >= 1
+            cur = nxt
+        edited = dict(chunks)
+        edited[(1, 0, 1)] = chunks[(1, 0, 1)].copy()
+        edited[(1, 0, 1)][(x & 31) + 32 * (z & 31) + 1024 * y] = cur
+        _check_chunks_vs_oracle(ctx, oracle, edited, dims, [(1, 0, 1), (0, 0, 0)])
+        ctx.region_destroy()
