@@ -50,3 +50,45 @@ def test_cuda_path_matches_golden_cfg1(ctx):
         assert hashlib.sha256(V[int(s["v_off"]): int(s["v_off"]) + g["v"]].tobytes()).hexdigest() == g["vertices"]
         assert hashlib.sha256(I[int(s["i_off"]): int(s["i_off"]) + g["i"]].astype("<u4").tobytes()).hexdigest() == g["indices"]
     ctx.region_destroy()
+
+
+CFG3_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cfg3_totals.json")
+
+
+@pytest.mark.gpu
+def test_cuda_path_matches_oracle_totals_cfg3(ctx):
+    """BASELINE.json configs[2] at full size (128x128x16 chunks, 40 GB of blocks): the device's vertex / index totals equal the
+    oracle's (tests/golden/make_cfg3_totals.py), with the chunk summaries on and off, and a sample of chunks is identical
+    between the two passes."""
+    import ballxworld_b200 as bxw
+
+    if not os.path.exists(CFG3_PATH):
+        pytest.skip("cfg3_totals.json not generated")
+    gold = json.load(open(CFG3_PATH))
+    nx, ny, nz = gold["dims"]
+    try:
+        ctx.region_create(*gold["origin"], nx, ny, nz)
+    except bxw.BxwError as e:  # needs ~50 GB of device memory
+        pytest.skip(f"region does not fit this device: {e}")
+    try:
+        av, ai = ctx.region_generate_and_mesh(gold["seed"], 64)
+        spans = ctx.region_mesh_spans().copy()
+        assert int(spans["v_count"].astype(np.int64).sum()) == gold["total_vertices"]
+        assert int(spans["i_count"].astype(np.int64).sum()) == gold["total_indices"]
+        listed, interior = ctx.region_mesh_candidates()
+        assert interior == nx * ny * nz and int((spans["v_count"] > 0).sum()) <= listed < interior // 4
+        V, I = ctx.region_mesh_fetch(av, ai)
+        ctx.set_option(ctx.OPT_CHUNK_SUMMARIES, 0)
+        av2, ai2 = ctx.region_mesh()
+        ctx.set_option(ctx.OPT_CHUNK_SUMMARIES, 1)
+        spans2 = ctx.region_mesh_spans()
+        assert np.array_equal(spans["v_count"], spans2["v_count"]) and np.array_equal(spans["i_count"], spans2["i_count"])
+        V2, I2 = ctx.region_mesh_fetch(av2, ai2)
+        nonempty = np.nonzero(spans["v_count"])[0]
+        for k in nonempty[:: max(1, len(nonempty) // 200)]:
+            a, b = spans[k], spans2[k]
+            n, m = int(a["v_count"]), int(a["i_count"])
+            assert V[int(a["v_off"]): int(a["v_off"]) + n].tobytes() == V2[int(b["v_off"]): int(b["v_off"]) + n].tobytes()
+            assert np.array_equal(I[int(a["i_off"]): int(a["i_off"]) + m], I2[int(b["i_off"]): int(b["i_off"]) + m])
+    finally:
+        ctx.region_destroy()
