@@ -26,7 +26,9 @@ __global__ void halo_plane_kernel(uint32_t *blocks, uint32_t *xface, unsigned lo
             if (sm && (!(sm & kUniformBit) || (uint32_t)sm != *p)) summary[c] = 0; // (also drops the solid-terrain bits)
         }
     } else {
-        *p = *v;
+        // the boundary plane is one of the chunk's x-face planes: read it from there (128-byte rows) instead of one voxel per
+        // 128-byte row of the block storage
+        *p = xface[((size_t)(sx + SX * (sz + SZ * sy))) * 2048 + (lx ? 1024 : 0) + ly * 32 + lz];
     }
 }
 
