@@ -91,3 +91,21 @@ def test_texture_ids_follow_the_manifest():
     keys = sorted((l.split("=")[0].strip() for l in sec.splitlines() if "=" in l), key=lambda s: s.encode())
     for name, tid in bxw.world.CLIENT_TEXTURE_IDS.items():
         assert keys.index(name) == tid
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/bxw_cuda.h must be consumable from C (cgo / bindgen read it as C): no C++-isms, no torch or CUDA types."""
+    import subprocess
+
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "bxw_cuda.h"\n'
+                   "int main(void) { bxw_mesh_span s; bxw_voxel_change c; bxw_block_def d; bxw_vertex v;\n"
+                   "  (void)s; (void)c; (void)d; return (int)sizeof(v) == 40 && sizeof(s) == 24 && sizeof(c) == 20 ? 0 : 1; }\n")
+    exe = tmp_path / "use_header"
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    assert subprocess.run([str(exe)]).returncode == 0
+    import re
+
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "bxw_cuda.h")).read(), flags=re.S)  # declarations only
+    for banned in ("torch", "at::", "cudaStream_t", "std::", "#include <cuda"):
+        assert banned not in text, banned
