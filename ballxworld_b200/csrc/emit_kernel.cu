@@ -50,7 +50,7 @@ __device__ __forceinline__ void warp_copy_out(uint32_t *dst, const uint32_t *sta
         d4[0] = s4[0];
     }
 #pragma unroll 2
-    for (uint32_t k = lane + 1u; k < nfull; k += 32) d4[k] = s4[k];
+    for (uint32_t k = lane + 1u; k < nfull; k += 32) __stcs(&d4[k], s4[k]); // the meshes are not read again on the device
     const uint32_t rem = total & 3u; // tail words of the last, partial unit
     if (lane < rem && (nfull || !misal)) d0[nfull * 4u + lane] = stage16[nfull * 4u + lane]; // (a short misaligned run was all head)
 }
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(ENT, 4) emit_kernel(MeshParams p) {
                 __syncwarp();
                 const uint32_t nfh = nbf > 16u * h ? min(16u, nbf - 16u * h) : 0u;
                 uint4 *gq = reinterpret_cast<uint4 *>(vout + vq0 + h * 64u);
-                for (uint32_t k = lane; k < nfh * 10u; k += 32) gq[k] = stg[k];
+                for (uint32_t k = lane; k < nfh * 10u; k += 32) __stcs(&gq[k], stg[k]);
                 __syncwarp();
             }
         } else {

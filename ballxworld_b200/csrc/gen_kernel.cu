@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(256, 4) fill_kernel(FillParams p, GenParams g)
                 else v = p.id_void;
                 o[k] = v;
             }
-            dst[yc * 256] = make_uint4(o[0], o[1], o[2], o[3]); // 1024 voxels per y layer = 256 uint4
+            __stcs(&dst[yc * 256], make_uint4(o[0], o[1], o[2], o[3])); // 1024 voxels per y layer = 256 uint4; streaming store
         }
     }
 }
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(64) fill_xface_kernel(FillParams p) {
             else if (y < h - 5) v = p.id_stone;
             else if (y < h) v = p.id_dirt;
             else v = p.id_void;
-            dst[yc * 32] = v;
+            __stcs(&dst[yc * 32], v);
         }
     }
 }
