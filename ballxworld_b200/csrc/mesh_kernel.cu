@@ -690,6 +690,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
             // largest r1 with faces(r0..r1) <= FC and vertices(r0..r1) <= VC (a single row never exceeds 192 / 768)
             uint32_t lo = r0 + 1, hi = 1024;
             const uint32_t f0 = s.sc.rowF[r0], v0 = s.sc.rowV[r0], i0 = s.sc.rowI[r0];
+            if (s.sc.rowF[1024] - f0 <= (uint32_t)FC && s.sc.rowV[1024] - v0 <= (uint32_t)VC) lo = hi; // the rest fits one tile (terrain)
             while (lo < hi) {
                 const uint32_t mid = (lo + hi + 1) >> 1;
                 if (s.sc.rowF[mid] - f0 <= (uint32_t)FC && s.sc.rowV[mid] - v0 <= (uint32_t)VC) lo = mid;
