@@ -73,7 +73,8 @@ struct Smem {
     uint32_t nbr[27 + 5];
     uint32_t warp_tot[3][NW];
     unsigned long long vbase, ibase, fbase;
-    uint32_t work_item[2];
+    uint32_t work_item[2]; // work index of this / the next iteration (double buffered)
+    uint32_t work_c0[2], work_sp[2]; // its list entries, when there is a list
     uint32_t wref[NW];     // per-warp reference datum (trivial-chunk detection)
     uint32_t wflags[NW];   // per-warp shapes | mixed<<1
     uint32_t gen_cls[5];   // class of the five generator datums (void, grass, dirt, stone, snow_grass)
@@ -188,20 +189,31 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
         const uint32_t id = p.gen_datum[tid] >> 16;
         s.gen_cls[tid] = (p.hmap && id < p.reg.n && p.reg.kind[id] == 2) ? 1u : 0u;
     }
-    if (tid == 0) s.work_item[0] = (uint32_t)atomicAdd(&p.counters->work_next, 1ull);
     const uint32_t n_work = p.n_work_dev ? __ldg(p.n_work_dev) : p.n_work;
+    // Work items come from an atomic cursor. The last warp (it has no outer-layer unit in phase A, so it reaches the phase's
+    // barrier first) fetches the next item while the current chunk is staged: the atomic is issued at the top of the iteration
+    // and its result -- plus the list entries it selects -- is published just before that barrier, off the critical path.
+    constexpr int PF_TID = NT - 32;
+    if (tid == PF_TID) {
+        const uint32_t w0 = (uint32_t)atomicAdd(&p.counters->work_next, 1ull);
+        s.work_item[0] = w0;
+        if (p.work && w0 < n_work) {
+            s.work_c0[0] = p.work[w0];
+            s.work_sp[0] = p.work_span[w0];
+        }
+    }
 
     for (uint32_t iter = 0;; iter++) {
         __syncthreads();
         const uint32_t w = s.work_item[iter & 1];
         if (w >= n_work) break;
         PHASE_MARK(t_fetch);
-        // fetch the next work item now; its latency hides behind this chunk
-        if (tid == 0) s.work_item[(iter + 1) & 1] = (uint32_t)atomicAdd(&p.counters->work_next, 1ull);
+        uint32_t next_w = 0;
+        if (tid == PF_TID) next_w = (uint32_t)atomicAdd(&p.counters->work_next, 1ull); // consumed before the phase-A barrier
         uint32_t c0, span_slot;
         if (p.work) {
-            c0 = p.work[w];
-            span_slot = p.work_span[w];
+            c0 = s.work_c0[iter & 1];
+            span_slot = s.work_sp[iter & 1];
         } else {
             // The whole interior without a work list (no dependent global load). Order: x-tiles of 8 columns; inside a
             // tile z-rows, then the 8 columns, then the vertical stack fastest. Chunks whose halos overlap are then
@@ -552,6 +564,13 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
             if (lane == 0) s.wref[warp] = wref;
         }
         if (err) atomicOr(&p.counters->flags, kFlagUnknownId);
+        if (tid == PF_TID) { // publish the next work item (see above)
+            s.work_item[(iter + 1) & 1] = next_w;
+            if (p.work && next_w < n_work) {
+                s.work_c0[(iter + 1) & 1] = p.work[next_w];
+                s.work_sp[(iter + 1) & 1] = p.work_span[next_w];
+            }
+        }
         // one barrier for both flags: each warp publishes shapes | mixed<<1 (warp-reduced) next to its reference datum
         {
             const uint32_t wf = __reduce_or_sync(FULL, shapes | (mixed << 1));
