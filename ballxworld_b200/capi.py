@@ -46,6 +46,11 @@ class BlockDef(C.Structure):
     ]
 
 
+class ArenaStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("vertices_used", "indices_used", "vertices_garbage", "indices_garbage",
+                                          "vertices_capacity", "indices_capacity")]
+
+
 def library_path():
     return _LIB_PATH
 
@@ -99,9 +104,16 @@ def load_library():
         "bxw_region_mesh_spans": ([vp, vp], C.c_int),
         "bxw_region_mesh_fetch": ([vp, vp, C.c_uint64, vp, C.c_uint64], C.c_int),
         "bxw_region_mesh_fetch_async": ([vp, vp, C.c_uint64, vp, C.c_uint64], C.c_int),
+        "bxw_region_mesh_fetch_range": ([vp, C.c_uint64, C.c_uint64, vp, C.c_uint64, C.c_uint64, vp], C.c_int),
         "bxw_region_fetch_wait": ([vp], C.c_int),
         "bxw_region_apply_changes": ([vp, vp, C.c_uint32, u32p], C.c_int),
         "bxw_region_remesh_dirty": ([vp, u32p], C.c_int),
+        "bxw_region_arena_extent": ([vp, u64p, u64p], C.c_int),
+        "bxw_region_arena_stats": ([vp, C.POINTER(ArenaStats)], C.c_int),
+        "bxw_region_compact_arena": ([vp, u64p, u64p], C.c_int),
+        "bxw_region_set_origin": ([vp, C.c_int32, C.c_int32, C.c_int32], C.c_int),
+        "bxw_region_page_table": ([vp, C.POINTER(vp), u32p], C.c_int),
+        "bxw_region_download_pages": ([vp, vp], C.c_int),
         "bxw_region_halo_bytes": ([vp], C.c_size_t),
         "bxw_region_halo_export": ([vp, C.c_int, vp], C.c_int),
         "bxw_region_halo_import": ([vp, C.c_int, vp], C.c_int),
@@ -181,6 +193,7 @@ class Context:
 
     OPT_CHUNK_SUMMARIES = 0
     OPT_MESH_FROM_HEIGHT_MAP = 1
+    OPT_ELIDE_UNIFORM = 2
 
     def set_option(self, option, value):
         self._ck(self.L.bxw_set_option(self.h, option, int(value)))
@@ -342,6 +355,13 @@ class Context:
         self._ck(self.L.bxw_region_mesh_fetch(self.h, _ptr(v), n_vertices, _ptr(ix), n_indices))
         return v, ix
 
+    def region_mesh_fetch_span(self, span):
+        """One chunk's ChunkBuffers (voxrender.rs:34-37) from its span."""
+        v = np.empty(int(span["v_count"]), dtype=VERTEX_DTYPE)
+        ix = np.empty(int(span["i_count"]), dtype=np.uint32)
+        self._ck(self.L.bxw_region_mesh_fetch_range(self.h, int(span["v_off"]), v.size, _ptr(v), int(span["i_off"]), ix.size, _ptr(ix)))
+        return v, ix
+
     def region_mesh_fetch_ptr(self, vptr, n_vertices, iptr, n_indices):
         self._ck(self.L.bxw_region_mesh_fetch(self.h, C.c_void_p(vptr), n_vertices, C.c_void_p(iptr), n_indices))
 
@@ -361,6 +381,37 @@ class Context:
         n = C.c_uint32()
         self._ck(self.L.bxw_region_remesh_dirty(self.h, C.byref(n)))
         return n.value
+
+    def region_arena_extent(self):
+        v, i = C.c_uint64(), C.c_uint64()
+        self._ck(self.L.bxw_region_arena_extent(self.h, C.byref(v), C.byref(i)))
+        return v.value, i.value
+
+    def region_arena_stats(self):
+        st = ArenaStats()
+        self._ck(self.L.bxw_region_arena_stats(self.h, C.byref(st)))
+        return {n: int(getattr(st, n)) for n, _ in ArenaStats._fields_}
+
+    def region_compact_arena(self):
+        v, i = C.c_uint64(), C.c_uint64()
+        self._ck(self.L.bxw_region_compact_arena(self.h, C.byref(v), C.byref(i)))
+        return v.value, i.value
+
+    def region_set_origin(self, cx0, cy0, cz0):
+        self._ck(self.L.bxw_region_set_origin(self.h, cx0, cy0, cz0))
+        self.region_origin = (cx0, cy0, cz0)
+
+    def region_page_table(self):
+        """(device pointer of the u32 page table, number of shared single-datum pages behind the storage)"""
+        p, n = C.c_void_p(), C.c_uint32()
+        self._ck(self.L.bxw_region_page_table(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def region_download_pages(self):
+        nx, ny, nz = self.region_dims
+        out = np.empty((nx + 2) * (ny + 2) * (nz + 2), dtype=np.uint32)
+        self._ck(self.L.bxw_region_download_pages(self.h, _ptr(out)))
+        return out
 
     def region_halo_bytes(self):
         return int(self.L.bxw_region_halo_bytes(self.h))

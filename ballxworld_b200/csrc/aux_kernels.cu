@@ -9,26 +9,62 @@ namespace {
 // Halo planes. One x = const voxel plane over the whole storage extent in y and z (shell rows included so that
 // edges and corners travel too: AO samples diagonal neighbours, stdshapes.rs:131-152). Layout [gy][gz].
 // ------------------------------------------------------------------------------------------------------------
-__global__ void halo_plane_kernel(uint32_t *blocks, uint32_t *xface, unsigned long long *summary, int SX, int SY, int SZ, int sx, int lx,
-                                  uint32_t *plane, int import) {
+__global__ void halo_plane_kernel(uint32_t *blocks, uint32_t *xface, unsigned long long *summary, const uint32_t *page, int SX, int SY,
+                                  int SZ, int sx, int lx, uint32_t *plane, int import) {
     const int gz = blockIdx.x * blockDim.x + threadIdx.x;
     const int gy = blockIdx.y;
     if (gz >= SZ * 32) return;
     const int sy = gy >> 5, ly = gy & 31, sz = gz >> 5, lz = gz & 31;
-    uint32_t *v = blocks + ((size_t)(sx + SX * (sz + SZ * sy))) * kChunkVoxels + lx + 32 * lz + 1024 * ly;
+    const size_t c = (size_t)(sx + SX * (sz + SZ * sy));
     uint32_t *p = plane + (size_t)gy * (SZ * 32) + gz;
     if (import) {
-        *v = *p;
-        xface[((size_t)(sx + SX * (sz + SZ * sy))) * 2048 + (lx ? 1024 : 0) + ly * 32 + lz] = *p; // lx is 0 or 31 here
+        // a chunk that is still not materialised was checked by halo_check_kernel: the plane equals its uniform datum
+        if (page && page[c] != (uint32_t)c) return;
+        blocks[c * kChunkVoxels + lx + 32 * lz + 1024 * ly] = *p;
+        xface[c * 2048 + (lx ? 1024 : 0) + ly * 32 + lz] = *p; // lx is 0 or 31 here
         if (summary) { // the chunk stays known-uniform only if every imported voxel equals its uniform datum
-            const size_t c = (size_t)(sx + SX * (sz + SZ * sy));
             const unsigned long long sm = summary[c];
             if (sm && (!(sm & kUniformBit) || (uint32_t)sm != *p)) summary[c] = 0; // (also drops the solid-terrain bits)
         }
     } else {
         // the boundary plane is one of the chunk's x-face planes: read it from there (128-byte rows) instead of one voxel per
         // 128-byte row of the block storage
-        *p = xface[((size_t)(sx + SX * (sz + SZ * sy))) * 2048 + (lx ? 1024 : 0) + ly * 32 + lz];
+        const size_t g = page ? page[c] : c;
+        *p = xface[g * 2048 + (lx ? 1024 : 0) + ly * 32 + lz];
+    }
+}
+
+// import, step 1: which not-materialised chunks of the shell column receive a voxel that differs from their uniform datum?
+__global__ void halo_check_kernel(const unsigned long long *summary, const uint32_t *page, int SX, int SY, int SZ, int sx,
+                                  const uint32_t *plane, uint8_t *need) {
+    const int gz = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gy = blockIdx.y;
+    if (gz >= SZ * 32) return;
+    const size_t c = (size_t)(sx + SX * ((gz >> 5) + SZ * (gy >> 5)));
+    if (page[c] != (uint32_t)c && plane[(size_t)gy * (SZ * 32) + gz] != (uint32_t)summary[c]) need[c] = 1;
+}
+
+// Copies the shared uniform page of every listed / flagged chunk into the chunk's own storage and points its page entry back
+// at itself. chunks == nullptr: the (sy, sz) chunks of storage column `sx` whose need[] flag is set (halo import).
+__global__ void __launch_bounds__(256) materialise_kernel(uint32_t *blocks, uint32_t *xface, uint32_t *page, const uint32_t *chunks,
+                                                          uint8_t *need, int SX, int sx) {
+    const size_t c = chunks ? (size_t)chunks[blockIdx.x] : (size_t)sx + (size_t)SX * blockIdx.x;
+    if (need) {
+        if (!need[c]) return;
+    }
+    const uint32_t g = page[c];
+    if (g != (uint32_t)c) {
+        const uint4 *s = reinterpret_cast<const uint4 *>(blocks + (size_t)g * kChunkVoxels);
+        uint4 *d = reinterpret_cast<uint4 *>(blocks + c * kChunkVoxels);
+        for (int i = threadIdx.x; i < kChunkVoxels / 4; i += 256) d[i] = s[i];
+        const uint4 *sxf = reinterpret_cast<const uint4 *>(xface + (size_t)g * 2048);
+        uint4 *dxf = reinterpret_cast<uint4 *>(xface + c * 2048);
+        for (int i = threadIdx.x; i < 512; i += 256) dxf[i] = sxf[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        page[c] = (uint32_t)c;
+        if (need) need[c] = 0;
     }
 }
 
@@ -112,13 +148,14 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *w
 // lie in a later segment: the first head of every segment goes to shared memory and a suffix-minimum gives each thread
 // the first head after its segment, so no thread ever walks a long run voxel by voxel.
 template <bool WRITE>
-__global__ void __launch_bounds__(RT) rle_compress_kernel(const uint32_t *dense, const uint32_t *ids, size_t n_chunks,
+__global__ void __launch_bounds__(RT) rle_compress_kernel(const uint32_t *dense, const uint32_t *ids, const uint32_t *page, size_t n_chunks,
                                                           const uint64_t *offsets, uint32_t *out_words, uint32_t *out_len) {
     __shared__ uint32_t warp_tot[RT / 32];
     __shared__ uint32_t first_head[RT + 1];
     const size_t c = blockIdx.x;
     if (c >= n_chunks) return;
-    const uint32_t *d = dense + (ids ? (size_t)ids[c] : c) * kChunkVoxels;
+    const size_t cc = ids ? (size_t)ids[c] : c;
+    const uint32_t *d = dense + (page ? (size_t)page[cc] : cc) * kChunkVoxels; // a chunk that is not materialised reads its uniform page
     const int t = threadIdx.x;
     const int b = t * RSEG;
     // pass 1: heads of this segment as a 128-bit mask; words they contribute
@@ -227,7 +264,7 @@ __global__ void __launch_bounds__(RT) rle_decompress_kernel(const uint32_t *word
     __shared__ uint8_t seg_map[RT];   // 2 bits per start state -> end state
     __shared__ uint8_t seg_start[RT];
     __shared__ uint32_t n_long;
-    __shared__ uint32_t long_runs[256][3]; // value, start, length of runs too long for one thread
+    __shared__ uint32_t long_runs[512][3]; // value, start, length of runs too long for one thread (32768 / 64 = 512 at most)
     __shared__ int bad;
     const size_t c = blockIdx.x;
     if (c >= n_chunks) return;
@@ -292,12 +329,12 @@ __global__ void __launch_bounds__(RT) rle_decompress_kernel(const uint32_t *word
             const uint32_t n = w[i], v = w[i - 1];
             if (n >= 64) {
                 const uint32_t q = atomicAdd(&n_long, 1u);
-                if (q < 256) {
+                if (q < 512) {
                     long_runs[q][0] = v;
                     long_runs[q][1] = pos;
                     long_runs[q][2] = n;
                 } else {
-                    for (uint32_t k = 0; k < n; k++) out[pos + k] = v; // more than 256 long runs cannot fit 32768 voxels at n>=64... defensive
+                    for (uint32_t k = 0; k < n; k++) out[pos + k] = v; // unreachable: a valid stream holds at most 32768 / 66 long runs
                 }
             } else {
                 for (uint32_t k = 0; k < n; k++) out[pos + k] = v;
@@ -309,7 +346,7 @@ __global__ void __launch_bounds__(RT) rle_decompress_kernel(const uint32_t *word
         s = rle_step(s, eq);
     }
     __syncthreads();
-    const uint32_t nl = min(n_long, 256u);
+    const uint32_t nl = min(n_long, 512u);
     for (uint32_t q = 0; q < nl; q++) {
         const uint32_t v = long_runs[q][0], st = long_runs[q][1], n = long_runs[q][2];
         for (uint32_t k = t; k < n; k += RT) out[st + k] = v;
@@ -403,10 +440,19 @@ void launch_fill_synthetic(uint32_t *blocks, int SX, int SY, int SZ, int32_t cx_
     fill_synthetic_kernel<<<(unsigned)((size_t)SX * SY * SZ), 256, 0, stream>>>(blocks, SX, SY, SZ, cx_min, cy_min, cz_min, seed, void_threshold);
 }
 
-void launch_halo_plane(uint32_t *blocks, uint32_t *xface, unsigned long long *summary, int SX, int SY, int SZ, int sx, int lx, uint32_t *plane,
-                       int import, cudaStream_t stream) {
+void launch_halo_plane(uint32_t *blocks, uint32_t *xface, unsigned long long *summary, uint32_t *page, uint8_t *need, int SX, int SY, int SZ,
+                       int sx, int lx, uint32_t *plane, int import, cudaStream_t stream) {
     dim3 grid((SZ * 32 + 127) / 128, SY * 32);
-    halo_plane_kernel<<<grid, 128, 0, stream>>>(blocks, xface, summary, SX, SY, SZ, sx, lx, plane, import);
+    if (import && page) {
+        // chunks of the shell column that are not materialised stay that way unless the plane brings a different voxel
+        halo_check_kernel<<<grid, 128, 0, stream>>>(summary, page, SX, SY, SZ, sx, plane, need);
+        materialise_kernel<<<(unsigned)(SY * SZ), 256, 0, stream>>>(blocks, xface, page, nullptr, need, SX, sx);
+    }
+    halo_plane_kernel<<<grid, 128, 0, stream>>>(blocks, xface, summary, page, SX, SY, SZ, sx, lx, plane, import);
+}
+
+void launch_materialise(uint32_t *blocks, uint32_t *xface, uint32_t *page, const uint32_t *chunks, uint32_t n, cudaStream_t stream) {
+    if (n) materialise_kernel<<<n, 256, 0, stream>>>(blocks, xface, page, chunks, nullptr, 0, 0);
 }
 
 void launch_apply_changes(const EditParams &p, cudaStream_t stream) {
@@ -419,23 +465,24 @@ void launch_dirty_list(uint8_t *dirty, uint32_t n, int nx, int nz, int SX, int S
     dirty_list_kernel<<<(n + 255) / 256, 256, 0, stream>>>(dirty, n, nx, nz, SX, SZ, work, work_span, count, clear);
 }
 
-void launch_rle_compress(const uint32_t *dense, const uint32_t *ids, size_t n_chunks, uint32_t *len, uint64_t *offsets,
+void launch_rle_compress(const uint32_t *dense, const uint32_t *ids, const uint32_t *page, size_t n_chunks, uint32_t *len, uint64_t *offsets,
                          uint32_t *out_words, int phase, cudaStream_t stream) {
     if (phase == 0) {
-        rle_compress_kernel<false><<<(unsigned)n_chunks, RT, 0, stream>>>(dense, ids, n_chunks, nullptr, nullptr, len);
+        rle_compress_kernel<false><<<(unsigned)n_chunks, RT, 0, stream>>>(dense, ids, page, n_chunks, nullptr, nullptr, len);
         offsets_scan_kernel<<<1, RT, 0, stream>>>(len, n_chunks, offsets);
     } else {
-        rle_compress_kernel<true><<<(unsigned)n_chunks, RT, 0, stream>>>(dense, ids, n_chunks, offsets, out_words, nullptr);
+        rle_compress_kernel<true><<<(unsigned)n_chunks, RT, 0, stream>>>(dense, ids, page, n_chunks, offsets, out_words, nullptr);
     }
 }
 
 // Copy n decoded chunks into region storage at chunk indices ids[], refresh their x-face planes and mark every interior
 // chunk within one chunk of them dirty (their meshes read the new voxels).
 __global__ void chunk_scatter_kernel(const uint32_t *src, const uint32_t *ids, uint32_t *blocks, uint32_t *xface,
-                                     unsigned long long *summary, int SX, int SY, int SZ, uint8_t *dirty) {
+                                     unsigned long long *summary, uint32_t *page, int SX, int SY, int SZ, uint8_t *dirty) {
     const size_t k = blockIdx.x;
     const size_t c = ids[k];
     if (summary && threadIdx.x == 0) summary[c] = 0; // no longer known uniform
+    if (page && threadIdx.x == 0) page[c] = (uint32_t)c; // every voxel is overwritten below: materialised
     const uint4 *s = reinterpret_cast<const uint4 *>(src + k * kChunkVoxels);
     uint4 *d = reinterpret_cast<uint4 *>(blocks + c * kChunkVoxels);
     for (int i = threadIdx.x; i < kChunkVoxels / 4; i += blockDim.x) d[i] = s[i];
@@ -453,8 +500,17 @@ __global__ void chunk_scatter_kernel(const uint32_t *src, const uint32_t *ids, u
 }
 
 void launch_chunk_scatter(const uint32_t *src, const uint32_t *ids, size_t n, uint32_t *blocks, uint32_t *xface,
-                          unsigned long long *summary, int SX, int SY, int SZ, uint8_t *dirty, cudaStream_t stream) {
-    if (n) chunk_scatter_kernel<<<(unsigned)n, 256, 0, stream>>>(src, ids, blocks, xface, summary, SX, SY, SZ, dirty);
+                          unsigned long long *summary, uint32_t *page, int SX, int SY, int SZ, uint8_t *dirty, cudaStream_t stream) {
+    if (n) chunk_scatter_kernel<<<(unsigned)n, 256, 0, stream>>>(src, ids, blocks, xface, summary, page, SX, SY, SZ, dirty);
+}
+
+// page[c] = c for c in [0, n): every chunk lives in its own storage
+__global__ void page_identity_kernel(uint32_t *page, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) page[i] = i;
+}
+void launch_page_identity(uint32_t *page, uint32_t n, cudaStream_t stream) {
+    if (n) page_identity_kernel<<<(n + 255) / 256, 256, 0, stream>>>(page, n);
 }
 
 void launch_rle_decompress(const uint32_t *words, const uint64_t *offsets, size_t n_chunks, uint32_t *out_dense, uint32_t *status,
@@ -575,6 +631,7 @@ __global__ void __launch_bounds__(256) cand_write_kernel(StorageCandParams p, ui
         sp.v_off = sp.i_off = 0;
         sp.v_count = sp.i_count = 0;
         p.spans[slot] = sp;
+        if (p.span_cap) p.span_cap[slot] = make_uint2(0u, 0u);
     }
 }
 
@@ -584,6 +641,94 @@ void launch_storage_candidates(const StorageCandParams &p, cudaStream_t stream) 
     cand_flags_kernel<<<nb, 256, 0, stream>>>(p, n);
     cand_scan_kernel<<<1, 1024, 0, stream>>>(p.blk, nb, p.count);
     cand_write_kernel<<<nb, 256, 0, stream>>>(p, n);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Arena compaction: every live span moves to the prefix sum of the reservations before it (slot order), into a second arena.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) compact_offsets_kernel(const bxw_mesh_span *spans, uint2 *span_cap, uint32_t n,
+                                                               unsigned long long *new_off, MeshCounters *counters) {
+    // one CTA: exclusive scan of the (tightened) reservations; new_off[2 s] / [2 s + 1] = new vertex / index offset of slot s
+    __shared__ unsigned long long wv[32], wi[32];
+    __shared__ unsigned long long carry_v, carry_i;
+    if (threadIdx.x == 0) carry_v = carry_i = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < n; base += 1024u) {
+        const uint32_t s = base + threadIdx.x;
+        unsigned long long cv = 0, ci = 0;
+        if (s < n && (spans[s].v_count | spans[s].i_count)) {
+            // keep the slack of re-meshed chunks, drop reservations of empty meshes
+            cv = span_cap[s].x;
+            ci = span_cap[s].y;
+        }
+        unsigned long long iv = cv, ii = ci;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long a = __shfl_up_sync(0xFFFFFFFFu, iv, o), b = __shfl_up_sync(0xFFFFFFFFu, ii, o);
+            if (lane >= (uint32_t)o) {
+                iv += a;
+                ii += b;
+            }
+        }
+        if (lane == 31u) {
+            wv[warp] = iv;
+            wi[warp] = ii;
+        }
+        __syncthreads();
+        unsigned long long bv = carry_v, bi = carry_i;
+        for (uint32_t k = 0; k < warp; k++) {
+            bv += wv[k];
+            bi += wi[k];
+        }
+        if (s < n) {
+            new_off[2 * (size_t)s] = bv + iv - cv;
+            new_off[2 * (size_t)s + 1] = bi + ii - ci;
+            if (!(cv | ci)) span_cap[s] = make_uint2(0u, 0u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) {
+            carry_v = bv + iv;
+            carry_i = bi + ii;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        counters->v_alloc = carry_v;
+        counters->i_alloc = carry_i;
+        counters->v_garbage = 0;
+        counters->i_garbage = 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) compact_copy_kernel(bxw_mesh_span *spans, const unsigned long long *new_off, const bxw_vertex *v_old,
+                                                           const uint32_t *i_old, bxw_vertex *v_new, uint32_t *i_new) {
+    const uint32_t s = blockIdx.x;
+    const bxw_mesh_span sp = spans[s];
+    if (!(sp.v_count | sp.i_count)) return;
+    const unsigned long long nv = new_off[2 * (size_t)s], ni = new_off[2 * (size_t)s + 1];
+    // spans start on multiples of 4 vertices (160 B) / 8 indices (32 B): 16-byte units on both sides
+    const uint4 *sv = reinterpret_cast<const uint4 *>(v_old + sp.v_off);
+    uint4 *dv = reinterpret_cast<uint4 *>(v_new + nv);
+    const uint32_t n16v = (uint32_t)(((size_t)sp.v_count * 40 + 15) / 16);
+    for (uint32_t k = threadIdx.x; k < n16v; k += 256) dv[k] = sv[k];
+    const uint4 *si = reinterpret_cast<const uint4 *>(i_old + sp.i_off);
+    uint4 *di = reinterpret_cast<uint4 *>(i_new + ni);
+    const uint32_t n16i = (sp.i_count + 3u) / 4u;
+    for (uint32_t k = threadIdx.x; k < n16i; k += 256) di[k] = si[k];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        spans[s].v_off = nv;
+        spans[s].i_off = ni;
+    }
+}
+
+void launch_compact_offsets(const bxw_mesh_span *spans, uint2 *span_cap, uint32_t n, unsigned long long *new_off, MeshCounters *counters,
+                            cudaStream_t stream) {
+    compact_offsets_kernel<<<1, 1024, 0, stream>>>(spans, span_cap, n, new_off, counters);
+}
+void launch_compact_copy(bxw_mesh_span *spans, const unsigned long long *new_off, uint32_t n, const bxw_vertex *v_old, const uint32_t *i_old,
+                         bxw_vertex *v_new, uint32_t *i_new, cudaStream_t stream) {
+    if (n) compact_copy_kernel<<<n, 256, 0, stream>>>(spans, new_off, v_old, i_old, v_new, i_new);
 }
 
 void launch_terragen_noise2(const TerragenTables *T, const double *xs, const double *ys, size_t n, double *out, cudaStream_t stream) {

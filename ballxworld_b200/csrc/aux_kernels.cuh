@@ -4,9 +4,13 @@
 
 namespace bxw {
 
-// import also clears the summaries of the chunks it writes
-void launch_halo_plane(uint32_t *blocks, uint32_t *xface, unsigned long long *summary, int SX, int SY, int SZ, int sx, int lx, uint32_t *plane,
-                       int import, cudaStream_t stream);
+// import also clears the summaries of the chunks it writes; chunks of the shell column that are not materialised (page[c] != c)
+// are materialised first when the plane brings a voxel that differs from their uniform datum (need: per-chunk scratch flags)
+void launch_halo_plane(uint32_t *blocks, uint32_t *xface, unsigned long long *summary, uint32_t *page, uint8_t *need, int SX, int SY, int SZ,
+                       int sx, int lx, uint32_t *plane, int import, cudaStream_t stream);
+// give the listed chunks their own storage back (copy of their shared uniform page), before a writer touches single voxels
+void launch_materialise(uint32_t *blocks, uint32_t *xface, uint32_t *page, const uint32_t *chunks, uint32_t n, cudaStream_t stream);
+void launch_page_identity(uint32_t *page, uint32_t n, cudaStream_t stream);
 
 struct EditParams {
     uint32_t *blocks;
@@ -25,12 +29,18 @@ void launch_dirty_list(uint8_t *dirty, uint32_t n, int nx, int nz, int SX, int S
 
 // phase 0: per-chunk word counts -> offsets (n+1); phase 1: write words at offsets
 // ids (optional): chunk k is read from dense + ids[k]*32768 instead of dense + k*32768
-void launch_rle_compress(const uint32_t *dense, const uint32_t *ids, size_t n_chunks, uint32_t *len, uint64_t *offsets,
+void launch_rle_compress(const uint32_t *dense, const uint32_t *ids, const uint32_t *page, size_t n_chunks, uint32_t *len, uint64_t *offsets,
                          uint32_t *out_words, int phase, cudaStream_t stream);
 void launch_chunk_scatter(const uint32_t *src, const uint32_t *ids, size_t n, uint32_t *blocks, uint32_t *xface,
-                          unsigned long long *summary, int SX, int SY, int SZ, uint8_t *dirty, cudaStream_t stream);
+                          unsigned long long *summary, uint32_t *page, int SX, int SY, int SZ, uint8_t *dirty, cudaStream_t stream);
 void launch_rle_decompress(const uint32_t *words, const uint64_t *offsets, size_t n_chunks, uint32_t *out_dense, uint32_t *status,
                            cudaStream_t stream);
+
+// arena compaction (bxw_region_compact_arena): new offsets of every live span, then the copy into the second arena
+void launch_compact_offsets(const bxw_mesh_span *spans, uint2 *span_cap, uint32_t n, unsigned long long *new_off, MeshCounters *counters,
+                            cudaStream_t stream);
+void launch_compact_copy(bxw_mesh_span *spans, const unsigned long long *new_off, uint32_t n, const bxw_vertex *v_old, const uint32_t *i_old,
+                         bxw_vertex *v_new, uint32_t *i_new, cudaStream_t stream);
 
 struct TerragenTables {
     uint16_t perm[2048];

@@ -48,8 +48,20 @@ struct Region {
     uint16_t fill_ids[5] = {0, 0, 0, 0, 0}; // generator block ids of the last fill (what the solid-terrain bits refer to)
     uint8_t *cand_keep = nullptr;          // candidate-list scratch
     uint32_t *cand_blk = nullptr;
+    // Uniform-chunk elision: page[c] = chunk slot that holds chunk c's voxels: c itself, or one of the kSharedPages slots
+    // behind the storage (n_storage() + k) that hold a single datum. Readers go through the table, writers materialise first.
+    uint32_t *page = nullptr;
+    uint32_t shared_datum[2] = {0, 0};     // datum of shared page 0 (void) / 1 (stone) of the last fill
+    bool shared_valid = false;
+    uint8_t *need = nullptr;               // [n_storage] scratch flags (halo import)
+    uint2 *span_cap = nullptr;             // [n_work] arena reservation behind each span (device_common.cuh)
+    bxw_mesh_span *spans_bak = nullptr;    // re-mesh passes: spans / reservations before the pass (restored if the arena must grow)
+    uint2 *span_cap_bak = nullptr;
+    uint64_t gen_seed = 0;                 // seed / precision of the last generate (bxw_region_heightmap's raw output)
+    int gen_precision = 64;
     size_t n_storage() const { return (size_t)SX * SY * SZ; }
 };
+constexpr uint32_t kSharedPages = 2;
 
 } // namespace
 
@@ -85,6 +97,7 @@ struct bxw_ctx {
     double mesh_ms = 0.0, fill_ms = 0.0, hmap_ms = 0.0;
     uint64_t mesh_launches = 0, fill_launches = 0, hmap_launches = 0;
     bool use_summaries = true;                                     // BXW_OPT_CHUNK_SUMMARIES
+    bool elide_uniform = true;                                     // BXW_OPT_ELIDE_UNIFORM
     bool mesh_from_hmap = false;                                   // BXW_OPT_MESH_FROM_HEIGHT_MAP
     uint32_t last_candidates = 0, last_candidates_of = 0;          // last whole-region mesh: chunks listed / interior chunks
     // staging for host<->device codecs
@@ -96,6 +109,9 @@ struct bxw_ctx {
 };
 
 namespace {
+
+int ensure_io(bxw_ctx *ctx, size_t bytes_a, size_t bytes_b);
+int ensure_io_c(bxw_ctx *ctx, size_t bytes);
 
 int fail(bxw_ctx *c, int code, const char *fmt, ...) {
     if (c) {
@@ -193,6 +209,11 @@ void region_free(Region &r) {
     cudaFree(r.summary);
     cudaFree(r.cand_keep);
     cudaFree(r.cand_blk);
+    cudaFree(r.page);
+    cudaFree(r.need);
+    cudaFree(r.span_cap);
+    cudaFree(r.spans_bak);
+    cudaFree(r.span_cap_bak);
     if (r.h_counters) cudaFreeHost(r.h_counters);
     r = Region();
 }
@@ -214,14 +235,22 @@ int region_alloc(bxw_ctx *ctx, Region &r, int32_t cx0, int32_t cy0, int32_t cz0,
     const size_t nst = r.n_storage();
     if (nst >= (1ull << 32)) return fail(ctx, BXW_E_INVALID, "region too large");
     r.n_work = nx * ny * nz;
-    CK(cudaMalloc(&r.blocks, nst * kChunkVoxels * sizeof(uint32_t)));
-    CK(cudaMalloc(&r.xface, nst * 2048 * sizeof(uint32_t)));
+    CK(cudaMalloc(&r.blocks, (nst + kSharedPages) * kChunkVoxels * sizeof(uint32_t)));
+    CK(cudaMalloc(&r.xface, (nst + kSharedPages) * 2048 * sizeof(uint32_t)));
+    CK(cudaMalloc(&r.page, nst * sizeof(uint32_t)));
+    launch_page_identity(r.page, (uint32_t)nst, ctx->stream);
+    CK(cudaMalloc(&r.need, nst));
+    CK(cudaMemsetAsync(r.need, 0, nst, ctx->stream));
+    CK(cudaMalloc(&r.span_cap, r.n_work * sizeof(uint2)));
+    CK(cudaMemsetAsync(r.span_cap, 0, r.n_work * sizeof(uint2), ctx->stream));
+    CK(cudaMalloc(&r.spans_bak, r.n_work * sizeof(bxw_mesh_span)));
+    CK(cudaMalloc(&r.span_cap_bak, r.n_work * sizeof(uint2)));
     CK(cudaMalloc(&r.hmap, (size_t)r.SX * 32 * r.SZ * 32 * sizeof(int32_t)));
     CK(cudaMalloc(&r.work, r.n_work * sizeof(uint32_t)));
     CK(cudaMalloc(&r.work_span, r.n_work * sizeof(uint32_t)));
     CK(cudaMalloc(&r.spans, r.n_work * sizeof(bxw_mesh_span)));
     CK(cudaMalloc(&r.counters, sizeof(MeshCounters)));
-    CK(cudaMallocHost(&r.h_counters, sizeof(MeshCounters)));
+    CK(cudaMallocHost(&r.h_counters, 2 * sizeof(MeshCounters))); // [1] receives the candidate-list length
     CK(cudaMalloc(&r.dirty, r.n_work));
     CK(cudaMalloc(&r.dirty_work, r.n_work * sizeof(uint32_t)));
     CK(cudaMalloc(&r.dirty_span, r.n_work * sizeof(uint32_t)));
@@ -267,14 +296,9 @@ int flush_gen_timing(bxw_ctx *ctx) {
     return BXW_OK;
 }
 
-int region_generate(bxw_ctx *ctx, Region &r, uint64_t seed, int precision, bool want_raw) {
-    CK(cudaSetDevice(ctx->device));
-    {
-        int rc0 = flush_gen_timing(ctx);
-        if (rc0) return rc0;
-    }
+// cell-point table + kernel parameters of the region's column grid
+int gen_setup(bxw_ctx *ctx, Region &r, uint64_t seed, int precision, GenParams &gp) {
     if (precision != 32 && precision != 64) return fail(ctx, BXW_E_INVALID, "precision must be 32 or 64");
-    if (!ctx->have_gen_ids) return fail(ctx, BXW_E_NO_REGISTRY, "bxw_set_gen_ids not called");
     int rc = ensure_gen_tables(ctx, seed);
     if (rc) return rc;
     const int32_t W = r.SX * 32, D = r.SZ * 32;
@@ -284,14 +308,15 @@ int region_generate(bxw_ctx *ctx, Region &r, uint64_t seed, int precision, bool 
     const int32_t cw = cell_x1 - cell_x0 + 1, cd = cell_z1 - cell_z0 + 1;
     const size_t need = (size_t)cw * cd * 4;
     if (need > r.cells_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
         cudaFree(r.cells);
         r.cells = nullptr;
+        r.cells_cap = 0;
         CK(cudaMalloc(&r.cells, need * sizeof(CellPointDev)));
         r.cells_cap = need;
     }
-    if (want_raw && !r.raw) CK(cudaMalloc(&r.raw, (size_t)W * D * sizeof(double)));
     launch_cellpoints_kernel(seed, cell_x0, cell_z0, cw, cd, ctx->d_gen, r.cells, precision, ctx->stream);
-    GenParams gp;
+    ctx->launches += 1;
     gp.seed = seed;
     gp.x0 = x0;
     gp.z0 = z0;
@@ -304,20 +329,16 @@ int region_generate(bxw_ctx *ctx, Region &r, uint64_t seed, int precision, bool 
     gp.cells = r.cells;
     gp.tables = ctx->d_gen;
     gp.hmap = r.hmap;
-    gp.raw = want_raw ? r.raw : nullptr;
-    // want_raw (bxw_region_heightmap's f64 output) keeps the stand-alone height map kernel; otherwise the fill kernel
-    // computes the column parameters itself
-    const bool fused_gen = !want_raw;
-    CK(cudaEventRecord(ctx->ev_g0, ctx->stream));
-    if (!fused_gen) launch_heightmap_kernel(gp, precision, ctx->stream);
-    CK(cudaEventRecord(ctx->ev_g1, ctx->stream));
-    FillParams fp;
+    gp.raw = nullptr;
+    return BXW_OK;
+}
+
+void fill_params(bxw_ctx *ctx, Region &r, bool elide, FillParams &fp) {
     fp.hmap = r.hmap;
-    fp.W = W;
+    fp.W = r.SX * 32;
     fp.blocks = r.blocks;
     fp.xface = r.xface;
     fp.summary = r.summary;
-    for (int i = 0; i < 5; i++) r.fill_ids[i] = ctx->gen_ids[i];
     fp.SX = r.SX;
     fp.SY = r.SY;
     fp.SZ = r.SZ;
@@ -327,15 +348,75 @@ int region_generate(bxw_ctx *ctx, Region &r, uint64_t seed, int precision, bool 
     fp.id_dirt = (uint32_t)ctx->gen_ids[2] << 16;
     fp.id_stone = (uint32_t)ctx->gen_ids[3] << 16;
     fp.id_snow = (uint32_t)ctx->gen_ids[4] << 16;
-    if (fused_gen) launch_gen_fill_kernel(fp, gp, precision, ctx->stream);
-    else launch_fill_kernel(fp, ctx->stream);
+    fp.page = r.page;
+    fp.elide = elide ? 1 : 0;
+    fp.page_void = (uint32_t)r.n_storage();
+    fp.page_stone = (uint32_t)r.n_storage() + 1u;
+    fp.list = nullptr;
+    fp.n_list = 0;
+}
+
+// the two shared single-datum pages behind the storage hold the void / stone datum of the current generator ids
+int ensure_shared_pages(bxw_ctx *ctx, Region &r) {
+    const uint32_t dv = (uint32_t)ctx->gen_ids[0] << 16, ds = (uint32_t)ctx->gen_ids[3] << 16;
+    if (r.shared_valid && r.shared_datum[0] == dv && r.shared_datum[1] == ds) return BXW_OK;
+    if (r.shared_valid) {
+        // chunks of an earlier fill may still point at the shared pages: give them their own storage before the pages change
+        std::vector<uint32_t> pg(r.n_storage());
+        CK(cudaMemcpyAsync(pg.data(), r.page, pg.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        std::vector<uint32_t> list;
+        for (size_t c = 0; c < pg.size(); c++)
+            if (pg[c] != (uint32_t)c) list.push_back((uint32_t)c);
+        if (!list.empty()) {
+            int rc = ensure_io(ctx, 16, list.size() * sizeof(uint32_t));
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(ctx->io_b, list.data(), list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+            launch_materialise(r.blocks, r.xface, r.page, (const uint32_t *)ctx->io_b, (uint32_t)list.size(), ctx->stream);
+            ctx->launches += 1;
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    launch_uniform_page(r.blocks, r.xface, (uint32_t)r.n_storage(), dv, ctx->stream);
+    launch_uniform_page(r.blocks, r.xface, (uint32_t)r.n_storage() + 1u, ds, ctx->stream);
+    ctx->launches += 2;
+    r.shared_datum[0] = dv;
+    r.shared_datum[1] = ds;
+    r.shared_valid = true;
+    return BXW_OK;
+}
+
+int region_generate(bxw_ctx *ctx, Region &r, uint64_t seed, int precision, bool elide) {
+    CK(cudaSetDevice(ctx->device));
+    {
+        int rc0 = flush_gen_timing(ctx);
+        if (rc0) return rc0;
+    }
+    if (!ctx->have_gen_ids) return fail(ctx, BXW_E_NO_REGISTRY, "bxw_set_gen_ids not called");
+    GenParams gp;
+    int rc = gen_setup(ctx, r, seed, precision, gp);
+    if (rc) return rc;
+    if (elide) {
+        rc = ensure_shared_pages(ctx, r);
+        if (rc) return rc;
+    }
+    // the fill kernel computes the column parameters of its 32x32 columns itself (FP64 phase of some CTAs overlaps the
+    // store phase of others) and writes them to the height map
+    CK(cudaEventRecord(ctx->ev_g0, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_g1, ctx->stream));
+    FillParams fp;
+    fill_params(ctx, r, elide, fp);
+    for (int i = 0; i < 5; i++) r.fill_ids[i] = ctx->gen_ids[i];
+    launch_gen_fill_kernel(fp, gp, precision, ctx->stream);
     CK(cudaEventRecord(ctx->ev_g2, ctx->stream));
     ctx->gen_pending = true;
-    ctx->gen_pending_fused = fused_gen;
+    ctx->gen_pending_fused = true;
     launch_fill_xface_kernel(fp, ctx->stream);
-    ctx->launches += fused_gen ? 3 : 4;
+    ctx->launches += 2;
     CK(cudaGetLastError());
     r.have_hmap = true;
+    r.gen_seed = seed;
+    r.gen_precision = precision;
     return BXW_OK;
 }
 
@@ -379,7 +460,8 @@ int faces_resize(bxw_ctx *ctx, Region &r, unsigned long long f_cap) {
     return BXW_OK;
 }
 
-// Runs the mesher over a work list. append=false restarts arena allocation at 0.
+// Runs the mesher over a work list. append=false restarts arena allocation at 0; append=true is a re-mesh pass: a chunk whose
+// new mesh fits its old arena reservation is rewritten in place, the others move to the end of the arena.
 int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *work_span, uint32_t n_work, bool append,
                 bool from_hmap = false) {
     CK(cudaSetDevice(ctx->device));
@@ -387,6 +469,7 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
     MeshParams p;
     p.blocks = r.blocks;
     p.xface = r.xface;
+    p.page = r.page;
     p.SX = r.SX;
     p.SY = r.SY;
     p.SZ = r.SZ;
@@ -395,6 +478,8 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
     p.n_work = n_work;
     p.n_work_dev = nullptr;
     p.spans = r.spans;
+    p.span_cap = r.span_cap;
+    p.reuse = append ? 1 : 0;
     p.counters = r.counters;
     p.tables = ctx->d_tables;
     p.reg = dev_registry(ctx);
@@ -403,45 +488,47 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
     p.cy_min = 0;
     p.gen_all_cubes = 0;
     for (int i = 0; i < 5; i++) p.gen_datum[i] = 0;
+    auto is_cube = [&](uint16_t id) { return id < ctx->reg_n && ctx->reg_host[id].present && ctx->reg_host[id].mesh_kind != 0; };
+    // whole-region passes over a device-built candidate list: the list kernels run once per attempt (they also clear the
+    // spans of the chunks they drop)
+    const bool cand_hmap = from_hmap && !work;
+    const bool cand_storage = !from_hmap && !work && ctx->use_summaries;
     if (from_hmap) { // fused generate+mesh: the region holds pristine StdGenerator terrain and its column parameters
         p.hmap = r.hmap;
         p.hmap_W = r.SX * 32;
         p.cy_min = r.cy0 - 1;
         for (int i = 0; i < 5; i++) p.gen_datum[i] = (uint32_t)ctx->gen_ids[i] << 16;
-        auto is_cube = [&](uint16_t id) { return id < ctx->reg_n && ctx->reg_host[id].present && ctx->reg_host[id].mesh_kind != 0; };
         p.gen_all_cubes = is_cube(ctx->gen_ids[1]) && is_cube(ctx->gen_ids[2]) && is_cube(ctx->gen_ids[3]) && is_cube(ctx->gen_ids[4]);
-        if (!work) {
-            // whole interior: only chunks the surface passes through can have a mesh; list them on the device
-            CandidateParams c;
-            c.hmap = p.hmap;
-            c.hmap_W = p.hmap_W;
-            c.cy_min = p.cy_min;
-            c.SX = r.SX;
-            c.SY = r.SY;
-            c.SZ = r.SZ;
-            c.void_is_empty = !is_cube(ctx->gen_ids[0]);
-            c.gen_all_cubes = p.gen_all_cubes;
-            c.work = r.dirty_work;
-            c.work_span = r.dirty_span;
-            c.count = r.dirty_count;
-            c.spans = r.spans;
-            CK(cudaMemsetAsync(r.dirty_count, 0, sizeof(uint32_t), ctx->stream));
-            launch_hmap_candidates(c, ctx->stream);
-            ctx->launches += 1;
-            p.work = r.dirty_work;
-            p.work_span = r.dirty_span;
-            p.n_work_dev = r.dirty_count;
-        }
     }
-    if (!from_hmap && !work && ctx->use_summaries) {
+    if (cand_hmap) {
+        // whole interior: only chunks the surface passes through can have a mesh; list them on the device
+        CandidateParams c;
+        c.hmap = p.hmap;
+        c.hmap_W = p.hmap_W;
+        c.cy_min = p.cy_min;
+        c.SX = r.SX;
+        c.SY = r.SY;
+        c.SZ = r.SZ;
+        c.void_is_empty = !is_cube(ctx->gen_ids[0]);
+        c.gen_all_cubes = p.gen_all_cubes;
+        c.work = r.dirty_work;
+        c.work_span = r.dirty_span;
+        c.count = r.dirty_count;
+        c.spans = r.spans;
+        c.span_cap = r.span_cap;
+        CK(cudaMemsetAsync(r.dirty_count, 0, sizeof(uint32_t), ctx->stream));
+        launch_hmap_candidates(c, ctx->stream);
+        ctx->launches += 1;
+        p.work = r.dirty_work;
+        p.work_span = r.dirty_span;
+        p.n_work_dev = r.dirty_count;
+    }
+    if (cand_storage) {
         // whole interior from storage: drop the chunks whose summaries prove an empty mesh, keep the tiled order
         StorageCandParams c;
         c.summary = r.summary;
-        {
-            // solid terrain = grass, dirt, stone, snow grass of the last fill: do they all mesh as cubes today?
-            auto cube = [&](uint16_t id) { return id < ctx->reg_n && ctx->reg_host[id].present && ctx->reg_host[id].mesh_kind != 0; };
-            c.solids_are_cubes = cube(r.fill_ids[1]) && cube(r.fill_ids[2]) && cube(r.fill_ids[3]) && cube(r.fill_ids[4]);
-        }
+        // solid terrain = grass, dirt, stone, snow grass of the last fill: do they all mesh as cubes today?
+        c.solids_are_cubes = is_cube(r.fill_ids[1]) && is_cube(r.fill_ids[2]) && is_cube(r.fill_ids[3]) && is_cube(r.fill_ids[4]);
         c.SX = r.SX;
         c.SY = r.SY;
         c.SZ = r.SZ;
@@ -452,28 +539,28 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
         c.work_span = r.dirty_span;
         c.count = r.dirty_count;
         c.spans = r.spans;
+        c.span_cap = r.span_cap;
         launch_storage_candidates(c, ctx->stream);
         ctx->launches += 3;
         p.work = r.dirty_work;
         p.work_span = r.dirty_span;
         p.n_work_dev = r.dirty_count;
     }
-    unsigned long long base_v = 0, base_i = 0;
+    MeshCounters base; // allocator state the pass starts from
+    std::memset(&base, 0, sizeof base);
     if (append) {
         CK(cudaMemcpyAsync(r.h_counters, r.counters, sizeof(MeshCounters), cudaMemcpyDeviceToHost, ctx->stream));
+        // a re-mesh pass edits spans and reservations in place: keep what they were in case the arena has to grow
+        CK(cudaMemcpyAsync(r.spans_bak, r.spans, r.n_work * sizeof(bxw_mesh_span), cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(r.span_cap_bak, r.span_cap, r.n_work * sizeof(uint2), cudaMemcpyDeviceToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        base_v = r.h_counters->v_alloc;
-        base_i = r.h_counters->i_alloc;
+        base.v_alloc = r.h_counters->v_alloc;
+        base.i_alloc = r.h_counters->i_alloc;
+        base.v_garbage = r.h_counters->v_garbage;
+        base.i_garbage = r.h_counters->i_garbage;
     }
     for (int attempt = 0; attempt < 3; attempt++) {
-        MeshCounters init;
-        init.v_alloc = base_v;
-        init.i_alloc = base_i;
-        init.flags = 0;
-        init.work_next = 0;
-        init.f_alloc = 0;
-        for (int k = 0; k < 12; k++) init.phase[k] = 0;
-        *r.h_counters = init;
+        *r.h_counters = base;
         CK(cudaMemcpyAsync(r.counters, r.h_counters, sizeof(MeshCounters), cudaMemcpyHostToDevice, ctx->stream));
         const bool count_only = (r.varena == nullptr);
         p.varena = r.varena;
@@ -495,7 +582,10 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
         }
         CK(cudaEventRecord(ctx->ev_m1, ctx->stream));
         CK(cudaGetLastError());
+        // one copy brings back the allocator state, the error flags and (behind it, in the same pinned block) the length of the
+        // candidate list
         CK(cudaMemcpyAsync(r.h_counters, r.counters, sizeof(MeshCounters), cudaMemcpyDeviceToHost, ctx->stream));
+        if (p.n_work_dev) CK(cudaMemcpyAsync(r.h_counters + 1, p.n_work_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, ctx->ev_m0, ctx->ev_m1));
@@ -508,16 +598,19 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
         const unsigned long long need_v = r.h_counters->v_alloc, need_i = r.h_counters->i_alloc;
         if (count_only || (r.h_counters->flags & kFlagArenaOverflow)) {
             // size the arena from the measured need (+ slack so small edits can append) and run again
-            int rc = arena_resize(ctx, r, need_v + need_v / 8 + 4096, need_i + need_i / 8 + 8192, base_v, base_i);
+            int rc = arena_resize(ctx, r, need_v + need_v / 8 + 4096, need_i + need_i / 8 + 8192, base.v_alloc, base.i_alloc);
             if (rc) return rc;
             const unsigned long long need_f = r.h_counters->f_alloc;
             rc = faces_resize(ctx, r, need_f + need_f / 8 + 4096);
             if (rc) return rc;
+            if (append) {
+                CK(cudaMemcpyAsync(r.spans, r.spans_bak, r.n_work * sizeof(bxw_mesh_span), cudaMemcpyDeviceToDevice, ctx->stream));
+                CK(cudaMemcpyAsync(r.span_cap, r.span_cap_bak, r.n_work * sizeof(uint2), cudaMemcpyDeviceToDevice, ctx->stream));
+            }
             continue;
         }
         if (p.n_work_dev) { // whole-region pass over a device-built candidate list: remember its length (statistics)
-            CK(cudaMemcpyAsync(&ctx->last_candidates, p.n_work_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
+            ctx->last_candidates = *reinterpret_cast<const uint32_t *>(r.h_counters + 1);
             ctx->last_candidates_of = n_work;
         } else if (!work) { // whole region without a candidate list: everything was read
             ctx->last_candidates = n_work;
@@ -546,8 +639,23 @@ int ensure_io(bxw_ctx *ctx, size_t bytes_a, size_t bytes_b) {
     return BXW_OK;
 }
 
+int ensure_io_c(bxw_ctx *ctx, size_t bytes) {
+    if (bytes > ctx->io_c_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->io_c);
+        ctx->io_c = nullptr;
+        ctx->io_c_cap = 0;
+        CK(cudaMalloc(&ctx->io_c, bytes));
+        ctx->io_c_cap = bytes;
+    }
+    return BXW_OK;
+}
+
 // host RLE words -> device dense chunks (decompress_rle, lib.rs:304-345)
 int rle_decode_into(bxw_ctx *ctx, const uint32_t *words, const uint64_t *offsets, size_t n, uint32_t *d_dense) {
+    // the kernel reads words[offsets[c] .. offsets[c+1]) out of an upload of offsets[n] words: the offsets must not go backwards
+    for (size_t i = 0; i < n; i++)
+        if (offsets[i + 1] < offsets[i]) return fail(ctx, BXW_E_INVALID, "RLE offsets must be non-decreasing (chunk %zu)", i);
     const size_t nwords = offsets[n];
     const size_t a_bytes = (nwords ? nwords : 1) * sizeof(uint32_t);
     const size_t b_bytes = (n + 1) * sizeof(uint64_t) + n * sizeof(uint32_t);
@@ -683,6 +791,10 @@ int bxw_set_option(bxw_ctx *ctx, int option, int value) {
         ctx->mesh_from_hmap = value != 0;
         return BXW_OK;
     }
+    if (option == BXW_OPT_ELIDE_UNIFORM) {
+        ctx->elide_uniform = value != 0;
+        return BXW_OK;
+    }
     return fail(ctx, BXW_E_INVALID, "unknown option %d", option);
 }
 
@@ -742,7 +854,7 @@ int bxw_gen_chunk(bxw_ctx *ctx, uint64_t seed, int32_t cx, int32_t cy, int32_t c
     box.cy0 = cy + 1;
     box.cz0 = cz + 1;
     box.raw = nullptr;
-    rc = region_generate(ctx, box, seed, 64, false);
+    rc = region_generate(ctx, box, seed, 64, false); // no elision: the caller wants the voxels
     ctx->scratch.cells = box.cells; // region_generate may have grown the cell table
     ctx->scratch.cells_cap = box.cells_cap;
     if (rc) return rc;
@@ -835,7 +947,7 @@ int bxw_rle_compress(bxw_ctx *ctx, const uint32_t *dense, size_t n_chunks, uint3
     uint64_t *d_offs = (uint64_t *)ctx->io_b;
     uint32_t *d_len = (uint32_t *)(d_offs + n_chunks + 1);
     CK(cudaMemcpyAsync(d_dense, dense, dense_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    launch_rle_compress(d_dense, nullptr, n_chunks, d_len, d_offs, nullptr, 0, ctx->stream);
+    launch_rle_compress(d_dense, nullptr, nullptr, n_chunks, d_len, d_offs, nullptr, 0, ctx->stream);
     CK(cudaMemcpyAsync(out_offsets, d_offs, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     const size_t nwords = out_offsets[n_chunks];
@@ -846,7 +958,7 @@ int bxw_rle_compress(bxw_ctx *ctx, const uint32_t *dense, size_t n_chunks, uint3
         CK(cudaMalloc(&ctx->io_c, nwords * sizeof(uint32_t)));
         ctx->io_c_cap = nwords * sizeof(uint32_t);
     }
-    launch_rle_compress(d_dense, nullptr, n_chunks, d_len, d_offs, (uint32_t *)ctx->io_c, 1, ctx->stream);
+    launch_rle_compress(d_dense, nullptr, nullptr, n_chunks, d_len, d_offs, (uint32_t *)ctx->io_c, 1, ctx->stream);
     ctx->launches += 3;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out_words, ctx->io_c, nwords * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -887,7 +999,7 @@ int bxw_region_destroy(bxw_ctx *ctx) {
 
 int bxw_region_generate(bxw_ctx *ctx, uint64_t seed, int precision) {
     if (!ctx || !ctx->region.live) return fail(ctx, BXW_E_INVALID, "no region");
-    return region_generate(ctx, ctx->region, seed, precision, false);
+    return region_generate(ctx, ctx->region, seed, precision, ctx->elide_uniform);
 }
 
 int bxw_region_heightmap(bxw_ctx *ctx, int32_t *height, uint8_t *elevation, double *raw_height) {
@@ -895,9 +1007,19 @@ int bxw_region_heightmap(bxw_ctx *ctx, int32_t *height, uint8_t *elevation, doub
     Region &r = ctx->region;
     const size_t n = (size_t)r.SX * 32 * r.SZ * 32;
     if (raw_height) {
-        // recompute with the raw output enabled (same kernels, same seed/precision=64)
-        int rc = region_generate(ctx, r, ctx->gen_seed, 64, true);
+        // A getter must not touch the region: evaluate the column function again (stand-alone height map kernel, the seed and
+        // precision of the region's last generate) into scratch buffers; blocks, planes, summaries and hmap stay as they are.
+        GenParams gp;
+        int rc = gen_setup(ctx, r, r.gen_seed, r.gen_precision, gp);
         if (rc) return rc;
+        if (!r.raw) CK(cudaMalloc(&r.raw, n * sizeof(double)));
+        rc = ensure_io_c(ctx, n * sizeof(int32_t));
+        if (rc) return rc;
+        gp.hmap = (int32_t *)ctx->io_c;
+        gp.raw = r.raw;
+        launch_heightmap_kernel(gp, r.gen_precision, ctx->stream);
+        ctx->launches += 1;
+        CK(cudaGetLastError());
         CK(cudaMemcpyAsync(raw_height, r.raw, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
     std::vector<int32_t> packed(n);
@@ -914,6 +1036,8 @@ int bxw_region_upload_chunk(bxw_ctx *ctx, int32_t lx, int32_t ly, int32_t lz, co
     if (!ctx || !ctx->region.live || !blocks_yzx) return fail(ctx, BXW_E_INVALID, "no region / null");
     Region &r = ctx->region;
     if (!local_ok(r, lx, ly, lz)) return fail(ctx, BXW_E_INVALID, "chunk (%d,%d,%d) outside region+shell", lx, ly, lz);
+    const uint32_t cid = (uint32_t)storage_index(r, lx, ly, lz);
+    CK(cudaMemcpyAsync(r.page + cid, &cid, sizeof cid, cudaMemcpyHostToDevice, ctx->stream)); // every voxel is overwritten: materialised
     CK(cudaMemcpyAsync(r.blocks + storage_index(r, lx, ly, lz) * kChunkVoxels, blocks_yzx, kChunkVoxels * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(r.summary + storage_index(r, lx, ly, lz), 0, sizeof(unsigned long long), ctx->stream)); // no longer known uniform
     launch_xface_extract(r.blocks, r.xface, nullptr, (uint32_t)storage_index(r, lx, ly, lz), 1, ctx->stream);
@@ -926,7 +1050,10 @@ int bxw_region_download_chunk(bxw_ctx *ctx, int32_t lx, int32_t ly, int32_t lz, 
     if (!ctx || !ctx->region.live || !blocks_yzx) return fail(ctx, BXW_E_INVALID, "no region / null");
     Region &r = ctx->region;
     if (!local_ok(r, lx, ly, lz)) return fail(ctx, BXW_E_INVALID, "chunk (%d,%d,%d) outside region+shell", lx, ly, lz);
-    CK(cudaMemcpyAsync(blocks_yzx, r.blocks + storage_index(r, lx, ly, lz) * kChunkVoxels, kChunkVoxels * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    uint32_t pg = 0; // a chunk that is not materialised is read from its shared uniform page
+    CK(cudaMemcpyAsync(&pg, r.page + storage_index(r, lx, ly, lz), sizeof pg, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(blocks_yzx, r.blocks + (size_t)pg * kChunkVoxels, kChunkVoxels * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return BXW_OK;
 }
@@ -945,17 +1072,6 @@ static int upload_chunk_ids(bxw_ctx *ctx, const Region &r, const int32_t *lpos, 
     return BXW_OK;
 }
 
-static int ensure_io_c(bxw_ctx *ctx, size_t bytes) {
-    if (bytes > ctx->io_c_cap) {
-        cudaFree(ctx->io_c);
-        ctx->io_c = nullptr;
-        ctx->io_c_cap = 0;
-        CK(cudaMalloc(&ctx->io_c, bytes));
-        ctx->io_c_cap = bytes;
-    }
-    return BXW_OK;
-}
-
 int bxw_region_export_rle(bxw_ctx *ctx, const int32_t *lpos, size_t n_chunks, uint32_t *out_words, size_t cap_words,
                           uint64_t *out_offsets) {
     if (!ctx || !ctx->region.live || !lpos || !out_offsets || n_chunks == 0) return fail(ctx, BXW_E_INVALID, "no region / null argument");
@@ -968,7 +1084,7 @@ int bxw_region_export_rle(bxw_ctx *ctx, const int32_t *lpos, size_t n_chunks, ui
     uint32_t *d_ids = nullptr;
     rc = upload_chunk_ids(ctx, r, lpos, n_chunks, meta_bytes, &d_ids);
     if (rc) return rc;
-    launch_rle_compress(r.blocks, d_ids, n_chunks, d_len, d_offs, nullptr, 0, ctx->stream);
+    launch_rle_compress(r.blocks, d_ids, r.page, n_chunks, d_len, d_offs, nullptr, 0, ctx->stream);
     ctx->launches += 2;
     CK(cudaMemcpyAsync(out_offsets, d_offs, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -977,7 +1093,7 @@ int bxw_region_export_rle(bxw_ctx *ctx, const int32_t *lpos, size_t n_chunks, ui
     if (nwords > cap_words) return fail(ctx, BXW_E_NOSPACE, "RLE export needs %zu words, buffer holds %zu", nwords, cap_words);
     rc = ensure_io_c(ctx, nwords * sizeof(uint32_t));
     if (rc) return rc;
-    launch_rle_compress(r.blocks, d_ids, n_chunks, d_len, d_offs, (uint32_t *)ctx->io_c, 1, ctx->stream);
+    launch_rle_compress(r.blocks, d_ids, r.page, n_chunks, d_len, d_offs, (uint32_t *)ctx->io_c, 1, ctx->stream);
     ctx->launches += 1;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out_words, ctx->io_c, nwords * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1002,7 +1118,7 @@ int bxw_region_import_rle(bxw_ctx *ctx, const int32_t *lpos, size_t n_chunks, co
     uint32_t *d_ids = nullptr;
     rc = upload_chunk_ids(ctx, r, lpos, n_chunks, meta_bytes, &d_ids);
     if (rc) return rc;
-    launch_chunk_scatter((const uint32_t *)ctx->io_c, d_ids, n_chunks, r.blocks, r.xface, r.summary, r.SX, r.SY, r.SZ, r.dirty, ctx->stream);
+    launch_chunk_scatter((const uint32_t *)ctx->io_c, d_ids, n_chunks, r.blocks, r.xface, r.summary, r.page, r.SX, r.SY, r.SZ, r.dirty, ctx->stream);
     ctx->launches += 1;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1067,6 +1183,7 @@ int bxw_region_mesh_sphere(bxw_ctx *ctx, int32_t ax, int32_t ay, int32_t az, uin
     const uint32_t n = (uint32_t)items.size();
     if (n_meshed) *n_meshed = n;
     CK(cudaMemsetAsync(r.spans, 0, r.n_work * sizeof(bxw_mesh_span), ctx->stream));
+    CK(cudaMemsetAsync(r.span_cap, 0, r.n_work * sizeof(uint2), ctx->stream));
     if (n == 0) {
         if (arena_vertices) *arena_vertices = 0;
         if (arena_indices) *arena_indices = 0;
@@ -1102,6 +1219,18 @@ int bxw_region_mesh_fetch(bxw_ctx *ctx, bxw_vertex *vertices, uint64_t n_vertice
     if (n_vertices > r.v_cap || n_indices > r.i_cap) return fail(ctx, BXW_E_INVALID, "fetch exceeds arena");
     if (n_vertices && vertices) CK(cudaMemcpyAsync(vertices, r.varena, n_vertices * sizeof(bxw_vertex), cudaMemcpyDeviceToHost, ctx->stream));
     if (n_indices && indices) CK(cudaMemcpyAsync(indices, r.iarena, n_indices * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BXW_OK;
+}
+
+int bxw_region_mesh_fetch_range(bxw_ctx *ctx, uint64_t v_off, uint64_t n_vertices, bxw_vertex *vertices, uint64_t i_off, uint64_t n_indices,
+                                uint32_t *indices) {
+    if (!ctx || !ctx->region.live) return fail(ctx, BXW_E_INVALID, "no region");
+    Region &r = ctx->region;
+    if (v_off + n_vertices > r.v_cap || i_off + n_indices > r.i_cap) return fail(ctx, BXW_E_INVALID, "fetch exceeds arena");
+    if (n_vertices && vertices)
+        CK(cudaMemcpyAsync(vertices, r.varena + v_off, n_vertices * sizeof(bxw_vertex), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_indices && indices) CK(cudaMemcpyAsync(indices, r.iarena + i_off, n_indices * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return BXW_OK;
 }
@@ -1156,11 +1285,24 @@ int bxw_region_apply_changes(bxw_ctx *ctx, const bxw_voxel_change *changes, uint
     }
     const uint32_t n_runs = (uint32_t)runs.size();
     runs.push_back((uint32_t)keyed.size());
+    std::vector<uint32_t> touched; // distinct storage chunks that receive a change
     if (n_runs) {
-        int rc = ensure_io(ctx, sorted.size() * sizeof(bxw_voxel_change), runs.size() * sizeof(uint32_t));
+        for (uint32_t k = 0; k < n_runs; k++) {
+            const bxw_voxel_change &c = sorted[runs[k]];
+            const int sx = (c.x - x_min) >> 5, sy = (c.y - y_min) >> 5, sz = (c.z - z_min) >> 5;
+            touched.push_back((uint32_t)(sx + r.SX * (sz + r.SZ * sy)));
+        }
+        std::sort(touched.begin(), touched.end());
+        touched.erase(std::unique(touched.begin(), touched.end()), touched.end());
+        int rc = ensure_io(ctx, sorted.size() * sizeof(bxw_voxel_change), (runs.size() + touched.size()) * sizeof(uint32_t));
         if (rc) return rc;
         CK(cudaMemcpyAsync(ctx->io_a, sorted.data(), sorted.size() * sizeof(bxw_voxel_change), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->io_b, runs.data(), runs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        // single-voxel writes need the chunk's own storage: chunks still on a shared uniform page get a copy of it first
+        uint32_t *d_touched = (uint32_t *)ctx->io_b + runs.size();
+        CK(cudaMemcpyAsync(d_touched, touched.data(), touched.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        launch_materialise(r.blocks, r.xface, r.page, d_touched, (uint32_t)touched.size(), ctx->stream);
+        ctx->launches += 1;
         EditParams ep;
         ep.blocks = r.blocks;
         ep.xface = r.xface;
@@ -1200,8 +1342,97 @@ int bxw_region_remesh_dirty(bxw_ctx *ctx, uint32_t *n_remeshed) {
     CK(cudaStreamSynchronize(ctx->stream));
     if (n_remeshed) *n_remeshed = nd;
     if (nd == 0) return BXW_OK;
-    // fresh arena space is appended; the old spans of these chunks become garbage until the next full mesh
-    return region_mesh(ctx, r, r.dirty_work, r.dirty_span, nd, true);
+    // A chunk whose new mesh fits its old arena reservation is rewritten in place; the others move to the end of the arena and
+    // their old reservation becomes garbage (the reference drops the old ChunkBuffers when the new one lands,
+    // voxrender.rs:398-413). Once a quarter of the used arena is garbage the live spans are compacted.
+    int rc = region_mesh(ctx, r, r.dirty_work, r.dirty_span, nd, true);
+    if (rc) return rc;
+    const unsigned long long gv = r.h_counters->v_garbage, gi = r.h_counters->i_garbage;
+    if (gv * 4ull > r.h_counters->v_alloc + 65536ull || gi * 4ull > r.h_counters->i_alloc + 98304ull) return bxw_region_compact_arena(ctx, nullptr, nullptr);
+    return BXW_OK;
+}
+
+int bxw_region_arena_extent(bxw_ctx *ctx, uint64_t *arena_vertices, uint64_t *arena_indices) {
+    if (!ctx || !ctx->region.live) return fail(ctx, BXW_E_INVALID, "no region");
+    Region &r = ctx->region;
+    CK(cudaMemcpyAsync(r.h_counters, r.counters, sizeof(MeshCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (arena_vertices) *arena_vertices = r.h_counters->v_alloc;
+    if (arena_indices) *arena_indices = r.h_counters->i_alloc;
+    return BXW_OK;
+}
+
+int bxw_region_arena_stats(bxw_ctx *ctx, bxw_arena_stats *out) {
+    if (!ctx || !ctx->region.live || !out) return fail(ctx, BXW_E_INVALID, "no region / null");
+    Region &r = ctx->region;
+    CK(cudaMemcpyAsync(r.h_counters, r.counters, sizeof(MeshCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    out->vertices_used = r.h_counters->v_alloc;
+    out->indices_used = r.h_counters->i_alloc;
+    out->vertices_garbage = r.h_counters->v_garbage;
+    out->indices_garbage = r.h_counters->i_garbage;
+    out->vertices_capacity = r.v_cap;
+    out->indices_capacity = r.i_cap;
+    return BXW_OK;
+}
+
+int bxw_region_compact_arena(bxw_ctx *ctx, uint64_t *arena_vertices, uint64_t *arena_indices) {
+    if (!ctx || !ctx->region.live) return fail(ctx, BXW_E_INVALID, "no region");
+    Region &r = ctx->region;
+    if (!r.varena) return fail(ctx, BXW_E_INVALID, "no mesh arena yet");
+    if (ctx->copy_pending) { // an asynchronous fetch may still read the arena that is about to be replaced
+        CK(cudaEventSynchronize(ctx->ev_copy_done));
+        ctx->copy_pending = false;
+    }
+    int rc = ensure_io_c(ctx, (size_t)r.n_work * 2 * sizeof(unsigned long long));
+    if (rc) return rc;
+    unsigned long long *new_off = (unsigned long long *)ctx->io_c;
+    bxw_vertex *nv = nullptr;
+    uint32_t *ni = nullptr;
+    CK(cudaMalloc(&nv, r.v_cap * sizeof(bxw_vertex)));
+    if (cudaMalloc(&ni, r.i_cap * sizeof(uint32_t)) != cudaSuccess) {
+        cudaFree(nv);
+        return fail(ctx, BXW_E_NOMEM, "no device memory for the second arena");
+    }
+    launch_compact_offsets(r.spans, r.span_cap, r.n_work, new_off, r.counters, ctx->stream);
+    launch_compact_copy(r.spans, new_off, r.n_work, r.varena, r.iarena, nv, ni, ctx->stream);
+    ctx->launches += 2;
+    CK(cudaMemcpyAsync(r.h_counters, r.counters, sizeof(MeshCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    cudaFree(r.varena);
+    cudaFree(r.iarena);
+    r.varena = nv;
+    r.iarena = ni;
+    if (arena_vertices) *arena_vertices = r.h_counters->v_alloc;
+    if (arena_indices) *arena_indices = r.h_counters->i_alloc;
+    return BXW_OK;
+}
+
+int bxw_region_set_origin(bxw_ctx *ctx, int32_t cx0, int32_t cy0, int32_t cz0) {
+    if (!ctx || !ctx->region.live) return fail(ctx, BXW_E_INVALID, "no region");
+    Region &r = ctx->region;
+    CK(cudaStreamSynchronize(ctx->stream));
+    r.cx0 = cx0;
+    r.cy0 = cy0;
+    r.cz0 = cz0;
+    r.have_hmap = false; // the stored voxels belong to the old position until the next generate / upload
+    return BXW_OK;
+}
+
+int bxw_region_page_table(bxw_ctx *ctx, void **pages, uint32_t *n_shared) {
+    if (!ctx || !ctx->region.live) return fail(ctx, BXW_E_INVALID, "no region");
+    if (pages) *pages = ctx->region.page;
+    if (n_shared) *n_shared = kSharedPages;
+    return BXW_OK;
+}
+
+int bxw_region_download_pages(bxw_ctx *ctx, uint32_t *pages) {
+    if (!ctx || !ctx->region.live || !pages) return fail(ctx, BXW_E_INVALID, "no region / null");
+    Region &r = ctx->region;
+    CK(cudaMemcpyAsync(pages, r.page, r.n_storage() * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BXW_OK;
 }
 
 size_t bxw_region_halo_bytes(const bxw_ctx *ctx) {
@@ -1212,7 +1443,7 @@ int bxw_region_halo_export(bxw_ctx *ctx, int face, void *dev_buf) {
     if (!ctx || !ctx->region.live || !dev_buf || (face != 0 && face != 1)) return fail(ctx, BXW_E_INVALID, "bad halo export");
     Region &r = ctx->region;
     // the interior's own boundary plane: x- face = storage chunk column 1, local x 0; x+ face = column nx, local x 31
-    launch_halo_plane(r.blocks, r.xface, nullptr, r.SX, r.SY, r.SZ, face == 0 ? 1 : (int)r.nx, face == 0 ? 0 : 31, (uint32_t *)dev_buf, 0, ctx->stream);
+    launch_halo_plane(r.blocks, r.xface, nullptr, r.page, r.need, r.SX, r.SY, r.SZ, face == 0 ? 1 : (int)r.nx, face == 0 ? 0 : 31, (uint32_t *)dev_buf, 0, ctx->stream);
     ctx->launches += 1;
     CK(cudaGetLastError());
     return BXW_OK;
@@ -1222,8 +1453,8 @@ int bxw_region_halo_import(bxw_ctx *ctx, int face, const void *dev_buf) {
     if (!ctx || !ctx->region.live || !dev_buf || (face != 0 && face != 1)) return fail(ctx, BXW_E_INVALID, "bad halo import");
     Region &r = ctx->region;
     // into the shell: x- shell = column 0, local x 31; x+ shell = column nx+1, local x 0
-    launch_halo_plane(r.blocks, r.xface, r.summary, r.SX, r.SY, r.SZ, face == 0 ? 0 : (int)r.nx + 1, face == 0 ? 31 : 0, (uint32_t *)dev_buf, 1, ctx->stream);
-    ctx->launches += 1;
+    launch_halo_plane(r.blocks, r.xface, r.summary, r.page, r.need, r.SX, r.SY, r.SZ, face == 0 ? 0 : (int)r.nx + 1, face == 0 ? 31 : 0, (uint32_t *)dev_buf, 1, ctx->stream);
+    ctx->launches += 3;
     CK(cudaGetLastError());
     return BXW_OK;
 }
@@ -1270,6 +1501,7 @@ int bxw_region_fill_synthetic(bxw_ctx *ctx, uint64_t seed, uint32_t void_thresho
     if (!ctx || !ctx->region.live) return fail(ctx, BXW_E_INVALID, "no region");
     Region &r = ctx->region;
     CK(cudaMemsetAsync(r.summary, 0, r.n_storage() * sizeof(unsigned long long), ctx->stream));
+    launch_page_identity(r.page, (uint32_t)r.n_storage(), ctx->stream);
     launch_fill_synthetic(r.blocks, r.SX, r.SY, r.SZ, r.cx0 - 1, r.cy0 - 1, r.cz0 - 1, seed, void_threshold, ctx->stream);
     launch_xface_extract(r.blocks, r.xface, nullptr, 0, (uint32_t)r.n_storage(), ctx->stream);
     ctx->launches += 2;

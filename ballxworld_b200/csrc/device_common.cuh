@@ -29,20 +29,30 @@ struct MeshCounters {
     unsigned long long flags;
     unsigned long long work_next; // dynamic work-list cursor
     unsigned long long f_alloc;   // next free face-record slot (a chunk takes a multiple of 32)
+    unsigned long long v_garbage; // arena space that no span refers to any more (re-meshes that moved, unloaded meshes)
+    unsigned long long i_garbage;
     // -DBXW_PHASE_TIMING builds only: SM cycles of CTA thread 0 summed over chunks: [0] work fetch + neighbour table,
     // [1] phase A, [2] phases B + scan + allocation, [3] phase C, [4] chunks that reached phase C, [5] chunks
     unsigned long long phase[12]; // [6] tile setup, [7] C1, [8] warp 0's batches, [9] tile-end barrier wait
 };
 
 struct MeshParams {
-    const uint32_t *blocks; // region storage: chunk c at blocks + c*32768, voxel x + 32 z + 1024 y
-    const uint32_t *xface;  // per chunk the x=0 and x=31 voxel planes, [chunk][side][y][z] (2 x 4 KB): the mesher's x-halo source
+    const uint32_t *blocks; // region storage: chunk page g at blocks + g*32768, voxel x + 32 z + 1024 y
+    const uint32_t *xface;  // per chunk page the x=0 and x=31 voxel planes, [page][side][y][z] (2 x 4 KB): the mesher's x-halo source
+    // page[c] = where chunk c's voxels live: c itself, or one of the shared pages behind the storage that hold a single
+    // datum (chunks the generator proved uniform are not materialised; device analogue of a 3-word VChunk, lib.rs:263-294)
+    const uint32_t *page;
     int SX, SY, SZ;         // storage dims in chunks (shell included); chunk index sx + SX*(sz + SZ*sy)
     const uint32_t *work;   // [n_work] storage chunk index of each chunk to mesh
     const uint32_t *work_span; // [n_work] span slot of each work item
     uint32_t n_work;           // upper bound of the list length (grid sizing)
     const uint32_t *n_work_dev; // optional: the actual list length lives on the device (candidate list built by a kernel)
     bxw_mesh_span *spans;
+    // span_cap[slot] = arena space (vertices, indices) reserved behind the slot's span. reuse = 1 (re-mesh passes): a chunk
+    // whose new mesh fits its old reservation is rewritten in place, otherwise it moves to the arena's end (with slack) and the
+    // old reservation is counted as garbage (the reference drops the old ChunkBuffers when the new one lands, voxrender.rs:398-413)
+    uint2 *span_cap;
+    int reuse;
     bxw_vertex *varena;
     uint32_t *iarena;
     unsigned long long v_cap, i_cap;
@@ -83,6 +93,7 @@ struct CandidateParams {
     int void_is_empty, gen_all_cubes;
     uint32_t *work, *work_span, *count;
     bxw_mesh_span *spans;
+    uint2 *span_cap;
 };
 void launch_hmap_candidates(const CandidateParams &p, cudaStream_t stream);
 
@@ -107,6 +118,7 @@ struct StorageCandParams {
     uint32_t *blk;       // [ceil(n_work / 256) + 1] scratch: per-block keep counts -> exclusive offsets
     uint32_t *work, *work_span, *count;
     bxw_mesh_span *spans;
+    uint2 *span_cap;
 };
 void launch_storage_candidates(const StorageCandParams &p, cudaStream_t stream);
 int mesh_kernel_max_ctas_per_sm();
@@ -145,9 +157,17 @@ struct FillParams {
     int SX, SY, SZ;
     int32_t cy_min;      // world chunk y of storage layer 0
     uint32_t id_void, id_grass, id_dirt, id_stone, id_snow; // already shifted datums (id << 16)
+    // uniform-chunk elision: a chunk proven all void / all stone is not written; page[c] points at the shared page instead
+    uint32_t *page;
+    int elide;
+    uint32_t page_void, page_stone;
+    // list mode (load deltas): entry k = storage chunk index; the CTA handles that one chunk instead of a whole stack
+    const uint32_t *list;
+    uint32_t n_list;
 };
 void launch_fill_kernel(const FillParams &p, cudaStream_t stream);
 void launch_fill_xface_kernel(const FillParams &p, cudaStream_t stream);
+void launch_uniform_page(uint32_t *blocks, uint32_t *xface, uint32_t slot, uint32_t datum, cudaStream_t stream);
 // height map + block selection in one kernel (g.hmap is written, g.raw is ignored)
 void launch_gen_fill_kernel(const FillParams &p, const GenParams &g, int precision, cudaStream_t stream);
 

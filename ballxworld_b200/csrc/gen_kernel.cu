@@ -303,7 +303,19 @@ __global__ void __launch_bounds__(128) heightmap_kernel(GenParams p) {
 // FP64 phase share an SM with CTAs in their store phase, which hides the height map behind the HBM writes.
 template <int GEN>
 __global__ void __launch_bounds__(256, 4) fill_kernel(FillParams p, GenParams g) {
-    const int sx = blockIdx.x, sz = blockIdx.y;
+    int sx, sz, sy_lo, sy_hi;
+    if (p.list) { // load deltas: one listed chunk per CTA (the reference's granularity, generation.rs:96-148)
+        const uint32_t c = p.list[blockIdx.x];
+        sx = (int)(c % (uint32_t)p.SX);
+        sz = (int)((c / (uint32_t)p.SX) % (uint32_t)p.SZ);
+        sy_lo = (int)(c / (uint32_t)(p.SX * p.SZ));
+        sy_hi = sy_lo + 1;
+    } else {
+        sx = blockIdx.x;
+        sz = blockIdx.y;
+        sy_lo = 0;
+        sy_hi = p.SY;
+    }
     const int q = threadIdx.x & 7, zr = threadIdx.x >> 3;
     int4 hm;
     if (GEN == 0) {
@@ -317,39 +329,39 @@ __global__ void __launch_bounds__(256, 4) fill_kernel(FillParams p, GenParams g)
     }
     const int hh[4] = {hm.x >> 2, hm.y >> 2, hm.z >> 2, hm.w >> 2};
     const int el[4] = {hm.x & 3, hm.y & 3, hm.z & 3, hm.w & 3};
+    // chunk summaries of the stack: above every column -> all void; more than 5 below every column -> all stone; at or below
+    // every column (of the chunk / of one of its four side planes) -> solid terrain (device_common.cuh: kSolidShift)
+    __shared__ int red[6][8];
+    const int big = 0x7FFFFFFF;
+    int lo = min(min(hh[0], hh[1]), min(hh[2], hh[3])), hi = max(max(hh[0], hh[1]), max(hh[2], hh[3]));
+    int lx0 = q == 0 ? hh[0] : big, lx1 = q == 7 ? hh[3] : big;
+    int lz0 = zr == 0 ? lo : big, lz1 = zr == 31 ? lo : big;
+    lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+    hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+    lx0 = __reduce_min_sync(0xFFFFFFFFu, lx0);
+    lx1 = __reduce_min_sync(0xFFFFFFFFu, lx1);
+    lz0 = __reduce_min_sync(0xFFFFFFFFu, lz0);
+    lz1 = __reduce_min_sync(0xFFFFFFFFu, lz1);
+    if ((threadIdx.x & 31) == 0) {
+        const int w = threadIdx.x >> 5;
+        red[0][w] = lo;
+        red[1][w] = hi;
+        red[2][w] = lx0;
+        red[3][w] = lx1;
+        red[4][w] = lz0;
+        red[5][w] = lz1;
+    }
+    __syncthreads();
+    for (int k = 0; k < 8; k++) {
+        lo = min(lo, red[0][k]);
+        hi = max(hi, red[1][k]);
+        lx0 = min(lx0, red[2][k]);
+        lx1 = min(lx1, red[3][k]);
+        lz0 = min(lz0, red[4][k]);
+        lz1 = min(lz1, red[5][k]);
+    }
     if (p.summary) {
-        // chunk summaries of the stack: above every column -> all void; more than 5 below every column -> all stone; at or below
-        // every column (of the chunk / of one of its four side planes) -> solid terrain (device_common.cuh: kSolidShift)
-        __shared__ int red[6][8];
-        const int big = 0x7FFFFFFF;
-        int lo = min(min(hh[0], hh[1]), min(hh[2], hh[3])), hi = max(max(hh[0], hh[1]), max(hh[2], hh[3]));
-        int lx0 = q == 0 ? hh[0] : big, lx1 = q == 7 ? hh[3] : big;
-        int lz0 = zr == 0 ? lo : big, lz1 = zr == 31 ? lo : big;
-        lo = __reduce_min_sync(0xFFFFFFFFu, lo);
-        hi = __reduce_max_sync(0xFFFFFFFFu, hi);
-        lx0 = __reduce_min_sync(0xFFFFFFFFu, lx0);
-        lx1 = __reduce_min_sync(0xFFFFFFFFu, lx1);
-        lz0 = __reduce_min_sync(0xFFFFFFFFu, lz0);
-        lz1 = __reduce_min_sync(0xFFFFFFFFu, lz1);
-        if ((threadIdx.x & 31) == 0) {
-            const int w = threadIdx.x >> 5;
-            red[0][w] = lo;
-            red[1][w] = hi;
-            red[2][w] = lx0;
-            red[3][w] = lx1;
-            red[4][w] = lz0;
-            red[5][w] = lz1;
-        }
-        __syncthreads();
-        for (int k = 0; k < 8; k++) {
-            lo = min(lo, red[0][k]);
-            hi = max(hi, red[1][k]);
-            lx0 = min(lx0, red[2][k]);
-            lx1 = min(lx1, red[3][k]);
-            lz0 = min(lz0, red[4][k]);
-            lz1 = min(lz1, red[5][k]);
-        }
-        for (int sy = threadIdx.x; sy < p.SY; sy += 256) {
+        for (int sy = sy_lo + (int)threadIdx.x; sy < sy_hi; sy += 256) {
             const int ybase = (p.cy_min + sy) * 32, ytop = ybase + 31;
             unsigned long long sum = 0;
             if (ybase > hi) sum = kUniformBit | p.id_void;
@@ -360,9 +372,19 @@ __global__ void __launch_bounds__(256, 4) fill_kernel(FillParams p, GenParams g)
             p.summary[(size_t)(sx + p.SX * (sz + p.SZ * sy))] = sum | ((unsigned long long)solid << kSolidShift);
         }
     }
-    for (int sy = 0; sy < p.SY; sy++) {
-        uint4 *dst = reinterpret_cast<uint4 *>(p.blocks + ((size_t)(sx + p.SX * (sz + p.SZ * sy))) * kChunkVoxels + zr * 32 + q * 4);
+    for (int sy = sy_lo; sy < sy_hi; sy++) {
+        const uint32_t c = (uint32_t)(sx + p.SX * (sz + p.SZ * sy));
         const int ybase = (p.cy_min + sy) * 32;
+        // Uniform chunks are not materialised: their page entry points at the shared all-void / all-stone page (every reader
+        // goes through the page table; the first writer materialises the chunk). Same test as the summary above.
+        uint32_t pg = c;
+        if (p.elide) {
+            if (ybase > hi) pg = p.page_void;
+            else if (ybase + 31 < lo - 5) pg = p.page_stone;
+        }
+        if (p.page && threadIdx.x == 0) p.page[c] = pg;
+        if (pg != c) continue;
+        uint4 *dst = reinterpret_cast<uint4 *>(p.blocks + (size_t)c * kChunkVoxels + zr * 32 + q * 4);
 #pragma unroll 4
         for (int yc = 0; yc < 32; yc++) {
             const int y = ybase + yc;
@@ -385,12 +407,26 @@ __global__ void __launch_bounds__(256, 4) fill_kernel(FillParams p, GenParams g)
 // The x=0 / x=31 voxel planes of every chunk, straight from the column parameters (same selection rule as fill_kernel).
 // One CTA per (sx, sz) chunk column, thread = (side, z); loops over all layers; coalesced 128-byte stores.
 __global__ void __launch_bounds__(64) fill_xface_kernel(FillParams p) {
-    const int sx = blockIdx.x, sz = blockIdx.y;
+    int sx, sz, sy_lo, sy_hi;
+    if (p.list) {
+        const uint32_t c = p.list[blockIdx.x];
+        sx = (int)(c % (uint32_t)p.SX);
+        sz = (int)((c / (uint32_t)p.SX) % (uint32_t)p.SZ);
+        sy_lo = (int)(c / (uint32_t)(p.SX * p.SZ));
+        sy_hi = sy_lo + 1;
+    } else {
+        sx = blockIdx.x;
+        sz = blockIdx.y;
+        sy_lo = 0;
+        sy_hi = p.SY;
+    }
     const int side = threadIdx.x >> 5, z = threadIdx.x & 31;
     const int hm = __ldg(p.hmap + (size_t)(sz * 32 + z) * p.W + sx * 32 + (side ? 31 : 0));
     const int h = hm >> 2, el = hm & 3;
-    for (int sy = 0; sy < p.SY; sy++) {
-        uint32_t *dst = p.xface + ((size_t)(sx + p.SX * (sz + p.SZ * sy))) * 2048 + side * 1024 + z;
+    for (int sy = sy_lo; sy < sy_hi; sy++) {
+        const uint32_t c = (uint32_t)(sx + p.SX * (sz + p.SZ * sy));
+        if (p.page && p.page[c] != c) continue; // not materialised: the shared page carries its planes
+        uint32_t *dst = p.xface + (size_t)c * 2048 + side * 1024 + z;
         const int ybase = (p.cy_min + sy) * 32;
         for (int yc = 0; yc < 32; yc++) {
             const int y = ybase + yc;
@@ -433,21 +469,36 @@ void launch_heightmap_kernel(const GenParams &p, int precision, cudaStream_t str
     else heightmap_kernel<64><<<grid, 128, 0, stream>>>(p);
 }
 
+static dim3 fill_grid(const FillParams &p) { return p.list ? dim3(p.n_list) : dim3(p.SX, p.SZ); }
+
 void launch_fill_kernel(const FillParams &p, cudaStream_t stream) {
-    dim3 grid(p.SX, p.SZ);
-    fill_kernel<0><<<grid, 256, 0, stream>>>(p, GenParams{});
+    if (p.list && !p.n_list) return;
+    fill_kernel<0><<<fill_grid(p), 256, 0, stream>>>(p, GenParams{});
 }
 
 void launch_gen_fill_kernel(const FillParams &p, const GenParams &g, int precision, cudaStream_t stream) {
     ensure_constants();
-    dim3 grid(p.SX, p.SZ);
-    if (precision == 32) fill_kernel<32><<<grid, 256, 0, stream>>>(p, g);
-    else fill_kernel<64><<<grid, 256, 0, stream>>>(p, g);
+    if (p.list && !p.n_list) return;
+    if (precision == 32) fill_kernel<32><<<fill_grid(p), 256, 0, stream>>>(p, g);
+    else fill_kernel<64><<<fill_grid(p), 256, 0, stream>>>(p, g);
 }
 
 void launch_fill_xface_kernel(const FillParams &p, cudaStream_t stream) {
-    dim3 grid(p.SX, p.SZ);
-    if (p.xface) fill_xface_kernel<<<grid, 64, 0, stream>>>(p);
+    if (p.list && !p.n_list) return;
+    if (p.xface) fill_xface_kernel<<<fill_grid(p), 64, 0, stream>>>(p);
+}
+
+// the shared single-datum pages behind the storage (blocks + x-face planes)
+__global__ void uniform_page_kernel(uint32_t *blocks, uint32_t *xface, uint32_t slot, uint32_t datum) {
+    const uint4 v = make_uint4(datum, datum, datum, datum);
+    uint4 *b = reinterpret_cast<uint4 *>(blocks + (size_t)slot * kChunkVoxels);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kChunkVoxels / 4; i += gridDim.x * blockDim.x) b[i] = v;
+    uint4 *x = reinterpret_cast<uint4 *>(xface + (size_t)slot * 2048);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 512; i += gridDim.x * blockDim.x) x[i] = v;
+}
+
+void launch_uniform_page(uint32_t *blocks, uint32_t *xface, uint32_t slot, uint32_t datum, cudaStream_t stream) {
+    uniform_page_kernel<<<8, 256, 0, stream>>>(blocks, xface, slot, datum);
 }
 
 } // namespace bxw

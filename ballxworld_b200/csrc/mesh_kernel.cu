@@ -169,6 +169,17 @@ __device__ __forceinline__ void row_visibility(const Smem &s, int y, int z, unsi
     out[5] = C & ~solid_word(s, r + 1) & M;
 }
 
+// the slot's arena reservation is given up (its mesh moved or became empty): count it as garbage
+__device__ __forceinline__ void release_span(const MeshParams &p, uint32_t span_slot) {
+    if (!p.span_cap) return;
+    if (p.reuse) {
+        const uint2 oc = p.span_cap[span_slot];
+        if (oc.x) atomicAdd(&p.counters->v_garbage, (unsigned long long)oc.x);
+        if (oc.y) atomicAdd(&p.counters->i_garbage, (unsigned long long)oc.y);
+    }
+    p.span_cap[span_slot] = make_uint2(0u, 0u);
+}
+
 #ifdef BXW_PHASE_TIMING
 #define PHASE_MARK(var) const long long var = clock64()
 #define PHASE_ADD(slot, a, b) do { if (tid == 0) atomicAdd(&p.counters->phase[slot], (unsigned long long)((b) - (a))); } while (0)
@@ -231,7 +242,8 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
             const int sx = (int)(c0 % (uint32_t)p.SX), sz = (int)((c0 / (uint32_t)p.SX) % (uint32_t)p.SZ),
                       sy = (int)(c0 / (uint32_t)(p.SX * p.SZ));
             const int rx = tid % 3, rz = (tid / 3) % 3, ry = tid / 9;
-            s.nbr[tid] = (uint32_t)((sx + rx - 1) + p.SX * ((sz + rz - 1) + p.SZ * (sy + ry - 1)));
+            const uint32_t nc = (uint32_t)((sx + rx - 1) + p.SX * ((sz + rz - 1) + p.SZ * (sy + ry - 1)));
+            s.nbr[tid] = p.page ? __ldg(p.page + nc) : nc; // where the neighbour's voxels live (itself or a shared uniform page)
         }
         __syncthreads();
 
@@ -401,7 +413,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
             uint8_t *const ring = &s.ring[warp][0][0];
             // rows of the chunk itself (yy 1..32, zz 1..32) come straight off this pointer; only the boundary rows look up
             // a neighbour chunk
-            const uint32_t *const center_q = p.blocks + (size_t)c0 * kChunkVoxels + q * 4;
+            const uint32_t *const center_q = p.blocks + (size_t)s.nbr[13] * kChunkVoxels + q * 4;
             auto issue = [&](int g, int slot) {
                 if (g < N_UNITS) {
                     const int yy = g / 3, part = g - yy * 3;
@@ -593,6 +605,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                 sp.v_off = sp.i_off = 0;
                 sp.v_count = sp.i_count = 0;
                 p.spans[span_slot] = sp;
+                release_span(p, span_slot);
             }
             continue;
         }
@@ -674,13 +687,32 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                 unsigned long long vb = 0, ib = 0, fb = 0;
                 int emit = 0;
                 if (TV | TI) {
-                    vb = atomicAdd(&p.counters->v_alloc, padV);
-                    ib = atomicAdd(&p.counters->i_alloc, padI);
-                    fb = atomicAdd(&p.counters->f_alloc, padF);
-                    if (!p.count_only) {
-                        if (vb + padV <= p.v_cap && ib + padI <= p.i_cap && fb + padF <= p.f_cap) emit = 1;
-                        else atomicOr(&p.counters->flags, kFlagArenaOverflow);
+                    const uint2 oc = p.reuse ? p.span_cap[span_slot] : make_uint2(0u, 0u);
+                    if (p.reuse && padV <= oc.x && padI <= oc.y) {
+                        // the new mesh fits the chunk's old reservation: rewrite it in place
+                        vb = p.spans[span_slot].v_off;
+                        ib = p.spans[span_slot].i_off;
+                        fb = atomicAdd(&p.counters->f_alloc, padF);
+                        if (!p.count_only) {
+                            if (fb + padF <= p.f_cap) emit = 1;
+                            else atomicOr(&p.counters->flags, kFlagArenaOverflow);
+                        }
+                    } else {
+                        // re-meshes reserve some slack so that the next edit of the chunk can stay in place
+                        const unsigned long long capV = p.reuse ? ((TV + TV / 8ull + 16ull + 3ull) & ~3ull) : padV;
+                        const unsigned long long capI = p.reuse ? ((TI + TI / 8ull + 24ull + 7ull) & ~7ull) : padI;
+                        release_span(p, span_slot);
+                        vb = atomicAdd(&p.counters->v_alloc, capV);
+                        ib = atomicAdd(&p.counters->i_alloc, capI);
+                        fb = atomicAdd(&p.counters->f_alloc, padF);
+                        if (p.span_cap) p.span_cap[span_slot] = make_uint2((uint32_t)capV, (uint32_t)capI);
+                        if (!p.count_only) {
+                            if (vb + capV <= p.v_cap && ib + capI <= p.i_cap && fb + padF <= p.f_cap) emit = 1;
+                            else atomicOr(&p.counters->flags, kFlagArenaOverflow);
+                        }
                     }
+                } else {
+                    release_span(p, span_slot);
                 }
                 bxw_mesh_span sp;
                 sp.v_off = vb;
@@ -701,7 +733,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
         PHASE_ADD(4, 0, 1);
 
         // ---------------- phase C: the chunk's face records, in emission order, tile by tile ----------------
-        const uint32_t *center = p.blocks + (size_t)c0 * kChunkVoxels;
+        const uint32_t *center = p.blocks + (size_t)s.nbr[13] * kChunkVoxels;
         const unsigned long long fbase = s.fbase;
         const bool quads_only = !has_shapes; // every side has 4 vertices / 6 indices
         for (uint32_t r0 = 0; r0 < 1024;) {
@@ -852,6 +884,7 @@ __global__ void __launch_bounds__(256) hmap_candidates_kernel(CandidateParams p)
             sp.v_off = sp.i_off = 0;
             sp.v_count = sp.i_count = 0;
             p.spans[slot] = sp;
+            if (p.span_cap) p.span_cap[slot] = make_uint2(0u, 0u);
         } else {
             const uint32_t k = atomicAdd(p.count, 1u);
             p.work[k] = (uint32_t)(ix + 1) + (uint32_t)p.SX * ((uint32_t)(iz + 1) + (uint32_t)p.SZ * (uint32_t)(iy + 1));

@@ -22,6 +22,7 @@
 #pragma once
 
 #include <array>
+#include <atomic>
 #include <cstdint>
 #include <cstring>
 #include <functional>
@@ -168,54 +169,69 @@ class VoxelRegistry { // voxregistry.rs:26-150; Default holds core:void (id 0, n
             def_.texture_mapping = ids;
             return *this;
         }
-        // Ok(()) / Err(AlreadyExists): returns nullopt on success like Result<(), E>::err()
+        // Ok(()) / Err(AlreadyExists): returns nullopt on success like Result<(), E>::err(). As in voxregistry.rs:63-82 the
+        // error is raised only when the ID slot is occupied; a duplicate NAME re-points the name lookup at the new definition.
         std::optional<VoxelDefinitionError> finish() {
-            if (reg_.name_lut_.count(def_.name)) return VoxelDefinitionError::AlreadyExists;
-            def_.id = (VoxelId)reg_.definitions_.size();
+            const size_t idx = def_.id;
+            if (reg_.definitions_.size() <= idx) reg_.definitions_.resize(idx * 2 + 1);
+            else if (reg_.definitions_[idx].has_value()) return VoxelDefinitionError::AlreadyExists;
             reg_.name_lut_[def_.name] = def_.id;
-            reg_.definitions_.push_back(def_);
+            reg_.definitions_[idx] = def_;
             reg_.version_++;
             return std::nullopt;
         }
 
       private:
         friend class VoxelRegistry;
-        explicit Builder(VoxelRegistry &r) : reg_(r) {}
+        Builder(VoxelRegistry &r, VoxelId id) : reg_(r) { def_.id = id; }
         VoxelRegistry &reg_;
         VoxelDefinition def_;
     };
 
-    VoxelRegistry() {
-        Builder b(*this);
-        b.name("core:void").set_mesh(VoxelMesh::None).debug_color(0, 0, 0).finish();
-    }
-    Builder build_definition() { return Builder(*this); }
+    VoxelRegistry() : token_(next_token()) { build_definition().name("core:void").set_mesh(VoxelMesh::None).debug_color(0, 0, 0).finish(); }
+    // the id is taken here (last_free_id += 1, voxregistry.rs:118-133): an abandoned builder consumes an id
+    Builder build_definition() { return Builder(*this, last_free_id_++); }
     const VoxelDefinition &get_definition_from_id(VoxelId id) const {
-        if (id >= definitions_.size()) throw Error(BXW_E_UNKNOWN_ID, "no definition for block id " + std::to_string(id)); // unwrap() panic
-        return definitions_[id];
+        if (id >= definitions_.size() || !definitions_[id].has_value())
+            throw Error(BXW_E_UNKNOWN_ID, "no definition for block id " + std::to_string(id)); // unwrap() panic
+        return *definitions_[id];
     }
     const VoxelDefinition &get_definition_from_datum(VoxelDatum d) const { return get_definition_from_id(d.id()); }
     const VoxelDefinition *get_definition_from_name(const std::string &name) const {
         auto it = name_lut_.find(name);
-        return it == name_lut_.end() ? nullptr : &definitions_[it->second];
+        return it == name_lut_.end() ? nullptr : &*definitions_[it->second];
     }
-    size_t len() const { return definitions_.size(); }
+    // number of id slots up to the highest defined one (what the device registry holds)
+    size_t len() const {
+        size_t n = definitions_.size();
+        while (n && !definitions_[n - 1].has_value()) n--;
+        return n;
+    }
     uint64_t version() const { return version_; }
+    uint64_t token() const { return token_; } // process-wide unique: addresses of registries recur
     std::vector<bxw_block_def> as_defs() const {
-        std::vector<bxw_block_def> out(definitions_.size());
-        for (size_t i = 0; i < definitions_.size(); i++) {
+        std::vector<bxw_block_def> out(len());
+        for (size_t i = 0; i < out.size(); i++) {
+            out[i] = bxw_block_def{};
+            if (!definitions_[i].has_value()) continue; // free slot: present = 0
             out[i].present = 1;
-            out[i].mesh_kind = definitions_[i].mesh == VoxelMesh::None ? 0 : 1;
-            for (int k = 0; k < 3; k++) out[i].debug_color[k] = definitions_[i].debug_color[k];
-            for (int k = 0; k < 6; k++) out[i].tex[k] = definitions_[i].texture_mapping.mapping[k];
+            out[i].mesh_kind = definitions_[i]->mesh == VoxelMesh::None ? 0 : 1;
+            for (int k = 0; k < 3; k++) out[i].debug_color[k] = definitions_[i]->debug_color[k];
+            for (int k = 0; k < 6; k++) out[i].tex[k] = definitions_[i]->texture_mapping.mapping[k];
         }
         return out;
     }
 
   private:
-    std::vector<VoxelDefinition> definitions_;
+    static uint64_t next_token() {
+        static std::atomic<uint64_t> n{1};
+        return n.fetch_add(1);
+    }
+    std::vector<std::optional<VoxelDefinition>> definitions_;
     std::map<std::string, VoxelId> name_lut_;
+    VoxelId last_free_id_ = 0;
     uint64_t version_ = 0;
+    uint64_t token_;
 };
 
 // blocks/mod.rs:6-65
@@ -258,10 +274,10 @@ class Gpu {
     }
     // upload the registry when it changed since the last call on this context
     void bind(const VoxelRegistry &reg) {
-        if (bound_ == &reg && bound_version_ == reg.version()) return;
+        if (bound_token_ == reg.token() && bound_version_ == reg.version()) return;
         const auto defs = reg.as_defs();
         check(bxw_set_registry(raw(), defs.data(), (uint32_t)defs.size()));
-        bound_ = &reg;
+        bound_token_ = reg.token();
         bound_version_ = reg.version();
     }
     uint64_t kernel_launches() const { return bxw_kernel_launches(raw()); }
@@ -271,7 +287,7 @@ class Gpu {
         void operator()(bxw_ctx *c) const { bxw_destroy(c); }
     };
     std::unique_ptr<bxw_ctx, Del> ctx_;
-    const VoxelRegistry *bound_ = nullptr;
+    uint64_t bound_token_ = 0;
     uint64_t bound_version_ = 0;
 };
 
@@ -453,11 +469,22 @@ class Region {
         gpu_.check(bxw_region_apply_changes(gpu_.raw(), ch.data(), (uint32_t)ch.size(), &nd));
         return nd;
     }
+    // MeshDataHandler re-running create_chunk_update_task for the dirty chunks (worldmgr.rs:335-356). The arena extent may
+    // have grown (moved meshes) or changed altogether (compaction): arena() is what fetch_arena wants afterwards.
     uint32_t remesh_dirty() {
         gpu_.bind(registry_);
         uint32_t n = 0;
         gpu_.check(bxw_region_remesh_dirty(gpu_.raw(), &n));
         return n;
+    }
+    std::pair<uint64_t, uint64_t> arena() const {
+        uint64_t v = 0, i = 0;
+        gpu_.check(bxw_region_arena_extent(gpu_.raw(), &v, &i));
+        return {v, i};
+    }
+    ChunkBuffers fetch() const {
+        const auto a = arena();
+        return fetch_arena(a.first, a.second);
     }
 
   private:

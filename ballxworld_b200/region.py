@@ -91,8 +91,18 @@ class Region:
         return self.ctx.region_apply_changes(ch)
 
     def remesh_dirty(self):
+        """Re-mesh the chunks the edits made dirty (worldmgr.rs:335-356). Meshes that no longer fit their old arena space move
+        to the arena's end (or the arena is compacted), so the extent is refreshed: fetch() / chunk_buffers() after this call
+        see the new meshes."""
+        self.registry.bind(self.ctx)
         n = self.ctx.region_remesh_dirty()
+        self.arena = self.ctx.region_arena_extent()
         return n
+
+    def set_origin(self, origin):
+        """Re-position the box (slab streaming / sliding window); the voxels are stale until the next generate."""
+        self.ctx.region_set_origin(*origin)
+        self.origin = tuple(origin)
 
     def close(self):
         self.ctx.region_destroy()

@@ -12,6 +12,8 @@ All compute happens in libbxw_cuda.so; nothing here evaluates noise, RLE or geom
 import os
 from dataclasses import dataclass, field
 
+import itertools
+
 import numpy as np
 
 from .capi import Context
@@ -132,26 +134,77 @@ class VoxelDefinition:
     texture_mapping: tuple  # 6 ids by signed axis index (lib.rs:624-626)
 
 
+class VoxelDefinitionBuilder:
+    """voxregistry.rs:16-92. The id is taken when the builder is created (build_definition, :118-133), so an abandoned
+    builder consumes an id exactly as in the reference."""
+
+    def __init__(self, registry, id):
+        self.registry = registry
+        self.id = id
+        self._name = ""
+        self._mesh = "CubeAndSlopes"
+        self._debug_color = (1.0, 1.0, 1.0)
+        self._texture_mapping = (0,) * 6
+
+    def name(self, v):
+        self._name = str(v)
+        return self
+
+    def debug_color(self, r, g, b):
+        self._debug_color = (float(r), float(g), float(b))
+        return self
+
+    def set_mesh(self, mesh):
+        self._mesh = mesh
+        return self
+
+    def texture_mapping(self, t):
+        self._texture_mapping = tuple(t)
+        return self
+
+    def finish(self):
+        """voxregistry.rs:63-82: AlreadyExists only when the id slot is occupied; a duplicate NAME simply re-points the
+        name lookup at the new definition."""
+        reg = self.registry
+        d = VoxelDefinition(self.id, self._name, self._mesh, self._debug_color, self._texture_mapping)
+        if len(reg.definitions) <= d.id:
+            reg.definitions.extend([None] * (d.id * 2 + 1 - len(reg.definitions)))
+        elif reg.definitions[d.id] is not None:
+            raise ValueError("AlreadyExists")
+        reg.name_lut[d.name] = d.id
+        reg.definitions[d.id] = d
+        reg.version += 1
+        return d
+
+
+_registry_tokens = itertools.count(1)
+
+
 class VoxelRegistry:
     """voxregistry.rs:94-150. Default registry holds core:void (id 0, mesh None)."""
 
     def __init__(self):
-        self.definitions = []
+        self.definitions = []  # Vec<Option<VoxelDefinition>>: None = free slot
         self.name_lut = {}
+        self.last_free_id = 0
         self.version = 0
-        self.register("core:void", mesh="None", debug_color=(0.0, 0.0, 0.0), texture_mapping=(0,) * 6)
+        self.token = next(_registry_tokens)  # process-wide unique: id() values are recycled after garbage collection
+        self.build_definition().name("core:void").debug_color(0.0, 0.0, 0.0).set_mesh("None").finish()
+
+    def build_definition(self):
+        b = VoxelDefinitionBuilder(self, self.last_free_id)
+        self.last_free_id += 1
+        return b
 
     def register(self, name, mesh="CubeAndSlopes", debug_color=(1.0, 1.0, 1.0), texture_mapping=(0,) * 6):
-        if name in self.name_lut:
-            raise ValueError("AlreadyExists")
-        d = VoxelDefinition(len(self.definitions), name, mesh, tuple(debug_color), tuple(texture_mapping))
-        self.definitions.append(d)
-        self.name_lut[name] = d.id
-        self.version += 1
-        return d
+        """build_definition().name(..)...finish() in one call."""
+        return self.build_definition().name(name).set_mesh(mesh).debug_color(*debug_color).texture_mapping(texture_mapping).finish()
 
     def get_definition_from_id(self, id):
-        return self.definitions[id]  # IndexError ~ the reference's unwrap() panic
+        d = self.definitions[id] if 0 <= id < len(self.definitions) else None
+        if d is None:
+            raise IndexError(f"no definition for block id {id}")  # the reference's unwrap() panic (voxregistry.rs:141-143)
+        return d
 
     def get_definition_from_datum(self, datum):
         return self.get_definition_from_id(VoxelDatum.id(datum))
@@ -161,13 +214,17 @@ class VoxelRegistry:
         return None if i is None else self.definitions[i]
 
     def as_defs(self):
-        return [
-            dict(present=1, mesh_kind=0 if d.mesh == "None" else 1, debug_color=d.debug_color, tex=d.texture_mapping)
-            for d in self.definitions
-        ]
+        n = max((d.id for d in self.definitions if d is not None), default=-1) + 1
+        out = []
+        for d in self.definitions[:n]:
+            if d is None:
+                out.append(dict(present=0, mesh_kind=0, debug_color=(0.0, 0.0, 0.0), tex=(0,) * 6))
+            else:
+                out.append(dict(present=1, mesh_kind=0 if d.mesh == "None" else 1, debug_color=d.debug_color, tex=d.texture_mapping))
+        return out
 
     def bind(self, ctx):
-        key = (id(self), self.version)
+        key = (self.token, self.version)
         if getattr(ctx, "_bound_registry", None) != key:
             ctx.set_registry(self.as_defs())
             ctx._bound_registry = key

@@ -82,8 +82,12 @@ int bxw_set_stream(bxw_ctx *ctx, void *cuda_stream);
 /* Tuning switches. BXW_OPT_CHUNK_SUMMARIES (default 1): whole-region mesh passes consult the per-chunk uniformity
  * summaries and skip chunks proven empty; 0 = read and mesh every chunk (same output; used to measure the streaming rate).
  * BXW_OPT_MESH_FROM_HEIGHT_MAP (default 0): bxw_region_generate_and_mesh derives the mesher's class table from the column
- * parameters instead of reading the freshly written voxels (same output). */
-enum { BXW_OPT_CHUNK_SUMMARIES = 0, BXW_OPT_MESH_FROM_HEIGHT_MAP = 1 };
+ * parameters instead of reading the freshly written voxels (same output).
+ * BXW_OPT_ELIDE_UNIFORM (default 1): chunks the generator proves uniform (all void above the terrain, all stone below it)
+ * are not written voxel by voxel: their entry of the region's page table points at a shared single-datum page (the device
+ * analogue of the reference's 3-word VChunk, bxw_world/src/lib.rs:263-294); the first writer (edit, upload, import, halo
+ * import that differs) gives the chunk its own storage back. 0 = every chunk materialised. Same results either way. */
+enum { BXW_OPT_CHUNK_SUMMARIES = 0, BXW_OPT_MESH_FROM_HEIGHT_MAP = 1, BXW_OPT_ELIDE_UNIFORM = 2 };
 int bxw_set_option(bxw_ctx *ctx, int option, int value);
 int bxw_synchronize(bxw_ctx *ctx);
 /* Number of this library's kernels launched since creation (bench.py's gpu_launches evidence). */
@@ -167,6 +171,9 @@ int bxw_region_mesh_spans(bxw_ctx *ctx, bxw_mesh_span *spans);
 /* Copy arena extents [0,arena_vertices) / [0,arena_indices) to host (pinned memory recommended). */
 int bxw_region_mesh_fetch(bxw_ctx *ctx, bxw_vertex *vertices, uint64_t n_vertices, uint32_t *indices,
                           uint64_t n_indices);
+/* One piece of the arena, e.g. a single chunk's ChunkBuffers (its span's offsets and counts). */
+int bxw_region_mesh_fetch_range(bxw_ctx *ctx, uint64_t v_off, uint64_t n_vertices, bxw_vertex *vertices, uint64_t i_off,
+                                uint64_t n_indices, uint32_t *indices);
 /* The same copy on the context's copy stream, returning at once: the next generate / mesh pass overlaps the transfer (only
  * the kernel that rewrites the arena waits for it). The host buffers (pinned) are valid after bxw_region_fetch_wait. */
 int bxw_region_mesh_fetch_async(bxw_ctx *ctx, bxw_vertex *vertices, uint64_t n_vertices, uint32_t *indices,
@@ -175,8 +182,25 @@ int bxw_region_fetch_wait(bxw_ctx *ctx);
 /* World::apply_voxel_changes (worldmgr.rs:312-357): CAS each change in order, mark touching_chunks
  * (lib.rs:110-135) dirty. n_dirty = interior chunks now dirty. */
 int bxw_region_apply_changes(bxw_ctx *ctx, const bxw_voxel_change *changes, uint32_t n, uint32_t *n_dirty);
-/* Re-mesh the dirty interior chunks into fresh arena space; their spans are updated. */
+/* Re-mesh the dirty interior chunks; their spans are updated. A chunk whose new mesh fits the arena space reserved behind
+ * its old span is rewritten in place, otherwise it moves to the end of the arena and the old space is garbage (the reference
+ * drops the old ChunkBuffers when the new one lands, src/client/render/voxrender.rs:398-413); when a quarter of the arena is
+ * garbage the live spans are compacted (offsets change: re-read the spans). The arena extent to fetch afterwards is
+ * bxw_region_arena_extent. */
 int bxw_region_remesh_dirty(bxw_ctx *ctx, uint32_t *n_remeshed);
+/* Current arena extents (what bxw_region_mesh returned, plus whatever re-mesh passes appended since). */
+int bxw_region_arena_extent(bxw_ctx *ctx, uint64_t *arena_vertices, uint64_t *arena_indices);
+typedef struct {
+    uint64_t vertices_used, indices_used;         /* arena extents */
+    uint64_t vertices_garbage, indices_garbage;   /* inside the extents, referenced by no span */
+    uint64_t vertices_capacity, indices_capacity; /* allocated */
+} bxw_arena_stats;
+int bxw_region_arena_stats(bxw_ctx *ctx, bxw_arena_stats *out);
+/* Move every live span to the front of a fresh arena (slot order); spans' offsets change, garbage becomes 0. */
+int bxw_region_compact_arena(bxw_ctx *ctx, uint64_t *arena_vertices, uint64_t *arena_indices);
+/* Re-position the region box without reallocating it (slab streaming: generate -> mesh -> retire, box by box; a sliding
+ * view window). The stored voxels are stale until the next generate / upload. */
+int bxw_region_set_origin(bxw_ctx *ctx, int32_t cx0, int32_t cy0, int32_t cz0);
 /* Multi-GPU slab boundary: the 1-voxel plane adjacent to face 0 (x-) or 1 (x+) of the interior, packed for the
  * neighbouring rank ((nz+2)*32 x (ny+2)*32 u32, [y][z]). export packs interior boundary voxels into dev_buf;
  * import writes a received plane into this region's shell. dev_buf is device memory (e.g. a torch tensor). */
@@ -185,6 +209,12 @@ int bxw_region_halo_export(bxw_ctx *ctx, int face, void *dev_buf);
 int bxw_region_halo_import(bxw_ctx *ctx, int face, const void *dev_buf);
 /* Device pointers for zero-copy consumers (e.g. graphics interop); valid until the next mesh/destroy call. */
 int bxw_region_device_ptrs(bxw_ctx *ctx, void **blocks, void **vertices, void **indices);
+/* The region's page table (device, u32 per storage chunk, index sx + SX*(sz + SZ*sy) over the shell-padded box): chunk c's
+ * voxels are at blocks + pages[c] * 32768; pages[c] == c unless the chunk is uniform and not materialised, in which case it
+ * is one of the n_shared single-datum pages stored behind the box. */
+int bxw_region_page_table(bxw_ctx *ctx, void **pages, uint32_t *n_shared);
+/* The same table copied to the host: (nx+2)*(ny+2)*(nz+2) entries. */
+int bxw_region_download_pages(bxw_ctx *ctx, uint32_t *pages);
 
 /* ---- bxw_terragen in-tree SuperSimplex (bxw_terragen/src/supersimplex.rs:20-107), batched ---- */
 int bxw_terragen_noise2(bxw_ctx *ctx, uint64_t seed, const double *xs, const double *ys, size_t n, double *out);

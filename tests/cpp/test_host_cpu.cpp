@@ -69,7 +69,6 @@ static void registry_rules() { // voxregistry.rs:63-150, blocks/mod.rs:6-65
     for (int i = 0; i < 8; i++) CHECK(reg.get_definition_from_name(names[i])->id == i);
     CHECK((reg.get_definition_from_name("core:grass")->texture_mapping.mapping == std::array<uint32_t, 6>{16, 16, 15, 29, 16, 16})); // new_tsb
     CHECK((reg.get_definition_from_name("core:debug")->texture_mapping.mapping == std::array<uint32_t, 6>{12, 13, 10, 14, 11, 9}));
-    CHECK(reg.build_definition().name("core:dirt").finish() == VoxelDefinitionError::AlreadyExists);
     CHECK(reg.get_definition_from_name("core:nope") == nullptr);
     bool threw = false;
     try {
@@ -82,6 +81,23 @@ static void registry_rules() { // voxregistry.rs:63-150, blocks/mod.rs:6-65
     CHECK((ids == std::array<VoxelId, 5>{0, 1, 3, 4, 2}));
     const auto defs = reg.as_defs();
     CHECK(defs.size() == 8 && defs[0].mesh_kind == 0 && defs[4].mesh_kind == 1 && defs[4].tex[0] == 56);
+    // voxregistry.rs:63-82,118-133: a builder takes its id when it is created; an abandoned builder consumes one; a duplicate
+    // NAME is not an error, the name lookup moves to the new definition (AlreadyExists needs an occupied id slot)
+    { auto abandoned = reg.build_definition(); (void)abandoned; } // id 8 is gone
+    CHECK(!reg.build_definition().name("core:dirt").finish().has_value()); // id 9
+    CHECK(reg.get_definition_from_name("core:dirt")->id == 9 && reg.get_definition_from_id(3).name == "core:dirt");
+    CHECK(reg.len() == 10);
+    {
+        const auto defs = reg.as_defs();
+        CHECK(defs.size() == 10 && defs[8].present == 0 && defs[9].present == 1 && defs[3].present == 1);
+        bool threw8 = false;
+        try {
+            reg.get_definition_from_id(8);
+        } catch (const Error &e) {
+            threw8 = e.code == BXW_E_UNKNOWN_ID;
+        }
+        CHECK(threw8);
+    }
 }
 
 static void save_blob_rules() { // generation.rs:158-194

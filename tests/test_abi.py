@@ -60,13 +60,33 @@ def test_host_mirror_types():
     assert n[13] == bxw.ChunkPosition(0, 0, 0) and n[3] == bxw.ChunkPosition(-1, -1, 0)
     assert len(list(bxw.iter_neighbors(bxw.ChunkPosition(5, 5, 5), False))) == 26
     reg = bxw.standard_registry()
-    assert [d.name for d in reg.definitions] == ["core:void", "core:grass", "core:snow_grass", "core:dirt", "core:stone",
+    assert [d.name for d in reg.definitions if d is not None] == ["core:void", "core:grass", "core:snow_grass", "core:dirt", "core:stone",
                                                  "core:diamond_ore", "core:debug", "core:table"]
     assert reg.get_definition_from_name("core:grass").texture_mapping == (16, 16, 15, 29, 16, 16)
     assert bxw.StdGenerator.resolve_ids(reg) == [0, 1, 3, 4, 2]
     assert list(bxw.VChunk().vox) == [0, 0, 32768]  # VChunkData::default (lib.rs:249-255)
     with pytest.raises(ValueError):
         bxw.VChunk.deserialize(bxw.ChunkPosition(0, 0, 0), b"\x00\x01\x02")
+
+
+def test_registry_follows_the_reference_builder_rules():
+    """voxregistry.rs:63-82,118-133: the id is taken by build_definition() (an abandoned builder consumes one), finish() fails
+    only on an occupied id slot, a duplicate name re-points the lookup; registries never share a bind-cache key."""
+    import ballxworld_b200 as bxw
+
+    reg = bxw.standard_registry()
+    reg.build_definition()  # abandoned: id 8 is gone
+    d = reg.register("core:dirt", texture_mapping=(7,) * 6)
+    assert d.id == 9 and reg.get_definition_from_name("core:dirt").id == 9 and reg.get_definition_from_id(3).name == "core:dirt"
+    defs = reg.as_defs()
+    assert len(defs) == 10 and defs[8]["present"] == 0 and defs[9]["present"] == 1
+    with pytest.raises(IndexError):
+        reg.get_definition_from_id(8)
+    b = reg.build_definition()
+    b.id = 3
+    with pytest.raises(ValueError):
+        b.name("x").finish()  # occupied slot -> AlreadyExists
+    assert bxw.standard_registry().token != bxw.standard_registry().token
 
 
 def test_registry_matches_oracle_registry(oracle):

@@ -92,3 +92,47 @@ def test_cuda_path_matches_oracle_totals_cfg3(ctx):
             assert np.array_equal(I[int(a["i_off"]): int(a["i_off"]) + m], I2[int(b["i_off"]): int(b["i_off"]) + m])
     finally:
         ctx.region_destroy()
+
+
+CFG2_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cfg2_golden.json")
+
+
+def test_oracle_reproduces_cfg2_golden_sample(oracle):
+    """CPU: the oracle still produces the committed mesh-only vectors (a few chunks of both variants)."""
+    gold = json.load(open(CFG2_PATH))
+    reg = oracle.OracleRegistry()
+    for thr, picks in (("128", [(0, 0, 0), (7, 9, 3)]), ("250", [(15, 15, 15), (4, 0, 11)])):
+        gv = gold["variants"][thr]
+        assert len(gv["digest8"]) == 4096
+        for (x, y, z) in picks:
+            d = [oracle.random_chunk(x + dx, y + dy, z + dz, seed=gold["seed"], void_threshold=int(thr))
+                 for dy in (-1, 0, 1) for dz in (-1, 0, 1) for dx in (-1, 0, 1)]
+            v, i = oracle.mesh_from_dense27(reg, d)
+            dg = hashlib.sha256(v.tobytes() + i.astype("<u4").tobytes()).digest()
+            assert dg[:8].hex() == gv["digest8"][x + 16 * (z + 16 * y)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("thr", ["128", "250"])
+def test_cuda_mesher_matches_golden_cfg2_full_size(ctx, thr):
+    """BASELINE.json configs[1] at its stated size: all 4096 chunks of hashed random blocks (every shape, every orientation),
+    per-chunk SHA-256 of vertex || index bytes against the oracle-made fixture."""
+    gold = json.load(open(CFG2_PATH))
+    gv = gold["variants"][thr]
+    n = 16
+    ctx.region_create(0, 0, 0, n, n, n)
+    ctx.region_fill_synthetic(gold["seed"], int(thr))
+    av, ai = ctx.region_mesh()
+    spans = ctx.region_mesh_spans()
+    assert int(spans["v_count"].astype(np.int64).sum()) == gv["total_vertices"]
+    assert int(spans["i_count"].astype(np.int64).sum()) == gv["total_indices"]
+    counts = np.stack([spans["v_count"].astype("<i8"), spans["i_count"].astype("<i8")], axis=-1)
+    assert hashlib.sha256(np.ascontiguousarray(counts).tobytes()).hexdigest() == gv["counts_sha256"]
+    digests = []
+    for k in range(4096):  # chunk by chunk: the dense variant's arena is 45 GB
+        v, i = ctx.region_mesh_fetch_span(spans[k])
+        digests.append(hashlib.sha256(v.tobytes() + i.tobytes()).digest())
+    bad = [k for k in range(4096) if digests[k][:8].hex() != gv["digest8"][k]]
+    assert not bad, f"{len(bad)} chunks differ, first {bad[:5]}"
+    assert hashlib.sha256(b"".join(digests)).hexdigest() == gv["all_digests_sha256"]
+    ctx.region_destroy()
