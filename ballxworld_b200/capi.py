@@ -448,7 +448,7 @@ class Context:
         self._ck(self.L.bxw_mesh_kernel_time_ms(self.h, C.byref(ms), C.byref(n), 1 if reset else 0))
         return ms.value, n.value
 
-    KERNEL_MESH, KERNEL_FILL, KERNEL_HEIGHTMAP = 0, 1, 2
+    KERNEL_MESH, KERNEL_FILL, KERNEL_HEIGHTMAP, KERNEL_EMIT = 0, 1, 2, 3
 
     def kernel_time_ms(self, which, reset=False):
         ms, n = C.c_float(), C.c_uint64()

@@ -37,7 +37,7 @@ struct Region {
     uint32_t *iarena = nullptr;
     unsigned long long v_cap = 0, i_cap = 0;
     uint4 *frec = nullptr;             // face records between mesh_kernel and emit_kernel (device_common.cuh)
-    uint32_t *fslot = nullptr;         // span slot per 32 records
+    uint4 *fslot = nullptr;            // per 32 records: the arena offsets of their chunk (v_off, i_off as two u64)
     unsigned long long f_cap = 0;
     bool reserved = false;
     MeshCounters *counters = nullptr;
@@ -88,13 +88,13 @@ struct bxw_ctx {
     Region region;  // the user's region
     Region scratch; // 3x3x3 storage behind the per-chunk drop-ins
     // timing
-    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_m0 = nullptr, ev_m1 = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_m0 = nullptr, ev_m1 = nullptr, ev_mm = nullptr; // ev_mm: between mesh_kernel and emit_kernel
     cudaEvent_t ev_g0 = nullptr, ev_g1 = nullptr, ev_g2 = nullptr; // before heightmap / before fill / after fill
     cudaStream_t copy_stream = nullptr;                            // bxw_region_mesh_fetch_async
     cudaEvent_t ev_mesh_done = nullptr, ev_copy_done = nullptr;
     bool copy_pending = false;                                     // ev_copy_done recorded and not yet waited for
     bool gen_pending = false, gen_pending_fused = false;          // ev_g* recorded, not yet read
-    double mesh_ms = 0.0, fill_ms = 0.0, hmap_ms = 0.0;
+    double mesh_ms = 0.0, fill_ms = 0.0, hmap_ms = 0.0, emit_ms = 0.0;
     uint64_t mesh_launches = 0, fill_launches = 0, hmap_launches = 0;
     bool use_summaries = true;                                     // BXW_OPT_CHUNK_SUMMARIES
     bool elide_uniform = true;                                     // BXW_OPT_ELIDE_UNIFORM
@@ -455,7 +455,7 @@ int faces_resize(bxw_ctx *ctx, Region &r, unsigned long long f_cap) {
     r.f_cap = 0;
     f_cap = (f_cap + 31ull) & ~31ull;
     CK(cudaMalloc(&r.frec, f_cap * sizeof(uint4)));
-    CK(cudaMalloc(&r.fslot, (f_cap / 32) * sizeof(uint32_t)));
+    CK(cudaMalloc(&r.fslot, (f_cap / 32) * sizeof(uint4)));
     r.f_cap = f_cap;
     return BXW_OK;
 }
@@ -574,6 +574,7 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
         CK(cudaEventRecord(ctx->ev_m0, ctx->stream));
         launch_mesh_kernel(p, ctx->sm_count, ctx->stream);
         ctx->launches += 1;
+        CK(cudaEventRecord(ctx->ev_mm, ctx->stream));
         if (!count_only) { // vertices and indices of the recorded sides (returns at once if a chunk did not fit)
             // the arena is rewritten from here on: an asynchronous fetch of the previous meshes has to be through
             if (ctx->copy_pending) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done, 0));
@@ -592,6 +593,9 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
         if (!count_only) {
             ctx->mesh_ms += ms;
             ctx->mesh_launches += 1;
+            float ems = 0.f;
+            CK(cudaEventElapsedTime(&ems, ctx->ev_mm, ctx->ev_m1));
+            ctx->emit_ms += ems;
         }
         if (r.h_counters->flags & kFlagUnknownId)
             return fail(ctx, BXW_E_UNKNOWN_ID, "a voxel references a block id without a registry definition");
@@ -718,6 +722,7 @@ int bxw_create(int device, bxw_ctx **out) {
     ctx->stream = ctx->own_stream;
     if (cudaEventCreate(&ctx->ev_a) != cudaSuccess || cudaEventCreate(&ctx->ev_b) != cudaSuccess ||
         cudaEventCreate(&ctx->ev_m0) != cudaSuccess || cudaEventCreate(&ctx->ev_m1) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev_mm) != cudaSuccess ||
         cudaEventCreate(&ctx->ev_g0) != cudaSuccess || cudaEventCreate(&ctx->ev_g1) != cudaSuccess ||
         cudaEventCreate(&ctx->ev_g2) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -759,6 +764,7 @@ void bxw_destroy(bxw_ctx *ctx) {
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
     if (ctx->ev_m0) cudaEventDestroy(ctx->ev_m0);
     if (ctx->ev_m1) cudaEventDestroy(ctx->ev_m1);
+    if (ctx->ev_mm) cudaEventDestroy(ctx->ev_mm);
     if (ctx->ev_g0) cudaEventDestroy(ctx->ev_g0);
     if (ctx->ev_g1) cudaEventDestroy(ctx->ev_g1);
     if (ctx->ev_g2) cudaEventDestroy(ctx->ev_g2);
@@ -1529,6 +1535,7 @@ int bxw_mesh_kernel_time_ms(bxw_ctx *ctx, float *ms, uint64_t *launches, int res
     if (launches) *launches = ctx->mesh_launches;
     if (reset) {
         ctx->mesh_ms = 0.0;
+        ctx->emit_ms = 0.0;
         ctx->mesh_launches = 0;
     }
     return BXW_OK;
@@ -1541,9 +1548,18 @@ int bxw_kernel_time_ms(bxw_ctx *ctx, int which, float *ms, uint64_t *launches, i
     double *acc;
     uint64_t *cnt;
     switch (which) {
-    case BXW_KERNEL_MESH: acc = &ctx->mesh_ms; cnt = &ctx->mesh_launches; break;
+    case BXW_KERNEL_MESH:
+        acc = &ctx->mesh_ms;
+        cnt = &ctx->mesh_launches;
+        if (reset) ctx->emit_ms = 0.0;
+        break;
     case BXW_KERNEL_FILL: acc = &ctx->fill_ms; cnt = &ctx->fill_launches; break;
     case BXW_KERNEL_HEIGHTMAP: acc = &ctx->hmap_ms; cnt = &ctx->hmap_launches; break;
+    case BXW_KERNEL_EMIT: // the emit_kernel part of BXW_KERNEL_MESH (same launches; reset together with it)
+        if (ms) *ms = (float)ctx->emit_ms;
+        if (launches) *launches = ctx->mesh_launches;
+        if (reset) ctx->emit_ms = 0.0;
+        return BXW_OK;
     default: return fail(ctx, BXW_E_INVALID, "unknown kernel selector %d", which);
     }
     if (ms) *ms = (float)*acc;

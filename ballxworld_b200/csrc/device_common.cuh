@@ -59,7 +59,7 @@ struct MeshParams {
     // face records between mesh_kernel (stage, cull, count, order) and emit_kernel (vertex / index construction): f_cap
     // records + f_cap / 32 span slots, see kFacePad below
     uint4 *frec;
-    uint32_t *fslot;
+    uint4 *fslot;
     unsigned long long f_cap;
     MeshCounters *counters;
     const MeshTables *tables;
@@ -75,7 +75,8 @@ struct MeshParams {
 void launch_mesh_kernel(const MeshParams &p, int sm_count, cudaStream_t stream);
 
 // Face record: one uint4 per visible side, frec[k], in the reference's emission order; every chunk's records start on a
-// multiple of 32 and are padded to one, and fslot[k / 32] holds the chunk's span slot (where its arena offsets are).
+// multiple of 32 and are padded to one, and fslot[k / 32] holds the chunk's arena offsets (v_off, i_off as two u64), so that
+// emit_kernel's only global loads are the two it prefetches one batch ahead.
 //   x: row (y*32+z, 10 bits) | x << 10 | world dir << 15 | class << 18; 0xFFFFFFFF = padding (no face)
 //   y: first vertex of the side, chunk-relative (20 bits) | (block id & 0xFFF) << 20
 //   z: first index of the side, chunk-relative (21 bits) | (block id >> 12) << 21

@@ -22,47 +22,109 @@ namespace {
 constexpr int ENT = 256;      // threads per CTA
 constexpr int ENW = ENT / 32; // warps per CTA
 constexpr int EREGC = 64;     // registry entries cached in shared memory
-constexpr int STG4 = 244;     // staging per warp in 16-byte units: 16 sides x 6 vertices x 40 B + one unit of misalignment
+constexpr int STGW = 328;     // staging words per warp: 32 vertices x 10 words + 2 words of misalignment, rounded to 16 bytes
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 
+struct alignas(16) SideRec { // what the vertex pass needs of a side (written by its lane in the side pass)
+    uint32_t cell_id;  // cell (x + 32 z + 1024 y) | block id << 16
+    uint32_t ks_tab;   // occluder count of vertex j at bits 3j (6 x 3 bits) | (class * 36 + world dir * 6) << 18
+    uint32_t tex;      // texture id of the local side as f32 bits
+    uint32_t pos0;     // as_wxyz10 of the cell's minimum corner: x << 24 | y << 14 | z << 4
+    uint32_t fb[4];    // barycentric_color_offset
+};
+
+// 32-bit vertex descriptor [class][dir][vertex], derived from MeshTables::vdesc when a CTA starts: everything the vertex pass
+// adds to the side's words sits at its final bit position.
+//   bit 0 texcoord u, bit 1 texcoord v, bits 4 / 14 / 24 corner z / y / x (position delta), bits 17-19 barycentric flags (index
+//   word), bits 5-12 index into aolut (corner * 27 + AO normal code)
+constexpr uint32_t kVdPos = (1u << 24) | (1u << 14) | (1u << 4);
+constexpr uint32_t kVdFlags = 7u << 17;
+
 struct ESmem {
-    alignas(16) uint4 wstage[ENW][STG4];
+    alignas(16) uint32_t wstage[ENW][2][STGW]; // two staging buffers per warp: one is filled while the bulk copy drains the other
+    SideRec rec[ENW][32];
+    float4 bigreg[ENW][32];           // debug_color + local-side texture id of sides whose block id is not in the cached registry
+    uint8_t vmap[ENW][192];           // vertex of the batch -> side (lane) << 3 | vertex of the side
     uint32_t stab[kNumClasses * 6 + 2];
     uint32_t aolut[8 * 27];           // AO sample mask per (vertex corner, AO normal code)
     uint32_t col_lut[EREGC * 8];      // as_rgba8(debug_color * ao_k) per cached block id and occluder count k
     float reg_color[EREGC * 3];
     float reg_texf[EREGC * 6];
     float ao_lut[8];
-    uint16_t vdesc[kNumClasses * 36]; // vertex descriptors [class][dir][vertex] (tables.hpp)
+    uint32_t vd32[kNumClasses * 36];  // vertex descriptors [class][dir][vertex] (above)
 };
 
-// Warp copy of n 32-bit words from the warp's staging slice to global memory with 16-byte stores. The data was staged at
-// stage16 + misal, misal = (dst / 4) & 3, so source and destination share their position inside a 16-byte unit.
+// Warp copy of n 32-bit words (n even) from the warp's staging slice to global memory with 16-byte stores. The data was staged
+// at stage16 + misal, misal = (dst / 4) & 3 (0 or 2 here), so source and destination share their position inside a 16-byte unit.
 __device__ __forceinline__ void warp_copy_out(uint32_t *dst, const uint32_t *stage16, uint32_t misal, uint32_t n, uint32_t lane) {
     uint32_t *d0 = dst - misal; // 16-byte aligned
     const uint32_t total = misal + n, nfull = total >> 2;
     const uint4 *s4 = reinterpret_cast<const uint4 *>(stage16);
     uint4 *d4 = reinterpret_cast<uint4 *>(d0);
-    // unit 0 may start with `misal` words that belong to the previous side: lanes 1..3 write its own words one by one
+    // unit 0 may start with `misal` words that belong to the previous side: its own words go out one by one
     if (misal) {
         if (lane >= misal && lane < 4u && lane < total) d0[lane] = stage16[lane];
     } else if (lane == 0 && nfull) {
-        d4[0] = s4[0];
+        __stcs(&d4[0], s4[0]);
     }
-#pragma unroll 2
+#pragma unroll 3
     for (uint32_t k = lane + 1u; k < nfull; k += 32) __stcs(&d4[k], s4[k]); // the meshes are not read again on the device
     const uint32_t rem = total & 3u; // tail words of the last, partial unit
     if (lane < rem && (nfull || !misal)) d0[nfull * 4u + lane] = stage16[nfull * 4u + lane]; // (a short misaligned run was all head)
 }
 
+// Registry entry of a block id beyond the entries cached in shared memory (rare). Not inlined on purpose: inlined, the loads
+// become predicated instructions on the common path, and the first use of their (unused) result waits on the same scoreboard
+// as the record prefetch of the next batch.
+__device__ __noinline__ void fetch_big_registry_entry(const DeviceRegistry reg, uint32_t id, uint32_t ls, float4 *out) {
+    float4 bc;
+    bc.x = __ldg(reg.color + id * 3);
+    bc.y = __ldg(reg.color + id * 3 + 1);
+    bc.z = __ldg(reg.color + id * 3 + 2);
+    bc.w = __ldg(reg.texf + id * 6 + ls);
+    *out = bc;
+}
+
+// One vertex pass leaves the warp's staging buffer: n words (10 per vertex) staged at stage16 + misal (misal 0 or 2, the run
+// starts 8 bytes into a 16-byte unit when the first vertex index is odd). The whole 16-byte units go out as ONE bulk copy
+// shared -> global issued by lane 0 (cp.async.bulk, the TMA engine: no LDS / STG wavefronts on the L1 path, which is what
+// bounded this kernel); the 8-byte halves at either end are ordinary stores. The caller has fenced the staging writes towards
+// the async proxy and synchronised the warp.
+__device__ __forceinline__ void warp_bulk_out_vertices(uint32_t *dst, const uint32_t *stage16, uint32_t misal, uint32_t n, uint32_t lane) {
+    const uint32_t total = misal + n, nfull = total >> 2;
+    const uint32_t first = misal ? 1u : 0u;
+    if (lane == 0u) {
+#ifndef BXW_EXP_NO_STORE
+        if (nfull > first) {
+#else
+        if (nfull > first && dst == nullptr) {
+#endif
+            const uint32_t bytes = (nfull - first) * 16u;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst - misal + first * 4u),
+                         "r"((uint32_t)__cvta_generic_to_shared(stage16 + first * 4u)), "r"(bytes)
+                         : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    // lane 1: head half (run starts odd), lane 2: tail half (run ends odd)
+    const uint32_t w = lane == 1u ? 2u : nfull * 4u;
+    if ((lane == 1u && misal) || (lane == 2u && (total & 2u)))
+        __stcs(reinterpret_cast<uint2 *>(dst - misal + w), *reinterpret_cast<const uint2 *>(stage16 + w));
+}
+
 __global__ void __launch_bounds__(ENT, 4) emit_kernel(MeshParams p) {
-    __shared__ ESmem s;
+    extern __shared__ __align__(16) unsigned char esmem_raw[];
+    ESmem &s = *reinterpret_cast<ESmem *>(esmem_raw);
     const int tid = threadIdx.x;
     const uint32_t lane = tid & 31, warp = tid >> 5;
     const MeshTables *T = p.tables;
 
     for (int i = tid; i < kNumClasses * 6; i += ENT) s.stab[i] = (&T->stab[0][0])[i];
-    for (int i = tid; i < kNumClasses * 36; i += ENT) s.vdesc[i] = (&T->vdesc[0][0][0])[i];
+    for (int i = tid; i < kNumClasses * 36; i += ENT) {
+        const uint32_t e = (&T->vdesc[0][0][0])[i];
+        s.vd32[i] = ((e >> 3) & 3u) | ((e & 4u) << 2) | ((e & 2u) << 13) | ((e & 1u) << 24) | (((e >> 5) & 7u) << 17) |
+                    (((e & 7u) * 27u + (e >> 8)) << 5);
+    }
     for (int i = tid; i < 8 * 27; i += ENT) s.aolut[i] = T->aolut[i];
     if (tid < 8) s.ao_lut[tid] = T->ao_lut[tid];
     for (int i = tid; i < EREGC * 3; i += ENT) s.reg_color[i] = (uint32_t)(i / 3) < p.reg.n ? p.reg.color[i] : 0.0f;
@@ -83,188 +145,192 @@ __global__ void __launch_bounds__(ENT, 4) emit_kernel(MeshParams p) {
     // a chunk that did not fit left its records unwritten: the host grows the arenas and runs both kernels again
     if (p.counters->flags & kFlagArenaOverflow) return;
     const unsigned long long n_batches = p.counters->f_alloc >> 5;
-    uint4 *const stg = &s.wstage[warp][0];
-    uint2 *const st2 = reinterpret_cast<uint2 *>(stg);
-    uint32_t *const stw = reinterpret_cast<uint32_t *>(stg);
+    uint32_t *const stw = &s.wstage[warp][0][0];
+    uint32_t npass = 0; // vertex passes of this warp so far (selects the staging buffer)
+    SideRec *const rec = &s.rec[warp][0];
+    uint8_t *const vmap = &s.vmap[warp][0];
 
     // the records of the warp's next batch (one 16-byte load per lane + the batch's span slot) are loaded one batch ahead
     const unsigned long long bstep = (unsigned long long)gridDim.x * ENW;
+    // NB these two are the ONLY global loads inside the loop: a wait on any other load would also wait for the prefetch behind
+    // it (scoreboards count in order), i.e. expose a full memory latency per batch.
     uint4 q = make_uint4(kFacePad, 0u, 0u, 0u);
-    uint32_t qslot = 0;
+    uint4 qw = make_uint4(0u, 0u, 0u, 0u);
     auto fetch = [&](unsigned long long bb) {
         if (bb < n_batches) {
             q = __ldg(p.frec + bb * 32ull + lane);
-            qslot = __ldg(p.fslot + bb);
+            qw = __ldg(p.fslot + bb);
         }
     };
     fetch((unsigned long long)blockIdx.x * ENW + warp);
     for (unsigned long long b = (unsigned long long)blockIdx.x * ENW + warp; b < n_batches; b += bstep) {
-        const uint32_t r0 = q.x, r1 = q.y, r2 = q.z, nb = q.w, slot0 = qslot;
+        const uint32_t r0 = q.x, r1 = q.y, r2 = q.z, nb = q.w;
+        // the chunk's arena span
+        const unsigned long long v_off = (unsigned long long)qw.x | ((unsigned long long)qw.y << 32),
+                                 i_off = (unsigned long long)qw.z | ((unsigned long long)qw.w << 32);
         fetch(b + bstep);
         const bool act = r0 != kFacePad;          // padding only ever follows the faces of a chunk
         const uint32_t nbf = __popc(__ballot_sync(FULL, act));
-        uint32_t vq = 0, iq = 0, nv = 0, ni = 0, texbits = 0, cell = 0, st = 0, id = 0;
-        uint32_t fb0 = 0, fb1 = 0, fb2 = 0, fb3 = 0;
-        uint32_t w_pos[6], w_col[6], w_uvi[6]; // w_uvi: u | v<<1 | barycentric flags<<2
-#pragma unroll
-        for (int j = 0; j < 6; j++) w_pos[j] = w_col[j] = w_uvi[j] = 0;
+        // ---------------- side pass: lane = side (voxmesh.rs:122-153) ----------------
+        uint32_t vq = 0, iq = 0, nv = 0, ni = 0;
         if (act) {
             vq = r1 & 0xFFFFFu;
             iq = r2 & 0x1FFFFFu;
-            id = (r1 >> 20) | ((r2 >> 21) << 12);
-            st = s.stab[(r0 >> 18) * 6 + ((r0 >> 15) & 7u)];
+            const uint32_t id = (r1 >> 20) | ((r2 >> 21) << 12);
+            const uint32_t tabi = (r0 >> 18) * 6u + ((r0 >> 15) & 7u); // class * 6 + world dir
+            const uint32_t st = s.stab[tabi];
             nv = (st >> 3) & 7u;
             ni = (st >> 6) & 7u;
-        }
-        // Per-face data. NVMAX = 4 when every side of the batch is a quad (all of a cube chunk; the common case everywhere):
-        // the vertex loop is then free of predicates.
-        auto face = [&](auto nvmax_tag) {
-            constexpr uint32_t NVMAX = decltype(nvmax_tag)::value;
-            const uint32_t row = r0 & 1023u, x = (r0 >> 10) & 31u, d = (r0 >> 15) & 7u, cx = r0 >> 18;
-            const uint32_t y = row >> 5, z = row & 31u;
+            const uint32_t row = r0 & 1023u, x = (r0 >> 10) & 31u;
             const uint32_t ls = st & 7u, signs = st >> 9;
-            float dc0, dc1, dc2, texid;
-            const bool small_id = id < (uint32_t)EREGC;
-            if (small_id) {
-                dc0 = s.reg_color[id * 3];
-                dc1 = s.reg_color[id * 3 + 1];
-                dc2 = s.reg_color[id * 3 + 2];
-                texid = s.reg_texf[id * 6 + ls]; // texture of the LOCAL side (voxmesh.rs:146)
-            } else {
-                dc0 = __ldg(p.reg.color + id * 3);
-                dc1 = __ldg(p.reg.color + id * 3 + 1);
-                dc2 = __ldg(p.reg.color + id * 3 + 2);
-                texid = __ldg(p.reg.texf + id * 6 + ls);
-            }
-            texbits = __float_as_uint(texid);
-            cell = x + 32u * z + 1024u * y;
-            // as_wxyz10 of (ipos + voffset + 0.5)/32 (voxmesh.rs:36-41,139-145,165): every vertex sits on a voxel corner, so
-            // each 10-bit field is 16 * corner coordinate (<= 512); w = (1/32*2) as u32 = 0
-            const uint32_t pos0 = (x << 24) | (y << 14) | (z << 4);
-            // per vertex: descriptor, number of occluding AO samples (voxmesh.rs:128-137; every meshed shape occludes), colour,
-            // position, and the in-order barycentric colour sum
-            const uint16_t *vds = &s.vdesc[cx * 36u + d * 6u];
-            float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, b3 = 0.0f;
+            // block ids beyond the cached registry entries (rare) fetch theirs into the warp's slots first, so that the common
+            // path holds no global load
+            const bool big = id >= (uint32_t)EREGC;
+            if (big) fetch_big_registry_entry(p.reg, id, ls, &s.bigreg[warp][lane]);
+            const float *rc = big ? &s.bigreg[warp][lane].x : &s.reg_color[id * 3];
+            const float dc0 = rc[0], dc1 = rc[1], dc2 = rc[2];
+            const float texid = big ? rc[3] : s.reg_texf[id * 6 + ls]; // texture of the LOCAL side (voxmesh.rs:146)
+            // per vertex: number of occluding AO samples (voxmesh.rs:128-137; every meshed shape occludes) and the in-order
+            // barycentric colour sum (voxmesh.rs:124,153,172-174): sum += sign as f32 * colour with sign in {-1, 0, 1}. -1 * c is
+            // exactly -c and a + (-c) is a - c; a 0 * c term is +-0 and never changes the sum (which starts at +0 and cannot
+            // become -0 under round-to-nearest), so the multiplications by the sign fold into add / subtract / skip. The fourth
+            // component sums sign * 1.0: small integers, exact in any order.
+            const uint32_t *vds = &s.vd32[tabi * 6u];
+            float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f;
+            uint32_t ks = 0;
 #pragma unroll
-            for (uint32_t j = 0; j < NVMAX; j++) {
-                if (NVMAX == 4 || j < nv) {
-                    const uint32_t e = vds[j];
-                    const uint32_t k = __popc(nb & s.aolut[(e & 7u) * 27u + (e >> 8)]);
-                    const float sg = (float)((int)((signs >> (2 * j)) & 3u) - 1);
+            for (uint32_t j = 0; j < 6; j++) {
+                if (j < nv) {
+                    const uint32_t k = __popc(nb & s.aolut[(vds[j] >> 5) & 255u]);
+                    const uint32_t code = (signs >> (2 * j)) & 3u; // sign + 1
                     const float aj = s.ao_lut[k];
-                    b0 = __fadd_rn(b0, __fmul_rn(sg, __fmul_rn(dc0, aj)));
-                    b1 = __fadd_rn(b1, __fmul_rn(sg, __fmul_rn(dc1, aj)));
-                    b2 = __fadd_rn(b2, __fmul_rn(sg, __fmul_rn(dc2, aj)));
-                    b3 = __fadd_rn(b3, __fmul_rn(sg, 1.0f));
-                    w_pos[j] = pos0 + (((e & 1u) << 24) | ((e & 2u) << 13) | ((e & 4u) << 2));
-                    if (small_id) {
-                        w_col[j] = s.col_lut[id * 8 + k];
-                    } else {
-                        const float c0f = __fmul_rn(dc0, aj), c1f = __fmul_rn(dc1, aj), c2f = __fmul_rn(dc2, aj);
-                        w_col[j] = ((__float2uint_rz(__fmul_rn(c0f, 255.0f)) & 0xFFu) << 24) | ((__float2uint_rz(__fmul_rn(c1f, 255.0f)) & 0xFFu) << 16) |
-                                   ((__float2uint_rz(__fmul_rn(c2f, 255.0f)) & 0xFFu) << 8) | 0xFFu;
+                    ks |= k << (3 * j);
+                    if (code != 1u) {
+                        const uint32_t neg = (code == 0u) ? 0x80000000u : 0u;
+                        b0 = __fadd_rn(b0, __uint_as_float(__float_as_uint(__fmul_rn(dc0, aj)) ^ neg));
+                        b1 = __fadd_rn(b1, __uint_as_float(__float_as_uint(__fmul_rn(dc1, aj)) ^ neg));
+                        b2 = __fadd_rn(b2, __uint_as_float(__float_as_uint(__fmul_rn(dc2, aj)) ^ neg));
                     }
-                    w_uvi[j] = (e >> 3) & 31u;
                 }
             }
-            fb0 = __float_as_uint(b0);
-            fb1 = __float_as_uint(b1);
-            fb2 = __float_as_uint(b2);
-            fb3 = __float_as_uint(b3);
-        };
-        const bool all_quads = __all_sync(FULL, !act || nv == 4u);
-        if (all_quads) {
-            if (act) face(std::integral_constant<uint32_t, 4>());
-        } else {
-            if (act) face(std::integral_constant<uint32_t, 6>());
+            // sum of (code - 1) over the side's vertices (codes past nv are 0 in the table)
+            const float b3 = (float)((int)(__popc(signs & 0x555u) + 2 * __popc(signs & 0xAAAu)) - (int)nv);
+            SideRec sr;
+            sr.cell_id = (x + 32u * (row & 31u) + 1024u * (row >> 5)) | (id << 16);
+            sr.ks_tab = ks | ((tabi * 6u) << 18);
+            sr.tex = __float_as_uint(texid);
+            sr.pos0 = (x << 24) | ((row >> 5) << 14) | ((row & 31u) << 4);
+            sr.fb[0] = __float_as_uint(b0);
+            sr.fb[1] = __float_as_uint(b1);
+            sr.fb[2] = __float_as_uint(b2);
+            sr.fb[3] = __float_as_uint(b3);
+            rec[lane] = sr;
         }
-        // the chunk's arena span
-        const unsigned long long v_off = p.spans[slot0].v_off, i_off = p.spans[slot0].i_off;
-        bxw_vertex *const vout = p.varena + v_off;
-        uint32_t *const iout = p.iarena + i_off;
         const uint32_t vq0 = __shfl_sync(FULL, vq, 0), iq0 = __shfl_sync(FULL, iq, 0);
         const uint32_t vqe = __shfl_sync(FULL, vq + nv, (int)nbf - 1), iqe = __shfl_sync(FULL, iq + ni, (int)nbf - 1);
-        // record: position, color, texcoord (u, v, texture id), index | barycentric flags, barycentric_color_offset[4]
-        // (src/client/render/voxrender.rs:39-49)
-        auto tu = [&](int j) { return (w_uvi[j] & 1u) ? 0x3F800000u : 0u; };
-        auto tv = [&](int j) { return (w_uvi[j] & 2u) ? 0x3F800000u : 0u; };
-        auto ix = [&](int j) { return cell | ((w_uvi[j] >> 2) << 17); };
-        if (all_quads && !(vq0 & 1u)) {
-            // 32 quads = 128 vertices from a 16-byte aligned address: two passes of 16 quads (2560 B)
+        if (act) {
+            const uint32_t vs = vq - vq0; // the sides of a batch are consecutive in the chunk's vertex buffer
 #pragma unroll
-            for (uint32_t h = 0; h < 2; h++) {
-                if (act && (lane >> 4) == h) {
-                    uint4 *o = stg + (lane & 15u) * 10u;
-                    o[0] = make_uint4(w_pos[0], w_col[0], tu(0), tv(0));
-                    o[1] = make_uint4(texbits, ix(0), fb0, fb1);
-                    o[2] = make_uint4(fb2, fb3, w_pos[1], w_col[1]);
-                    o[3] = make_uint4(tu(1), tv(1), texbits, ix(1));
-                    o[4] = make_uint4(fb0, fb1, fb2, fb3);
-                    o[5] = make_uint4(w_pos[2], w_col[2], tu(2), tv(2));
-                    o[6] = make_uint4(texbits, ix(2), fb0, fb1);
-                    o[7] = make_uint4(fb2, fb3, w_pos[3], w_col[3]);
-                    o[8] = make_uint4(tu(3), tv(3), texbits, ix(3));
-                    o[9] = make_uint4(fb0, fb1, fb2, fb3);
-                }
-                __syncwarp();
-                const uint32_t nfh = nbf > 16u * h ? min(16u, nbf - 16u * h) : 0u;
-                uint4 *gq = reinterpret_cast<uint4 *>(vout + vq0 + h * 64u);
-                for (uint32_t k = lane; k < nfh * 10u; k += 32) __stcs(&gq[k], stg[k]);
-                __syncwarp();
-            }
-        } else {
-            // mixed sides (3, 4 or 6 vertices): 16 sides (<= 96 vertices) per pass; a vertex is 40 bytes, so the run starts 0 or
-            // 8 bytes into a 16-byte unit
-#pragma unroll 1
-            for (uint32_t h = 0; h < 2; h++) {
-                if (h * 16u >= nbf) break;
-                const int first = (int)(h * 16u), last = (int)min(h * 16u + 15u, nbf - 1u);
-                const uint32_t vb = __shfl_sync(FULL, vq, first), ve = __shfl_sync(FULL, vq + nv, last);
-                const uint32_t mis = (vb & 1u) * 2u; // v_off is a multiple of 4
-                if (act && (lane >> 4) == h) {
-                    uint2 *o = st2 + (mis >> 1) + (vq - vb) * 5u;
-#pragma unroll
-                    for (uint32_t j = 0; j < 6; j++) {
-                        if (j < nv) {
-                            o[j * 5 + 0] = make_uint2(w_pos[j], w_col[j]);
-                            o[j * 5 + 1] = make_uint2(tu(j), tv(j));
-                            o[j * 5 + 2] = make_uint2(texbits, ix(j));
-                            o[j * 5 + 3] = make_uint2(fb0, fb1);
-                            o[j * 5 + 4] = make_uint2(fb2, fb3);
-                        }
-                    }
-                }
-                __syncwarp();
-                warp_copy_out(reinterpret_cast<uint32_t *>(vout + vb), stw, mis, (ve - vb) * 10u, lane);
-                __syncwarp();
-            }
+            for (uint32_t j = 0; j < 6; j++)
+                if (j < nv) vmap[vs + j] = (uint8_t)((lane << 3) | j);
         }
-        (void)vqe;
+        __syncwarp();
+        bxw_vertex *const vout = p.varena + v_off;
+        uint32_t *const iout = p.iarena + i_off;
+        // ---------------- vertex pass: lane = vertex ----------------
+        // record: position, color, texcoord (u, v, texture id), index | barycentric flags, barycentric_color_offset[4]
+        // (src/client/render/voxrender.rs:39-49). A vertex is 40 bytes and v_off is a multiple of 4 vertices, so an even vertex
+        // index is 16-byte aligned: passes are cut at even indices (the first takes 31 vertices when the batch starts odd) and
+        // every pass leaves as whole 16-byte units except for one 8-byte half at the very start / end of the batch's run.
+        const uint32_t nvt = vqe - vq0;
+        for (uint32_t tb = 0; tb < nvt;) {
+            const uint32_t mis = ((vq0 + tb) & 1u) * 2u;
+            const uint32_t cnt = min(nvt - tb, 32u - (mis >> 1));
+            uint32_t *const buf = stw + (npass & 1u) * STGW;
+            uint2 *const st2 = reinterpret_cast<uint2 *>(buf);
+            npass++;
+            // the bulk copy that last read this buffer (two passes ago) must be through with it
+            if (lane == 0u) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+#ifdef BXW_EXP_NO_COMPUTE
+            if (lane < cnt) {
+                uint2 *o = st2 + (mis >> 1) + lane * 5u;
+                o[0] = make_uint2(tb, lane);
+                o[1] = make_uint2(tb, lane);
+                o[2] = make_uint2(tb, lane);
+                o[3] = make_uint2(tb, lane);
+                o[4] = make_uint2(tb, lane);
+            }
+            if (false) {
+#else
+            if (lane < cnt) {
+#endif
+                const uint32_t m = vmap[tb + lane];
+                const SideRec *sr = &rec[m >> 3];
+                const uint4 a = *reinterpret_cast<const uint4 *>(sr);
+                const uint4 fbv = *reinterpret_cast<const uint4 *>(&sr->fb[0]);
+                const uint32_t j = m & 7u;
+                const uint32_t cell = a.x & 0x7FFFu, id = a.x >> 16;
+                const uint32_t vd = s.vd32[(a.y >> 18) + j];
+                const uint32_t k = (a.y >> (3u * j)) & 7u;
+                uint32_t col;
+                if (id < (uint32_t)EREGC) {
+                    col = s.col_lut[id * 8 + k];
+                } else { // as_rgba8(debug_color * ao) (voxmesh.rs:29-34,147-152)
+                    const float aj = s.ao_lut[k];
+                    const float4 bc = s.bigreg[warp][m >> 3];
+                    const float c0f = __fmul_rn(bc.x, aj), c1f = __fmul_rn(bc.y, aj), c2f = __fmul_rn(bc.z, aj);
+                    col = ((__float2uint_rz(__fmul_rn(c0f, 255.0f)) & 0xFFu) << 24) | ((__float2uint_rz(__fmul_rn(c1f, 255.0f)) & 0xFFu) << 16) |
+                          ((__float2uint_rz(__fmul_rn(c2f, 255.0f)) & 0xFFu) << 8) | 0xFFu;
+                }
+                // as_wxyz10 of (ipos + voffset + 0.5)/32 (voxmesh.rs:36-41,139-145,165): every vertex sits on a voxel corner, so
+                // each 10-bit field is 16 * corner coordinate (<= 512); w = (1/32*2) as u32 = 0
+                uint2 *o = st2 + (mis >> 1) + lane * 5u; // lanes 40 bytes apart: conflict-free 8-byte stores
+                o[0] = make_uint2(a.w + (vd & kVdPos), col);
+                o[1] = make_uint2((vd & 1u) * 0x3F800000u, ((vd >> 1) & 1u) * 0x3F800000u); // texcoord u, v: 0.0f or 1.0f
+                o[2] = make_uint2(a.z, cell | (vd & kVdFlags));
+                o[3] = make_uint2(fbv.x, fbv.y);
+                o[4] = make_uint2(fbv.z, fbv.w);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // staging writes -> visible to the bulk copy engine
+            __syncwarp();
+            warp_bulk_out_vertices(reinterpret_cast<uint32_t *>(vout + vq0 + tb), buf, mis, cnt * 10u, lane);
+            tb += cnt;
+        }
         // indices: QUAD_INDICES [0,1,2,2,3,0] for quads (stdshapes.rs:198), 0..n-1 for the triangle lists; they refer to the
         // chunk's own vertex buffer (voff = vbuf.len(), voxmesh.rs:123,175)
         {
             const uint32_t imis = iq0 & 3u; // i_off is a multiple of 8
+            // staged in the buffer the next vertex pass would take: only the last pass's bulk copy (other buffer) may be in flight
+            uint32_t *const ist = stw + (npass & 1u) * STGW;
+            if (lane == 0u) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
             if (act) {
-                uint32_t *o = stw + imis + (iq - iq0);
+                uint32_t *o = ist + imis + (iq - iq0);
                 const uint32_t pat = nv == 4u ? 0x032210u : 0x543210u;
 #pragma unroll
                 for (uint32_t k = 0; k < 6; k++)
                     if (k < ni) o[k] = vq + ((pat >> (4 * k)) & 15u);
             }
             __syncwarp();
-            warp_copy_out(iout + iq0, stw, imis, iqe - iq0, lane);
+            warp_copy_out(iout + iq0, ist, imis, iqe - iq0, lane);
             __syncwarp();
         }
     }
+    // bulk copies still in flight read this CTA's shared memory
+    if (lane == 0u) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 } // namespace
 
+static_assert(sizeof(ESmem) <= 56 * 1024, "emit_kernel's shared memory no longer fits four times on an SM");
+
 void launch_emit_kernel(const MeshParams &p, int sm_count, cudaStream_t stream) {
+    cudaFuncSetAttribute(emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ESmem));
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, emit_kernel, ENT, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, emit_kernel, ENT, sizeof(ESmem));
     if (per_sm < 1) per_sm = 1;
-    emit_kernel<<<(unsigned)(sm_count * per_sm), ENT, 0, stream>>>(p);
+    emit_kernel<<<(unsigned)(sm_count * per_sm), ENT, sizeof(ESmem), stream>>>(p);
 }
 
 } // namespace bxw

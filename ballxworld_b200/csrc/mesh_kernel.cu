@@ -69,6 +69,7 @@ struct Smem {
     uint32_t solid[34 * 34];         // per (y',z') row: bit x set when voxel x (0..31) has a mesh (class != 0)
     uint8_t solid_halo[34 * 34 + 4]; // bit0: x=-1 solid, bit1: x=32 solid
     uint32_t ctab[kNumClasses + 3];
+    uint16_t spread6[64];            // bit d of the index -> bits 2d, 2d+1 (mask over the 2-bit per-direction codes)
     uint8_t reg_kind[256];
     uint32_t nbr[27 + 5];
     uint32_t warp_tot[3][NW];
@@ -124,17 +125,14 @@ __device__ __forceinline__ uint32_t cell_visibility(const Smem &s, int at, uint3
     return vis;
 }
 
-// vertices / indices / faces of a cell, packed V | I<<10 | F<<21
-__device__ __forceinline__ uint32_t cell_counts(uint32_t vis, uint32_t t) {
-    const uint32_t codes = t >> 18;
-    uint32_t v = 0, i = 0;
-#pragma unroll
-    for (int d = 0; d < 6; d++) {
-        const uint32_t code = (codes >> (2 * d)) & 3u;
-        const bool on = (vis >> d) & 1u;
-        v += on ? code + 2u + (code == 3u) : 0u;
-        i += on ? (code == 1u ? 3u : 6u) : 0u;
-    }
+// vertices / indices / faces of a cell, packed V | I<<10 | F<<21. The class word holds a 2-bit vertex-count code per direction
+// (0 none, 1 three, 2 four, 3 six vertices; indices 3 / 6 / 6): mask the codes of the visible directions and count the codes of
+// each kind with three popcounts.
+__device__ __forceinline__ uint32_t cell_counts(const Smem &s, uint32_t vis, uint32_t t) {
+    const uint32_t c = (t >> 18) & s.spread6[vis];
+    const uint32_t lo = c & 0x555u, hi = (c >> 1) & 0x555u;
+    const uint32_t n1 = __popc(lo & ~hi), n2 = __popc(hi & ~lo), n3 = __popc(lo & hi);
+    const uint32_t v = 3u * n1 + 4u * n2 + 6u * n3, i = 3u * n1 + 6u * (n2 + n3);
     return v | (i << 10) | ((uint32_t)__popc(vis) << 21);
 }
 
@@ -196,6 +194,11 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
 
     for (int i = tid; i < kNumClasses; i += NT) s.ctab[i] = T->ctab[i];
     for (int i = tid; i < 256; i += NT) s.reg_kind[i] = (uint32_t)i < p.reg.n ? p.reg.kind[i] : (uint8_t)0;
+    if (tid < 64) {
+        uint32_t m = 0;
+        for (int d = 0; d < 6; d++) m |= ((tid >> d) & 1) ? (3u << (2 * d)) : 0u;
+        s.spread6[tid] = (uint16_t)m;
+    }
     if (tid < 5) { // class of the generator's datums (meta 0): cube (class 1) when the block has a mesh, else 0
         const uint32_t id = p.gen_datum[tid] >> 16;
         s.gen_cls[tid] = (p.hmap && id < p.reg.n && p.reg.kind[id] == 2) ? 1u : 0u;
@@ -626,7 +629,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                 uint32_t cnt = 0;
                 if (__any_sync(FULL, c != 0)) {
                     const uint32_t t = s.ctab[c];
-                    cnt = __reduce_add_sync(FULL, cell_counts(cell_visibility(s, at, t), t));
+                    cnt = __reduce_add_sync(FULL, cell_counts(s, cell_visibility(s, at, t), t));
                 }
                 if (lane == 0) s.sc.rowV[row] = cnt;
             }
@@ -738,14 +741,19 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
         const bool quads_only = !has_shapes; // every side has 4 vertices / 6 indices
         for (uint32_t r0 = 0; r0 < 1024;) {
             PHASE_MARK(t_t0);
-            // largest r1 with faces(r0..r1) <= FC and vertices(r0..r1) <= VC (a single row never exceeds 192 / 768)
-            uint32_t lo = r0 + 1, hi = 1024;
+            // largest r1 with faces(r0..r1) <= FC and vertices(r0..r1) <= VC (a single row never exceeds 192 / 768). The test is
+            // monotone in r1: every warp finds it with two 32-way votes (rows r0+1, r0+33, ... then the 32 rows behind the hit).
             const uint32_t f0 = s.sc.rowF[r0], v0 = s.sc.rowV[r0], i0 = s.sc.rowI[r0];
-            if (s.sc.rowF[1024] - f0 <= (uint32_t)FC && s.sc.rowV[1024] - v0 <= (uint32_t)VC) lo = hi; // the rest fits one tile (terrain)
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi + 1) >> 1;
-                if (s.sc.rowF[mid] - f0 <= (uint32_t)FC && s.sc.rowV[mid] - v0 <= (uint32_t)VC) lo = mid;
-                else hi = mid - 1;
+            uint32_t lo = 1024;
+            if (!(s.sc.rowF[1024] - f0 <= (uint32_t)FC && s.sc.rowV[1024] - v0 <= (uint32_t)VC)) { // else: the rest fits one tile (terrain)
+                auto fits = [&](uint32_t r) {
+                    r = min(r, 1024u);
+                    return s.sc.rowF[r] - f0 <= (uint32_t)FC && s.sc.rowV[r] - v0 <= (uint32_t)VC;
+                };
+                const uint32_t coarse = __ballot_sync(FULL, fits(r0 + 1u + 32u * (uint32_t)lane)); // lane 0 always fits
+                const uint32_t base = r0 + 1u + 32u * (31u - (uint32_t)__clz(coarse));
+                const uint32_t fine = __ballot_sync(FULL, fits(base + (uint32_t)lane));
+                lo = min(base + (31u - (uint32_t)__clz(fine)), 1024u);
             }
             const uint32_t r1 = lo;
             const uint32_t tileF = s.sc.rowF[r1] - f0;
@@ -783,7 +791,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                     const uint32_t c = s.cls[at];
                     const uint32_t t = s.ctab[c];
                     const uint32_t vis = c ? cell_visibility(s, at, t) : 0u;
-                    const uint32_t pk = cell_counts(vis, t);
+                    const uint32_t pk = cell_counts(s, vis, t);
                     uint32_t incl = pk;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
@@ -848,7 +856,9 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
             const uint32_t TF = s.sc.rowF[1024];
             const uint32_t padF = (TF + 31u) & ~31u;
             if (tid < padF - TF) p.frec[fbase + TF + tid] = make_uint4(kFacePad, 0u, 0u, 0u);
-            for (uint32_t t = tid; t < (padF >> 5); t += NT) p.fslot[(fbase >> 5) + t] = span_slot;
+            const unsigned long long vb = s.vbase, ib = s.ibase;
+            const uint4 where = make_uint4((uint32_t)vb, (uint32_t)(vb >> 32), (uint32_t)ib, (uint32_t)(ib >> 32));
+            for (uint32_t t = tid; t < (padF >> 5); t += NT) p.fslot[(fbase >> 5) + t] = where;
         }
         PHASE_MARK(t_c1);
         PHASE_ADD(3, t_b1, t_c1);

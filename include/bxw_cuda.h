@@ -226,7 +226,7 @@ int bxw_timer_stop_ms(bxw_ctx *ctx, float *ms); /* records, synchronises, return
 int bxw_mesh_kernel_time_ms(bxw_ctx *ctx, float *ms, uint64_t *launches, int reset);
 /* The same for the generator's kernels: which = BXW_KERNEL_MESH / _FILL (block selection, stdgen.rs:349-373) /
  * _HEIGHTMAP (calc_voxel_params, stdgen.rs:215-276). */
-enum { BXW_KERNEL_MESH = 0, BXW_KERNEL_FILL = 1, BXW_KERNEL_HEIGHTMAP = 2 };
+enum { BXW_KERNEL_MESH = 0, BXW_KERNEL_FILL = 1, BXW_KERNEL_HEIGHTMAP = 2, BXW_KERNEL_EMIT = 3 /* emit_kernel's share of _MESH */ };
 int bxw_kernel_time_ms(bxw_ctx *ctx, int which, float *ms, uint64_t *launches, int reset);
 /* Statistics of the last whole-region mesh pass: chunks that were actually meshed (the rest were proven empty from
  * their summaries, the device analogue of is_chunk_trivial on a 3-word RLE chunk, voxmesh.rs:16-25) / interior chunks. */

@@ -33,6 +33,7 @@ def main():
     ctx.mesh_kernel_time_ms(reset=True)
     for _ in range(a.steps):
         av, ai = ctx.region_mesh()
+    ems, _ = ctx.kernel_time_ms(ctx.KERNEL_EMIT)
     ms, n = ctx.mesh_kernel_time_ms()
     spans = ctx.region_mesh_spans()
     V = int(spans["v_count"].astype(np.uint64).sum())
@@ -46,6 +47,7 @@ def main():
         peak = float(json.load(open(p))["hbm_gbs"])
     print(json.dumps({"workload": f"mesh-only {nx}x{nz}x{ny} chunks, hashed random blocks, void threshold {a.threshold}",
                       "chunks": n_chunks, "vertices": V, "indices": I, "ms_per_launch": per,
+                      "mesh_kernel_ms": (ms - ems) / n, "emit_kernel_ms": ems / n,
                       "chunks_per_s": n_chunks / (per / 1e3), "algorithmic_bytes": alg,
                       "achieved_gbs": alg / (per / 1e3) / 1e9, "peak_gbs": peak, "frac": alg / (per / 1e3) / 1e9 / peak}))
     ctx.close()
