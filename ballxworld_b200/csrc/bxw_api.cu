@@ -57,6 +57,10 @@ struct Region {
     uint2 *span_cap = nullptr;             // [n_work] arena reservation behind each span (device_common.cuh)
     bxw_mesh_span *spans_bak = nullptr;    // re-mesh passes: spans / reservations before the pass (restored if the arena must grow)
     uint2 *span_cap_bak = nullptr;
+    // cubes-only mesher: chunks it hands over to the general kernel; shape_hint: 0 = storage holds generator output and edits
+    // only (cubes, the odd edited shape), 2 = bulk content of unknown shapes (synthetic fill, uploads, imports)
+    uint32_t *fb_work = nullptr, *fb_span = nullptr, *fb_count = nullptr;
+    int shape_hint = 0;
     uint64_t gen_seed = 0;                 // seed / precision of the last generate (bxw_region_heightmap's raw output)
     int gen_precision = 64;
     size_t n_storage() const { return (size_t)SX * SY * SZ; }
@@ -98,6 +102,7 @@ struct bxw_ctx {
     uint64_t mesh_launches = 0, fill_launches = 0, hmap_launches = 0;
     bool use_summaries = true;                                     // BXW_OPT_CHUNK_SUMMARIES
     bool elide_uniform = true;                                     // BXW_OPT_ELIDE_UNIFORM
+    bool lean_mesher = true;                                       // BXW_OPT_CUBES_ONLY_MESHER
     bool mesh_from_hmap = false;                                   // BXW_OPT_MESH_FROM_HEIGHT_MAP
     uint32_t last_candidates = 0, last_candidates_of = 0;          // last whole-region mesh: chunks listed / interior chunks
     // staging for host<->device codecs
@@ -210,6 +215,9 @@ void region_free(Region &r) {
     cudaFree(r.cand_keep);
     cudaFree(r.cand_blk);
     cudaFree(r.page);
+    cudaFree(r.fb_work);
+    cudaFree(r.fb_span);
+    cudaFree(r.fb_count);
     cudaFree(r.need);
     cudaFree(r.span_cap);
     cudaFree(r.spans_bak);
@@ -239,6 +247,9 @@ int region_alloc(bxw_ctx *ctx, Region &r, int32_t cx0, int32_t cy0, int32_t cz0,
     CK(cudaMalloc(&r.xface, (nst + kSharedPages) * 2048 * sizeof(uint32_t)));
     CK(cudaMalloc(&r.page, nst * sizeof(uint32_t)));
     launch_page_identity(r.page, (uint32_t)nst, ctx->stream);
+    CK(cudaMalloc(&r.fb_work, r.n_work * sizeof(uint32_t)));
+    CK(cudaMalloc(&r.fb_span, r.n_work * sizeof(uint32_t)));
+    CK(cudaMalloc(&r.fb_count, sizeof(uint32_t)));
     CK(cudaMalloc(&r.need, nst));
     CK(cudaMemsetAsync(r.need, 0, nst, ctx->stream));
     CK(cudaMalloc(&r.span_cap, r.n_work * sizeof(uint2)));
@@ -415,6 +426,7 @@ int region_generate(bxw_ctx *ctx, Region &r, uint64_t seed, int precision, bool 
     ctx->launches += 2;
     CK(cudaGetLastError());
     r.have_hmap = true;
+    r.shape_hint = 0;
     r.gen_seed = seed;
     r.gen_precision = precision;
     return BXW_OK;
@@ -481,6 +493,7 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
     p.span_cap = r.span_cap;
     p.reuse = append ? 1 : 0;
     p.counters = r.counters;
+    p.cursor = &r.counters->work_next;
     p.tables = ctx->d_tables;
     p.reg = dev_registry(ctx);
     p.hmap = nullptr;
@@ -546,6 +559,10 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
         p.work_span = r.dirty_span;
         p.n_work_dev = r.dirty_count;
     }
+    const bool lean = ctx->lean_mesher && !from_hmap && r.shape_hint < 2;
+    p.fallback_work = r.fb_work;
+    p.fallback_span = r.fb_span;
+    p.fallback_count = r.fb_count;
     MeshCounters base; // allocator state the pass starts from
     std::memset(&base, 0, sizeof base);
     if (append) {
@@ -572,8 +589,22 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
         p.f_cap = r.f_cap;
         p.count_only = count_only ? 1 : 0;
         CK(cudaEventRecord(ctx->ev_m0, ctx->stream));
-        launch_mesh_kernel(p, ctx->sm_count, ctx->stream);
-        ctx->launches += 1;
+        if (lean) {
+            // cubes-and-void chunks (all of generated terrain) go through the lean instantiation at twice the occupancy; what it
+            // cannot handle (a slope / corner placed by an edit) lands on the fallback list for the general kernel
+            CK(cudaMemsetAsync(r.fb_count, 0, sizeof(uint32_t), ctx->stream));
+            launch_mesh_kernel(p, ctx->sm_count, ctx->stream, true, !work && !p.n_work_dev);
+            MeshParams pf = p;
+            pf.work = r.fb_work;
+            pf.work_span = r.fb_span;
+            pf.n_work_dev = r.fb_count;
+            pf.cursor = &r.counters->work_next2;
+            launch_mesh_kernel(pf, ctx->sm_count, ctx->stream, false, false);
+            ctx->launches += 2;
+        } else {
+            launch_mesh_kernel(p, ctx->sm_count, ctx->stream, false, false);
+            ctx->launches += 1;
+        }
         CK(cudaEventRecord(ctx->ev_mm, ctx->stream));
         if (!count_only) { // vertices and indices of the recorded sides (returns at once if a chunk did not fit)
             // the arena is rewritten from here on: an asynchronous fetch of the previous meshes has to be through
@@ -795,6 +826,10 @@ int bxw_set_option(bxw_ctx *ctx, int option, int value) {
     }
     if (option == BXW_OPT_MESH_FROM_HEIGHT_MAP) {
         ctx->mesh_from_hmap = value != 0;
+        return BXW_OK;
+    }
+    if (option == BXW_OPT_CUBES_ONLY_MESHER) {
+        ctx->lean_mesher = value != 0;
         return BXW_OK;
     }
     if (option == BXW_OPT_ELIDE_UNIFORM) {
@@ -1508,6 +1543,7 @@ int bxw_region_fill_synthetic(bxw_ctx *ctx, uint64_t seed, uint32_t void_thresho
     Region &r = ctx->region;
     CK(cudaMemsetAsync(r.summary, 0, r.n_storage() * sizeof(unsigned long long), ctx->stream));
     launch_page_identity(r.page, (uint32_t)r.n_storage(), ctx->stream);
+    r.shape_hint = 2;
     launch_fill_synthetic(r.blocks, r.SX, r.SY, r.SZ, r.cx0 - 1, r.cy0 - 1, r.cz0 - 1, seed, void_threshold, ctx->stream);
     launch_xface_extract(r.blocks, r.xface, nullptr, 0, (uint32_t)r.n_storage(), ctx->stream);
     ctx->launches += 2;

@@ -28,6 +28,7 @@ struct MeshCounters {
     unsigned long long i_alloc; // next free index slot
     unsigned long long flags;
     unsigned long long work_next; // dynamic work-list cursor
+    unsigned long long work_next2; // the same for the general kernel's pass over the cubes-only kernel's fallback list
     unsigned long long f_alloc;   // next free face-record slot (a chunk takes a multiple of 32)
     unsigned long long v_garbage; // arena space that no span refers to any more (re-meshes that moved, unloaded meshes)
     unsigned long long i_garbage;
@@ -62,8 +63,10 @@ struct MeshParams {
     uint4 *fslot;
     unsigned long long f_cap;
     MeshCounters *counters;
+    unsigned long long *cursor; // the launch's work-list cursor (inside *counters)
     const MeshTables *tables;
     DeviceRegistry reg;
+    uint32_t *fallback_work, *fallback_span, *fallback_count; // lean kernel only: chunks left to the general kernel
     int count_only; // 1: fill spans' counts only (offsets = running totals), no vertex/index writes
     // fused generate+mesh (pristine StdGenerator terrain): derive the 34^3 table from the column parameters
     const int32_t *hmap;   // nullptr = read the block storage
@@ -72,7 +75,10 @@ struct MeshParams {
     int gen_all_cubes;     // grass, dirt, stone and snow grass all classify as cubes (1..24)
 };
 
-void launch_mesh_kernel(const MeshParams &p, int sm_count, cudaStream_t stream);
+// lean = the cubes-and-void instantiation (no class table, 4-5 CTAs per SM); chunks it cannot handle are appended to the
+// fallback list for a second launch of the general kernel
+// mostly_uniform: the work list is a whole region with the uniform chunks still in it (picks the lean variant tuned for them)
+void launch_mesh_kernel(const MeshParams &p, int sm_count, cudaStream_t stream, bool lean, bool mostly_uniform);
 
 // Face record: one uint4 per visible side, frec[k], in the reference's emission order; every chunk's records start on a
 // multiple of 32 and are padded to one, and fslot[k / 32] holds the chunk's arena offsets (v_off, i_off as two u64), so that

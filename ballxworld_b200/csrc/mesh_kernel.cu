@@ -42,7 +42,6 @@ constexpr int VC = 4096;     // vertices per record tile (the tile-relative firs
 
 // phase-A staging: every warp streams its share of the 34^3 neighbourhood through a private cp.async ring.
 // One unit = a third of a y' layer: 3 warp copies of 4 rows (12 rows x 128 B) + (first third only) the layer's x-halo.
-constexpr int RSLOTS = 4;
 constexpr int RSLOT_BYTES = 3 * 512 + 128 + 128 + 16;
 
 struct Scratch { // phases B, S, C
@@ -55,13 +54,27 @@ struct Scratch { // phases B, S, C
     uint32_t frecC[FC];   // block id | class<<16 (tiles with non-quad sides)
     uint32_t frecE[FC];   // occupancy of the cell's 3x3x3 neighbourhood, bit (dy+1)*9 + (dz+1)*3 + (dx+1) (ditto)
 };
+struct ScratchLean { // the cubes-only kernel: every side is a quad, C2 recomputes the rest
+    uint32_t rowV[1028];
+    uint32_t rowI[1028];
+    uint32_t rowF[1028];
+    uint32_t frecA[FC];
+};
 
-struct Smem {
-    uint8_t cls[CLS_BYTES];
+// Two instantiations of the kernel share this file's code:
+//   LEAN = false: the general kernel. 34^3 class table (46 KB) + four-slot rings: 110 KB, two CTAs per SM.
+//   LEAN = true:  cubes and void only (all of generated terrain). No class table -- visibility needs only the solid words --
+//                 two-slot rings, a quarter of the record scratch: 36 KB, so four to five CTAs per SM hide the staging latency
+//                 that bounds the general kernel on surface chunks. A chunk in which it meets another shape is handed to the
+//                 general kernel through a fallback list.
+template <bool LEAN>
+struct SmemT {
+    static constexpr int RSLOTS = LEAN ? 2 : 4;
+    uint8_t cls[LEAN ? 16 : CLS_BYTES];
     union {
-        Scratch sc;                                          // phases B, S, C
+        std::conditional_t<LEAN, ScratchLean, Scratch> sc;   // phases B, S, C
         alignas(16) uint8_t ring[NW][RSLOTS][RSLOT_BYTES];   // phase A
-        struct {                                             // phase A of the fused generate+mesh path
+        struct {                                             // phase A of the fused generate+mesh path (general kernel)
             int32_t hm[34 * 36];                             // packed column parameters (height*4 + elevation), [zz][xx]
             int32_t red[2][NW];
         } gen;
@@ -81,6 +94,7 @@ struct Smem {
     uint32_t gen_cls[5];   // class of the five generator datums (void, grass, dirt, stone, snow_grass)
     int emit;
 };
+using Smem = SmemT<false>;
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
@@ -94,7 +108,8 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-__device__ __forceinline__ uint32_t classify(uint32_t d, const Smem &s, const DeviceRegistry &reg, uint32_t &err) {
+template <class S>
+__device__ __forceinline__ uint32_t classify(uint32_t d, const S &s, const DeviceRegistry &reg, uint32_t &err) {
     // voxmesh.rs:76-78 -> stdshapes.rs:51-72
     const uint32_t id = d >> 16;
     const uint32_t k = id < 256u ? (uint32_t)s.reg_kind[id] : (id < reg.n ? (uint32_t)__ldg(reg.kind + id) : 0u);
@@ -108,8 +123,21 @@ __device__ __forceinline__ uint32_t classify(uint32_t d, const Smem &s, const De
     return 1u + shape * 24u + o;
 }
 
+// The cubes-only kernel needs less of a voxel in phase A: 0 = no mesh, 1 = a cube (any orientation), 25 = another shape (which
+// sends the chunk to the general kernel).
+template <class S>
+__device__ __forceinline__ uint32_t classify_lean(uint32_t d, const S &s, const DeviceRegistry &reg, uint32_t &err) {
+    const uint32_t id = d >> 16;
+    const uint32_t k = id < 256u ? (uint32_t)s.reg_kind[id] : (id < reg.n ? (uint32_t)__ldg(reg.kind + id) : 0u);
+    if (k == 0u) err = 1u;
+    if (k != 2u) return 0u;
+    const uint32_t shape = d & 63u;
+    return (shape - 1u < 3u) ? 25u : 1u;
+}
+
 // visibility of the 6 sides of the cell at byte `at` -- voxmesh.rs:104-121
-__device__ __forceinline__ uint32_t cell_visibility(const Smem &s, int at, uint32_t t) {
+template <class S>
+__device__ __forceinline__ uint32_t cell_visibility(const S &s, int at, uint32_t t) {
     const uint32_t ec = (t >> 6) & 63u, eu = (t >> 12) & 63u;
     uint32_t vis = eu;
     if (ec) {
@@ -128,7 +156,8 @@ __device__ __forceinline__ uint32_t cell_visibility(const Smem &s, int at, uint3
 // vertices / indices / faces of a cell, packed V | I<<10 | F<<21. The class word holds a 2-bit vertex-count code per direction
 // (0 none, 1 three, 2 four, 3 six vertices; indices 3 / 6 / 6): mask the codes of the visible directions and count the codes of
 // each kind with three popcounts.
-__device__ __forceinline__ uint32_t cell_counts(const Smem &s, uint32_t vis, uint32_t t) {
+template <class S>
+__device__ __forceinline__ uint32_t cell_counts(const S &s, uint32_t vis, uint32_t t) {
     const uint32_t c = (t >> 18) & s.spread6[vis];
     const uint32_t lo = c & 0x555u, hi = (c >> 1) & 0x555u;
     const uint32_t n1 = __popc(lo & ~hi), n2 = __popc(hi & ~lo), n3 = __popc(lo & hi);
@@ -137,13 +166,15 @@ __device__ __forceinline__ uint32_t cell_counts(const Smem &s, uint32_t vis, uin
 }
 
 // the 34-bit solid word of row rr (bit 0: x=-1, bits 1..32: x=0..31, bit 33: x=32)
-__device__ __forceinline__ unsigned long long solid_word(const Smem &s, int rr) {
+template <class S>
+__device__ __forceinline__ unsigned long long solid_word(const S &s, int rr) {
     const unsigned long long h = s.solid_halo[rr];
     return ((unsigned long long)s.solid[rr] << 1) | (h & 1ull) | ((h >> 1) << 33);
 }
 
 // occupancy (class != 0) of the 3x3x3 neighbourhood of cell (x, y, z), bit (dy+1)*9 + (dz+1)*3 + (dx+1)
-__device__ __forceinline__ uint32_t neighbourhood27(const Smem &s, int y, int z, int x) {
+template <class S>
+__device__ __forceinline__ uint32_t neighbourhood27(const S &s, int y, int z, int x) {
     uint32_t nb = 0;
 #pragma unroll
     for (int dy = 0; dy < 3; dy++)
@@ -156,7 +187,8 @@ __device__ __forceinline__ uint32_t neighbourhood27(const Smem &s, int y, int z,
 }
 
 // visible-side words of a cubes-and-void row: bit x+1 of out[d] = side d of cell x is visible
-__device__ __forceinline__ void row_visibility(const Smem &s, int y, int z, unsigned long long out[6]) {
+template <class S>
+__device__ __forceinline__ void row_visibility(const S &s, int y, int z, unsigned long long out[6]) {
     const int r = (y + 1) * 34 + (z + 1);
     const unsigned long long C = solid_word(s, r), M = 0x1FFFFFFFEull;
     out[0] = C & ~(C << 1) & M;
@@ -178,6 +210,94 @@ __device__ __forceinline__ void release_span(const MeshParams &p, uint32_t span_
     p.span_cap[span_slot] = make_uint2(0u, 0u);
 }
 
+// x-halo class bytes / solid bits of layer yy: lane z owns row zz = z+1, lanes 0 and 2 also the corner rows 0 / 33
+template <bool LEAN>
+__device__ __forceinline__ void halo_store(SmemT<LEAN> &s, int lane, int yy, uint32_t cm, uint32_t cp, uint32_t ce, uint32_t co) {
+    if (!LEAN) {
+        uint8_t *row = &s.cls[yy * PLANE + (lane + 1) * ROWB + XOFF];
+        row[-1] = (uint8_t)cm;
+        row[32] = (uint8_t)cp;
+    }
+    s.solid_halo[yy * 34 + lane + 1] = (uint8_t)((cm != 0u) | ((cp != 0u) << 1));
+    if (lane == 0 || lane == 2) {
+        const int zz = lane ? 33 : 0;
+        if (!LEAN) {
+            s.cls[yy * PLANE + zz * ROWB + XOFF - 1] = (uint8_t)ce;
+            s.cls[yy * PLANE + zz * ROWB + XOFF + 32] = (uint8_t)co;
+        }
+        s.solid_halo[yy * 34 + zz] = (uint8_t)((ce != 0u) | ((co != 0u) << 1));
+    }
+}
+
+template <bool LEAN>
+__device__ __forceinline__ uint32_t classify_any(uint32_t d, const SmemT<LEAN> &s, const DeviceRegistry &reg, uint32_t &err) {
+    return LEAN ? classify_lean(d, s, reg, err) : classify(d, s, reg, err);
+}
+
+// A staged unit (a third of a layer: 12 rows + in the first third the layer's x-halo) that is NOT one single datum: per-voxel
+// classification into class bytes and solid words. Kept out of line on purpose: the unit loop of phase A is unrolled three
+// ways and inlining this body into each copy made the kernel outgrow the instruction cache (a third of all stall cycles on
+// surface chunks were instruction fetches). Returns shapes | err << 1.
+template <bool LEAN>
+__device__ __forceinline__ uint32_t classify_unit_body(SmemT<LEAN> &s, const uint8_t *reg_kind, uint32_t reg_n, int yy, int PART, uint4 v0,
+                                                       uint4 v1, uint4 v2, uint32_t hm, uint32_t hp, uint32_t he) {
+    const int lane = threadIdx.x & 31, q = lane & 7, zsub = lane >> 3;
+    DeviceRegistry reg;
+    reg.kind = reg_kind;
+    reg.texf = nullptr;
+    reg.color = nullptr;
+    reg.n = reg_n;
+    uint32_t err = 0, shapes = 0;
+    uint32_t last_d = 0xFFFFFFFFu, last_c = 0; // (datum 0xFFFFFFFF: block id 65535 with meta 65535 -- classified like any other on a miss)
+    bool have = false;
+    if (PART == 0) {
+        const uint32_t cm = classify_any<LEAN>(hm, s, reg, err), cp = classify_any<LEAN>(hp, s, reg, err);
+        const uint32_t ce = lane < 4 ? classify_any<LEAN>(he, s, reg, err) : 0u;
+        const uint32_t co = __shfl_xor_sync(FULL, ce, 1); // the other side of the same corner row
+        shapes |= (cm > 24u) | (cp > 24u) | (ce > 24u);
+        halo_store<LEAN>(s, lane, yy, cm, cp, ce, co);
+    }
+#pragma unroll 1
+    for (int jj = 0; jj < 3; jj++) {
+        const uint4 v = jj == 0 ? v0 : (jj == 1 ? v1 : v2);
+        const int zz = 4 * (3 * PART + jj) + zsub;
+        const uint32_t first = __shfl_sync(FULL, v.x, 0);
+        const uint32_t diff = ((v.x ^ first) | (v.y ^ first)) | ((v.z ^ first) | (v.w ^ first));
+        uint32_t b, rowmask;
+        if (__all_sync(FULL, diff == 0u || zz >= 34)) { // all 128 voxels equal: classify once (cached)
+            if (!have || first != last_d) {
+                have = true;
+                last_d = first;
+                last_c = classify_any<LEAN>(first, s, reg, err);
+            }
+            b = last_c * 0x01010101u;
+            rowmask = last_c ? 0xFFFFFFFFu : 0u;
+            shapes |= (last_c > 24u);
+        } else {
+            const bool valid = zz < 34;
+            const uint32_t k0 = valid ? classify_any<LEAN>(v.x, s, reg, err) : 0u, k1 = valid ? classify_any<LEAN>(v.y, s, reg, err) : 0u,
+                           k2 = valid ? classify_any<LEAN>(v.z, s, reg, err) : 0u, k3 = valid ? classify_any<LEAN>(v.w, s, reg, err) : 0u;
+            b = k0 | (k1 << 8) | (k2 << 16) | (k3 << 24);
+            shapes |= (k0 > 24u) | (k1 > 24u) | (k2 > 24u) | (k3 > 24u);
+            uint32_t m = ((k0 != 0u) | ((k1 != 0u) << 1) | ((k2 != 0u) << 2) | ((k3 != 0u) << 3)) << (q * 4);
+            m |= __shfl_xor_sync(FULL, m, 1);
+            m |= __shfl_xor_sync(FULL, m, 2);
+            m |= __shfl_xor_sync(FULL, m, 4);
+            rowmask = m;
+        }
+        if (zz < 34) {
+            if (!LEAN) *reinterpret_cast<uint32_t *>(&s.cls[yy * PLANE + zz * ROWB + XOFF + q * 4]) = b;
+            if (q == 0) s.solid[yy * 34 + zz] = rowmask;
+        }
+    }
+    return shapes | (err << 1);
+}
+template <bool LEAN>
+__device__ __noinline__ uint32_t classify_unit_call(SmemT<LEAN> &s, const uint8_t *reg_kind, uint32_t reg_n, int yy, int PART, uint4 v0, uint4 v1,
+                                                    uint4 v2, uint32_t hm, uint32_t hp, uint32_t he) {
+    return classify_unit_body<LEAN>(s, reg_kind, reg_n, yy, PART, v0, v1, v2, hm, hp, he);
+}
+
 #ifdef BXW_PHASE_TIMING
 #define PHASE_MARK(var) const long long var = clock64()
 #define PHASE_ADD(slot, a, b) do { if (tid == 0) atomicAdd(&p.counters->phase[slot], (unsigned long long)((b) - (a))); } while (0)
@@ -186,9 +306,14 @@ __device__ __forceinline__ void release_span(const MeshParams &p, uint32_t span_
 #define PHASE_ADD(slot, a, b)
 #endif
 
-__global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
+// CALL_SLOW: the per-voxel branch of phase A is a function call instead of inline code (smaller kernel: better where most
+// chunks take that branch at high occupancy -- the candidate list of a terrain pass; worse where nearly every unit is uniform).
+template <bool LEAN, bool CALL_SLOW>
+__global__ void __launch_bounds__(NT, LEAN ? 4 : 2) mesh_kernel(MeshParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem &s = *reinterpret_cast<Smem *>(smem_raw);
+    using SM = SmemT<LEAN>;
+    SM &s = *reinterpret_cast<SM *>(smem_raw);
+    constexpr int RSLOTS = SM::RSLOTS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const MeshTables *T = p.tables;
 
@@ -209,7 +334,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
     // and its result -- plus the list entries it selects -- is published just before that barrier, off the critical path.
     constexpr int PF_TID = NT - 32;
     if (tid == PF_TID) {
-        const uint32_t w0 = (uint32_t)atomicAdd(&p.counters->work_next, 1ull);
+        const uint32_t w0 = (uint32_t)atomicAdd(p.cursor, 1ull);
         s.work_item[0] = w0;
         if (p.work && w0 < n_work) {
             s.work_c0[0] = p.work[w0];
@@ -223,7 +348,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
         if (w >= n_work) break;
         PHASE_MARK(t_fetch);
         uint32_t next_w = 0;
-        if (tid == PF_TID) next_w = (uint32_t)atomicAdd(&p.counters->work_next, 1ull); // consumed before the phase-A barrier
+        if (tid == PF_TID) next_w = (uint32_t)atomicAdd(p.cursor, 1ull); // consumed before the phase-A barrier
         uint32_t c0, span_slot;
         if (p.work) {
             c0 = s.work_c0[iter & 1];
@@ -257,7 +382,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
         uint32_t err = 0;
         uint32_t shapes = 0;  // saw a non-cube shape (class > 24)
         uint32_t mixed = 0;   // saw a voxel different from this warp's reference voxel
-        if (p.hmap) {
+        if (!LEAN && p.hmap) {
             // Fused generate+mesh: the blocks of pristine terrain are a pure function of the column parameters
             // (stdgen.rs:349-373), so the 34^3 table is derived from the 34x34 columns under the chunk instead of reading
             // 148 KB of voxels back from HBM.
@@ -340,6 +465,9 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
             if (lane == 0) s.wref[warp] = 0;
         } else {
             const int q = lane & 7, zsub = lane >> 3;
+            auto cls_of = [&](uint32_t d, const SM &sm, const DeviceRegistry &rg, uint32_t &e) {
+                return LEAN ? classify_lean(d, sm, rg, e) : classify(d, sm, rg, e);
+            };
             uint32_t last_d = 0, last_c = 0, wref = 0;
             bool have_ref = false;
             auto note_ref = [&](uint32_t x) { // first datum this warp sees: reference for trivial-chunk detection
@@ -347,7 +475,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                     have_ref = true;
                     wref = __shfl_sync(FULL, x, 0);
                     last_d = wref;
-                    last_c = classify(wref, s, p.reg, err);
+                    last_c = cls_of(wref, s, p.reg, err);
                 }
             };
             // source pointers of a layer's rows: zz = 0 / 1..32 / 33 live in the three z-column chunks at this ry
@@ -355,61 +483,6 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                 const int rz = zz == 0 ? 0 : (zz == 33 ? 2 : 1), bz = (zz - 1) & 31;
                 return p.blocks + (size_t)s.nbr[1 + 3 * rz + 9 * ry] * kChunkVoxels + by * 1024 + bz * 32 + q * 4;
             };
-            // one 128-voxel group (4 rows x 32) of layer yy: class bytes + solid words
-            auto do_group = [&](int yy, int j, uint4 v) {
-                const int zz = 4 * j + zsub;
-                const uint32_t first = __shfl_sync(FULL, v.x, 0);
-                const uint32_t diff = ((v.x ^ first) | (v.y ^ first)) | ((v.z ^ first) | (v.w ^ first));
-                uint32_t b, rowmask;
-                if (__all_sync(FULL, diff == 0u || zz >= 34)) { // all 128 voxels equal: classify once (cached)
-                    if (first != last_d) {
-                        last_d = first;
-                        last_c = classify(first, s, p.reg, err);
-                    }
-                    mixed |= (first != wref);
-                    b = last_c * 0x01010101u;
-                    rowmask = last_c ? 0xFFFFFFFFu : 0u;
-                    shapes |= (last_c > 24u);
-                } else {
-                    mixed = 1;
-                    const bool valid = zz < 34;
-                    const uint32_t k0 = valid ? classify(v.x, s, p.reg, err) : 0u, k1 = valid ? classify(v.y, s, p.reg, err) : 0u,
-                                   k2 = valid ? classify(v.z, s, p.reg, err) : 0u, k3 = valid ? classify(v.w, s, p.reg, err) : 0u;
-                    b = k0 | (k1 << 8) | (k2 << 16) | (k3 << 24);
-                    shapes |= (k0 > 24u) | (k1 > 24u) | (k2 > 24u) | (k3 > 24u);
-                    uint32_t m = ((k0 != 0u) | ((k1 != 0u) << 1) | ((k2 != 0u) << 2) | ((k3 != 0u) << 3)) << (q * 4);
-                    m |= __shfl_xor_sync(FULL, m, 1);
-                    m |= __shfl_xor_sync(FULL, m, 2);
-                    m |= __shfl_xor_sync(FULL, m, 4);
-                    rowmask = m;
-                }
-                if (zz < 34) {
-                    *reinterpret_cast<uint32_t *>(&s.cls[yy * PLANE + zz * ROWB + XOFF + q * 4]) = b;
-                    if (q == 0) s.solid[yy * 34 + zz] = rowmask;
-                }
-            };
-            // x-halo class bytes / solid bits of a layer: lane z owns row zz = z+1, lanes 0 and 2 also the corner rows 0 / 33
-            auto halo_store = [&](int yy, uint32_t cm, uint32_t cp, uint32_t ce, uint32_t co) {
-                uint8_t *row = &s.cls[yy * PLANE + (lane + 1) * ROWB + XOFF];
-                row[-1] = (uint8_t)cm;
-                row[32] = (uint8_t)cp;
-                s.solid_halo[yy * 34 + lane + 1] = (uint8_t)((cm != 0u) | ((cp != 0u) << 1));
-                if (lane == 0 || lane == 2) {
-                    const int zz = lane ? 33 : 0;
-                    s.cls[yy * PLANE + zz * ROWB + XOFF - 1] = (uint8_t)ce;
-                    s.cls[yy * PLANE + zz * ROWB + XOFF + 32] = (uint8_t)co;
-                    s.solid_halo[yy * 34 + zz] = (uint8_t)((ce != 0u) | ((co != 0u) << 1));
-                }
-            };
-            auto halo_general = [&](int yy, uint32_t hm, uint32_t hp, uint32_t he) {
-                const uint32_t cm = classify(hm, s, p.reg, err), cp = classify(hp, s, p.reg, err);
-                const uint32_t ce = lane < 4 ? classify(he, s, p.reg, err) : 0u;
-                const uint32_t co = __shfl_xor_sync(FULL, ce, 1); // the other side of the same corner row
-                mixed |= (hm != wref) | (hp != wref) | ((he != wref) & (lane < 4));
-                shapes |= (cm > 24u) | (cp > 24u) | (ce > 24u);
-                halo_store(yy, cm, cp, ce, co);
-            };
-
             // The 34 layers are cut into 102 units (layer, third); warp w takes units w, w+NW, ... and streams them through
             // its private ring, two units (6 warp copies + halo) ahead of their use.
             constexpr int N_UNITS = 34 * 3;
@@ -450,9 +523,9 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                 }
                 cp_async_commit();
             };
-            // one unit: PART is a compile-time third so the row-validity tests fold away for the first two
-            auto process = [&](int yy, const uint8_t *src, auto part_tag) {
-                constexpr int PART = decltype(part_tag)::value;
+            // one unit (PART = which third of the layer). One copy of this code per kernel: the unit loop below is not unrolled --
+            // unrolled six ways the kernel outgrew the instruction cache (a third of all stall cycles were instruction fetches).
+            auto process = [&](int yy, const uint8_t *src, const int PART) {
                 uint4 v[3];
 #pragma unroll
                 for (int jj = 0; jj < 3; jj++) v[jj] = *reinterpret_cast<const uint4 *>(src + jj * 512 + lane * 16);
@@ -478,27 +551,31 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                 if (__all_sync(FULL, d == 0u) && same_x0) {
                     if (x0 != last_d) {
                         last_d = x0;
-                        last_c = classify(x0, s, p.reg, err);
+                        last_c = cls_of(x0, s, p.reg, err);
                     }
                     mixed |= (x0 != wref);
                     shapes |= (last_c > 24u);
                     const uint32_t b = last_c * 0x01010101u, rowmask = last_c ? 0xFFFFFFFFu : 0u;
-                    uint8_t *cl = &s.cls[yy * PLANE + (12 * PART + zsub) * ROWB + XOFF + q * 4];
                     uint32_t *so = &s.solid[yy * 34 + 12 * PART + zsub];
-                    *reinterpret_cast<uint32_t *>(cl) = b;
-                    *reinterpret_cast<uint32_t *>(cl + 4 * ROWB) = b;
-                    if (last_valid) *reinterpret_cast<uint32_t *>(cl + 8 * ROWB) = b;
+                    if (!LEAN) {
+                        uint8_t *cl = &s.cls[yy * PLANE + (12 * PART + zsub) * ROWB + XOFF + q * 4];
+                        *reinterpret_cast<uint32_t *>(cl) = b;
+                        *reinterpret_cast<uint32_t *>(cl + 4 * ROWB) = b;
+                        if (last_valid) *reinterpret_cast<uint32_t *>(cl + 8 * ROWB) = b;
+                    }
                     if (q == 0) {
                         so[0] = rowmask;
                         so[4] = rowmask;
                         if (last_valid) so[8] = rowmask;
                     }
-                    if (PART == 0) halo_store(yy, last_c, last_c, last_c, last_c);
+                    if (PART == 0) halo_store<LEAN>(s, lane, yy, last_c, last_c, last_c, last_c);
                     return;
                 }
-                if (PART == 0) halo_general(yy, hm, hp, he);
-#pragma unroll
-                for (int jj = 0; jj < 3; jj++) do_group(yy, 3 * PART + jj, v[jj]);
+                mixed = 1;
+                const uint32_t fl = CALL_SLOW ? classify_unit_call<LEAN>(s, p.reg.kind, p.reg.n, yy, PART, v[0], v[1], v[2], hm, hp, he)
+                                              : classify_unit_body<LEAN>(s, p.reg.kind, p.reg.n, yy, PART, v[0], v[1], v[2], hm, hp, he);
+                shapes |= fl & 1u;
+                err |= fl >> 1;
             };
             // Unit schedule. The 32 layers that belong to the chunk's own y range (yy = 1..32, neighbours all at ry = 1) are
             // dealt 4 per warp: their addresses are per-chunk constant pointers + by*stride. The two outer layers (yy = 0, 33:
@@ -509,8 +586,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
             const uint32_t *const Xp = p.xface + (size_t)s.nbr[2 + 3 + 9] * 2048 + lane;                     // x+ neighbour, its x=0 plane
             const uint32_t *const Xc = p.xface + (size_t)s.nbr[((lane & 1) ? 2 : 0) + 3 * ((lane & 2) ? 2 : 0) + 9] * 2048 +
                                        ((lane & 1) ? 0 : 1024) + ((lane & 2) ? 0 : 31); // corner rows (lanes 0..3)
-            auto issue_inner = [&](int by, int slot_, auto part_tag) {
-                constexpr int PART = decltype(part_tag)::value;
+            auto issue_inner = [&](int by, int slot_, const int PART) {
                 uint8_t *dst = ring + slot_ * RSLOT_BYTES + lane * 16;
                 const uint32_t *rowbase = center_q + by * 1024 + (12 * PART + zsub - 1) * 32; // row of copy 0 (zz - 1)
                 if (PART == 0) {
@@ -533,47 +609,36 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                 }
                 cp_async_commit();
             };
-            const std::integral_constant<int, 0> P0;
-            const std::integral_constant<int, 1> P1;
-            const std::integral_constant<int, 2> P2;
             const int tail_g = warp < 6 ? (warp < 3 ? 0 : 33) * 3 + warp % 3 : N_UNITS; // N_UNITS = none (empty commit)
-            // The warp's 12 inner units u = 3 li + part (and then its outer unit, u = 12) go through slot u & 3, three units
-            // ahead of their use.
-            issue_inner(warp, 0, P0);
-            issue_inner(warp, 1, P1);
-            issue_inner(warp, 2, P2);
+            // The warp's 12 inner units u = 3 li + part (and then its outer unit, u = 12) go through slot u % RSLOTS, RSLOTS - 1
+            // units ahead of their use.
+            constexpr int DIST = RSLOTS - 1;
+            auto issue_unit = [&](int v, const int part) { // v: unit index, part = v % 3 (known at compile time at every call)
+                const int li2 = v / 3;
+                if (li2 < 4) issue_inner(warp + NW * li2, v % RSLOTS, part);
+                else if (v == 12) issue(tail_g, v % RSLOTS); // this warp's outer-layer unit
+                else cp_async_commit();
+            };
+#pragma unroll
+            for (int v = 0; v < DIST; v++) issue_unit(v, v % 3);
+#pragma unroll 1
             for (int li = 0; li < 4; li++) {
-                const int by = warp + NW * li; // layer yy = by + 1
-                const int u0 = 3 * li;
-                // unit (li, 0); meanwhile fetch (li + 1, 0) -- or this warp's outer-layer unit
-                __syncwarp();
-                if (li < 3) issue_inner(by + NW, (u0 + 3) & 3, P0);
-                else issue(tail_g, 0);
-                cp_async_wait<3>();
-                __syncwarp();
-                process(by + 1, ring + (u0 & 3) * RSLOT_BYTES, P0);
-                // unit (li, 1); fetch (li + 1, 1)
-                __syncwarp();
-                if (li < 3) issue_inner(by + NW, (u0 + 4) & 3, P1);
-                else cp_async_commit();
-                cp_async_wait<3>();
-                __syncwarp();
-                process(by + 1, ring + ((u0 + 1) & 3) * RSLOT_BYTES, P1);
-                // unit (li, 2); fetch (li + 1, 2)
-                __syncwarp();
-                if (li < 3) issue_inner(by + NW, (u0 + 5) & 3, P2);
-                else cp_async_commit();
-                cp_async_wait<3>();
-                __syncwarp();
-                process(by + 1, ring + ((u0 + 2) & 3) * RSLOT_BYTES, P2);
+                // the three thirds of a layer are unrolled (their row-validity tests fold away), the layers are not
+#pragma unroll
+                for (int part = 0; part < 3; part++) {
+                    const int u = 3 * li + part;
+                    __syncwarp();
+                    issue_unit(u + DIST, (part + DIST) % 3);
+                    cp_async_wait<DIST>();
+                    __syncwarp();
+                    process(warp + NW * li + 1, ring + (u % RSLOTS) * RSLOT_BYTES, part);
+                }
             }
             if (tail_g < N_UNITS) {
                 cp_async_wait<0>();
                 __syncwarp();
-                const int yy = tail_g / 3, part = tail_g - yy * 3;
-                if (part == 0) process(yy, ring, P0);
-                else if (part == 1) process(yy, ring, P1);
-                else process(yy, ring, P2);
+                const int yy = tail_g / 3;
+                process(yy, ring, tail_g - yy * 3);
             }
             cp_async_wait<0>();
             if (lane == 0) s.wref[warp] = wref;
@@ -600,6 +665,15 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
             has_shapes |= (int)(s.wflags[k] & 1u);
             any_mixed |= (int)(s.wflags[k] >> 1) | (int)(s.wref[k] != s.wref[0]); // did all warps see the same single datum?
         }
+        if (LEAN && has_shapes) {
+            // not a cubes-and-void neighbourhood: the general kernel meshes this chunk (second launch over the fallback list)
+            if (tid == 0) {
+                const uint32_t k = atomicAdd(p.fallback_count, 1u);
+                p.fallback_work[k] = c0;
+                p.fallback_span[k] = span_slot;
+            }
+            continue;
+        }
         if (!has_shapes && !any_mixed) {
             // The whole 34^3 neighbourhood is one datum and it is void or a cube: every side is either absent or
             // clipped by an identical neighbour (voxmesh.rs:100,119) -> empty mesh, nothing to count or emit.
@@ -614,14 +688,14 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
         }
 
         // ---------------- phase B: per-row counts (packed V | I<<10 | F<<21 into rowV) ----------------
-        if (!has_shapes) {
+        if (LEAN || !has_shapes) {
             for (int row = tid; row < 1024; row += NT) {
                 unsigned long long vw[6];
                 row_visibility(s, row >> 5, row & 31, vw);
                 const uint32_t nf = __popcll(vw[0]) + __popcll(vw[1]) + __popcll(vw[2]) + __popcll(vw[3]) + __popcll(vw[4]) + __popcll(vw[5]);
                 s.sc.rowV[row] = (nf * 4u) | ((nf * 6u) << 10) | (nf << 21);
             }
-        } else {
+        } else if (!LEAN) {
             for (int row = warp; row < 1024; row += NW) {
                 const int y = row >> 5, z = row & 31;
                 const int at = (y + 1) * PLANE + (z + 1) * ROWB + XOFF + lane;
@@ -738,7 +812,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
         // ---------------- phase C: the chunk's face records, in emission order, tile by tile ----------------
         const uint32_t *center = p.blocks + (size_t)s.nbr[13] * kChunkVoxels;
         const unsigned long long fbase = s.fbase;
-        const bool quads_only = !has_shapes; // every side has 4 vertices / 6 indices
+        const bool quads_only = LEAN || !has_shapes; // every side has 4 vertices / 6 indices
         for (uint32_t r0 = 0; r0 < 1024;) {
             PHASE_MARK(t_t0);
             // largest r1 with faces(r0..r1) <= FC and vertices(r0..r1) <= VC (a single row never exceeds 192 / 768). The test is
@@ -784,7 +858,7 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                         }
                     }
                 }
-            } else {
+            } else if constexpr (!LEAN) {
                 for (uint32_t row = r0 + warp; row < r1; row += NW) {
                     if (s.sc.rowF[row + 1] - s.sc.rowF[row] == 0) continue;
                     const int at = ((row >> 5) + 1) * PLANE + ((row & 31) + 1) * ROWB + XOFF + lane;
@@ -829,13 +903,19 @@ __global__ void __launch_bounds__(NT, 2) mesh_kernel(MeshParams p) {
                 const uint32_t a = s.sc.frecA[f];
                 const uint32_t row = a & 1023u, x = (a >> 10) & 31u;
                 const uint32_t y = row >> 5, z = row & 31u;
-                uint32_t id, cx, nb, is;
+                uint32_t id = 0, cx = 0, nb = 0, is = 0;
                 if (quads_only) {
-                    cx = s.cls[(y + 1) * PLANE + (z + 1) * ROWB + XOFF + (int)x];
-                    id = __ldg(center + row * 32 + x) >> 16; // an L2 hit: phase A just streamed the chunk
+                    const uint32_t datum = __ldg(center + row * 32 + x); // an L2 hit: phase A just streamed the chunk
+                    id = datum >> 16;
+                    if (LEAN) { // no class table: a cube's class is 1 + its orientation
+                        uint32_t e2 = 0;
+                        cx = classify(datum, s, p.reg, e2);
+                    } else {
+                        cx = s.cls[(y + 1) * PLANE + (z + 1) * ROWB + XOFF + (int)x];
+                    }
                     nb = neighbourhood27(s, (int)y, (int)z, (int)x);
                     is = f * 6u;
-                } else { // recorded by C1
+                } else if constexpr (!LEAN) { // recorded by C1
                     const uint32_t icr = s.sc.frecC[f];
                     id = icr & 0xFFFFu;
                     cx = icr >> 16;
@@ -909,23 +989,32 @@ void launch_hmap_candidates(const CandidateParams &p, cudaStream_t stream) {
 }
 
 // two CTAs per SM: 228 KB of shared memory per SM, 1 KB reserved per CTA
-static_assert(sizeof(Smem) <= 113 * 1024 - 512, "mesh_kernel's shared memory no longer fits twice on an SM");
+static_assert(sizeof(SmemT<false>) <= 113 * 1024 - 512, "mesh_kernel's shared memory no longer fits twice on an SM");
+static_assert(sizeof(SmemT<true>) <= 44 * 1024, "the cubes-only mesh_kernel's shared memory no longer fits five times on an SM");
 
 int mesh_kernel_max_ctas_per_sm() {
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mesh_kernel, NT, sizeof(Smem));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mesh_kernel<false, false>, NT, sizeof(SmemT<false>));
     return n;
 }
 
-void launch_mesh_kernel(const MeshParams &p, int sm_count, cudaStream_t stream) {
+template <bool LEAN, bool CALL_SLOW>
+static void launch_mesh_kernel_t(const MeshParams &p, int sm_count, cudaStream_t stream) {
     // per device (a process may own contexts on several GPUs); cheap enough to repeat on every launch
-    cudaFuncSetAttribute(mesh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-    int per_sm = mesh_kernel_max_ctas_per_sm();
+    cudaFuncSetAttribute(mesh_kernel<LEAN, CALL_SLOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemT<LEAN>));
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mesh_kernel<LEAN, CALL_SLOW>, NT, sizeof(SmemT<LEAN>));
     if (per_sm < 1) per_sm = 1;
     unsigned grid = (unsigned)(sm_count * per_sm);
     if (grid > p.n_work) grid = p.n_work;
     if (grid == 0) return;
-    mesh_kernel<<<grid, NT, sizeof(Smem), stream>>>(p);
+    mesh_kernel<LEAN, CALL_SLOW><<<grid, NT, sizeof(SmemT<LEAN>), stream>>>(p);
+}
+
+void launch_mesh_kernel(const MeshParams &p, int sm_count, cudaStream_t stream, bool lean, bool mostly_uniform) {
+    if (!lean) launch_mesh_kernel_t<false, false>(p, sm_count, stream);
+    else if (mostly_uniform) launch_mesh_kernel_t<true, false>(p, sm_count, stream);
+    else launch_mesh_kernel_t<true, true>(p, sm_count, stream);
 }
 
 } // namespace bxw

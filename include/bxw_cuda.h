@@ -86,8 +86,11 @@ int bxw_set_stream(bxw_ctx *ctx, void *cuda_stream);
  * BXW_OPT_ELIDE_UNIFORM (default 1): chunks the generator proves uniform (all void above the terrain, all stone below it)
  * are not written voxel by voxel: their entry of the region's page table points at a shared single-datum page (the device
  * analogue of the reference's 3-word VChunk, bxw_world/src/lib.rs:263-294); the first writer (edit, upload, import, halo
- * import that differs) gives the chunk its own storage back. 0 = every chunk materialised. Same results either way. */
-enum { BXW_OPT_CHUNK_SUMMARIES = 0, BXW_OPT_MESH_FROM_HEIGHT_MAP = 1, BXW_OPT_ELIDE_UNIFORM = 2 };
+ * import that differs) gives the chunk its own storage back. 0 = every chunk materialised. Same results either way.
+ * BXW_OPT_CUBES_ONLY_MESHER (default 1): regions holding generator output (plus edits) are meshed by the cubes-and-void
+ * instantiation of the mesher (no class table, twice the occupancy); chunks with other shapes fall back to the general
+ * kernel. 0 = general kernel only. Same results either way. */
+enum { BXW_OPT_CHUNK_SUMMARIES = 0, BXW_OPT_MESH_FROM_HEIGHT_MAP = 1, BXW_OPT_ELIDE_UNIFORM = 2, BXW_OPT_CUBES_ONLY_MESHER = 3 };
 int bxw_set_option(bxw_ctx *ctx, int option, int value);
 int bxw_synchronize(bxw_ctx *ctx);
 /* Number of this library's kernels launched since creation (bench.py's gpu_launches evidence). */
