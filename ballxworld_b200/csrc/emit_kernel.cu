@@ -245,7 +245,9 @@ __global__ void __launch_bounds__(ENT, 4) emit_kernel(MeshParams p) {
         const uint32_t nvt = vqe - vq0;
         for (uint32_t tb = 0; tb < nvt;) {
             const uint32_t mis = ((vq0 + tb) & 1u) * 2u;
-            const uint32_t cnt = min(nvt - tb, 32u - (mis >> 1));
+            // passes end on multiples of 16 vertices of the chunk's span (which starts on a 128-byte line): every piece but the
+            // first and last of a batch is then ten whole lines
+            const uint32_t cnt = min(nvt - tb, 32u - ((vq0 + tb) & 15u));
             uint32_t *const buf = stw + (npass & 1u) * STGW;
             uint2 *const st2 = reinterpret_cast<uint2 *>(buf);
             npass++;

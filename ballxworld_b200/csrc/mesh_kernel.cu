@@ -759,7 +759,9 @@ __global__ void __launch_bounds__(NT, LEAN ? 4 : 2) mesh_kernel(MeshParams p) {
                 s.sc.rowV[1024] = bv + tv;
                 s.sc.rowI[1024] = bi + ti;
                 s.sc.rowF[1024] = bf + tf;
-                const unsigned long long padV = (TV + 3ull) & ~3ull, padI = (TI + 7ull) & ~7ull;
+                // spans start on multiples of 16 vertices (640 B: emit_kernel's 32-vertex pieces are then whole 128-byte lines) and
+                // 8 indices
+                const unsigned long long padV = (TV + 15ull) & ~15ull, padI = (TI + 7ull) & ~7ull;
                 const unsigned long long padF = ((unsigned long long)(bf + tf) + 31ull) & ~31ull; // emit_kernel: a warp never straddles chunks
                 unsigned long long vb = 0, ib = 0, fb = 0;
                 int emit = 0;
@@ -776,7 +778,7 @@ __global__ void __launch_bounds__(NT, LEAN ? 4 : 2) mesh_kernel(MeshParams p) {
                         }
                     } else {
                         // re-meshes reserve some slack so that the next edit of the chunk can stay in place
-                        const unsigned long long capV = p.reuse ? ((TV + TV / 8ull + 16ull + 3ull) & ~3ull) : padV;
+                        const unsigned long long capV = p.reuse ? ((TV + TV / 8ull + 16ull + 15ull) & ~15ull) : padV;
                         const unsigned long long capI = p.reuse ? ((TI + TI / 8ull + 24ull + 7ull) & ~7ull) : padI;
                         release_span(p, span_slot);
                         vb = atomicAdd(&p.counters->v_alloc, capV);
