@@ -4,7 +4,7 @@ Host-side mirror of the reference's generator / mesher / chunk-handler interface
 csrc/libbxw_cuda.so (include/bxw_cuda.h). There is no CPU fallback: importing the bindings without the built
 CUDA library raises, and every compute call runs sm_100a kernels.
 """
-from .capi import BxwError, Context, VERTEX_DTYPE, SPAN_DTYPE, CHANGE_DTYPE, library_path  # noqa: F401
+from .capi import ANCHOR_DTYPE, DELTA_DTYPE, BxwError, Context, VERTEX_DTYPE, SPAN_DTYPE, CHANGE_DTYPE, library_path  # noqa: F401
 from .world import (  # noqa: F401
     CHUNK_DIM,
     CHUNK_DIM3,

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libbxw_cuda.so")
-SOURCES = ["bxw_api.cu", "mesh_kernel.cu", "emit_kernel.cu", "gen_kernel.cu", "aux_kernels.cu", "tables.cpp"]
+SOURCES = ["bxw_api.cu", "mesh_kernel.cu", "emit_kernel.cu", "gen_kernel.cu", "aux_kernels.cu", "sched_kernels.cu", "tables.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-cudart", "static", "--fmad=false",

@@ -18,7 +18,10 @@ VERTEX_DTYPE = np.dtype(
 )
 SPAN_DTYPE = np.dtype([("v_off", "<u8"), ("i_off", "<u8"), ("v_count", "<u4"), ("i_count", "<u4")])
 CHANGE_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("z", "<i4"), ("from", "<u4"), ("to", "<u4")])
+ANCHOR_DTYPE = np.dtype([("cx", "<i4"), ("cy", "<i4"), ("cz", "<i4"), ("radius", "<u4"), ("load_mesh", "<u4")])
+DELTA_DTYPE = np.dtype([("cx", "<i4"), ("cy", "<i4"), ("cz", "<i4"), ("kinds", "<u4"), ("unload", "<u4"), ("min_anchor_distance", "<i4")])
 assert VERTEX_DTYPE.itemsize == 40 and SPAN_DTYPE.itemsize == 24 and CHANGE_DTYPE.itemsize == 20
+assert ANCHOR_DTYPE.itemsize == 20 and DELTA_DTYPE.itemsize == 24
 
 ERROR_NAMES = {
     -1: "BXW_E_INVALID",
@@ -91,6 +94,7 @@ def load_library():
         "bxw_region_create": ([vp, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32], C.c_int),
         "bxw_region_destroy": ([vp], C.c_int),
         "bxw_region_generate": ([vp, C.c_uint64, C.c_int], C.c_int),
+        "bxw_region_generate_part": ([vp, C.c_uint64, C.c_int, C.c_int], C.c_int),
         "bxw_region_heightmap": ([vp, vp, vp, vp], C.c_int),
         "bxw_region_upload_chunk": ([vp, C.c_int32, C.c_int32, C.c_int32, vp], C.c_int),
         "bxw_region_download_chunk": ([vp, C.c_int32, C.c_int32, C.c_int32, vp], C.c_int),
@@ -108,6 +112,11 @@ def load_library():
         "bxw_region_fetch_wait": ([vp], C.c_int),
         "bxw_region_apply_changes": ([vp, vp, C.c_uint32, u32p], C.c_int),
         "bxw_region_remesh_dirty": ([vp, u32p], C.c_int),
+        "bxw_region_unload_all": ([vp], C.c_int),
+        "bxw_region_update_anchors": ([vp, vp, C.c_uint32, u32p, u32p], C.c_int),
+        "bxw_region_load_deltas": ([vp, vp, C.c_uint32, u32p], C.c_int),
+        "bxw_region_apply_deltas": ([vp, C.c_uint64, C.c_int, C.c_uint32, u32p], C.c_int),
+        "bxw_region_load_state": ([vp, vp, vp], C.c_int),
         "bxw_region_arena_extent": ([vp, u64p, u64p], C.c_int),
         "bxw_region_arena_stats": ([vp, C.POINTER(ArenaStats)], C.c_int),
         "bxw_region_compact_arena": ([vp, u64p, u64p], C.c_int),
@@ -287,6 +296,9 @@ class Context:
     def region_generate(self, seed, precision=64):
         self._ck(self.L.bxw_region_generate(self.h, seed, precision))
 
+    def region_generate_part(self, seed, precision, part):
+        self._ck(self.L.bxw_region_generate_part(self.h, seed, precision, part))
+
     def region_heightmap(self, raw=False):
         nx, ny, nz = self.region_dims
         W, D = (nx + 2) * 32, (nz + 2) * 32
@@ -382,6 +394,39 @@ class Context:
         n = C.c_uint32()
         self._ck(self.L.bxw_region_remesh_dirty(self.h, C.byref(n)))
         return n.value
+
+    # ---- load anchors (World::recalculate_load_deltas / main_loop_tick on the device) ----
+    def region_unload_all(self):
+        self._ck(self.L.bxw_region_unload_all(self.h))
+
+    def region_update_anchors(self, anchors):
+        """anchors: sequence of (cx, cy, cz, radius, load_mesh) -> (n_unload, n_load)"""
+        a = np.array([tuple(x) for x in anchors], dtype=ANCHOR_DTYPE) if not isinstance(anchors, np.ndarray) else np.ascontiguousarray(anchors, dtype=ANCHOR_DTYPE)
+        nu, nl = C.c_uint32(), C.c_uint32()
+        self._ck(self.L.bxw_region_update_anchors(self.h, _ptr(a) if a.size else None, a.size, C.byref(nu), C.byref(nl)))
+        return nu.value, nl.value
+
+    def region_load_deltas(self, cap=None):
+        n = C.c_uint32()
+        self._ck(self.L.bxw_region_load_deltas(self.h, None, 0, C.byref(n)))
+        m = n.value if cap is None else min(cap, n.value)
+        out = np.zeros(m, dtype=DELTA_DTYPE)
+        if m:
+            self._ck(self.L.bxw_region_load_deltas(self.h, _ptr(out), m, C.byref(n)))
+        return out
+
+    def region_apply_deltas(self, seed=0, precision=64, max_deltas=0):
+        """-> dict(consumed, generated, meshed, unmeshed)"""
+        st = (C.c_uint32 * 4)()
+        self._ck(self.L.bxw_region_apply_deltas(self.h, seed, precision, max_deltas, st))
+        return dict(consumed=st[0], generated=st[1], meshed=st[2], unmeshed=st[3])
+
+    def region_load_state(self):
+        nx, ny, nz = self.region_dims
+        b = np.empty((nx + 2) * (ny + 2) * (nz + 2), dtype=np.uint8)
+        m = np.empty(nx * ny * nz, dtype=np.uint8)
+        self._ck(self.L.bxw_region_load_state(self.h, _ptr(b), _ptr(m)))
+        return b, m
 
     def region_arena_extent(self):
         v, i = C.c_uint64(), C.c_uint64()

@@ -478,9 +478,10 @@ void launch_rle_compress(const uint32_t *dense, const uint32_t *ids, const uint3
 // Copy n decoded chunks into region storage at chunk indices ids[], refresh their x-face planes and mark every interior
 // chunk within one chunk of them dirty (their meshes read the new voxels).
 __global__ void chunk_scatter_kernel(const uint32_t *src, const uint32_t *ids, uint32_t *blocks, uint32_t *xface,
-                                     unsigned long long *summary, uint32_t *page, int SX, int SY, int SZ, uint8_t *dirty) {
+                                     unsigned long long *summary, uint32_t *page, uint8_t *blk_loaded, int SX, int SY, int SZ, uint8_t *dirty) {
     const size_t k = blockIdx.x;
     const size_t c = ids[k];
+    if (blk_loaded && threadIdx.x == 0) blk_loaded[c] = 1;
     if (summary && threadIdx.x == 0) summary[c] = 0; // no longer known uniform
     if (page && threadIdx.x == 0) page[c] = (uint32_t)c; // every voxel is overwritten below: materialised
     const uint4 *s = reinterpret_cast<const uint4 *>(src + k * kChunkVoxels);
@@ -500,8 +501,9 @@ __global__ void chunk_scatter_kernel(const uint32_t *src, const uint32_t *ids, u
 }
 
 void launch_chunk_scatter(const uint32_t *src, const uint32_t *ids, size_t n, uint32_t *blocks, uint32_t *xface,
-                          unsigned long long *summary, uint32_t *page, int SX, int SY, int SZ, uint8_t *dirty, cudaStream_t stream) {
-    if (n) chunk_scatter_kernel<<<(unsigned)n, 256, 0, stream>>>(src, ids, blocks, xface, summary, page, SX, SY, SZ, dirty);
+                          unsigned long long *summary, uint32_t *page, uint8_t *blk_loaded, int SX, int SY, int SZ, uint8_t *dirty,
+                          cudaStream_t stream) {
+    if (n) chunk_scatter_kernel<<<(unsigned)n, 256, 0, stream>>>(src, ids, blocks, xface, summary, page, blk_loaded, SX, SY, SZ, dirty);
 }
 
 // page[c] = c for c in [0, n): every chunk lives in its own storage

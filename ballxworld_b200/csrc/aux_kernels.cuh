@@ -32,7 +32,8 @@ void launch_dirty_list(uint8_t *dirty, uint32_t n, int nx, int nz, int SX, int S
 void launch_rle_compress(const uint32_t *dense, const uint32_t *ids, const uint32_t *page, size_t n_chunks, uint32_t *len, uint64_t *offsets,
                          uint32_t *out_words, int phase, cudaStream_t stream);
 void launch_chunk_scatter(const uint32_t *src, const uint32_t *ids, size_t n, uint32_t *blocks, uint32_t *xface,
-                          unsigned long long *summary, uint32_t *page, int SX, int SY, int SZ, uint8_t *dirty, cudaStream_t stream);
+                          unsigned long long *summary, uint32_t *page, uint8_t *blk_loaded, int SX, int SY, int SZ, uint8_t *dirty,
+                          cudaStream_t stream);
 void launch_rle_decompress(const uint32_t *words, const uint64_t *offsets, size_t n_chunks, uint32_t *out_dense, uint32_t *status,
                            cudaStream_t stream);
 

@@ -12,6 +12,7 @@
 #include <algorithm>
 
 #include "aux_kernels.cuh"
+#include "sched_kernels.cuh"
 #include "device_common.cuh"
 
 using namespace bxw;
@@ -61,8 +62,17 @@ struct Region {
     // only (cubes, the odd edited shape), 2 = bulk content of unknown shapes (synthetic fill, uploads, imports)
     uint32_t *fb_work = nullptr, *fb_span = nullptr, *fb_count = nullptr;
     int shape_hint = 0;
+    // load-anchor scheduler (sched_kernels.cu)
+    uint8_t *blk_loaded = nullptr, *mesh_loaded = nullptr, *sched_code = nullptr;
+    uint32_t *sched_key = nullptr, *sched_hist = nullptr, *sched_totals = nullptr, *sched_order = nullptr;
+    uint32_t *sched_gen = nullptr, *sched_mesh = nullptr, *sched_mesh_span = nullptr, *sched_unmesh = nullptr, *sched_counts = nullptr;
+    bxw_chunk_delta *sched_deltas = nullptr;
+    bxw_load_anchor *sched_anchors = nullptr;
+    uint32_t sched_anchor_cap = 0, sched_bins = 0, sched_n_unload = 0, sched_n_load = 0;
     uint64_t gen_seed = 0;                 // seed / precision of the last generate (bxw_region_heightmap's raw output)
     int gen_precision = 64;
+    bool part1_pending = false;            // bxw_region_generate_part(1) done, part 2 outstanding
+    GenParams part1_gp;
     size_t n_storage() const { return (size_t)SX * SY * SZ; }
 };
 constexpr uint32_t kSharedPages = 2;
@@ -214,6 +224,20 @@ void region_free(Region &r) {
     cudaFree(r.summary);
     cudaFree(r.cand_keep);
     cudaFree(r.cand_blk);
+    cudaFree(r.blk_loaded);
+    cudaFree(r.mesh_loaded);
+    cudaFree(r.sched_code);
+    cudaFree(r.sched_key);
+    cudaFree(r.sched_hist);
+    cudaFree(r.sched_totals);
+    cudaFree(r.sched_order);
+    cudaFree(r.sched_gen);
+    cudaFree(r.sched_mesh);
+    cudaFree(r.sched_mesh_span);
+    cudaFree(r.sched_unmesh);
+    cudaFree(r.sched_counts);
+    cudaFree(r.sched_deltas);
+    cudaFree(r.sched_anchors);
     cudaFree(r.page);
     cudaFree(r.fb_work);
     cudaFree(r.fb_span);
@@ -247,6 +271,10 @@ int region_alloc(bxw_ctx *ctx, Region &r, int32_t cx0, int32_t cy0, int32_t cz0,
     CK(cudaMalloc(&r.xface, (nst + kSharedPages) * 2048 * sizeof(uint32_t)));
     CK(cudaMalloc(&r.page, nst * sizeof(uint32_t)));
     launch_page_identity(r.page, (uint32_t)nst, ctx->stream);
+    CK(cudaMalloc(&r.blk_loaded, nst));
+    CK(cudaMalloc(&r.mesh_loaded, r.n_work));
+    CK(cudaMemsetAsync(r.blk_loaded, 0, nst, ctx->stream));
+    CK(cudaMemsetAsync(r.mesh_loaded, 0, r.n_work, ctx->stream));
     CK(cudaMalloc(&r.fb_work, r.n_work * sizeof(uint32_t)));
     CK(cudaMalloc(&r.fb_span, r.n_work * sizeof(uint32_t)));
     CK(cudaMalloc(&r.fb_count, sizeof(uint32_t)));
@@ -365,6 +393,7 @@ void fill_params(bxw_ctx *ctx, Region &r, bool elide, FillParams &fp) {
     fp.page_stone = (uint32_t)r.n_storage() + 1u;
     fp.list = nullptr;
     fp.n_list = 0;
+    fp.col_mode = 0;
 }
 
 // the two shared single-datum pages behind the storage hold the void / stone datum of the current generator ids
@@ -397,38 +426,56 @@ int ensure_shared_pages(bxw_ctx *ctx, Region &r) {
     return BXW_OK;
 }
 
-int region_generate(bxw_ctx *ctx, Region &r, uint64_t seed, int precision, bool elide) {
+// part: 0 = the whole box; 1 = only the two interior boundary chunk columns along x (what a slab-boundary halo export reads),
+// 2 = all the other columns (after a part-1 call with the same arguments): a multi-GPU step exports and sends the boundary
+// planes while part 2 is still running.
+int region_generate(bxw_ctx *ctx, Region &r, uint64_t seed, int precision, bool elide, int part = 0) {
     CK(cudaSetDevice(ctx->device));
-    {
+    if (part != 2) {
         int rc0 = flush_gen_timing(ctx);
         if (rc0) return rc0;
     }
     if (!ctx->have_gen_ids) return fail(ctx, BXW_E_NO_REGISTRY, "bxw_set_gen_ids not called");
     GenParams gp;
-    int rc = gen_setup(ctx, r, seed, precision, gp);
-    if (rc) return rc;
-    if (elide) {
+    int rc = BXW_OK;
+    if (part == 2) {
+        if (!r.part1_pending || r.gen_seed != seed || r.gen_precision != precision)
+            return fail(ctx, BXW_E_INVALID, "generate part 2 needs a preceding part 1 with the same seed and precision");
+        gp = r.part1_gp;
+    } else {
+        rc = gen_setup(ctx, r, seed, precision, gp);
+        if (rc) return rc;
+    }
+    if (elide && part != 2) {
         rc = ensure_shared_pages(ctx, r);
         if (rc) return rc;
     }
     // the fill kernel computes the column parameters of its 32x32 columns itself (FP64 phase of some CTAs overlaps the
     // store phase of others) and writes them to the height map
-    CK(cudaEventRecord(ctx->ev_g0, ctx->stream));
-    CK(cudaEventRecord(ctx->ev_g1, ctx->stream));
+    if (part != 2) {
+        CK(cudaEventRecord(ctx->ev_g0, ctx->stream));
+        CK(cudaEventRecord(ctx->ev_g1, ctx->stream));
+    }
     FillParams fp;
     fill_params(ctx, r, elide, fp);
+    fp.col_mode = part;
     for (int i = 0; i < 5; i++) r.fill_ids[i] = ctx->gen_ids[i];
     launch_gen_fill_kernel(fp, gp, precision, ctx->stream);
-    CK(cudaEventRecord(ctx->ev_g2, ctx->stream));
-    ctx->gen_pending = true;
-    ctx->gen_pending_fused = true;
+    if (part != 1) { // the fill timer covers part 1 + part 2 (and whatever ran between them on this stream)
+        CK(cudaEventRecord(ctx->ev_g2, ctx->stream));
+        ctx->gen_pending = true;
+        ctx->gen_pending_fused = true;
+    }
     launch_fill_xface_kernel(fp, ctx->stream);
     ctx->launches += 2;
     CK(cudaGetLastError());
-    r.have_hmap = true;
+    if (part != 1 && r.blk_loaded) CK(cudaMemsetAsync(r.blk_loaded, 1, r.n_storage(), ctx->stream)); // every chunk now holds block data
+    r.have_hmap = part != 1;
     r.shape_hint = 0;
     r.gen_seed = seed;
     r.gen_precision = precision;
+    r.part1_pending = part == 1;
+    r.part1_gp = gp;
     return BXW_OK;
 }
 
@@ -1043,6 +1090,12 @@ int bxw_region_generate(bxw_ctx *ctx, uint64_t seed, int precision) {
     return region_generate(ctx, ctx->region, seed, precision, ctx->elide_uniform);
 }
 
+int bxw_region_generate_part(bxw_ctx *ctx, uint64_t seed, int precision, int part) {
+    if (!ctx || !ctx->region.live) return fail(ctx, BXW_E_INVALID, "no region");
+    if (part != 1 && part != 2) return fail(ctx, BXW_E_INVALID, "part must be 1 (slab-boundary columns) or 2 (the rest)");
+    return region_generate(ctx, ctx->region, seed, precision, ctx->elide_uniform, part);
+}
+
 int bxw_region_heightmap(bxw_ctx *ctx, int32_t *height, uint8_t *elevation, double *raw_height) {
     if (!ctx || !ctx->region.live || !ctx->region.have_hmap) return fail(ctx, BXW_E_INVALID, "no generated region");
     Region &r = ctx->region;
@@ -1079,6 +1132,7 @@ int bxw_region_upload_chunk(bxw_ctx *ctx, int32_t lx, int32_t ly, int32_t lz, co
     if (!local_ok(r, lx, ly, lz)) return fail(ctx, BXW_E_INVALID, "chunk (%d,%d,%d) outside region+shell", lx, ly, lz);
     const uint32_t cid = (uint32_t)storage_index(r, lx, ly, lz);
     CK(cudaMemcpyAsync(r.page + cid, &cid, sizeof cid, cudaMemcpyHostToDevice, ctx->stream)); // every voxel is overwritten: materialised
+    CK(cudaMemsetAsync(r.blk_loaded + cid, 1, 1, ctx->stream));
     CK(cudaMemcpyAsync(r.blocks + storage_index(r, lx, ly, lz) * kChunkVoxels, blocks_yzx, kChunkVoxels * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(r.summary + storage_index(r, lx, ly, lz), 0, sizeof(unsigned long long), ctx->stream)); // no longer known uniform
     launch_xface_extract(r.blocks, r.xface, nullptr, (uint32_t)storage_index(r, lx, ly, lz), 1, ctx->stream);
@@ -1159,7 +1213,7 @@ int bxw_region_import_rle(bxw_ctx *ctx, const int32_t *lpos, size_t n_chunks, co
     uint32_t *d_ids = nullptr;
     rc = upload_chunk_ids(ctx, r, lpos, n_chunks, meta_bytes, &d_ids);
     if (rc) return rc;
-    launch_chunk_scatter((const uint32_t *)ctx->io_c, d_ids, n_chunks, r.blocks, r.xface, r.summary, r.page, r.SX, r.SY, r.SZ, r.dirty, ctx->stream);
+    launch_chunk_scatter((const uint32_t *)ctx->io_c, d_ids, n_chunks, r.blocks, r.xface, r.summary, r.page, r.blk_loaded, r.SX, r.SY, r.SZ, r.dirty, ctx->stream);
     ctx->launches += 1;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1180,6 +1234,7 @@ int bxw_region_mesh(bxw_ctx *ctx, uint64_t *arena_vertices, uint64_t *arena_indi
     int rc = region_mesh(ctx, r, nullptr, nullptr, r.n_work, false); // implicit interior enumeration
     if (rc) return rc;
     CK(cudaMemsetAsync(r.dirty, 0, r.n_work, ctx->stream));
+    CK(cudaMemsetAsync(r.mesh_loaded, 1, r.n_work, ctx->stream));
     if (arena_vertices) *arena_vertices = r.h_counters->v_alloc;
     if (arena_indices) *arena_indices = r.h_counters->i_alloc;
     return BXW_OK;
@@ -1196,6 +1251,7 @@ int bxw_region_generate_and_mesh(bxw_ctx *ctx, uint64_t seed, int precision, uin
     rc = region_mesh(ctx, r, nullptr, nullptr, r.n_work, false, ctx->mesh_from_hmap);
     if (rc) return rc;
     CK(cudaMemsetAsync(r.dirty, 0, r.n_work, ctx->stream));
+    CK(cudaMemsetAsync(r.mesh_loaded, 1, r.n_work, ctx->stream));
     if (arena_vertices) *arena_vertices = r.h_counters->v_alloc;
     if (arena_indices) *arena_indices = r.h_counters->i_alloc;
     return BXW_OK;
@@ -1243,6 +1299,172 @@ int bxw_region_mesh_sphere(bxw_ctx *ctx, int32_t ax, int32_t ay, int32_t az, uin
     if (rc) return rc;
     if (arena_vertices) *arena_vertices = r.h_counters->v_alloc;
     if (arena_indices) *arena_indices = r.h_counters->i_alloc;
+    return BXW_OK;
+}
+
+static int sched_ensure(bxw_ctx *ctx, Region &r, uint32_t n_anchors) {
+    const size_t nst = r.n_storage();
+    if (!r.sched_code) {
+        // one histogram bin per squared distance inside the box (anchors far outside share the last bin)
+        const unsigned long long d2 = (unsigned long long)r.SX * r.SX + (unsigned long long)r.SY * r.SY + (unsigned long long)r.SZ * r.SZ + 2ull;
+        r.sched_bins = (uint32_t)std::min<unsigned long long>(d2, 1ull << 24);
+        CK(cudaMalloc(&r.sched_code, nst));
+        CK(cudaMalloc(&r.sched_key, nst * sizeof(uint32_t)));
+        CK(cudaMalloc(&r.sched_hist, 2ull * r.sched_bins * sizeof(uint32_t)));
+        CK(cudaMalloc(&r.sched_totals, 2 * sizeof(uint32_t)));
+        CK(cudaMalloc(&r.sched_order, nst * sizeof(uint32_t)));
+        CK(cudaMalloc(&r.sched_gen, nst * sizeof(uint32_t)));
+        CK(cudaMalloc(&r.sched_mesh, r.n_work * sizeof(uint32_t)));
+        CK(cudaMalloc(&r.sched_mesh_span, r.n_work * sizeof(uint32_t)));
+        CK(cudaMalloc(&r.sched_unmesh, r.n_work * sizeof(uint32_t)));
+        CK(cudaMalloc(&r.sched_counts, 4 * sizeof(uint32_t)));
+        CK(cudaMalloc(&r.sched_deltas, nst * sizeof(bxw_chunk_delta)));
+    }
+    if (n_anchors > r.sched_anchor_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(r.sched_anchors);
+        r.sched_anchors = nullptr;
+        r.sched_anchor_cap = 0;
+        CK(cudaMalloc(&r.sched_anchors, (size_t)n_anchors * sizeof(bxw_load_anchor)));
+        r.sched_anchor_cap = n_anchors;
+    }
+    return BXW_OK;
+}
+
+static SchedParams sched_params(Region &r, uint32_t n_anchors) {
+    SchedParams p;
+    p.SX = r.SX;
+    p.SY = r.SY;
+    p.SZ = r.SZ;
+    p.cx_min = r.cx0 - 1;
+    p.cy_min = r.cy0 - 1;
+    p.cz_min = r.cz0 - 1;
+    p.n_storage = (uint32_t)r.n_storage();
+    p.anchors = r.sched_anchors;
+    p.n_anchors = n_anchors;
+    p.blk_loaded = r.blk_loaded;
+    p.mesh_loaded = r.mesh_loaded;
+    p.code = r.sched_code;
+    p.key = r.sched_key;
+    p.hist = r.sched_hist;
+    p.n_bins = r.sched_bins;
+    p.totals = r.sched_totals;
+    p.deltas = r.sched_deltas;
+    p.order = r.sched_order;
+    p.gen_list = r.sched_gen;
+    p.mesh_list = r.sched_mesh;
+    p.mesh_span = r.sched_mesh_span;
+    p.unmesh_span = r.sched_unmesh;
+    p.list_counts = r.sched_counts;
+    return p;
+}
+
+int bxw_region_unload_all(bxw_ctx *ctx) {
+    if (!ctx || !ctx->region.live) return fail(ctx, BXW_E_INVALID, "no region");
+    Region &r = ctx->region;
+    CK(cudaMemsetAsync(r.blk_loaded, 0, r.n_storage(), ctx->stream));
+    CK(cudaMemsetAsync(r.mesh_loaded, 0, r.n_work, ctx->stream));
+    CK(cudaMemsetAsync(r.spans, 0, r.n_work * sizeof(bxw_mesh_span), ctx->stream));
+    CK(cudaMemsetAsync(r.span_cap, 0, r.n_work * sizeof(uint2), ctx->stream));
+    CK(cudaMemsetAsync(r.counters, 0, sizeof(MeshCounters), ctx->stream));
+    CK(cudaMemsetAsync(r.dirty, 0, r.n_work, ctx->stream));
+    r.sched_n_unload = r.sched_n_load = 0;
+    return BXW_OK;
+}
+
+int bxw_region_update_anchors(bxw_ctx *ctx, const bxw_load_anchor *anchors, uint32_t n_anchors, uint32_t *n_unload, uint32_t *n_load) {
+    if (!ctx || !ctx->region.live || (n_anchors && !anchors)) return fail(ctx, BXW_E_INVALID, "no region / null");
+    Region &r = ctx->region;
+    int rc = sched_ensure(ctx, r, n_anchors ? n_anchors : 1);
+    if (rc) return rc;
+    if (n_anchors) CK(cudaMemcpyAsync(r.sched_anchors, anchors, (size_t)n_anchors * sizeof(bxw_load_anchor), cudaMemcpyHostToDevice, ctx->stream));
+    launch_delta_build(sched_params(r, n_anchors), ctx->stream);
+    ctx->launches += 3;
+    CK(cudaGetLastError());
+    uint32_t tot[2] = {0, 0};
+    CK(cudaMemcpyAsync(tot, r.sched_totals, sizeof tot, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream)); // (also: `anchors` may be a stack array of the caller)
+    r.sched_n_unload = tot[0];
+    r.sched_n_load = tot[1];
+    if (n_unload) *n_unload = tot[0];
+    if (n_load) *n_load = tot[1];
+    return BXW_OK;
+}
+
+int bxw_region_load_deltas(bxw_ctx *ctx, bxw_chunk_delta *out, uint32_t cap, uint32_t *n) {
+    if (!ctx || !ctx->region.live || !ctx->region.sched_deltas) return fail(ctx, BXW_E_INVALID, "no delta list (bxw_region_update_anchors first)");
+    Region &r = ctx->region;
+    const uint32_t total = r.sched_n_unload + r.sched_n_load, m = std::min(total, cap);
+    if (m && out) CK(cudaMemcpyAsync(out, r.sched_deltas, (size_t)m * sizeof(bxw_chunk_delta), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n) *n = total;
+    return BXW_OK;
+}
+
+int bxw_region_load_state(bxw_ctx *ctx, uint8_t *blocks_loaded, uint8_t *mesh_loaded) {
+    if (!ctx || !ctx->region.live) return fail(ctx, BXW_E_INVALID, "no region");
+    Region &r = ctx->region;
+    if (blocks_loaded) CK(cudaMemcpyAsync(blocks_loaded, r.blk_loaded, r.n_storage(), cudaMemcpyDeviceToHost, ctx->stream));
+    if (mesh_loaded) CK(cudaMemcpyAsync(mesh_loaded, r.mesh_loaded, r.n_work, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BXW_OK;
+}
+
+int bxw_region_apply_deltas(bxw_ctx *ctx, uint64_t seed, int precision, uint32_t max_deltas, uint32_t stats[4]) {
+    if (!ctx || !ctx->region.live || !ctx->region.sched_deltas) return fail(ctx, BXW_E_INVALID, "no delta list (bxw_region_update_anchors first)");
+    if (!ctx->have_gen_ids) return fail(ctx, BXW_E_NO_REGISTRY, "bxw_set_gen_ids not called");
+    Region &r = ctx->region;
+    const uint32_t total = r.sched_n_unload + r.sched_n_load;
+    const uint32_t limit = max_deltas ? std::min(max_deltas, total) : total;
+    SchedParams sp = sched_params(r, 0);
+    launch_delta_lists(sp, limit, ctx->stream);
+    ctx->launches += 1;
+    uint32_t cnt[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(cnt, r.sched_counts, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    // the list is consumed: a second apply without a new update must not replay it
+    r.sched_n_unload = r.sched_n_load = 0;
+    if (stats) {
+        stats[0] = cnt[3];
+        stats[1] = cnt[0];
+        stats[2] = cnt[1];
+        stats[3] = cnt[2];
+    }
+    if (cnt[2]) { // unloaded meshes give their arena space back
+        launch_unmesh(r.sched_unmesh, r.sched_counts + 2, cnt[2], r.spans, r.span_cap, r.counters, ctx->stream);
+        ctx->launches += 1;
+    }
+    if (cnt[0]) { // block loads: the generator for just these chunks (the reference's granularity, generation.rs:96-148)
+        GenParams gp;
+        int rc = gen_setup(ctx, r, seed, precision, gp);
+        if (rc) return rc;
+        if (ctx->elide_uniform) {
+            rc = ensure_shared_pages(ctx, r);
+            if (rc) return rc;
+        }
+        FillParams fp;
+        fill_params(ctx, r, ctx->elide_uniform, fp);
+        fp.list = r.sched_gen;
+        fp.n_list = cnt[0];
+        for (int i = 0; i < 5; i++) r.fill_ids[i] = ctx->gen_ids[i];
+        launch_gen_fill_kernel(fp, gp, precision, ctx->stream);
+        launch_fill_xface_kernel(fp, ctx->stream);
+        ctx->launches += 2;
+        CK(cudaGetLastError());
+        r.gen_seed = seed;
+        r.gen_precision = precision;
+    }
+    if (cnt[1]) { // mesh loads, nearest first
+        int rc = region_mesh(ctx, r, r.sched_mesh, r.sched_mesh_span, cnt[1], true);
+        if (rc) return rc;
+    } else if (cnt[2]) {
+        CK(cudaMemcpyAsync(r.h_counters, r.counters, sizeof(MeshCounters), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if ((cnt[1] || cnt[2]) && r.varena) { // the arena space of unloaded meshes is reclaimed once it is a quarter of the arena
+        const unsigned long long gv = r.h_counters->v_garbage, gi = r.h_counters->i_garbage;
+        if (gv * 4ull > r.h_counters->v_alloc + 65536ull || gi * 4ull > r.h_counters->i_alloc + 98304ull) return bxw_region_compact_arena(ctx, nullptr, nullptr);
+    }
     return BXW_OK;
 }
 
@@ -1544,6 +1766,7 @@ int bxw_region_fill_synthetic(bxw_ctx *ctx, uint64_t seed, uint32_t void_thresho
     CK(cudaMemsetAsync(r.summary, 0, r.n_storage() * sizeof(unsigned long long), ctx->stream));
     launch_page_identity(r.page, (uint32_t)r.n_storage(), ctx->stream);
     r.shape_hint = 2;
+    CK(cudaMemsetAsync(r.blk_loaded, 1, r.n_storage(), ctx->stream));
     launch_fill_synthetic(r.blocks, r.SX, r.SY, r.SZ, r.cx0 - 1, r.cy0 - 1, r.cz0 - 1, seed, void_threshold, ctx->stream);
     launch_xface_extract(r.blocks, r.xface, nullptr, 0, (uint32_t)r.n_storage(), ctx->stream);
     ctx->launches += 2;

@@ -171,6 +171,9 @@ struct FillParams {
     // list mode (load deltas): entry k = storage chunk index; the CTA handles that one chunk instead of a whole stack
     const uint32_t *list;
     uint32_t n_list;
+    // stack mode, which chunk columns along x: 0 = all, 1 = the two interior boundary columns (sx = 1 and SX - 2; what a
+    // multi-GPU halo export reads), 2 = all the others
+    int col_mode;
 };
 void launch_fill_kernel(const FillParams &p, cudaStream_t stream);
 void launch_fill_xface_kernel(const FillParams &p, cudaStream_t stream);

@@ -301,6 +301,14 @@ __global__ void __launch_bounds__(128) heightmap_kernel(GenParams p) {
 // GEN = 0: column parameters come from the height map. GEN = 32 / 64: the CTA first computes the parameters of its 32x32
 // columns itself (4 per thread, FP32 / f64 noise) and stores them to the height map, then writes the stack: CTAs in their
 // FP64 phase share an SM with CTAs in their store phase, which hides the height map behind the HBM writes.
+// chunk column of CTA b along x (FillParams::col_mode)
+__device__ __forceinline__ int fill_column(const FillParams &p, int b) {
+    const int nx = p.SX - 2;
+    if (p.col_mode == 1) return b == 0 ? 1 : nx;
+    if (p.col_mode == 2) return b == 0 ? 0 : (nx == 1 ? 2 : (b < nx - 1 ? b + 1 : b + 2));
+    return b;
+}
+
 template <int GEN>
 __global__ void __launch_bounds__(256, 4) fill_kernel(FillParams p, GenParams g) {
     int sx, sz, sy_lo, sy_hi;
@@ -311,7 +319,7 @@ __global__ void __launch_bounds__(256, 4) fill_kernel(FillParams p, GenParams g)
         sy_lo = (int)(c / (uint32_t)(p.SX * p.SZ));
         sy_hi = sy_lo + 1;
     } else {
-        sx = blockIdx.x;
+        sx = fill_column(p, (int)blockIdx.x);
         sz = blockIdx.y;
         sy_lo = 0;
         sy_hi = p.SY;
@@ -415,7 +423,7 @@ __global__ void __launch_bounds__(64) fill_xface_kernel(FillParams p) {
         sy_lo = (int)(c / (uint32_t)(p.SX * p.SZ));
         sy_hi = sy_lo + 1;
     } else {
-        sx = blockIdx.x;
+        sx = fill_column(p, (int)blockIdx.x);
         sz = blockIdx.y;
         sy_lo = 0;
         sy_hi = p.SY;
@@ -469,7 +477,12 @@ void launch_heightmap_kernel(const GenParams &p, int precision, cudaStream_t str
     else heightmap_kernel<64><<<grid, 128, 0, stream>>>(p);
 }
 
-static dim3 fill_grid(const FillParams &p) { return p.list ? dim3(p.n_list) : dim3(p.SX, p.SZ); }
+static dim3 fill_grid(const FillParams &p) {
+    if (p.list) return dim3(p.n_list);
+    const int nx = p.SX - 2;
+    const int cols = p.col_mode == 1 ? (nx == 1 ? 1 : 2) : (p.col_mode == 2 ? p.SX - (nx == 1 ? 1 : 2) : p.SX);
+    return dim3(cols, p.SZ);
+}
 
 void launch_fill_kernel(const FillParams &p, cudaStream_t stream) {
     if (p.list && !p.n_list) return;

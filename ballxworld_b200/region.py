@@ -26,6 +26,13 @@ class Region:
         self.ctx.set_gen_ids(*StdGenerator.resolve_ids(self.registry))
         self.ctx.region_generate(seed, precision)
 
+    def generate_part(self, part, seed=0, precision=64):
+        """part 1: the chunk columns next to the slab's x faces (what the halo export reads); part 2: the rest. A multi-GPU
+        step starts the halo transfer between the two so that it overlaps part 2 (slabs.start_exchange / finish_exchange)."""
+        if part == 1:
+            self.ctx.set_gen_ids(*StdGenerator.resolve_ids(self.registry))
+        self.ctx.region_generate_part(seed, precision, part)
+
     def mesh(self):
         self.registry.bind(self.ctx)
         self.arena = self.ctx.region_mesh()
@@ -103,6 +110,26 @@ class Region:
         """Re-position the box (slab streaming / sliding window); the voxels are stale until the next generate."""
         self.ctx.region_set_origin(*origin)
         self.origin = tuple(origin)
+
+    # ---- load anchors: World::check_load_deltas / recalculate_load_deltas / main_loop_tick (worldmgr.rs:407-732) ----
+    def unload_all(self):
+        self.ctx.region_unload_all()
+        self.arena = (0, 0)
+
+    def update_anchors(self, anchors):
+        """anchors: (cx, cy, cz, radius, load_mesh) per CLoadAnchor entity -> (n_unload_deltas, n_load_deltas)."""
+        return self.ctx.region_update_anchors(anchors)
+
+    def tick(self, anchors, seed=0, precision=64, max_deltas=0):
+        """One World::main_loop_tick for the box: rebuild the load deltas for the anchors and process them (nearest first):
+        unloads, block loads (generator), mesh loads. Meshes of newly generated chunks follow on the next tick, as in the
+        reference (their dependency is checked against the state before the tick)."""
+        self.registry.bind(self.ctx)
+        self.ctx.set_gen_ids(*StdGenerator.resolve_ids(self.registry))
+        self.ctx.region_update_anchors(anchors)
+        st = self.ctx.region_apply_deltas(seed, precision, max_deltas)
+        self.arena = self.ctx.region_arena_extent()
+        return st
 
     def close(self):
         self.ctx.region_destroy()

@@ -34,6 +34,32 @@ def slab_partition(total_nx, world, rank):
     return Slab(rank, world, x0, nx)
 
 
+def start_exchange(slab, dist, bufs, export_plane):
+    """First half of exchange_halos: pack this rank's boundary planes and start the point-to-point transfers. Returns the
+    pending work handles; whatever the caller launches next (the rest of the generation) overlaps the transfer."""
+    ops = []
+    if slab.has_lo:
+        export_plane(0, bufs["send_lo"])
+        ops.append(dist.P2POp(dist.isend, bufs["send_lo"], slab.rank - 1))
+        ops.append(dist.P2POp(dist.irecv, bufs["recv_lo"], slab.rank - 1))
+    if slab.has_hi:
+        export_plane(1, bufs["send_hi"])
+        ops.append(dist.P2POp(dist.isend, bufs["send_hi"], slab.rank + 1))
+        ops.append(dist.P2POp(dist.irecv, bufs["recv_hi"], slab.rank + 1))
+    return dist.batch_isend_irecv(ops) if ops else []
+
+
+def finish_exchange(slab, works, bufs, import_plane):
+    """Second half: wait for the transfers (the current stream waits, not the host) and write the received planes into the
+    shell."""
+    for w in works:
+        w.wait()
+    if slab.has_lo:
+        import_plane(0, bufs["recv_lo"])
+    if slab.has_hi:
+        import_plane(1, bufs["recv_hi"])
+
+
 def exchange_halos(slab, dist, bufs, export_plane, import_plane):
     """One halo exchange.
 

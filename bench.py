@@ -333,7 +333,7 @@ def cfg4_literal(ctx, reg, rank, world, dist, steps, stream):
     import torch
 
     import ballxworld_b200 as bxw
-    from ballxworld_b200.slabs import Slab, exchange_halos
+    from ballxworld_b200.slabs import finish_exchange, start_exchange
 
     TOTAL_X, BOX, NY, NZ = 512, 64, 16, 512
     per_rank = TOTAL_X // world
@@ -357,11 +357,14 @@ def cfg4_literal(ctx, reg, rank, world, dist, steps, stream):
 
     def run_pass(k, b):
         region.set_origin((rank * per_rank + b * BOX, 0, 0))
-        region.generate(SEED, 64)
         sl = PassSlab(k, b)
         if sl.has_lo or sl.has_hi:
-            exchange_halos(sl, dist, halo, lambda f, t: ctx.region_halo_export(f, t.data_ptr()),
-                           lambda f, t: ctx.region_halo_import(f, t.data_ptr()))
+            region.generate_part(1, SEED, 64)
+            works = start_exchange(sl, dist, halo, lambda f, t: ctx.region_halo_export(f, t.data_ptr()))
+            region.generate_part(2, SEED, 64)
+            finish_exchange(sl, works, halo, lambda f, t: ctx.region_halo_import(f, t.data_ptr()))
+        else:
+            region.generate(SEED, 64)
         return region.mesh()
 
     def run_all(collect):
@@ -449,7 +452,7 @@ def main():
         hb = ctx.region_halo_bytes()
         halo = {k: torch.empty(hb // 4, dtype=torch.int32, device="cuda") for k in ("send_lo", "send_hi", "recv_lo", "recv_hi")}
 
-    from ballxworld_b200.slabs import exchange_halos, slab_partition
+    from ballxworld_b200.slabs import exchange_halos, finish_exchange, slab_partition, start_exchange
 
     slab_info = slab_partition(nx * world, world, rank)
 
@@ -459,9 +462,14 @@ def main():
                        lambda f, t: ctx.region_halo_import(f, t.data_ptr()))
 
     def step():
-        region.generate(SEED, 64)
         if world > 1:
-            exchange()
+            # boundary chunk columns first, their planes are packed and sent while the rest of the slab is generated
+            region.generate_part(1, SEED, 64)
+            works = start_exchange(slab_info, dist, halo, lambda f, t: ctx.region_halo_export(f, t.data_ptr()))
+            region.generate_part(2, SEED, 64)
+            finish_exchange(slab_info, works, halo, lambda f, t: ctx.region_halo_import(f, t.data_ptr()))
+        else:
+            region.generate(SEED, 64)
         return region.mesh()
 
     def barrier():

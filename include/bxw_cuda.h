@@ -136,6 +136,10 @@ int bxw_region_destroy(bxw_ctx *ctx);
  * reference computes it; 32 = FP32 noise evaluation (north_star-literal variant; may flip voxels whose noise value
  * sits within rounding of a selection threshold). */
 int bxw_region_generate(bxw_ctx *ctx, uint64_t seed, int precision);
+/* The same in two calls, for multi-GPU steps: part 1 fills only the two chunk columns next to the x- and x+ faces of the
+ * interior (everything bxw_region_halo_export reads), part 2 all the others. Between the two the caller exports the boundary
+ * planes and starts their transfer, which then overlaps part 2; the received planes are imported after part 2. */
+int bxw_region_generate_part(bxw_ctx *ctx, uint64_t seed, int precision, int part);
 /* Column parameters of the last generate: height (round(h) as i32) and elevation class (0 LowLand,1 Hill,
  * 2 Mountain) for the (nx+2)*32 x (nz+2)*32 columns, row-major [z][x]; raw f64 height optional (may be NULL). */
 int bxw_region_heightmap(bxw_ctx *ctx, int32_t *height, uint8_t *elevation, double *raw_height);
@@ -169,6 +173,39 @@ int bxw_region_generate_and_mesh(bxw_ctx *ctx, uint64_t seed, int precision, uin
  * anchor is a world chunk position. n_meshed = chunks in the sphere that belong to this region. */
 int bxw_region_mesh_sphere(bxw_ctx *ctx, int32_t ax, int32_t ay, int32_t az, uint32_t radius, uint32_t *n_meshed,
                            uint64_t *arena_vertices, uint64_t *arena_indices);
+/* ---- load anchors on the device (World::recalculate_load_deltas / main_loop_tick, bxw_world/src/worldmgr.rs:407-567,633-790) ----
+ * The region box plays the part of the world: every chunk of the box (shell included) can hold block data, every interior
+ * chunk a mesh; coordinates outside the box are ignored. Each chunk carries the two load states of the reference's handlers
+ * (CHUNK_BLOCK_DATA, CHUNK_MESH_DATA): bxw_region_generate / _mesh set them for the whole box, bxw_region_unload_all clears
+ * them. */
+typedef struct {
+    int32_t cx, cy, cz;  /* anchor chunk position (ChunkPosition::from(CLocation.position)) */
+    uint32_t radius;     /* CLoadAnchor.radius, chunks */
+    uint32_t load_mesh;  /* CLoadAnchor.load_mesh: 0 = block data only (a server-side anchor) */
+} bxw_load_anchor;
+enum { BXW_KIND_BLOCKS = 1, BXW_KIND_MESH = 2 };
+typedef struct {        /* ChunkDelta (worldmgr.rs:96-102) */
+    int32_t cx, cy, cz;
+    uint32_t kinds;      /* BXW_KIND_* bits */
+    uint32_t unload;
+    int32_t min_anchor_distance; /* squared, chunks */
+} bxw_chunk_delta;
+int bxw_region_unload_all(bxw_ctx *ctx);
+/* recalculate_load_deltas on the device: chunks whose loaded kinds no anchor wants any more (unload deltas, keyed by the
+ * distance to the nearest anchor) and chunks inside an anchor sphere that miss a kind they may request now (load deltas: block
+ * data at once, a mesh when the block data of the chunk and its 26 neighbours is loaded), each list nearest first, interleaved
+ * unload / load like the reference's. The list stays on the device; n_unload / n_load receive the counts. */
+int bxw_region_update_anchors(bxw_ctx *ctx, const bxw_load_anchor *anchors, uint32_t n_anchors, uint32_t *n_unload, uint32_t *n_load);
+/* Copy of the list of the last bxw_region_update_anchors (at most cap entries), in processing order. */
+int bxw_region_load_deltas(bxw_ctx *ctx, bxw_chunk_delta *out, uint32_t cap, uint32_t *n);
+/* main_loop_tick over the first max_deltas entries of the list (0 = all), batched: unloads drop their data (a mesh's arena
+ * space becomes garbage), block loads run the generator for just those chunks, mesh loads run the mesher over just those
+ * chunks, nearest first. stats = {deltas consumed, chunks generated, chunks meshed, meshes unloaded}. Meshes need a second
+ * update + apply round after their block data has arrived, exactly as in the reference. */
+int bxw_region_apply_deltas(bxw_ctx *ctx, uint64_t seed, int precision, uint32_t max_deltas, uint32_t stats[4]);
+/* Load state of every chunk: blocks_loaded[(nx+2)(ny+2)(nz+2)] (storage order), mesh_loaded[nx*ny*nz] (span order); either
+ * may be NULL. */
+int bxw_region_load_state(bxw_ctx *ctx, uint8_t *blocks_loaded, uint8_t *mesh_loaded);
 /* spans: nx*ny*nz entries, chunk order x + nx*(z + nz*y). */
 int bxw_region_mesh_spans(bxw_ctx *ctx, bxw_mesh_span *spans);
 /* Copy arena extents [0,arena_vertices) / [0,arena_indices) to host (pinned memory recommended). */

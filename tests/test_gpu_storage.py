@@ -271,3 +271,32 @@ def test_rle_offsets_are_validated_and_long_runs_decode(ctx, oracle):
     assert (words[2::3][:n_runs] == 64).all()
     got = ctx.rle_decompress(words, np.array([0, len(words)], np.uint64))
     assert np.array_equal(got[0], dense)
+
+
+def test_generate_in_two_parts_equals_generate(ctx, oracle):
+    """bxw_region_generate_part: boundary chunk columns first, the rest second (multi-GPU steps overlap the halo transfer with
+    part 2). Same blocks, planes, summaries and meshes as one bxw_region_generate."""
+    for dims in [(4, 2, 2), (1, 2, 2), (2, 1, 1)]:
+        ctx.region_create(9, 0, -1, *dims)
+        ctx.region_generate(0, 64)
+        ctx.region_mesh()
+        ref = _download_all(ctx, dims)
+        ref_m = _meshes(ctx, dims)
+        ref_pages = ctx.region_download_pages()
+        ref_h = ctx.region_heightmap()
+        ctx.region_destroy()
+        ctx.region_create(9, 0, -1, *dims)
+        ctx.region_generate_part(0, 64, 1)
+        import ballxworld_b200 as bxw
+        with pytest.raises(bxw.BxwError):
+            ctx.region_generate_part(5, 64, 2)  # another seed than part 1
+        ctx.region_generate_part(0, 64, 2)
+        ctx.region_mesh()
+        got = _download_all(ctx, dims)
+        for k in ref:
+            assert np.array_equal(got[k], ref[k]), (dims, k)
+        assert _meshes(ctx, dims) == ref_m
+        assert np.array_equal(ctx.region_download_pages(), ref_pages)
+        h = ctx.region_heightmap()
+        assert np.array_equal(h[0], ref_h[0]) and np.array_equal(h[1], ref_h[1])
+        ctx.region_destroy()

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from ballxworld_b200.slabs import exchange_halos, slab_partition
+from ballxworld_b200.slabs import exchange_halos, finish_exchange, slab_partition, start_exchange
 
 
 def test_slab_partition_covers_region():
@@ -22,7 +22,7 @@ def test_slab_partition_covers_region():
         slab_partition(3, 4, 0)
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, split=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -42,7 +42,12 @@ def _worker(rank, world, port, q):
     def import_plane(face, t):
         blocks[0 if face == 0 else width + 1] = t.numpy()
 
-    exchange_halos(slab, dist, bufs, export_plane, import_plane)
+    if split:  # the overlapped form: work between the two halves must not disturb the transfer
+        works = start_exchange(slab, dist, bufs, export_plane)
+        blocks[1:-1, :] += 0  # (the rest of the generation would run here)
+        finish_exchange(slab, works, bufs, import_plane)
+    else:
+        exchange_halos(slab, dist, bufs, export_plane, import_plane)
     ok = True
     if slab.has_lo:
         ok &= bool((blocks[0] == (slab.x0 * 32 - 1) * 1000 + np.arange(n)).all())
@@ -56,15 +61,15 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_halo_exchange_over_gloo(world):
+@pytest.mark.parametrize("world,split", [(2, False), (3, False), (2, True), (3, True)])
+def test_halo_exchange_over_gloo(world, split):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, split)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=120) for _ in range(world))
