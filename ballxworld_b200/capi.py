@@ -128,6 +128,7 @@ def load_library():
         "bxw_region_halo_import": ([vp, C.c_int, vp], C.c_int),
         "bxw_region_device_ptrs": ([vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)], C.c_int),
         "bxw_terragen_noise2": ([vp, C.c_uint64, vp, vp, C.c_size_t, vp], C.c_int),
+        "bxw_stdgen_noise": ([vp, C.c_uint64, C.c_int, C.c_int, vp, vp, C.c_size_t, vp], C.c_int),
         "bxw_timer_start": ([vp], C.c_int),
         "bxw_timer_stop_ms": ([vp, C.POINTER(C.c_float)], C.c_int),
         "bxw_mesh_kernel_time_ms": ([vp, C.POINTER(C.c_float), u64p, C.c_int], C.c_int),
@@ -478,6 +479,14 @@ class Context:
         ys = np.ascontiguousarray(ys, dtype=np.float64)
         out = np.empty(xs.size, dtype=np.float64)
         self._ck(self.L.bxw_terragen_noise2(self.h, seed, _ptr(xs), _ptr(ys), xs.size, _ptr(out)))
+        return out
+
+    def stdgen_noise(self, seed, which, xs, ys, precision=64):
+        """Raw samples of StdGenerator(seed)'s noise function `which` (0..4 height maps, 5 elevation, 6 moisture)."""
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        ys = np.ascontiguousarray(ys, dtype=np.float64)
+        out = np.empty(xs.size, dtype=np.float64)
+        self._ck(self.L.bxw_stdgen_noise(self.h, seed, which, precision, _ptr(xs), _ptr(ys), xs.size, _ptr(out)))
         return out
 
     # ---- timing ----

@@ -1760,6 +1760,26 @@ int bxw_terragen_noise2(bxw_ctx *ctx, uint64_t seed, const double *xs, const dou
     return BXW_OK;
 }
 
+int bxw_stdgen_noise(bxw_ctx *ctx, uint64_t seed, int which, int precision, const double *xs, const double *ys, size_t n, double *out) {
+    if (!ctx || !xs || !ys || !out) return fail(ctx, BXW_E_INVALID, "null argument");
+    if (which < 0 || which > 6) return fail(ctx, BXW_E_INVALID, "noise function 0..6");
+    if (precision != 32 && precision != 64) return fail(ctx, BXW_E_INVALID, "precision must be 32 or 64");
+    if (n == 0) return BXW_OK;
+    int rc = ensure_gen_tables(ctx, seed);
+    if (rc) return rc;
+    rc = ensure_io(ctx, 2 * n * sizeof(double), n * sizeof(double));
+    if (rc) return rc;
+    double *dx = (double *)ctx->io_a, *dy = dx + n, *dout = (double *)ctx->io_b;
+    CK(cudaMemcpyAsync(dx, xs, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dy, ys, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    launch_noise_samples(ctx->d_gen, which, dx, dy, n, dout, precision, ctx->stream);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, dout, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BXW_OK;
+}
+
 int bxw_region_fill_synthetic(bxw_ctx *ctx, uint64_t seed, uint32_t void_threshold) {
     if (!ctx || !ctx->region.live) return fail(ctx, BXW_E_INVALID, "no region");
     Region &r = ctx->region;

@@ -154,6 +154,8 @@ struct GenParams {
 void launch_cellpoints_kernel(uint64_t seed, int32_t cell_x0, int32_t cell_z0, int32_t cells_w, int32_t cells_d,
                               const GenTables *tables, CellPointDev *cells, int precision, cudaStream_t stream);
 void launch_heightmap_kernel(const GenParams &p, int precision, cudaStream_t stream);
+void launch_noise_samples(const GenTables *tables, int which, const double *xs, const double *ys, size_t n, double *out, int precision,
+                          cudaStream_t stream);
 
 struct FillParams {
     const int32_t *hmap; // [D][W]

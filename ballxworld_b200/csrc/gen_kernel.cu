@@ -83,18 +83,23 @@ __device__ __noinline__ double super_simplex_2d(const uint8_t *__restrict__ perm
     return dmul(value, kNorm);
 }
 
-// FP32 evaluation of the same noise (north_star-literal variant). Lattice decisions are taken in f32 too.
-__device__ __noinline__ float super_simplex_2d_f32(const uint8_t *__restrict__ perm, float px, float py) {
-    const float to_simplex_offset = __fmul_rn(__fadd_rn(px, py), (float)kToSimplex);
-    const float sx = __fadd_rn(px, to_simplex_offset), sy = __fadd_rn(py, to_simplex_offset);
-    const float bxf = floorf(sx), byf = floorf(sy);
-    const int bxi = __float2int_rz(bxf), byi = __float2int_rz(byf);
-    const float rx = __fsub_rn(sx, bxf), ry = __fsub_rn(sy, byf);
-    const float region_sum = floorf(__fadd_rn(rx, ry));
-    const float half_rs = __fmul_rn(region_sum, 0.5f);
-    unsigned index = (region_sum >= 1.0f ? 1u : 0u) << 2;
-    index |= (__fsub_rn(__fadd_rn(__fsub_rn(rx, __fmul_rn(ry, 0.5f)), 1.0f), half_rs) >= 1.0f ? 1u : 0u) << 3;
-    index |= (__fsub_rn(__fadd_rn(__fsub_rn(ry, __fmul_rn(rx, 0.5f)), 1.0f), half_rs) >= 1.0f ? 1u : 0u) << 4;
+// FP32 evaluation of the same noise (the north_star-literal variant). The lattice cell (floor of the skewed coordinates) and the
+// three bits that pick the lattice-point group are taken in f64 exactly as above -- a dozen operations; at world coordinates of
+// 10^4 an f32 position has an error of 10^-3, which would move lattice decisions and broke the 1e-5 bound in round 1 -- so the
+// same lattice points and gradients are used as in the f64 path. Everything after that works on the relative coordinates in
+// [0, 1): offsets, attenuation, gradient dot products and the sum are f32 (about 80 % of the arithmetic).
+__device__ __noinline__ float super_simplex_2d_f32(const uint8_t *__restrict__ perm, double px, double py) {
+    const double to_simplex_offset = dmul(dadd(px, py), kToSimplex);
+    const double sx = dadd(px, to_simplex_offset), sy = dadd(py, to_simplex_offset);
+    const double bxf = floor(sx), byf = floor(sy);
+    const long long bxi = __double2ll_rz(bxf), byi = __double2ll_rz(byf);
+    const double rxd = dsub(sx, bxf), ryd = dsub(sy, byf);
+    const double region_sum = floor(dadd(rxd, ryd));
+    const double half_rs = dmul(region_sum, 0.5);
+    unsigned index = (region_sum >= 1.0 ? 1u : 0u) << 2;
+    index |= (dsub(dadd(dsub(rxd, dmul(ryd, 0.5)), 1.0), half_rs) >= 1.0 ? 1u : 0u) << 3;
+    index |= (dsub(dadd(dsub(ryd, dmul(rxd, 0.5)), 1.0), half_rs) >= 1.0 ? 1u : 0u) << 4;
+    const float rx = (float)rxd, ry = (float)ryd;
     const float to_real_offset = __fmul_rn(__fadd_rn(rx, ry), (float)kToReal);
     const float qx = __fadd_rn(rx, to_real_offset), qy = __fadd_rn(ry, to_real_offset);
     float value = 0.0f;
@@ -103,7 +108,7 @@ __device__ __noinline__ float super_simplex_2d_f32(const uint8_t *__restrict__ p
         const float dx = __fadd_rn(qx, (float)c_lat_off[index + k][0]), dy = __fadd_rn(qy, (float)c_lat_off[index + k][1]);
         const float attn = __fsub_rn(2.0f / 3.0f, __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
         if (attn > 0.0f) {
-            const int lx = bxi + c_lat_pt[index + k][0], ly = byi + c_lat_pt[index + k][1];
+            const long long lx = bxi + c_lat_pt[index + k][0], ly = byi + c_lat_pt[index + k][1];
             const unsigned h = __ldg(perm + (__ldg(perm + (unsigned)(lx & 0xff)) ^ (unsigned)(ly & 0xff)));
             const float diag = (float)kDiag;
             const float gx = (h & 4u) ? ((h & 1u) ? -diag : diag) : ((h & 2u) ? 0.0f : ((h & 1u) ? -1.0f : 1.0f));
@@ -118,7 +123,7 @@ __device__ __noinline__ float super_simplex_2d_f32(const uint8_t *__restrict__ p
 // precision-generic noise returning double
 template <int PREC>
 __device__ __forceinline__ double noise_at(const uint8_t *perm, double px, double py) {
-    if (PREC == 32) return (double)super_simplex_2d_f32(perm, (float)px, (float)py);
+    if (PREC == 32) return (double)super_simplex_2d_f32(perm, px, py);
     return super_simplex_2d(perm, px, py);
 }
 
@@ -448,6 +453,13 @@ __global__ void __launch_bounds__(64) fill_xface_kernel(FillParams p) {
     }
 }
 
+// raw SuperSimplex::get samples of one of the generator's seven noise functions (parity tests / the FP32 report)
+template <int PREC>
+__global__ void noise_samples_kernel(const GenTables *T, int which, const double *xs, const double *ys, size_t n, double *out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = noise_at<PREC>(T->perm[which], xs[i], ys[i]);
+}
+
 unsigned long long g_const_devices = 0; // bit d set: __constant__ tables uploaded on device d
 void ensure_constants() {
     int dev = 0;
@@ -468,6 +480,15 @@ void launch_cellpoints_kernel(uint64_t seed, int32_t cell_x0, int32_t cell_z0, i
         cellpoints_kernel<32><<<(n + 127) / 128, 128, 0, stream>>>(seed, cell_x0, cell_z0, cells_w, cells_d, tables, cells);
     else
         cellpoints_kernel<64><<<(n + 127) / 128, 128, 0, stream>>>(seed, cell_x0, cell_z0, cells_w, cells_d, tables, cells);
+}
+
+void launch_noise_samples(const GenTables *tables, int which, const double *xs, const double *ys, size_t n, double *out, int precision,
+                          cudaStream_t stream) {
+    ensure_constants();
+    if (!n) return;
+    const unsigned nb = (unsigned)((n + 127) / 128);
+    if (precision == 32) noise_samples_kernel<32><<<nb, 128, 0, stream>>>(tables, which, xs, ys, n, out);
+    else noise_samples_kernel<64><<<nb, 128, 0, stream>>>(tables, which, xs, ys, n, out);
 }
 
 void launch_heightmap_kernel(const GenParams &p, int precision, cudaStream_t stream) {

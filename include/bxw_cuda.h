@@ -259,6 +259,12 @@ int bxw_region_download_pages(bxw_ctx *ctx, uint32_t *pages);
 /* ---- bxw_terragen in-tree SuperSimplex (bxw_terragen/src/supersimplex.rs:20-107), batched ---- */
 int bxw_terragen_noise2(bxw_ctx *ctx, uint64_t seed, const double *xs, const double *ys, size_t n, double *out);
 
+/* ---- the generator's noise functions, raw (noise::SuperSimplex::get behind bxw_world/src/stdgen.rs:171-213) ----
+ * which: 0..4 = height_map_gen[i], 5 = elevation_map_gen, 6 = moisture_map_gen of StdGenerator(seed) (stdgen.rs:103-114).
+ * precision 64 = the reference's f64 arithmetic; 32 = the FP32 variant (lattice cell chosen in f64, attenuation / gradient
+ * arithmetic in f32): values agree with f64 within 1e-5 of the noise range. */
+int bxw_stdgen_noise(bxw_ctx *ctx, uint64_t seed, int which, int precision, const double *xs, const double *ys, size_t n, double *out);
+
 /* ---- device timing helpers (CUDA events on the context's stream) ---- */
 int bxw_timer_start(bxw_ctx *ctx);
 int bxw_timer_stop_ms(bxw_ctx *ctx, float *ms); /* records, synchronises, returns elapsed */
