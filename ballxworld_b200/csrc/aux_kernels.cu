@@ -81,16 +81,21 @@ __global__ void apply_changes_kernel(EditParams p) {
     // storage-local voxel coordinates (the host dropped changes outside the storage box)
     const int gx = c0.x - p.x_min, gy = c0.y - p.y_min, gz = c0.z - p.z_min;
     const int sx = gx >> 5, sy = gy >> 5, sz = gz >> 5, lx = gx & 31, ly = gy & 31, lz = gz & 31;
-    uint32_t *v = p.blocks + ((size_t)(sx + p.SX * (sz + p.SZ * sy))) * kChunkVoxels + lx + 32 * lz + 1024 * ly;
-    const uint32_t before = *v;
-    uint32_t cur = before;
-    for (uint32_t k = b; k < e; k++) {
-        const bxw_voxel_change c = p.changes[k];
-        if (cur == c.from) cur = c.to;
+    // load-anchor mode: a chunk without block data is skipped (worldmgr.rs:321-323 `get_chunk_index(cpos).is_none() -> continue`);
+    // the dirty marks below are set all the same, as in the reference
+    const bool present = !p.blk_loaded || p.blk_loaded[(size_t)(sx + p.SX * (sz + p.SZ * sy))];
+    if (present) {
+        uint32_t *v = p.blocks + ((size_t)(sx + p.SX * (sz + p.SZ * sy))) * kChunkVoxels + lx + 32 * lz + 1024 * ly;
+        const uint32_t before = *v;
+        uint32_t cur = before;
+        for (uint32_t k = b; k < e; k++) {
+            const bxw_voxel_change c = p.changes[k];
+            if (cur == c.from) cur = c.to;
+        }
+        *v = cur;
+        if (cur != before && p.summary) p.summary[(size_t)(sx + p.SX * (sz + p.SZ * sy))] = 0; // no longer known uniform
+        if (lx == 0 || lx == 31) p.xface[((size_t)(sx + p.SX * (sz + p.SZ * sy))) * 2048 + (lx ? 1024 : 0) + ly * 32 + lz] = cur;
     }
-    *v = cur;
-    if (cur != before && p.summary) p.summary[(size_t)(sx + p.SX * (sz + p.SZ * sy))] = 0; // no longer known uniform
-    if (lx == 0 || lx == 31) p.xface[((size_t)(sx + p.SX * (sz + p.SZ * sy))) * 2048 + (lx ? 1024 : 0) + ly * 32 + lz] = cur;
     auto mark = [&](int cx, int cy, int cz) { // interior chunks only carry meshes
         if (cx >= 1 && cx <= p.SX - 2 && cy >= 1 && cy <= p.SY - 2 && cz >= 1 && cz <= p.SZ - 2)
             p.dirty[(cx - 1) + (p.SX - 2) * ((cz - 1) + (p.SZ - 2) * (cy - 1))] = 1;
@@ -104,11 +109,14 @@ __global__ void apply_changes_kernel(EditParams p) {
     if (lz == 31) mark(sx, sy, sz + 1);
 }
 
-__global__ void dirty_list_kernel(uint8_t *dirty, uint32_t n, int nx, int nz, int SX, int SZ, uint32_t *work, uint32_t *work_span,
-                                  uint32_t *count, int clear) {
+__global__ void dirty_list_kernel(uint8_t *dirty, const uint8_t *mesh_loaded, uint32_t n, int nx, int nz, int SX, int SZ, uint32_t *work,
+                                  uint32_t *work_span, uint32_t *count, int clear) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !dirty[i]) return;
     if (clear) dirty[i] = 0;
+    // a chunk whose mesh is not loaded gets no update task (worldmgr.rs:346-348: status Unloaded -> continue); it is meshed
+    // from the then-current blocks when a load anchor asks for it
+    if (mesh_loaded && !mesh_loaded[i]) return;
     const uint32_t k = atomicAdd(count, 1u);
     const uint32_t ix = i % nx, iz = (i / nx) % nz, iy = i / (nx * nz);
     work[k] = (ix + 1) + SX * ((iz + 1) + SZ * (iy + 1));
@@ -460,9 +468,9 @@ void launch_apply_changes(const EditParams &p, cudaStream_t stream) {
     apply_changes_kernel<<<(p.n_runs + 127) / 128, 128, 0, stream>>>(p);
 }
 
-void launch_dirty_list(uint8_t *dirty, uint32_t n, int nx, int nz, int SX, int SZ, uint32_t *work, uint32_t *work_span, uint32_t *count,
-                       int clear, cudaStream_t stream) {
-    dirty_list_kernel<<<(n + 255) / 256, 256, 0, stream>>>(dirty, n, nx, nz, SX, SZ, work, work_span, count, clear);
+void launch_dirty_list(uint8_t *dirty, const uint8_t *mesh_loaded, uint32_t n, int nx, int nz, int SX, int SZ, uint32_t *work,
+                       uint32_t *work_span, uint32_t *count, int clear, cudaStream_t stream) {
+    dirty_list_kernel<<<(n + 255) / 256, 256, 0, stream>>>(dirty, mesh_loaded, n, nx, nz, SX, SZ, work, work_span, count, clear);
 }
 
 void launch_rle_compress(const uint32_t *dense, const uint32_t *ids, const uint32_t *page, size_t n_chunks, uint32_t *len, uint64_t *offsets,

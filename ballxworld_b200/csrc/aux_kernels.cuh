@@ -22,10 +22,11 @@ struct EditParams {
     const uint32_t *run_start;       // [n_runs + 1]
     uint32_t n_runs;
     uint8_t *dirty;                  // interior chunk flags
+    const uint8_t *blk_loaded;       // load-anchor mode: chunks without block data are skipped (nullptr = every chunk holds data)
 };
 void launch_apply_changes(const EditParams &p, cudaStream_t stream);
-void launch_dirty_list(uint8_t *dirty, uint32_t n, int nx, int nz, int SX, int SZ, uint32_t *work, uint32_t *work_span, uint32_t *count,
-                       int clear, cudaStream_t stream);
+void launch_dirty_list(uint8_t *dirty, const uint8_t *mesh_loaded, uint32_t n, int nx, int nz, int SX, int SZ, uint32_t *work,
+                       uint32_t *work_span, uint32_t *count, int clear, cudaStream_t stream);
 
 // phase 0: per-chunk word counts -> offsets (n+1); phase 1: write words at offsets
 // ids (optional): chunk k is read from dense + ids[k]*32768 instead of dense + k*32768

@@ -62,6 +62,7 @@ struct Region {
     // only (cubes, the odd edited shape), 2 = bulk content of unknown shapes (synthetic fill, uploads, imports)
     uint32_t *fb_work = nullptr, *fb_span = nullptr, *fb_count = nullptr;
     int shape_hint = 0;
+    bool streaming = false;                // load-anchor mode (bxw_region_unload_all / _update_anchors): chunks carry load states
     // load-anchor scheduler (sched_kernels.cu)
     uint8_t *blk_loaded = nullptr, *mesh_loaded = nullptr, *sched_code = nullptr;
     uint32_t *sched_key = nullptr, *sched_hist = nullptr, *sched_totals = nullptr, *sched_order = nullptr;
@@ -1369,6 +1370,7 @@ int bxw_region_unload_all(bxw_ctx *ctx) {
     CK(cudaMemsetAsync(r.counters, 0, sizeof(MeshCounters), ctx->stream));
     CK(cudaMemsetAsync(r.dirty, 0, r.n_work, ctx->stream));
     r.sched_n_unload = r.sched_n_load = 0;
+    r.streaming = true;
     return BXW_OK;
 }
 
@@ -1377,6 +1379,7 @@ int bxw_region_update_anchors(bxw_ctx *ctx, const bxw_load_anchor *anchors, uint
     Region &r = ctx->region;
     int rc = sched_ensure(ctx, r, n_anchors ? n_anchors : 1);
     if (rc) return rc;
+    r.streaming = true;
     if (n_anchors) CK(cudaMemcpyAsync(r.sched_anchors, anchors, (size_t)n_anchors * sizeof(bxw_load_anchor), cudaMemcpyHostToDevice, ctx->stream));
     launch_delta_build(sched_params(r, n_anchors), ctx->stream);
     ctx->launches += 3;
@@ -1580,11 +1583,12 @@ int bxw_region_apply_changes(bxw_ctx *ctx, const bxw_voxel_change *changes, uint
         ep.run_start = (const uint32_t *)ctx->io_b;
         ep.n_runs = n_runs;
         ep.dirty = r.dirty;
+        ep.blk_loaded = r.streaming ? r.blk_loaded : nullptr;
         launch_apply_changes(ep, ctx->stream);
         ctx->launches += 1;
     }
     CK(cudaMemsetAsync(r.dirty_count, 0, sizeof(uint32_t), ctx->stream));
-    launch_dirty_list(r.dirty, r.n_work, (int)r.nx, (int)r.nz, r.SX, r.SZ, r.dirty_work, r.dirty_span, r.dirty_count, 0, ctx->stream);
+    launch_dirty_list(r.dirty, nullptr, r.n_work, (int)r.nx, (int)r.nz, r.SX, r.SZ, r.dirty_work, r.dirty_span, r.dirty_count, 0, ctx->stream);
     ctx->launches += 1;
     CK(cudaGetLastError());
     uint32_t nd = 0;
@@ -1598,7 +1602,9 @@ int bxw_region_remesh_dirty(bxw_ctx *ctx, uint32_t *n_remeshed) {
     if (!ctx || !ctx->region.live) return fail(ctx, BXW_E_INVALID, "no region");
     Region &r = ctx->region;
     CK(cudaMemsetAsync(r.dirty_count, 0, sizeof(uint32_t), ctx->stream));
-    launch_dirty_list(r.dirty, r.n_work, (int)r.nx, (int)r.nz, r.SX, r.SZ, r.dirty_work, r.dirty_span, r.dirty_count, 1, ctx->stream);
+    // (a region that was never meshed as a whole and has no load anchors keeps the old behaviour: every dirty chunk is meshed)
+    launch_dirty_list(r.dirty, r.streaming ? r.mesh_loaded : nullptr, r.n_work, (int)r.nx, (int)r.nz, r.SX, r.SZ, r.dirty_work, r.dirty_span,
+                      r.dirty_count, 1, ctx->stream);
     ctx->launches += 1;
     uint32_t nd = 0;
     CK(cudaMemcpyAsync(&nd, r.dirty_count, sizeof nd, cudaMemcpyDeviceToHost, ctx->stream));

@@ -210,23 +210,40 @@ def slab_boundary_parity(ctx, region, reg, slab_x0, nx, ny, nz, rank, world, dis
 
 
 def edit_sweep(ctx, region, rank, world, dist, nx, ny, nz, steps=64, edits=4096, radius=10):
-    """BASELINE.json configs[4] (SURVEY.md section 8d cfg 5): a load anchor sweeps +x one chunk per step; every step this
-    rank draws `edits` random block placements inside its anchor sphere (radius 10 chunks, src/config.rs:35-36), the changes
-    that fall into a neighbour rank's storage box (its interior or its 1-chunk shell) are SENT to that rank (point-to-point,
-    counts first), every rank applies [lower rank's | own | higher rank's] through World::apply_voxel_changes semantics and
-    re-meshes its dirty chunks. Latency = host wall clock around exchange + apply + re-mesh, device synchronised."""
+    """BASELINE.json configs[4] (SURVEY.md section 8d cfg 5): the streaming view-distance sweep. The region starts unloaded; a
+    load anchor (radius 10 chunks, src/config.rs:35-36) sweeps +x one chunk per step. Every step (a) the device-side scheduler
+    rebuilds the load deltas (World::recalculate_load_deltas) and processes them -- block data of chunks that entered the
+    sphere is generated, their meshes follow on the second tick, what left the sphere is unloaded -- and (b) this rank draws
+    `edits` random block placements inside its anchor sphere; the changes that fall into a neighbour rank's storage box (its
+    interior or its 1-chunk shell) are SENT to that rank (point-to-point, counts first), every rank applies [lower rank's |
+    own | higher rank's] through World::apply_voxel_changes semantics and re-meshes its dirty chunks that have a mesh.
+    Latencies = host wall clock, device synchronised."""
     import numpy as np
     import torch
 
     import ballxworld_b200 as bxw
 
-    lat, dirty = [], 0
-    x_lo, x_hi = (rank * nx - 1) * 32, ((rank + 1) * nx + 1) * 32  # this rank's storage box along x (shell included)
+    lat, lat_tick, dirty, loads = [], [], 0, np.zeros(3, dtype=np.int64)
+    def anchor_at(step):
+        return (rank * nx + radius + (step % max(1, nx - 2 * radius)), ny // 4, nz // 2, radius, 1)
+    region.unload_all()
+    for _ in range(3):
+        region.tick([anchor_at(0)], SEED, 64)
     st0 = ctx.region_arena_stats()
     peak_used = st0["vertices_used"]
     for step in range(steps):
         rng = np.random.default_rng(1000 * step + rank + 1)
-        anchor = np.array([rank * nx + radius + (step % max(1, nx - 2 * radius)), ny // 4, nz // 2])
+        a = anchor_at(step)
+        ctx.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):  # block data of the newly exposed chunks, then (their dependency met) the meshes
+            st = region.tick([a], SEED, 64)
+            loads += (st["generated"], st["meshed"], st["unmeshed"])
+        ctx.synchronize()
+        lat_tick.append(time.perf_counter() - t0)
+        anchor = np.array(a[:3])
         off = rng.integers(-radius * 32, radius * 32, size=(edits * 2, 3))
         off = off[(off.astype(np.int64) ** 2).sum(axis=1) <= (radius * 32) ** 2][:edits]
         pos = anchor * 32 + off
@@ -262,8 +279,8 @@ def edit_sweep(ctx, region, rank, world, dist, nx, ny, nz, steps=64, edits=4096,
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
             def unpack(t):
-                a = t.cpu().numpy()
-                return a[1:1 + 5 * int(a[0])].view(bxw.CHANGE_DTYPE).copy()
+                arr = t.cpu().numpy()
+                return arr[1:1 + 5 * int(arr[0])].view(bxw.CHANGE_DTYPE).copy()
             parts = ([unpack(recv_lo)] if recv_lo is not None else []) + [ch] + ([unpack(recv_hi)] if recv_hi is not None else [])
         allch = np.concatenate(parts)
         nd = ctx.region_apply_changes(allch)
@@ -271,22 +288,30 @@ def edit_sweep(ctx, region, rank, world, dist, nx, ny, nz, steps=64, edits=4096,
         ctx.synchronize()
         lat.append(time.perf_counter() - t0)
         dirty += nr
-        assert nr == nd
+        assert nr <= nd
         if step % 8 == 7:
             peak_used = max(peak_used, ctx.region_arena_stats()["vertices_used"])
     st1 = ctx.region_arena_stats()
-    lat_t = torch.tensor(lat, dtype=torch.float64, device="cuda")
-    d_t = torch.tensor([dirty], dtype=torch.int64, device="cuda")
+    live = int(region.spans()["v_count"].astype(np.int64).sum())
+    lat_t = torch.tensor([lat, lat_tick], dtype=torch.float64, device="cuda")
+    d_t = torch.tensor([dirty] + loads.tolist(), dtype=torch.int64, device="cuda")
     if dist is not None:
         dist.all_reduce(lat_t, op=dist.ReduceOp.MAX)
         dist.all_reduce(d_t)
-    lat = np.array(lat_t.tolist()[4:])
-    return {"workload": f"{steps} steps x {edits} edits per GPU in a radius-{radius} anchor sphere sweeping +x, on the bench region; "
+    lat = np.array(lat_t[0].tolist()[4:])
+    lat_tick = np.array(lat_t[1].tolist()[4:])
+    tot = [int(x) for x in d_t.tolist()]
+    return {"workload": f"{steps} steps: a radius-{radius} load anchor per GPU sweeps +x over the bench region (loads / unloads by the device-side "
+                        f"scheduler, two ticks per step), then {edits} edits per GPU inside the sphere and a re-mesh of the dirty chunks; "
                         + ("changes near a slab boundary are sent to the neighbour rank" if dist is not None else "one GPU"),
-            "dirty_chunks_remeshed": int(d_t.item()), "dirty_chunks_per_s": float(d_t.item()) / (float(lat.sum()) * steps / len(lat)),
+            "dirty_chunks_remeshed": tot[0], "dirty_chunks_per_s": tot[0] / (float(lat.sum()) * steps / len(lat)),
             "edit_to_mesh_latency_ms_median": float(np.median(lat) * 1e3), "edit_to_mesh_latency_ms_p95": float(np.percentile(lat, 95) * 1e3),
-            "arena_vertices_before": st0["vertices_used"], "arena_vertices_after": st1["vertices_used"],
-            "arena_vertices_peak": max(peak_used, st1["vertices_used"]), "arena_garbage_after": st1["vertices_garbage"]}
+            "chunks_generated_by_load_deltas": tot[1], "chunks_meshed_by_load_deltas": tot[2], "meshes_unloaded": tot[3],
+            "load_deltas_per_s": (tot[1] + tot[2] + tot[3]) / (float(lat_tick.sum()) * steps / len(lat_tick)),
+            "anchor_move_latency_ms_median": float(np.median(lat_tick) * 1e3), "anchor_move_latency_ms_p95": float(np.percentile(lat_tick, 95) * 1e3),
+            "arena_vertices_first_sphere": st0["vertices_used"], "arena_vertices_after": st1["vertices_used"],
+            "arena_vertices_peak": max(peak_used, st1["vertices_used"]), "arena_garbage_after": st1["vertices_garbage"],
+            "live_vertices_after": live}
 
 
 def mesh_only_cfg2(ctx, reg, steps, warmup, peak):
@@ -605,8 +630,6 @@ def main():
                       "edits_changed_expected_mesh": bool(mn[2].item()),
                       "how": "every rank places blocks on its own x- voxel plane, the planes go through the halo exchange, the x- "
                              "neighbour's boundary chunks are meshed and compared with the oracle (vertices and indices, bytewise)"}
-        region.generate(SEED, 64)
-        region.mesh()
         edits_leg = edit_sweep(ctx, region, rank, world, dist, nx, ny, nz)
     region.close()
     if not args.no_extra_legs:
