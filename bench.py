@@ -314,7 +314,7 @@ def edit_sweep(ctx, region, rank, world, dist, nx, ny, nz, steps=64, edits=4096,
             "live_vertices_after": live}
 
 
-def mesh_only_cfg2(ctx, reg, steps, warmup, peak):
+def mesh_only_cfg2(ctx, reg, steps, warmup, peak, traffic=None):
     """BASELINE.json configs[1] (SURVEY.md section 8d cfg 2): 4096 chunks of hashed random blocks incl. oriented slopes / corner
     slopes, mesh only, one B200; totals checked against the oracle-made golden fixture."""
     import numpy as np
@@ -333,6 +333,7 @@ def mesh_only_cfg2(ctx, reg, steps, warmup, peak):
         ctx.kernel_time_ms(ctx.KERNEL_MESH, reset=True)
         for _ in range(steps):
             ctx.region_mesh()
+        ems, _ = ctx.kernel_time_ms(ctx.KERNEL_EMIT)
         ms, n = ctx.kernel_time_ms(ctx.KERNEL_MESH, reset=True)
         spans = ctx.region_mesh_spans()
         V, I = int(spans["v_count"].astype(np.uint64).sum()), int(spans["i_count"].astype(np.uint64).sum())
@@ -340,7 +341,9 @@ def mesh_only_cfg2(ctx, reg, steps, warmup, peak):
         per = ms / max(n, 1)
         d = {"void_threshold": thr, "chunks": 4096, "vertices": V, "indices": I, "ms": per, "algorithmic_bytes": alg,
              "achieved": alg / (per / 1e3) / 1e9, "unit": "GB/s", "peak": peak, "frac": alg / (per / 1e3) / 1e9 / peak,
-             "chunks_per_s": 4096 / (per / 1e3)}
+             "chunks_per_s": 4096 / (per / 1e3), "mesh_kernel_ms": (ms - ems) / max(n, 1), "emit_kernel_ms": ems / max(n, 1)}
+        if thr == 128 and traffic:
+            d["traffic"] = (traffic.get("cfg2_mesh_only") or {}).get("dram_bytes_per_launch")
         if gold:
             gv = gold["variants"][str(thr)]
             d["totals_match_oracle_golden"] = (V == gv["total_vertices"] and I == gv["total_indices"])
@@ -634,7 +637,12 @@ def main():
     region.close()
     if not args.no_extra_legs:
         if world == 1:
-            cfg2 = mesh_only_cfg2(ctx, reg, args.steps, args.warmup, peak)
+            tj = {}
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            except Exception:
+                pass
+            cfg2 = mesh_only_cfg2(ctx, reg, args.steps, args.warmup, peak, tj)
         elif 512 % (64 * world) == 0:
             cfg4 = cfg4_literal(ctx, reg, rank, world, dist, min(args.steps, 2), stream)
 
