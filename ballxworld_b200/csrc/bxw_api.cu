@@ -37,6 +37,8 @@ struct Region {
     bxw_vertex *varena = nullptr;
     uint32_t *iarena = nullptr;
     unsigned long long v_cap = 0, i_cap = 0;
+    bxw_vertex *varena2 = nullptr;         // compaction target (same capacities), kept between compactions
+    uint32_t *iarena2 = nullptr;
     uint4 *frec = nullptr;             // face records between mesh_kernel and emit_kernel (device_common.cuh)
     uint4 *fslot = nullptr;            // per 32 records: the arena offsets of their chunk (v_off, i_off as two u64)
     unsigned long long f_cap = 0;
@@ -215,6 +217,8 @@ void region_free(Region &r) {
     cudaFree(r.spans);
     cudaFree(r.varena);
     cudaFree(r.iarena);
+    cudaFree(r.varena2);
+    cudaFree(r.iarena2);
     cudaFree(r.frec);
     cudaFree(r.fslot);
     cudaFree(r.counters);
@@ -497,6 +501,10 @@ int arena_resize(bxw_ctx *ctx, Region &r, unsigned long long v_cap, unsigned lon
     CK(cudaStreamSynchronize(ctx->stream));
     cudaFree(r.varena);
     cudaFree(r.iarena);
+    cudaFree(r.varena2); // (sized like the old arena)
+    cudaFree(r.iarena2);
+    r.varena2 = nullptr;
+    r.iarena2 = nullptr;
     r.varena = nv;
     r.iarena = ni;
     r.v_cap = v_cap;
@@ -1656,23 +1664,24 @@ int bxw_region_compact_arena(bxw_ctx *ctx, uint64_t *arena_vertices, uint64_t *a
     int rc = ensure_io_c(ctx, (size_t)r.n_work * 2 * sizeof(unsigned long long));
     if (rc) return rc;
     unsigned long long *new_off = (unsigned long long *)ctx->io_c;
-    bxw_vertex *nv = nullptr;
-    uint32_t *ni = nullptr;
-    CK(cudaMalloc(&nv, r.v_cap * sizeof(bxw_vertex)));
-    if (cudaMalloc(&ni, r.i_cap * sizeof(uint32_t)) != cudaSuccess) {
-        cudaFree(nv);
-        return fail(ctx, BXW_E_NOMEM, "no device memory for the second arena");
+    // the second arena is allocated once and the two swap roles (a cudaMalloc / cudaFree pair of gigabytes per compaction was
+    // the 5 ms latency spike of the edit sweep)
+    if (!r.varena2) {
+        CK(cudaMalloc(&r.varena2, r.v_cap * sizeof(bxw_vertex)));
+        if (cudaMalloc(&r.iarena2, r.i_cap * sizeof(uint32_t)) != cudaSuccess) {
+            cudaFree(r.varena2);
+            r.varena2 = nullptr;
+            return fail(ctx, BXW_E_NOMEM, "no device memory for the second arena");
+        }
     }
     launch_compact_offsets(r.spans, r.span_cap, r.n_work, new_off, r.counters, ctx->stream);
-    launch_compact_copy(r.spans, new_off, r.n_work, r.varena, r.iarena, nv, ni, ctx->stream);
+    launch_compact_copy(r.spans, new_off, r.n_work, r.varena, r.iarena, r.varena2, r.iarena2, ctx->stream);
     ctx->launches += 2;
     CK(cudaMemcpyAsync(r.h_counters, r.counters, sizeof(MeshCounters), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
-    cudaFree(r.varena);
-    cudaFree(r.iarena);
-    r.varena = nv;
-    r.iarena = ni;
+    std::swap(r.varena, r.varena2);
+    std::swap(r.iarena, r.iarena2);
     if (arena_vertices) *arena_vertices = r.h_counters->v_alloc;
     if (arena_indices) *arena_indices = r.h_counters->i_alloc;
     return BXW_OK;

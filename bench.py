@@ -608,7 +608,14 @@ def main():
     del hvs, his
 
     t = torch.tensor([ms, e2e_s * 1000.0, mesh_ms, mat_ms, stream_ms, copy_s * 1000.0], dtype=torch.float64, device="cuda")
+    per_rank = None
     if world > 1:
+        # per-rank view of the same timed region: this rank's device time per step, its mesher time and its mesh size (the slabs
+        # hold different terrain, so the ranks do not carry the same mesh work)
+        mine = torch.tensor([ms / args.steps, mesh_ms / max(mesh_launches, 1), fill_ms / max(fill_launches, 1), float(tot_v)], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros(4, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [{"ms_per_step": float(a[0]), "mesh_ms": float(a[1]), "fill_ms": float(a[2]), "vertices": int(a[3])} for a in allr]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, e2e_ms, mesh_ms_max, mat_ms, stream_ms_max, copy_ms = (float(x) for x in t.tolist())
     tot = torch.tensor([tot_v, tot_i, launches], dtype=torch.int64, device="cuda")
@@ -718,7 +725,7 @@ def main():
             "fused_generate_and_mesh": None if fused_ms is None else {"ms_per_step": fused_ms, "value": n_chunks / (fused_ms / 1000.0), "unit": UNIT,
                                                                       "note": "bxw_region_generate_and_mesh with BXW_OPT_MESH_FROM_HEIGHT_MAP=1"},
             "mesh": {"vertices": tot_v_all, "indices": tot_i_all, "arena_vertices": av, "arena_indices": ai},
-            "multi_gpu_parity": parity, "cfg5_edits": edits_leg, "cfg2_mesh_only": cfg2, "cfg4_literal": cfg4,
+            "per_rank": per_rank, "multi_gpu_parity": parity, "cfg5_edits": edits_leg, "cfg2_mesh_only": cfg2, "cfg4_literal": cfg4,
         }
         if args.slab:
             line["config"]["workload"] += f" [DEBUG slab override {slab}: not the benchmark configuration]"
