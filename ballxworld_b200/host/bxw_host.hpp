@@ -477,6 +477,27 @@ class Region {
         gpu_.check(bxw_region_remesh_dirty(gpu_.raw(), &n));
         return n;
     }
+    // World::check_load_deltas + recalculate_load_deltas + the delta loop of main_loop_tick (worldmgr.rs:407-732) for the box:
+    // anchors = the CLoadAnchor entities (position, radius, load_mesh). Returns {deltas consumed, chunks generated, chunks
+    // meshed, meshes unloaded}; meshes of newly generated chunks follow on the next tick, as in the reference.
+    std::array<uint32_t, 4> tick(const std::vector<bxw_load_anchor> &anchors, uint64_t seed, int precision = 64, uint32_t max_deltas = 0) {
+        gpu_.bind(registry_);
+        const auto ids = StdGenerator::resolve_ids(registry_);
+        gpu_.check(bxw_set_gen_ids(gpu_.raw(), ids[0], ids[1], ids[2], ids[3], ids[4]));
+        uint32_t nu = 0, nl = 0;
+        gpu_.check(bxw_region_update_anchors(gpu_.raw(), anchors.data(), (uint32_t)anchors.size(), &nu, &nl));
+        std::array<uint32_t, 4> st{{0, 0, 0, 0}};
+        gpu_.check(bxw_region_apply_deltas(gpu_.raw(), seed, precision, max_deltas, st.data()));
+        return st;
+    }
+    void unload_all() { gpu_.check(bxw_region_unload_all(gpu_.raw())); }
+    std::vector<bxw_chunk_delta> load_deltas() const { // the ordered list of the last update_anchors
+        uint32_t n = 0;
+        gpu_.check(bxw_region_load_deltas(gpu_.raw(), nullptr, 0, &n));
+        std::vector<bxw_chunk_delta> out(n);
+        if (n) gpu_.check(bxw_region_load_deltas(gpu_.raw(), out.data(), n, &n));
+        return out;
+    }
     std::pair<uint64_t, uint64_t> arena() const {
         uint64_t v = 0, i = 0;
         gpu_.check(bxw_region_arena_extent(gpu_.raw(), &v, &i));

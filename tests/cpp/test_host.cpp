@@ -253,6 +253,35 @@ static void apply_voxel_changes_and_remesh() {
     CHECK(region.remesh_dirty() == 0);
 }
 
+// ---- load anchors: recalculate_load_deltas + main_loop_tick (worldmgr.rs:407-732) through Region::tick ----
+static void load_anchor_ticks() {
+    Region region(*g_gpu, {6, 0, -2}, {10, 3, 9}, *g_reg);
+    region.unload_all();
+    const std::vector<bxw_load_anchor> anchors = {{9, 1, 2, 3, 1}};
+    const auto t1 = region.tick(anchors, 0);          // nothing loaded: block data of the sphere (clipped to the box)
+    CHECK(t1[1] > 0 && t1[2] == 0 && t1[0] == t1[1]);
+    const auto t2 = region.tick(anchors, 0);          // now the meshes whose 27 chunks hold block data
+    CHECK(t2[1] == 0 && t2[2] > 0);
+    const auto t3 = region.tick(anchors, 0);
+    CHECK(t3[0] == 0);                                // steady state
+    // the anchor moves: the list interleaves unloads and loads, each nearest first
+    uint32_t nu = 0, nl = 0;
+    const std::vector<bxw_load_anchor> moved = {{12, 1, 2, 3, 1}};
+    g_gpu->check(bxw_region_update_anchors(g_gpu->raw(), moved.data(), 1, &nu, &nl));
+    CHECK(nu > 0 && nl > 0);
+    const auto deltas = region.load_deltas();
+    CHECK(deltas.size() == nu + nl);
+    int32_t last_u = -1, last_l = -1;
+    bool sorted = true;
+    for (size_t i = 0; i < deltas.size(); i++) {
+        int32_t &last = deltas[i].unload ? last_u : last_l;
+        sorted &= deltas[i].min_anchor_distance >= last;
+        last = deltas[i].min_anchor_distance;
+        if (i < 2 * std::min(nu, nl)) sorted &= (deltas[i].unload != 0) == (i % 2 == 0);
+    }
+    CHECK(sorted);
+}
+
 int main() {
     try {
         Gpu gpu(0);
@@ -273,6 +302,7 @@ int main() {
         RUN(mesh_from_chunk_panics_on_unknown_ids);
         RUN(region_generate_and_mesh_cfg1);
         RUN(apply_voxel_changes_and_remesh);
+        RUN(load_anchor_ticks);
         std::printf("test result: %s. %d passed; %d failed; %llu kernel launches\n", g_failed ? "FAILED" : "ok", g_run - g_failed, g_failed,
                     (unsigned long long)gpu.kernel_launches());
     } catch (const std::exception &e) {
