@@ -205,6 +205,7 @@ class Context:
     OPT_MESH_FROM_HEIGHT_MAP = 1
     OPT_ELIDE_UNIFORM = 2
     OPT_CUBES_ONLY_MESHER = 3
+    OPT_PIPELINED_MESHER = 4
 
     def set_option(self, option, value):
         self._ck(self.L.bxw_set_option(self.h, option, int(value)))

@@ -116,6 +116,11 @@ struct bxw_ctx {
     bool use_summaries = true;                                     // BXW_OPT_CHUNK_SUMMARIES
     bool elide_uniform = true;                                     // BXW_OPT_ELIDE_UNIFORM
     bool lean_mesher = true;                                       // BXW_OPT_CUBES_ONLY_MESHER
+    int pipeline_mode = 0;                                         // BXW_OPT_PIPELINED_MESHER: 0 off (default), 1 auto, 2 always
+    uint32_t mesh_epoch = 0;                                       // tag of the last pipelined pass (24 bits)
+    cudaStream_t emit_stream = nullptr;                            // emit_kernel of a pipelined pass
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    double last_faces_per_item = 0.0;                              // statistics of the last pass (the auto mode's heuristic)
     bool mesh_from_hmap = false;                                   // BXW_OPT_MESH_FROM_HEIGHT_MAP
     uint32_t last_candidates = 0, last_candidates_of = 0;          // last whole-region mesh: chunks listed / interior chunks
     // staging for host<->device codecs
@@ -524,6 +529,7 @@ int faces_resize(bxw_ctx *ctx, Region &r, unsigned long long f_cap) {
     f_cap = (f_cap + 31ull) & ~31ull;
     CK(cudaMalloc(&r.frec, f_cap * sizeof(uint4)));
     CK(cudaMalloc(&r.fslot, (f_cap / 32) * sizeof(uint4)));
+    CK(cudaMemsetAsync(r.fslot, 0, (f_cap / 32) * sizeof(uint4), ctx->stream)); // no entry may carry a pass tag by accident
     r.f_cap = f_cap;
     return BXW_OK;
 }
@@ -644,25 +650,57 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
         p.fslot = r.fslot;
         p.f_cap = r.f_cap;
         p.count_only = count_only ? 1 : 0;
+        // Pipelined pass: emit_kernel runs NEXT TO mesh_kernel on a second stream and consumes each chunk's record block as
+        // soon as it is published (mesh_kernel is compute / latency bound, emit_kernel memory bound). Both leave room for each
+        // other on every SM: mesh_kernel takes half its usual CTAs, emit_kernel two. Worth it when the pass emits a lot per
+        // chunk; a pass over mostly empty chunks keeps the full-occupancy mesh_kernel followed by emit_kernel.
+        const bool pipelined = !count_only && !getenv("BXW_EXP_NO_PIPELINE") &&
+                               (ctx->pipeline_mode == 2 || (ctx->pipeline_mode == 1 && ctx->last_faces_per_item >= 400.0));
+        p.pipelined = pipelined ? 1 : 0;
+        int mesh_cap = pipelined ? (lean ? 2 : 1) : 0, emit_ctas = 2;
+        if (pipelined && getenv("BXW_EXP_PIPE_MESH")) mesh_cap = atoi(getenv("BXW_EXP_PIPE_MESH")); // experiments only
+        if (pipelined && getenv("BXW_EXP_PIPE_EMIT")) emit_ctas = atoi(getenv("BXW_EXP_PIPE_EMIT"));
+        if (pipelined) {
+            ctx->mesh_epoch = (ctx->mesh_epoch % 0xFFFFFFu) + 1u;
+            if (ctx->mesh_epoch == 1u && r.fslot) CK(cudaMemsetAsync(r.fslot, 0, (r.f_cap / 32) * sizeof(uint4), ctx->stream)); // tags wrapped
+            p.epoch = ctx->mesh_epoch;
+            MeshParams pf0 = p; // grids first: emit_kernel has to know how many mesh CTAs will retire
+            pf0.n_work = n_work;
+            p.mesh_ctas = mesh_kernel_grid(p, ctx->sm_count, lean, mesh_cap) + (lean ? mesh_kernel_grid(pf0, ctx->sm_count, false, 1) : 0u);
+        } else {
+            p.epoch = 0;
+            p.mesh_ctas = 0;
+        }
         CK(cudaEventRecord(ctx->ev_m0, ctx->stream));
+        if (pipelined) {
+            // emit_kernel starts behind everything queued so far (counters upload, candidate list) and behind a pending fetch
+            CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->emit_stream, ctx->ev_fork, 0));
+            if (ctx->copy_pending) CK(cudaStreamWaitEvent(ctx->emit_stream, ctx->ev_copy_done, 0));
+        }
         if (lean) {
             // cubes-and-void chunks (all of generated terrain) go through the lean instantiation at twice the occupancy; what it
             // cannot handle (a slope / corner placed by an edit) lands on the fallback list for the general kernel
             CK(cudaMemsetAsync(r.fb_count, 0, sizeof(uint32_t), ctx->stream));
-            launch_mesh_kernel(p, ctx->sm_count, ctx->stream, true, !work && !p.n_work_dev);
+            launch_mesh_kernel(p, ctx->sm_count, ctx->stream, true, !work && !p.n_work_dev, mesh_cap);
             MeshParams pf = p;
             pf.work = r.fb_work;
             pf.work_span = r.fb_span;
             pf.n_work_dev = r.fb_count;
             pf.cursor = &r.counters->work_next2;
-            launch_mesh_kernel(pf, ctx->sm_count, ctx->stream, false, false);
+            launch_mesh_kernel(pf, ctx->sm_count, ctx->stream, false, false, pipelined ? 1 : 0);
             ctx->launches += 2;
         } else {
-            launch_mesh_kernel(p, ctx->sm_count, ctx->stream, false, false);
+            launch_mesh_kernel(p, ctx->sm_count, ctx->stream, false, false, mesh_cap);
             ctx->launches += 1;
         }
         CK(cudaEventRecord(ctx->ev_mm, ctx->stream));
-        if (!count_only) { // vertices and indices of the recorded sides (returns at once if a chunk did not fit)
+        if (pipelined) {
+            launch_emit_kernel_pipelined(p, ctx->sm_count, emit_ctas, ctx->emit_stream);
+            ctx->launches += 1;
+            CK(cudaEventRecord(ctx->ev_join, ctx->emit_stream));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+        } else if (!count_only) { // vertices and indices of the recorded sides (returns at once if a chunk did not fit)
             // the arena is rewritten from here on: an asynchronous fetch of the previous meshes has to be through
             if (ctx->copy_pending) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done, 0));
             launch_emit_kernel(p, ctx->sm_count, ctx->stream);
@@ -686,6 +724,8 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
         }
         if (r.h_counters->flags & kFlagUnknownId)
             return fail(ctx, BXW_E_UNKNOWN_ID, "a voxel references a block id without a registry definition");
+        if (r.h_counters->flags & kFlagPipelineTimeout)
+            return fail(ctx, BXW_E_CUDA, "pipelined emit_kernel timed out waiting for mesh_kernel (internal error)");
         const unsigned long long need_v = r.h_counters->v_alloc, need_i = r.h_counters->i_alloc;
         if (count_only || (r.h_counters->flags & kFlagArenaOverflow)) {
             // size the arena from the measured need (+ slack so small edits can append) and run again
@@ -699,6 +739,11 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
                 CK(cudaMemcpyAsync(r.span_cap, r.span_cap_bak, r.n_work * sizeof(uint2), cudaMemcpyDeviceToDevice, ctx->stream));
             }
             continue;
+        }
+        {
+            // faces per work item of this pass: what the next pass's pipelining decision goes by
+            const double items = p.n_work_dev ? (double)*reinterpret_cast<const uint32_t *>(r.h_counters + 1) : (double)n_work;
+            ctx->last_faces_per_item = items > 0 ? (double)r.h_counters->f_alloc / items : 0.0;
         }
         if (p.n_work_dev) { // whole-region pass over a device-built candidate list: remember its length (statistics)
             ctx->last_candidates = *reinterpret_cast<const uint32_t *>(r.h_counters + 1);
@@ -813,6 +858,9 @@ int bxw_create(int device, bxw_ctx **out) {
         cudaEventCreate(&ctx->ev_g0) != cudaSuccess || cudaEventCreate(&ctx->ev_g1) != cudaSuccess ||
         cudaEventCreate(&ctx->ev_g2) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->emit_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_mesh_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_copy_done, cudaEventDisableTiming) != cudaSuccess)
         return bail(BXW_E_CUDA);
@@ -859,6 +907,12 @@ void bxw_destroy(bxw_ctx *ctx) {
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamDestroy(ctx->copy_stream);
     }
+    if (ctx->emit_stream) {
+        cudaStreamSynchronize(ctx->emit_stream);
+        cudaStreamDestroy(ctx->emit_stream);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_mesh_done) cudaEventDestroy(ctx->ev_mesh_done);
     if (ctx->ev_copy_done) cudaEventDestroy(ctx->ev_copy_done);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -882,6 +936,10 @@ int bxw_set_option(bxw_ctx *ctx, int option, int value) {
     }
     if (option == BXW_OPT_MESH_FROM_HEIGHT_MAP) {
         ctx->mesh_from_hmap = value != 0;
+        return BXW_OK;
+    }
+    if (option == BXW_OPT_PIPELINED_MESHER) {
+        ctx->pipeline_mode = value < 0 ? 0 : (value > 2 ? 2 : value);
         return BXW_OK;
     }
     if (option == BXW_OPT_CUBES_ONLY_MESHER) {

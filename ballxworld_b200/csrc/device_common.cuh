@@ -22,6 +22,7 @@ struct DeviceRegistry {
 // error / status flags accumulated by kernels (atomicOr into MeshCounters::flags)
 constexpr unsigned long long kFlagUnknownId = 1ull;
 constexpr unsigned long long kFlagArenaOverflow = 2ull;
+constexpr unsigned long long kFlagPipelineTimeout = 4ull; // pipelined emit_kernel gave up waiting for mesh_kernel (a bug, not a state)
 
 struct MeshCounters {
     unsigned long long v_alloc; // next free vertex slot in the arena
@@ -30,6 +31,7 @@ struct MeshCounters {
     unsigned long long work_next; // dynamic work-list cursor
     unsigned long long work_next2; // the same for the general kernel's pass over the cubes-only kernel's fallback list
     unsigned long long f_alloc;   // next free face-record slot (a chunk takes a multiple of 32)
+    unsigned long long mesh_done; // pipelined passes: mesh_kernel CTAs that have retired
     unsigned long long v_garbage; // arena space that no span refers to any more (re-meshes that moved, unloaded meshes)
     unsigned long long i_garbage;
     // -DBXW_PHASE_TIMING builds only: SM cycles of CTA thread 0 summed over chunks: [0] work fetch + neighbour table,
@@ -67,6 +69,11 @@ struct MeshParams {
     const MeshTables *tables;
     DeviceRegistry reg;
     uint32_t *fallback_work, *fallback_span, *fallback_count; // lean kernel only: chunks left to the general kernel
+    // pipelined pass (mesh_kernel and emit_kernel side by side): tag of this pass in the fslot entries, number of mesh CTAs of
+    // all mesh launches of the pass
+    int pipelined;
+    uint32_t epoch;
+    unsigned long long mesh_ctas;
     int count_only; // 1: fill spans' counts only (offsets = running totals), no vertex/index writes
     // fused generate+mesh (pristine StdGenerator terrain): derive the 34^3 table from the column parameters
     const int32_t *hmap;   // nullptr = read the block storage
@@ -78,7 +85,7 @@ struct MeshParams {
 // lean = the cubes-and-void instantiation (no class table, 4-5 CTAs per SM); chunks it cannot handle are appended to the
 // fallback list for a second launch of the general kernel
 // mostly_uniform: the work list is a whole region with the uniform chunks still in it (picks the lean variant tuned for them)
-void launch_mesh_kernel(const MeshParams &p, int sm_count, cudaStream_t stream, bool lean, bool mostly_uniform);
+void launch_mesh_kernel(const MeshParams &p, int sm_count, cudaStream_t stream, bool lean, bool mostly_uniform, int max_per_sm = 0);
 
 // Face record: one uint4 per visible side, frec[k], in the reference's emission order; every chunk's records start on a
 // multiple of 32 and are padded to one, and fslot[k / 32] holds the chunk's arena offsets (v_off, i_off as two u64), so that
@@ -90,6 +97,9 @@ void launch_mesh_kernel(const MeshParams &p, int sm_count, cudaStream_t stream, 
 constexpr uint32_t kFacePad = 0xFFFFFFFFu;
 // Second half of mesh_from_chunk (voxmesh.rs:122-177): builds the vertices and indices of every recorded side.
 void launch_emit_kernel(const MeshParams &p, int sm_count, cudaStream_t stream);
+void launch_emit_kernel_pipelined(const MeshParams &p, int sm_count, int ctas_per_sm, cudaStream_t stream);
+// grid of the mesh_kernel launch launch_mesh_kernel would make (max_per_sm: cap on CTAs per SM, 0 = none)
+unsigned mesh_kernel_grid(const MeshParams &p, int sm_count, bool lean, int max_per_sm);
 
 // Fused generate+mesh: list the interior chunks of pristine terrain that can have a mesh (the surface passes through
 // their 34^3 neighbourhood) and zero the spans of all others, from the height map alone.

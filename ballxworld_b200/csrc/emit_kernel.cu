@@ -14,6 +14,8 @@
 // corner: field = 16 * corner, voxmesh.rs:36-41).
 #include "device_common.cuh"
 
+#include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 namespace bxw {
@@ -112,6 +114,23 @@ __device__ __forceinline__ void warp_bulk_out_vertices(uint32_t *dst, const uint
         __stcs(reinterpret_cast<uint2 *>(dst - misal + w), *reinterpret_cast<const uint2 *>(stage16 + w));
 }
 
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// PIPE = false: launched after mesh_kernel has finished, over the f_alloc / 32 batches it left.
+// PIPE = true: launched NEXT TO mesh_kernel (another stream; mesh_kernel is compute / latency bound, this kernel memory bound):
+// a batch is consumed as soon as its chunk's record block is published -- mesh_kernel writes the batch's fslot entry last,
+// tagged with the pass's epoch, after a fence -- and the loop ends when every mesh CTA has retired (counters->mesh_done) and
+// the batch index has passed the final f_alloc.
+template <bool PIPE>
 __global__ void __launch_bounds__(ENT, 4) emit_kernel(MeshParams p) {
     extern __shared__ __align__(16) unsigned char esmem_raw[];
     ESmem &s = *reinterpret_cast<ESmem *>(esmem_raw);
@@ -143,8 +162,8 @@ __global__ void __launch_bounds__(ENT, 4) emit_kernel(MeshParams p) {
     __syncthreads();
 
     // a chunk that did not fit left its records unwritten: the host grows the arenas and runs both kernels again
-    if (p.counters->flags & kFlagArenaOverflow) return;
-    const unsigned long long n_batches = p.counters->f_alloc >> 5;
+    if (!PIPE && (p.counters->flags & kFlagArenaOverflow)) return;
+    const unsigned long long n_batches = PIPE ? ~0ull : (p.counters->f_alloc >> 5);
     uint32_t *const stw = &s.wstage[warp][0][0];
     uint32_t npass = 0; // vertex passes of this warp so far (selects the staging buffer)
     SideRec *const rec = &s.rec[warp][0];
@@ -156,19 +175,53 @@ __global__ void __launch_bounds__(ENT, 4) emit_kernel(MeshParams p) {
     // it (scoreboards count in order), i.e. expose a full memory latency per batch.
     uint4 q = make_uint4(kFacePad, 0u, 0u, 0u);
     uint4 qw = make_uint4(0u, 0u, 0u, 0u);
+    bool have = false; // PIPE: q / qw hold the (published) batch of the coming iteration
     auto fetch = [&](unsigned long long bb) {
-        if (bb < n_batches) {
+        if (PIPE) {
+            // only what is published already may be read ahead (the tag is the last word mesh_kernel writes for a batch)
+            have = (ld_acquire_u32(&p.fslot[bb].w) >> 8) == p.epoch;
+            if (have) {
+                q = __ldcg(p.frec + bb * 32ull + lane);
+                qw = __ldcg(p.fslot + bb);
+            }
+        } else if (bb < n_batches) {
             q = __ldg(p.frec + bb * 32ull + lane);
             qw = __ldg(p.fslot + bb);
         }
     };
+    if (PIPE && (unsigned long long)blockIdx.x * ENW + warp >= p.f_cap / 32ull) return; // (no such batch can exist)
     fetch((unsigned long long)blockIdx.x * ENW + warp);
     for (unsigned long long b = (unsigned long long)blockIdx.x * ENW + warp; b < n_batches; b += bstep) {
+        if (PIPE && !have) {
+            // wait for the batch to be published, or for the end of production
+            const long long t_start = clock64();
+            int stop = 0;
+            for (;;) {
+                if ((ld_acquire_u32(&p.fslot[b].w) >> 8) == p.epoch) break;
+                if (ld_acquire_u64(&p.counters->mesh_done) == p.mesh_ctas) {
+                    // every mesh CTA has retired: f_alloc is final. A batch below it that is still untagged belongs to a chunk
+                    // that did not fit the arenas (the host grows them and runs the pass again).
+                    if ((ld_acquire_u32(&p.fslot[b].w) >> 8) == p.epoch) break;
+                    stop = 1;
+                    break;
+                }
+                if (clock64() - t_start > (1ll << 32)) { // ~2 s: something is wrong; fail loudly instead of hanging the device
+                    if (lane == 0) atomicOr(&p.counters->flags, kFlagPipelineTimeout);
+                    stop = 1;
+                    break;
+                }
+                __nanosleep(256);
+            }
+            if (stop) break;
+            q = __ldcg(p.frec + b * 32ull + lane);
+            qw = __ldcg(p.fslot + b);
+        }
         const uint32_t r0 = q.x, r1 = q.y, r2 = q.z, nb = q.w;
-        // the chunk's arena span
+        // the chunk's arena span (fslot: v_off as 64 bits, i_off as 40 bits, the pass's epoch in the top 24)
         const unsigned long long v_off = (unsigned long long)qw.x | ((unsigned long long)qw.y << 32),
-                                 i_off = (unsigned long long)qw.z | ((unsigned long long)qw.w << 32);
-        fetch(b + bstep);
+                                 i_off = (unsigned long long)qw.z | ((unsigned long long)(qw.w & 0xFFu) << 32);
+        if (!PIPE || b + bstep < p.f_cap / 32ull) fetch(b + bstep);
+        else have = false;
         const bool act = r0 != kFacePad;          // padding only ever follows the faces of a chunk
         const uint32_t nbf = __popc(__ballot_sync(FULL, act));
         // ---------------- side pass: lane = side (voxmesh.rs:122-153) ----------------
@@ -328,11 +381,21 @@ __global__ void __launch_bounds__(ENT, 4) emit_kernel(MeshParams p) {
 static_assert(sizeof(ESmem) <= 56 * 1024, "emit_kernel's shared memory no longer fits four times on an SM");
 
 void launch_emit_kernel(const MeshParams &p, int sm_count, cudaStream_t stream) {
-    cudaFuncSetAttribute(emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ESmem));
+    cudaFuncSetAttribute(emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ESmem));
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, emit_kernel, ENT, sizeof(ESmem));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, emit_kernel<false>, ENT, sizeof(ESmem));
+    // three CTAs per SM, not four: the kernel is bound by the write stream, and with fewer writers in flight DRAM takes it
+    // faster (hashed-block chunks 10.9 -> 9.9 ms, terrain 0.95 -> 0.92 ms)
+    per_sm = std::min(per_sm, 3);
     if (per_sm < 1) per_sm = 1;
-    emit_kernel<<<(unsigned)(sm_count * per_sm), ENT, sizeof(ESmem), stream>>>(p);
+    if (const char *e = getenv("BXW_EXP_EMIT_CTAS")) per_sm = std::min(per_sm, std::max(1, atoi(e))); // experiments only
+    emit_kernel<false><<<(unsigned)(sm_count * per_sm), ENT, sizeof(ESmem), stream>>>(p);
+}
+
+void launch_emit_kernel_pipelined(const MeshParams &p, int sm_count, int ctas_per_sm, cudaStream_t stream) {
+    cudaFuncSetAttribute(emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ESmem));
+    cudaFuncSetAttribute(emit_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    emit_kernel<true><<<(unsigned)(sm_count * ctas_per_sm), ENT, sizeof(ESmem), stream>>>(p);
 }
 
 } // namespace bxw

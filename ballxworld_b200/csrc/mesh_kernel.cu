@@ -22,6 +22,8 @@
 //   C  face records in tiles of <=1024 sides: (C1) the sides in emission order with their first vertex / index; (C2) thread per
 //      side: class, block id, the 27-bit occupancy of the cell's 3x3x3 neighbourhood (all the AO test needs,
 //      voxmesh.rs:128-137), written as one uint4 (device_common.cuh).
+#include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "device_common.cuh"
@@ -939,11 +941,24 @@ __global__ void __launch_bounds__(NT, LEAN ? 4 : 2) mesh_kernel(MeshParams p) {
             const uint32_t padF = (TF + 31u) & ~31u;
             if (tid < padF - TF) p.frec[fbase + TF + tid] = make_uint4(kFacePad, 0u, 0u, 0u);
             const unsigned long long vb = s.vbase, ib = s.ibase;
-            const uint4 where = make_uint4((uint32_t)vb, (uint32_t)(vb >> 32), (uint32_t)ib, (uint32_t)(ib >> 32));
+            // v_off, i_off (40 bits) and the pass's tag: in a pipelined pass emit_kernel polls the tag, so every record of the
+            // chunk has to be visible before it
+            const uint4 where = make_uint4((uint32_t)vb, (uint32_t)(vb >> 32), (uint32_t)ib, ((uint32_t)(ib >> 32) & 0xFFu) | (p.epoch << 8));
+            if (p.pipelined) {
+                __threadfence();
+                __syncthreads();
+            }
             for (uint32_t t = tid; t < (padF >> 5); t += NT) p.fslot[(fbase >> 5) + t] = where;
         }
         PHASE_MARK(t_c1);
         PHASE_ADD(3, t_b1, t_c1);
+    }
+    if (p.pipelined) { // this CTA's records are all published: tell emit_kernel (it stops when every mesh CTA has retired)
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(&p.counters->mesh_done, 1ull);
+        }
     }
 }
 
@@ -1001,22 +1016,38 @@ int mesh_kernel_max_ctas_per_sm() {
 }
 
 template <bool LEAN, bool CALL_SLOW>
-static void launch_mesh_kernel_t(const MeshParams &p, int sm_count, cudaStream_t stream) {
+static unsigned mesh_grid_t(const MeshParams &p, int sm_count, int max_per_sm) {
     // per device (a process may own contexts on several GPUs); cheap enough to repeat on every launch
     cudaFuncSetAttribute(mesh_kernel<LEAN, CALL_SLOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemT<LEAN>));
+    // the same shared-memory carve-out for every kernel of the mesher: CTAs of mesh_kernel and emit_kernel share SMs in a
+    // pipelined pass, and an SM cannot change its carve-out while it holds CTAs
+    cudaFuncSetAttribute(mesh_kernel<LEAN, CALL_SLOW>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         p.pipelined ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault);
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mesh_kernel<LEAN, CALL_SLOW>, NT, sizeof(SmemT<LEAN>));
     if (per_sm < 1) per_sm = 1;
+    if (max_per_sm > 0) per_sm = std::min(per_sm, max_per_sm);
+    if (const char *e = getenv("BXW_EXP_MESH_CTAS")) per_sm = std::min(per_sm, std::max(1, atoi(e))); // experiments only
     unsigned grid = (unsigned)(sm_count * per_sm);
     if (grid > p.n_work) grid = p.n_work;
+    return grid;
+}
+
+template <bool LEAN, bool CALL_SLOW>
+static void launch_mesh_kernel_t(const MeshParams &p, int sm_count, cudaStream_t stream, int max_per_sm) {
+    const unsigned grid = mesh_grid_t<LEAN, CALL_SLOW>(p, sm_count, max_per_sm);
     if (grid == 0) return;
     mesh_kernel<LEAN, CALL_SLOW><<<grid, NT, sizeof(SmemT<LEAN>), stream>>>(p);
 }
 
-void launch_mesh_kernel(const MeshParams &p, int sm_count, cudaStream_t stream, bool lean, bool mostly_uniform) {
-    if (!lean) launch_mesh_kernel_t<false, false>(p, sm_count, stream);
-    else if (mostly_uniform) launch_mesh_kernel_t<true, false>(p, sm_count, stream);
-    else launch_mesh_kernel_t<true, true>(p, sm_count, stream);
+unsigned mesh_kernel_grid(const MeshParams &p, int sm_count, bool lean, int max_per_sm) {
+    return lean ? mesh_grid_t<true, true>(p, sm_count, max_per_sm) : mesh_grid_t<false, false>(p, sm_count, max_per_sm);
+}
+
+void launch_mesh_kernel(const MeshParams &p, int sm_count, cudaStream_t stream, bool lean, bool mostly_uniform, int max_per_sm) {
+    if (!lean) launch_mesh_kernel_t<false, false>(p, sm_count, stream, max_per_sm);
+    else if (mostly_uniform) launch_mesh_kernel_t<true, false>(p, sm_count, stream, max_per_sm);
+    else launch_mesh_kernel_t<true, true>(p, sm_count, stream, max_per_sm);
 }
 
 } // namespace bxw

@@ -89,8 +89,13 @@ int bxw_set_stream(bxw_ctx *ctx, void *cuda_stream);
  * import that differs) gives the chunk its own storage back. 0 = every chunk materialised. Same results either way.
  * BXW_OPT_CUBES_ONLY_MESHER (default 1): regions holding generator output (plus edits) are meshed by the cubes-and-void
  * instantiation of the mesher (no class table, twice the occupancy); chunks with other shapes fall back to the general
- * kernel. 0 = general kernel only. Same results either way. */
-enum { BXW_OPT_CHUNK_SUMMARIES = 0, BXW_OPT_MESH_FROM_HEIGHT_MAP = 1, BXW_OPT_ELIDE_UNIFORM = 2, BXW_OPT_CUBES_ONLY_MESHER = 3 };
+ * kernel. 0 = general kernel only. Same results either way.
+ * BXW_OPT_PIPELINED_MESHER (default 0): the mesher's two kernels run side by side on two streams, emit_kernel consuming
+ * each chunk's face records as soon as mesh_kernel has published them. 1 = when the previous pass emitted at least 400
+ * sides per listed chunk, 2 = always, 0 = one after the other. Same results; on B200 the two kernels slow each other down
+ * by more than the overlap gains (profiles/r02_summary.md), so it is off unless asked for. */
+enum { BXW_OPT_CHUNK_SUMMARIES = 0, BXW_OPT_MESH_FROM_HEIGHT_MAP = 1, BXW_OPT_ELIDE_UNIFORM = 2, BXW_OPT_CUBES_ONLY_MESHER = 3,
+       BXW_OPT_PIPELINED_MESHER = 4 };
 int bxw_set_option(bxw_ctx *ctx, int option, int value);
 int bxw_synchronize(bxw_ctx *ctx);
 /* Number of this library's kernels launched since creation (bench.py's gpu_launches evidence). */

@@ -300,3 +300,61 @@ def test_generate_in_two_parts_equals_generate(ctx, oracle):
         h = ctx.region_heightmap()
         assert np.array_equal(h[0], ref_h[0]) and np.array_equal(h[1], ref_h[1])
         ctx.region_destroy()
+
+
+def test_pipelined_mesher_equals_sequential(ctx, oracle):
+    """BXW_OPT_PIPELINED_MESHER: emit_kernel next to mesh_kernel (two streams, record blocks consumed as they are published)
+    produces the same meshes as one kernel after the other -- hashed blocks with every shape, terrain, a re-mesh pass, and a
+    pass that overflows the arena and is repeated."""
+    import ballxworld_b200 as bxw
+
+    try:
+        for kind in ("hashed", "terrain"):
+            dims = (5, 4, 5) if kind == "hashed" else (8, 3, 8)
+            ctx.region_create(9, 0, -2, *dims)
+            if kind == "hashed":
+                ctx.region_fill_synthetic(3, 160)
+            else:
+                ctx.region_generate(0, 64)
+            ctx.set_option(ctx.OPT_PIPELINED_MESHER, 0)
+            ctx.region_mesh()
+            ref = _meshes(ctx, dims)
+            ctx.set_option(ctx.OPT_PIPELINED_MESHER, 2)
+            for _ in range(3):
+                ctx.region_mesh()
+                assert _meshes(ctx, dims) == ref, kind
+            # a chunk against the oracle directly
+            chunks = _download_all(ctx, dims)
+            assert ref[(2, 1, 2)] == _oracle_mesh(oracle, chunks, (2, 1, 2))
+            # edits + re-mesh in pipelined mode
+            gx, gy, gz = 9 * 32 + 70, 40, -2 * 32 + 70
+            k = (2, 1, 2)
+            vi = (gx % 32) + 32 * (gz % 32) + 1024 * (gy % 32)
+            old = int(chunks[k][vi])
+            to = int(bxw.VoxelDatum.new(6, bxw.StdMeta.from_parts(2, 7)))
+            nd = ctx.region_apply_changes(np.array([(gx, gy, gz, old, to)], dtype=bxw.CHANGE_DTYPE))
+            assert ctx.region_remesh_dirty() == nd
+            chunks[k] = chunks[k].copy()
+            chunks[k][vi] = to
+            assert _meshes(ctx, dims)[k] == _oracle_mesh(oracle, chunks, k)
+            ctx.region_destroy()
+        # arena too small for a pipelined pass: the pass is repeated after the arenas grew
+        dims = (4, 4, 4)
+        ctx.region_create(0, 0, 0, *dims)
+        ctx.region_fill_synthetic(5, 250)
+        ctx.set_option(ctx.OPT_PIPELINED_MESHER, 0)
+        ctx.region_mesh()
+        ctx.region_fill_synthetic(5, 100)   # many more sides than the arena was sized for
+        ctx.region_mesh()
+        ref = _meshes(ctx, dims)
+        ctx.region_destroy()
+        ctx.region_create(0, 0, 0, *dims)
+        ctx.region_fill_synthetic(5, 250)
+        ctx.set_option(ctx.OPT_PIPELINED_MESHER, 2)
+        ctx.region_mesh()
+        ctx.region_fill_synthetic(5, 100)
+        ctx.region_mesh()
+        assert _meshes(ctx, dims) == ref
+        ctx.region_destroy()
+    finally:
+        ctx.set_option(ctx.OPT_PIPELINED_MESHER, 0)

@@ -24,6 +24,8 @@ def main():
     a = ap.parse_args()
     nx, ny, nz = (int(x) for x in a.dims.split(","))
     ctx = bxw.Context(0)
+    if os.environ.get("BXW_PIPE"):
+        ctx.set_option(ctx.OPT_PIPELINED_MESHER, int(os.environ["BXW_PIPE"]))
     reg = bxw.standard_registry()
     reg.bind(ctx)
     ctx.region_create(0, 0, 0, nx, ny, nz)

@@ -11,6 +11,8 @@ import ballxworld_b200 as bxw  # noqa: E402
 
 dims = tuple(int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "128,16,128").split(","))
 ctx = bxw.Context(0)
+if os.environ.get("BXW_PIPE"):
+    ctx.set_option(ctx.OPT_PIPELINED_MESHER, int(os.environ["BXW_PIPE"]))
 reg = bxw.standard_registry()
 region = bxw.Region((0, 0, 0), dims, reg, ctx=ctx)
 out = {}
