@@ -163,7 +163,8 @@ __global__ void __launch_bounds__(ENT, 4) emit_kernel(MeshParams p) {
 
     // a chunk that did not fit left its records unwritten: the host grows the arenas and runs both kernels again
     if (!PIPE && (p.counters->flags & kFlagArenaOverflow)) return;
-    const unsigned long long n_batches = PIPE ? ~0ull : (p.counters->f_alloc >> 5);
+    // (pipelined: the final count is not known yet; no batch can lie beyond the record buffer)
+    const unsigned long long n_batches = PIPE ? (p.f_cap >> 5) : (p.counters->f_alloc >> 5);
     uint32_t *const stw = &s.wstage[warp][0][0];
     uint32_t npass = 0; // vertex passes of this warp so far (selects the staging buffer)
     SideRec *const rec = &s.rec[warp][0];
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(ENT, 4) emit_kernel(MeshParams p) {
     uint4 q = make_uint4(kFacePad, 0u, 0u, 0u);
     uint4 qw = make_uint4(0u, 0u, 0u, 0u);
     bool have = false; // PIPE: q / qw hold the (published) batch of the coming iteration
-    auto fetch = [&](unsigned long long bb) {
+    auto fetch = [&](unsigned long long bb) { // bb < n_batches
         if (PIPE) {
             // only what is published already may be read ahead (the tag is the last word mesh_kernel writes for a batch)
             have = (ld_acquire_u32(&p.fslot[bb].w) >> 8) == p.epoch;
@@ -184,13 +185,12 @@ __global__ void __launch_bounds__(ENT, 4) emit_kernel(MeshParams p) {
                 q = __ldcg(p.frec + bb * 32ull + lane);
                 qw = __ldcg(p.fslot + bb);
             }
-        } else if (bb < n_batches) {
+        } else {
             q = __ldg(p.frec + bb * 32ull + lane);
             qw = __ldg(p.fslot + bb);
         }
     };
-    if (PIPE && (unsigned long long)blockIdx.x * ENW + warp >= p.f_cap / 32ull) return; // (no such batch can exist)
-    fetch((unsigned long long)blockIdx.x * ENW + warp);
+    if ((unsigned long long)blockIdx.x * ENW + warp < n_batches) fetch((unsigned long long)blockIdx.x * ENW + warp);
     for (unsigned long long b = (unsigned long long)blockIdx.x * ENW + warp; b < n_batches; b += bstep) {
         if (PIPE && !have) {
             // wait for the batch to be published, or for the end of production
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(ENT, 4) emit_kernel(MeshParams p) {
         // the chunk's arena span (fslot: v_off as 64 bits, i_off as 40 bits, the pass's epoch in the top 24)
         const unsigned long long v_off = (unsigned long long)qw.x | ((unsigned long long)qw.y << 32),
                                  i_off = (unsigned long long)qw.z | ((unsigned long long)(qw.w & 0xFFu) << 32);
-        if (!PIPE || b + bstep < p.f_cap / 32ull) fetch(b + bstep);
+        if (b + bstep < n_batches) fetch(b + bstep);
         else have = false;
         const bool act = r0 != kFacePad;          // padding only ever follows the faces of a chunk
         const uint32_t nbf = __popc(__ballot_sync(FULL, act));

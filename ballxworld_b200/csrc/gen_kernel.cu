@@ -64,18 +64,11 @@ __device__ __noinline__ double super_simplex_2d(const uint8_t *__restrict__ perm
         const double attn = dsub(2.0 / 3.0, dadd(dmul(dx, dx), dmul(dy, dy)));
         if (attn > 0.0) {
             const long long lx = bxi + c_lat_pt[index + k][0], ly = byi + c_lat_pt[index + k][1];
-            const unsigned h = __ldg(perm + (__ldg(perm + (unsigned)(lx & 0xff)) ^ (unsigned)(ly & 0xff)));
-            double gx, gy;
-            switch (h & 7u) { // gradient::grad2
-            case 0: gx = 1.0; gy = 0.0; break;
-            case 1: gx = -1.0; gy = 0.0; break;
-            case 2: gx = 0.0; gy = 1.0; break;
-            case 3: gx = 0.0; gy = -1.0; break;
-            case 4: gx = kDiag; gy = kDiag; break;
-            case 5: gx = -kDiag; gy = kDiag; break;
-            case 6: gx = kDiag; gy = -kDiag; break;
-            default: gx = -kDiag; gy = -kDiag; break;
-            }
+            // (plain loads: the table may live in shared memory, see fill_kernel)
+            const unsigned h = perm[perm[(unsigned)(lx & 0xff)] ^ (unsigned)(ly & 0xff)];
+            // gradient::grad2(h % 8) = (1,0) (-1,0) (0,1) (0,-1) (d,d) (-d,d) (d,-d) (-d,-d), as selects: a switch diverges eight ways
+            const double gx = (h & 4u) ? ((h & 1u) ? -kDiag : kDiag) : ((h & 2u) ? 0.0 : ((h & 1u) ? -1.0 : 1.0));
+            const double gy = (h & 4u) ? ((h & 2u) ? -kDiag : kDiag) : ((h & 2u) ? ((h & 1u) ? -1.0 : 1.0) : 0.0);
             const double a2 = dmul(attn, attn);
             value = dadd(value, dmul(dmul(a2, a2), dadd(dmul(gx, dx), dmul(gy, dy))));
         }
@@ -109,7 +102,7 @@ __device__ __noinline__ float super_simplex_2d_f32(const uint8_t *__restrict__ p
         const float attn = __fsub_rn(2.0f / 3.0f, __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
         if (attn > 0.0f) {
             const long long lx = bxi + c_lat_pt[index + k][0], ly = byi + c_lat_pt[index + k][1];
-            const unsigned h = __ldg(perm + (__ldg(perm + (unsigned)(lx & 0xff)) ^ (unsigned)(ly & 0xff)));
+            const unsigned h = perm[perm[(unsigned)(lx & 0xff)] ^ (unsigned)(ly & 0xff)];
             const float diag = (float)kDiag;
             const float gx = (h & 4u) ? ((h & 1u) ? -diag : diag) : ((h & 2u) ? 0.0f : ((h & 1u) ? -1.0f : 1.0f));
             const float gy = (h & 4u) ? ((h & 2u) ? -diag : diag) : ((h & 2u) ? ((h & 1u) ? -1.0f : 1.0f) : 0.0f);
@@ -127,16 +120,41 @@ __device__ __forceinline__ double noise_at(const uint8_t *perm, double px, doubl
     return super_simplex_2d(perm, px, py);
 }
 
+// The scaled column coordinates x / sf, z / sf of the four noise scales (elevation 2560, plains 1200, hills 1600, mountains
+// 2000). A true division each (sf has no exact reciprocal), and a software routine of ~25 FP64 operations on this chip: the
+// fill kernel computes them once per CTA row / column (64 x 4 divisions) instead of eight per column.
+struct ColCoords {
+    double ex, ez, px, pz, hx, hz, mx, mz;
+};
+__device__ __forceinline__ ColCoords col_coords(int32_t x, int32_t z) {
+    ColCoords c;
+    c.ex = ddiv((double)x, 2560.0);
+    c.ez = ddiv((double)z, 2560.0);
+    c.px = ddiv((double)x, 1200.0);
+    c.pz = ddiv((double)z, 1200.0);
+    c.hx = ddiv((double)x, 1600.0);
+    c.hz = ddiv((double)z, 1600.0);
+    c.mx = ddiv((double)x, 2000.0);
+    c.mz = ddiv((double)z, 2000.0);
+    return c;
+}
+
+// (n + 1) / 2 of the reference is computed as (n + 1) * 0.5: halving is exact in binary floating point either way
+template <int PREC>
+__device__ __forceinline__ double elevation_noise_at(const GenTables *T, double ex, double ez) {
+    return dmul(dadd(noise_at<PREC>(T->perm[5], ex, ez), 1.0), 0.5);
+}
+
 template <int PREC>
 __device__ __forceinline__ double elevation_noise(const GenTables *T, int32_t x, int32_t z) {
     // stdgen.rs:171-175: GLOBAL_BIOME_SCALE * GLOBAL_SCALE_MOD = 2560
     const double sf = 256.0 * 10.0;
-    return ddiv(dadd(noise_at<PREC>(T->perm[5], ddiv((double)x, sf), ddiv((double)z, sf)), 1.0), 2.0);
+    return elevation_noise_at<PREC>(T, ddiv((double)x, sf), ddiv((double)z, sf));
 }
 
 template <int PREC>
 __device__ __forceinline__ double h_n(const GenTables *T, int i, double px, double pz) {
-    return ddiv(dadd(noise_at<PREC>(T->perm[i], px, pz), 1.0), 2.0); // stdgen.rs:178-180
+    return dmul(dadd(noise_at<PREC>(T->perm[i], px, pz), 1.0), 0.5); // stdgen.rs:178-180 ((n + 1) / 2, exact as * 0.5)
 }
 template <int PREC>
 __device__ __forceinline__ double h_rn(const GenTables *T, int i, double px, double pz) {
@@ -144,20 +162,16 @@ __device__ __forceinline__ double h_rn(const GenTables *T, int i, double px, dou
 }
 
 template <int PREC>
-__device__ double plains_height(const GenTables *T, int32_t x, int32_t z) {
-    // stdgen.rs:187-192
-    const double sf = 10.0 * 120.0;
-    const double px = ddiv((double)x, sf), pz = ddiv((double)z, sf);
+__device__ double plains_height(const GenTables *T, double px, double pz) {
+    // stdgen.rs:187-192; px, pz = pos / (10 * 120)
     const double a = dmul(0.75, h_n<PREC>(T, 0, px, pz));
     const double b = dmul(0.25, h_n<PREC>(T, 1, dmul(px, 2.0), dmul(pz, 2.0)));
     return dadd(dmul(dadd(a, b), 5.0), 10.0);
 }
 
 template <int PREC>
-__device__ double hills_height(const GenTables *T, int32_t x, int32_t z) {
-    // stdgen.rs:194-200
-    const double sf = 10.0 * 160.0;
-    const double px = ddiv((double)x, sf), pz = ddiv((double)z, sf);
+__device__ double hills_height(const GenTables *T, double px, double pz) {
+    // stdgen.rs:194-200; px, pz = pos / (10 * 160)
     const double a = dmul(0.60, h_n<PREC>(T, 0, px, pz));
     const double b = dmul(0.25, h_n<PREC>(T, 1, dmul(px, 1.5), dmul(pz, 1.5)));
     const double c = dmul(0.15, h_n<PREC>(T, 2, dmul(px, 3.0), dmul(pz, 3.0)));
@@ -165,10 +179,8 @@ __device__ double hills_height(const GenTables *T, int32_t x, int32_t z) {
 }
 
 template <int PREC>
-__device__ double mountains_height(const GenTables *T, int32_t x, int32_t z) {
-    // stdgen.rs:202-213
-    const double sf = 10.0 * 200.0;
-    const double px = ddiv((double)x, sf), pz = ddiv((double)z, sf);
+__device__ double mountains_height(const GenTables *T, double px, double pz) {
+    // stdgen.rs:202-213; px, pz = pos / (10 * 200)
     const double h0 = dmul(0.50, h_rn<PREC>(T, 0, px, pz));
     const double h01 = dadd(dmul(0.25, h_rn<PREC>(T, 1, dmul(px, 2.0), dmul(pz, 2.0))), h0);
     const double q = ddiv(h01, 0.75);
@@ -220,37 +232,52 @@ __global__ void cellpoints_kernel(uint64_t seed, int32_t cell_x0, int32_t cell_z
 
 // CellGen::calc_voxel_params (stdgen.rs:215-276) of column (ix, iz) of the height map: returns height*4 + elevation class
 template <int PREC>
-__device__ __forceinline__ int32_t column_params(const GenParams &p, int ix, int iz, double *raw_out) {
+// cands != nullptr: the 36 cell points around the column's super-cell in the reference's visiting order (cdx outer, cdy inner,
+// point index innermost), gathered once per CTA (every column of a chunk lies in one super-cell); T: the permutation tables
+__device__ __forceinline__ int32_t column_params(const GenParams &p, const GenTables *T, const CellPointDev *cands, int ix, int iz,
+                                                 double *raw_out, const ColCoords &cc) {
     const int32_t x = p.x0 + ix, z = p.z0 + iz;
-    const GenTables *T = p.tables;
 
     // find_nearest_cell_points(pos, 1) (stdgen.rs:149-169): truncating division, first minimum wins
-    const int32_t cellx = x / 128, cellz = z / 128;
     int32_t best = 0x7FFFFFFF;
     double cec = 0.0;
     bool have = false;
-    for (int cdx = -1; cdx <= 1; cdx++)
-        for (int cdy = -1; cdy <= 1; cdy++) {
-            const CellPointDev *c = p.cells + ((size_t)(cellz + cdy - p.cell_z0) * p.cells_w + (cellx + cdx - p.cell_x0)) * 4;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int32_t dx = c[k].px - x, dz = c[k].pz - z;
-                const int32_t dist = dx * dx + dz * dz;
-                if (!have || dist < best) {
-                    have = true;
-                    best = dist;
-                    cec = c[k].elevation_class;
-                }
+    if (cands) {
+#pragma unroll 4
+        for (int k = 0; k < 36; k++) {
+            const int32_t dx = cands[k].px - x, dz = cands[k].pz - z;
+            const int32_t dist = dx * dx + dz * dz;
+            if (!have || dist < best) {
+                have = true;
+                best = dist;
+                cec = cands[k].elevation_class;
             }
         }
-    const double ec = elevation_noise<PREC>(T, x, z);
+    } else {
+        const int32_t cellx = x / 128, cellz = z / 128;
+        for (int cdx = -1; cdx <= 1; cdx++)
+            for (int cdy = -1; cdy <= 1; cdy++) {
+                const CellPointDev *c = p.cells + ((size_t)(cellz + cdy - p.cell_z0) * p.cells_w + (cellx + cdx - p.cell_x0)) * 4;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int32_t dx = c[k].px - x, dz = c[k].pz - z;
+                    const int32_t dist = dx * dx + dz * dz;
+                    if (!have || dist < best) {
+                        have = true;
+                        best = dist;
+                        cec = c[k].elevation_class;
+                    }
+                }
+            }
+    }
+    const double ec = elevation_noise_at<PREC>(T, cc.ex, cc.ez);
     // stdgen.rs:222-243: <0.4 plains / <0.5 lerp plains-hills / <0.7 hills / <0.8 lerp hills-mountains / else mountains.
     // Each biome height is evaluated at most once per column and at one call site.
     const bool need_p = ec < 0.5, need_h = !(ec < 0.4) && ec < 0.8, need_m = !(ec < 0.7);
     double ph = 0.0, hh = 0.0, mh = 0.0;
-    if (need_p) ph = plains_height<PREC>(T, x, z);
-    if (need_h) hh = hills_height<PREC>(T, x, z);
-    if (need_m) mh = mountains_height<PREC>(T, x, z);
+    if (need_p) ph = plains_height<PREC>(T, cc.px, cc.pz);
+    if (need_h) hh = hills_height<PREC>(T, cc.hx, cc.hz);
+    if (need_m) mh = mountains_height<PREC>(T, cc.mx, cc.mz);
     double height;
     if (ec < 0.4) {
         height = ph;
@@ -296,7 +323,7 @@ __global__ void __launch_bounds__(128) heightmap_kernel(GenParams p) {
     const int iz = blockIdx.y;
     if (ix >= p.W) return;
     double raw;
-    p.hmap[(size_t)iz * p.W + ix] = column_params<PREC>(p, ix, iz, &raw);
+    p.hmap[(size_t)iz * p.W + ix] = column_params<PREC>(p, p.tables, nullptr, ix, iz, &raw, col_coords(p.x0 + ix, p.z0 + iz));
     if (p.raw) p.raw[(size_t)iz * p.W + ix] = raw;
 }
 
@@ -334,14 +361,53 @@ __global__ void __launch_bounds__(256, 4) fill_kernel(FillParams p, GenParams g)
     if (GEN == 0) {
         hm = __ldg(reinterpret_cast<const int4 *>(p.hmap + (size_t)(sz * 32 + zr) * p.W + sx * 32 + q * 4));
     } else {
+        // scaled coordinates of the CTA's 32 x values and 32 z values at the four noise scales: one division per thread
+        __shared__ double s_coord[4][2][32];
+        __shared__ GenTables s_tab;         // the seven permutation tables (1.8 KB): two dependent lookups per lattice point
+        __shared__ CellPointDev s_cand[36]; // the cell points around this chunk column's super-cell, in visiting order
+        for (int i = threadIdx.x; i < (int)(sizeof(GenTables) / 4); i += 256)
+            reinterpret_cast<uint32_t *>(&s_tab)[i] = reinterpret_cast<const uint32_t *>(g.tables)[i];
+        // A chunk is 32 columns wide and a super-cell 128, so its columns share pos / 128 -- unless the chunk starts at a
+        // negative multiple of 128: the division truncates (stdgen.rs:150), -128 / 128 = -1 but -127 / 128 = 0. Those chunks
+        // search per column.
+        const int32_t cx_lo = g.x0 + sx * 32, cz_lo = g.z0 + sz * 32;
+        const bool one_cell = (cx_lo / 128 == (cx_lo + 31) / 128) && (cz_lo / 128 == (cz_lo + 31) / 128);
+        if (threadIdx.x < 36 && one_cell) {
+            const int32_t cellx = cx_lo / 128, cellz = cz_lo / 128;
+            const int k = threadIdx.x, cdx = k / 12 - 1, cdy = (k / 4) % 3 - 1;
+            s_cand[k] = g.cells[((size_t)(cellz + cdy - g.cell_z0) * g.cells_w + (cellx + cdx - g.cell_x0)) * 4 + (k & 3)];
+        }
+        {
+            const int t = threadIdx.x, sc = t >> 6, axis = (t >> 5) & 1, i = t & 31;
+            const double sf = sc == 0 ? 2560.0 : (sc == 1 ? 1200.0 : (sc == 2 ? 1600.0 : 2000.0));
+            const int32_t coord = axis ? g.z0 + sz * 32 + i : g.x0 + sx * 32 + i;
+            s_coord[sc][axis][i] = ddiv((double)coord, sf);
+        }
+        __syncthreads();
         int hv[4];
 #pragma unroll 1
-        for (int k = 0; k < 4; k++) hv[k] = column_params<(GEN == 0 ? 64 : GEN)>(g, sx * 32 + q * 4 + k, sz * 32 + zr, nullptr);
+        for (int k = 0; k < 4; k++) {
+            const int xi = q * 4 + k;
+            ColCoords cc;
+            cc.ex = s_coord[0][0][xi];
+            cc.ez = s_coord[0][1][zr];
+            cc.px = s_coord[1][0][xi];
+            cc.pz = s_coord[1][1][zr];
+            cc.hx = s_coord[2][0][xi];
+            cc.hz = s_coord[2][1][zr];
+            cc.mx = s_coord[3][0][xi];
+            cc.mz = s_coord[3][1][zr];
+            hv[k] = column_params<(GEN == 0 ? 64 : GEN)>(g, &s_tab, one_cell ? s_cand : nullptr, sx * 32 + q * 4 + k, sz * 32 + zr, nullptr, cc);
+        }
         hm = make_int4(hv[0], hv[1], hv[2], hv[3]);
         *reinterpret_cast<int4 *>(g.hmap + (size_t)(sz * 32 + zr) * p.W + sx * 32 + q * 4) = hm;
     }
     const int hh[4] = {hm.x >> 2, hm.y >> 2, hm.z >> 2, hm.w >> 2};
     const int el[4] = {hm.x & 3, hm.y & 3, hm.z & 3, hm.w & 3};
+    // the block at y == h: snow grass on mountains above 80, else grass (stdgen.rs:361-366) -- a per-column constant
+    uint32_t top[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) top[k] = (el[k] == 2 && hh[k] > 80) ? p.id_snow : p.id_grass;
     // chunk summaries of the stack: above every column -> all void; more than 5 below every column -> all stone; at or below
     // every column (of the chunk / of one of its four side planes) -> solid terrain (device_common.cuh: kSolidShift)
     __shared__ int red[6][8];
@@ -404,13 +470,8 @@ __global__ void __launch_bounds__(256, 4) fill_kernel(FillParams p, GenParams g)
             uint32_t o[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const int h = hh[k];
-                uint32_t v;
-                if (y == h) v = (el[k] == 2 && y > 80) ? p.id_snow : p.id_grass;
-                else if (y < h - 5) v = p.id_stone;
-                else if (y < h) v = p.id_dirt;
-                else v = p.id_void;
-                o[k] = v;
+                const int t = hh[k] - y; // depth below the surface (stdgen.rs:359-372)
+                o[k] = t < 0 ? p.id_void : (t == 0 ? top[k] : (t <= 5 ? p.id_dirt : p.id_stone));
             }
             __stcs(&dst[yc * 256], make_uint4(o[0], o[1], o[2], o[3])); // 1024 voxels per y layer = 256 uint4; streaming store
         }

@@ -8,10 +8,28 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("seed", [0, 0x13372137CAFE])
 def test_gen_chunk_matches_oracle(ctx, oracle, seed):
     g = oracle.StdGen(seed)
-    for pos in [(0, 0, 0), (9, 0, 0), (9, 1, 0), (-3, 0, -5), (40, 2, -17), (300 // 32, 0, 28 // 32), (-1, 0, -1)]:
+    for pos in [(0, 0, 0), (9, 0, 0), (9, 1, 0), (-3, 0, -5), (40, 2, -17), (300 // 32, 0, 28 // 32), (-1, 0, -1),
+                (-4, 0, -8), (-4, 1, 3), (2, 0, -4), (-8, 0, -4)]:  # chunks that start at a negative multiple of 128 (see below)
         got = ctx.gen_chunk(seed, *pos)
         want = g.generate_chunk(*pos)
         assert np.array_equal(got, want), f"seed {seed} chunk {pos}: {np.count_nonzero(got != want)} voxels differ"
+
+
+def test_truncating_cell_division_across_negative_cell_edges(ctx, oracle):
+    """find_nearest_cell_points divides by 128 with truncation (stdgen.rs:150): -128 / 128 = -1 but -127 / 128 = 0, so a chunk
+    that starts at a negative multiple of 128 straddles two super-cells. Every column of such a region against the oracle."""
+    origin, dims = (-6, 0, -6), (4, 1, 4)
+    ctx.region_create(*origin, *dims)
+    for seed in (0, 0x13372137CAFE):
+        ctx.region_generate(seed, 64)
+        h, e, raw = ctx.region_heightmap(raw=True)
+        g = oracle.StdGen(seed)
+        x0, z0 = (origin[0] - 1) * 32, (origin[2] - 1) * 32
+        for iz in range(0, h.shape[0], 3):
+            for ix in list(range(0, h.shape[1], 5)) + [x - x0 for x in (-129, -128, -127, -97, -96) if 0 <= x - x0 < h.shape[1]]:
+                p = g.params(x0 + ix, z0 + iz)
+                assert h[iz, ix] == p.height and e[iz, ix] == p.elevation and raw[iz, ix] == p.height_f64, (seed, x0 + ix, z0 + iz)
+    ctx.region_destroy()
 
 
 def test_region_generate_matches_oracle(ctx, oracle):
