@@ -84,3 +84,47 @@ def exchange_halos(slab, dist, bufs, export_plane, import_plane):
         import_plane(0, bufs["recv_lo"])
     if slab.has_hi:
         import_plane(1, bufs["recv_hi"])
+
+
+def rebalance_slabs(widths, costs, min_width=8):
+    """Slab widths for the next pass from the measured cost of the last one.
+
+    widths[r] chunk columns cost costs[r] (device time of rank r's own kernels for one step; the slabs hold different terrain,
+    so equal widths are not equal work). Model: a slab's cost is spread evenly over its columns. The new boundaries cut the
+    cumulative cost into equal parts; the total width is unchanged and no slab gets narrower than min_width. Every rank calls
+    this with the same inputs and gets the same answer.
+    """
+    world, total = len(widths), sum(widths)
+    if world != len(costs) or any(w <= 0 for w in widths) or any(c <= 0 for c in costs) or total < world * min_width:
+        raise ValueError("bad rebalance input")
+    per_column = []
+    for w, c in zip(widths, costs):
+        per_column += [c / w] * w
+    target = sum(costs) / world
+    bounds, acc, k = [0], 0.0, 1
+    for x, c in enumerate(per_column):
+        # boundary k goes to whichever side of column x is closer to k * target
+        while k < world and acc + c >= k * target:
+            bounds.append(x + 1 if (acc + c - k * target) <= (k * target - acc) else x)
+            k += 1
+        acc += c
+    while len(bounds) < world:
+        bounds.append(total)
+    bounds.append(total)
+    for k in range(1, world):  # minimum width, left to right, then right to left
+        bounds[k] = max(bounds[k], bounds[k - 1] + min_width)
+    for k in range(world - 1, 0, -1):
+        bounds[k] = min(bounds[k], bounds[k + 1] - min_width)
+    return [bounds[k + 1] - bounds[k] for k in range(world)]
+
+
+def agree_on_widths(dist, widths, my_cost, device="cpu", min_width=8):
+    """All ranks exchange their measured cost (one all_gather of a scalar, outside the data path) and compute the same new
+    widths. Returns (new_widths, costs)."""
+    import torch
+
+    mine = torch.tensor([float(my_cost)], dtype=torch.float64, device=device)
+    allc = [torch.zeros(1, dtype=torch.float64, device=device) for _ in range(len(widths))]
+    dist.all_gather(allc, mine)
+    costs = [float(c.item()) for c in allc]
+    return rebalance_slabs(list(widths), costs, min_width), costs

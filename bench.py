@@ -143,7 +143,7 @@ def workload_config(n):
     nx, ny, nz = SLAB
     return {
         "workload": f"full worldgen+mesh, StdGenerator seed {SEED}, {nx * n}x{nz}x{ny} chunk region (x-slabs of {nx}x{nz}x{ny} per GPU"
-                    f"{', NCCL halo exchange of slab-boundary voxel planes' if n > 1 else ''}); BASELINE.json configs[2] per GPU",
+                    f"{', slab widths re-cut from measured per-slab cost (same world, same total), NCCL halo exchange of slab-boundary voxel planes' if n > 1 else ''}); BASELINE.json configs[2] per GPU",
         "chunks_per_gpu": nx * ny * nz, "l2": "inputs larger than L2 (32 GiB of blocks per GPU per step)", "precision": "f64 noise",
     }
 
@@ -445,6 +445,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--slab", default=None, help="override nx,ny,nz interior chunks per rank (debug only; invalidates the number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-rebalance", action="store_true", help="N>1: keep equal slab widths (default: widths follow the measured per-slab cost)")
     ap.add_argument("--no-extra-legs", action="store_true", help="skip cfg2 / cfg4 / cfg5 legs (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -473,14 +474,15 @@ def main():
     ctx.set_stream(stream.cuda_stream)
     reg = bxw.standard_registry()
     region = bxw.Region((rank * nx, 0, 0), (nx, ny, nz), reg, ctx=ctx)
-    n_chunks = nx * ny * nz
+    widths = [nx] * world  # chunk columns per rank; N>1 re-cuts them below from the measured per-slab cost
+    total_chunks = world * nx * ny * nz
 
     halo = None
     if world > 1:
         hb = ctx.region_halo_bytes()
         halo = {k: torch.empty(hb // 4, dtype=torch.int32, device="cuda") for k in ("send_lo", "send_hi", "recv_lo", "recv_hi")}
 
-    from ballxworld_b200.slabs import exchange_halos, finish_exchange, slab_partition, start_exchange
+    from ballxworld_b200.slabs import agree_on_widths, exchange_halos, finish_exchange, slab_partition, start_exchange
 
     slab_info = slab_partition(nx * world, world, rank)
 
@@ -520,6 +522,47 @@ def main():
     barrier()
     tot_v, tot_i, spans = region_totals(region)
 
+    # ---------------- N>1: slab widths from measured cost ----------------
+    # The slabs hold different terrain (mesh sizes differ by up to 20 %), and every step couples a rank to its neighbours, so
+    # the step time is the heaviest slab's. Each rank measures the device time of its own kernels, the ranks exchange the
+    # scalars and all compute the same new cut of the SAME world (total columns unchanged); the best cut measured is kept.
+    rebalance = None
+    if world > 1 and not args.no_rebalance:
+        ut = torch.tensor([tot_v, tot_i], dtype=torch.int64, device="cuda")
+        dist.all_reduce(ut)
+        history, best = [], None
+        for it in range(4):
+            for k in (ctx.KERNEL_MESH, ctx.KERNEL_FILL):
+                ctx.kernel_time_ms(k, reset=True)
+            for _ in range(2):
+                step()
+            barrier()
+            cost = (ctx.kernel_time_ms(ctx.KERNEL_MESH, reset=True)[0] + ctx.kernel_time_ms(ctx.KERNEL_FILL, reset=True)[0]) / 2
+            new_w, costs = agree_on_widths(dist, widths, cost, "cuda", min_width=32)
+            history.append({"widths": list(widths), "own_kernel_ms": [round(c, 3) for c in costs]})
+            if best is None or max(costs) < best[0]:
+                best = (max(costs), list(widths))
+            done = it == 3 or max(costs) < 1.01 * sum(costs) / world or new_w == widths
+            target = best[1] if done else new_w  # at the end: the best cut that was measured
+            if target != widths:
+                widths = target
+                region.close()
+                region = bxw.Region((sum(widths[:rank]), 0, 0), (widths[rank], ny, nz), reg, ctx=ctx)
+                for _ in range(2):
+                    arena = step()
+                barrier()
+            if done:
+                break
+        tot_v, tot_i, spans = region_totals(region)
+        rt = torch.tensor([tot_v, tot_i], dtype=torch.int64, device="cuda")
+        dist.all_reduce(rt)
+        rebalance = {"widths": list(widths), "measured": history, "world_totals_unchanged": bool((rt == ut).all().item()),
+                     "how": "per-rank device time of fill + mesh kernels over 2 steps, one scalar all_gather, every rank computes the same "
+                            "new cut (slabs.rebalance_slabs); total columns and the global mesh are unchanged"}
+        if not rebalance["world_totals_unchanged"]:
+            raise RuntimeError("rebalanced slabs changed the global mesh totals")
+    n_chunks = widths[rank] * ny * nz  # this rank's interior chunks
+
     # ---------------- device-resident timing ----------------
     for k in (ctx.KERNEL_MESH, ctx.KERNEL_FILL, ctx.KERNEL_HEIGHTMAP):
         ctx.kernel_time_ms(k, reset=True)
@@ -540,7 +583,7 @@ def main():
     fill_ms, fill_launches = ctx.kernel_time_ms(ctx.KERNEL_FILL, reset=True)
     meshed_chunks, _ = ctx.region_mesh_candidates()
     pages = ctx.region_download_pages()
-    storage_chunks = (nx + 2) * (ny + 2) * (nz + 2)
+    storage_chunks = (widths[rank] + 2) * (ny + 2) * (nz + 2)
     materialised_chunks = int((pages == np.arange(pages.size, dtype=np.uint32)).sum())
     side = min(args.steps, 3)
     # ---------------- the same step with every chunk materialised (BXW_OPT_ELIDE_UNIFORM=0): round-1's figure ----------------
@@ -615,7 +658,8 @@ def main():
         mine = torch.tensor([ms / args.steps, mesh_ms / max(mesh_launches, 1), fill_ms / max(fill_launches, 1), float(tot_v)], dtype=torch.float64, device="cuda")
         allr = [torch.zeros(4, dtype=torch.float64, device="cuda") for _ in range(world)]
         dist.all_gather(allr, mine)
-        per_rank = [{"ms_per_step": float(a[0]), "mesh_ms": float(a[1]), "fill_ms": float(a[2]), "vertices": int(a[3])} for a in allr]
+        per_rank = [{"columns": widths[i], "ms_per_step": float(a[0]), "mesh_ms": float(a[1]), "fill_ms": float(a[2]), "vertices": int(a[3])}
+                    for i, a in enumerate(allr)]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, e2e_ms, mesh_ms_max, mat_ms, stream_ms_max, copy_ms = (float(x) for x in t.tolist())
     tot = torch.tensor([tot_v, tot_i, launches], dtype=torch.int64, device="cuda")
@@ -629,6 +673,9 @@ def main():
     if not args.no_extra_legs:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         if world > 1:
+            if widths != [nx] * world:  # the legs below address slabs as rank * nx: back to the equal cut
+                region.close()
+                region = bxw.Region((rank * nx, 0, 0), (nx, ny, nz), reg, ctx=ctx)
             region.generate(SEED, 64)
             par = slab_boundary_parity(ctx, region, reg, rank * nx, nx, ny, nz, rank, world, dist, halo, exchange)
             pt = torch.tensor([par["boundary_chunks_checked"], int(par["bit_exact"]), int(par["edits_changed_expected_mesh"] or rank == world - 1)],
@@ -655,7 +702,7 @@ def main():
 
     if rank == 0:
         ms_per_step = ms / args.steps
-        value = world * n_chunks / (ms_per_step / 1000.0)
+        value = total_chunks / (ms_per_step / 1000.0)
         # Rooflines (DESIGN.md "Measurement"), this rank's launches, CUDA events inside the library.
         #  mesh: algorithmic bytes = 131072 per interior chunk + 40 V + 4 I.
         #  fill: algorithmic bytes = 131072 per chunk written.
@@ -709,7 +756,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64+u32", "data": "synthetic", "config": workload_config(world),
-            "e2e": {"value": world * n_chunks / (e2e_ms / 1000.0 / args.steps), "unit": UNIT,
+            "e2e": {"value": total_chunks / (e2e_ms / 1000.0 / args.steps), "unit": UNIT,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "d2h_gbs_per_gpu": d2h / (e2e_ms / 1000.0 / args.steps) / 1e9,
                     "host_limit_gbs_per_gpu": d2h / (copy_ms / 1000.0) / 1e9,
@@ -720,12 +767,12 @@ def main():
                            "`noise 0.8.2` crate cannot be built here (no cargo), so generator parity is UNPINNED; RNG crates pinned by "
                            "their published vectors; mesher / RLE / orientations restated from in-tree source",
             "roofline": dominant, "roofline_mesh": roof_mesh, "roofline_fill": roof_fill,
-            "everything_materialised": {"ms_per_step": mat_ms, "value": world * n_chunks / (mat_ms / 1000.0), "unit": UNIT,
+            "everything_materialised": {"ms_per_step": mat_ms, "value": total_chunks / (mat_ms / 1000.0), "unit": UNIT,
                                         "note": "BXW_OPT_ELIDE_UNIFORM=0 (round 1's storage): every chunk written voxel by voxel"},
             "fused_generate_and_mesh": None if fused_ms is None else {"ms_per_step": fused_ms, "value": n_chunks / (fused_ms / 1000.0), "unit": UNIT,
                                                                       "note": "bxw_region_generate_and_mesh with BXW_OPT_MESH_FROM_HEIGHT_MAP=1"},
             "mesh": {"vertices": tot_v_all, "indices": tot_i_all, "arena_vertices": av, "arena_indices": ai},
-            "per_rank": per_rank, "multi_gpu_parity": parity, "cfg5_edits": edits_leg, "cfg2_mesh_only": cfg2, "cfg4_literal": cfg4,
+            "per_rank": per_rank, "slab_rebalance": rebalance, "multi_gpu_parity": parity, "cfg5_edits": edits_leg, "cfg2_mesh_only": cfg2, "cfg4_literal": cfg4,
         }
         if args.slab:
             line["config"]["workload"] += f" [DEBUG slab override {slab}: not the benchmark configuration]"

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from ballxworld_b200.slabs import exchange_halos, finish_exchange, slab_partition, start_exchange
+from ballxworld_b200.slabs import agree_on_widths, exchange_halos, finish_exchange, rebalance_slabs, slab_partition, start_exchange
 
 
 def test_slab_partition_covers_region():
@@ -76,3 +76,50 @@ def test_halo_exchange_over_gloo(world, split):
     for p in procs:
         p.join(timeout=60)
     assert res == [(r, True) for r in range(world)]
+
+
+def test_rebalance_slabs_equalises_modelled_cost():
+    # equal cost: nothing moves; the total never changes; a slab that costs 3x gives up columns
+    assert rebalance_slabs([128] * 8, [1.0] * 8) == [128] * 8
+    assert rebalance_slabs([128, 128], [1.0, 3.0]) == [171, 85]
+    w = rebalance_slabs([128] * 4, [3.86, 3.59, 3.46, 4.13])
+    assert sum(w) == 512 and w[3] < 128 < w[2]
+    # under the model (cost spread evenly over a slab's columns) the new cut is balanced to within one column
+    density = [3.86 / 128] * 128 + [3.59 / 128] * 128 + [3.46 / 128] * 128 + [4.13 / 128] * 128
+    x, parts = 0, []
+    for wk in w:
+        parts.append(sum(density[x:x + wk]))
+        x += wk
+    assert max(parts) - min(parts) < 2 * max(density)
+    # minimum width is respected and the order of the slabs is kept
+    assert rebalance_slabs([16, 16], [1.0, 100.0]) == [24, 8]
+    w = rebalance_slabs([64, 64, 64], [100.0, 1.0, 1.0], min_width=32)
+    assert sum(w) == 192 and w[0] == 32 and min(w) >= 32
+    for bad in (([128], [1.0, 2.0]), ([128, 0], [1.0, 1.0]), ([128, 128], [1.0, 0.0]), ([4, 4], [1.0, 1.0])):
+        with pytest.raises(ValueError):
+            rebalance_slabs(*bad)
+
+
+def _rebalance_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    new_w, costs = agree_on_widths(dist, [128] * world, 1.0 + 2.0 * rank)
+    q.put((rank, new_w, costs))
+    dist.destroy_process_group()
+
+
+def test_ranks_agree_on_widths_over_gloo():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rebalance_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert res[0][1] == res[1][1] == [171, 85] and res[0][2] == res[1][2] == [1.0, 3.0]
