@@ -203,6 +203,7 @@ int ensure_gen_tables(bxw_ctx *ctx, uint64_t seed) {
     GenTables t;
     uint64_t sd = seed; // SplitMix64::seed_from_u64 (stdgen.rs:106)
     for (int i = 0; i < 7; i++) permutation_table(splitmix_next_u32(sd), t.perm[i]);
+    fill_noise_constants(t);
     if (!ctx->d_gen) CK(cudaMalloc(&ctx->d_gen, sizeof(GenTables)));
     CK(cudaMemcpyAsync(ctx->d_gen, &t, sizeof t, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream)); // t is a stack object

@@ -141,9 +141,20 @@ void launch_storage_candidates(const StorageCandParams &p, cudaStream_t stream);
 int mesh_kernel_max_ctas_per_sm();
 
 // generation -------------------------------------------------------------------------------------------------
+// A lattice point of super_simplex_2d's per-region table: offset in real space and integer lattice step
+struct alignas(16) LatticeEntry {
+    double ox, oy;
+    int32_t px, py;
+    int32_t pad[2];
+};
 struct GenTables {
     uint8_t perm[7][256]; // height_map_gen[0..5], elevation_map_gen, moisture_map_gen (stdgen.rs:82-84,103-114)
+    // seed-independent tables of the noise function, next to the permutations so that a CTA stages all of it in shared memory
+    // with one copy (indexed per lane: constant memory would serialise the lookups)
+    alignas(16) double grad[8][2];  // gradient::grad2
+    LatticeEntry lat[8][2];          // lattice points 2 and 3 of each of the 8 groups (points 0 and 1 are the same in every group)
 };
+void fill_noise_constants(GenTables &t); // gen_kernel.cu
 
 struct CellPointDev {
     int32_t px, pz;

@@ -13,9 +13,6 @@ namespace bxw {
 namespace {
 
 // ---- noise 0.8.2 super_simplex_2d constants (see oracle/noise.c for provenance: crate source not vendored) ----
-__constant__ double c_lat_off[32][2];
-__constant__ signed char c_lat_pt[32][2];
-
 constexpr double kToReal = -0.211324865405187;
 constexpr double kToSimplex = 0.366025403784439;
 constexpr double kNorm = 1.0 / 0.05428295288661623;
@@ -44,34 +41,43 @@ __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a,
 
 // noise::SuperSimplex::get([x, y]) (f64). One copy per kernel (not inlined): the height map kernel calls it from 11 sites and
 // fully inlined it was 141 KB of SASS, more than half of its warp stalls were instruction-cache misses.
-__device__ __noinline__ double super_simplex_2d(const uint8_t *__restrict__ perm, double px, double py) {
+__device__ __noinline__ double super_simplex_2d(const GenTables *__restrict__ T, int which, double px, double py) {
+    const uint8_t *perm = T->perm[which];
     const double to_simplex_offset = dmul(dadd(px, py), kToSimplex);
     const double sx = dadd(px, to_simplex_offset), sy = dadd(py, to_simplex_offset);
     const double bxf = floor(sx), byf = floor(sy);
-    const long long bxi = __double2ll_rz(bxf), byi = __double2ll_rz(byf);
+    // only the low 8 bits of the lattice coordinates reach the permutation table
+    const unsigned bxi = (unsigned)__double2ll_rz(bxf), byi = (unsigned)__double2ll_rz(byf);
     const double rx = dsub(sx, bxf), ry = dsub(sy, byf);
     const double region_sum = floor(dadd(rx, ry));
     const double half_rs = dmul(region_sum, 0.5);
-    unsigned index = (region_sum >= 1.0 ? 1u : 0u) << 2;
-    index |= (dsub(dadd(dsub(rx, dmul(ry, 0.5)), 1.0), half_rs) >= 1.0 ? 1u : 0u) << 3;
-    index |= (dsub(dadd(dsub(ry, dmul(rx, 0.5)), 1.0), half_rs) >= 1.0 ? 1u : 0u) << 4;
+    unsigned group = region_sum >= 1.0 ? 1u : 0u;
+    group |= (dsub(dadd(dsub(rx, dmul(ry, 0.5)), 1.0), half_rs) >= 1.0 ? 1u : 0u) << 1;
+    group |= (dsub(dadd(dsub(ry, dmul(rx, 0.5)), 1.0), half_rs) >= 1.0 ? 1u : 0u) << 2;
     const double to_real_offset = dmul(dadd(rx, ry), kToReal);
     const double qx = dadd(rx, to_real_offset), qy = dadd(ry, to_real_offset);
     double value = 0.0;
-#pragma unroll
-    for (unsigned k = 0; k < 4; k++) {
-        const double dx = dadd(qx, c_lat_off[index + k][0]), dy = dadd(qy, c_lat_off[index + k][1]);
+    auto point = [&](double ox, double oy, unsigned lpx, unsigned lpy) {
+        const double dx = dadd(qx, ox), dy = dadd(qy, oy);
         const double attn = dsub(2.0 / 3.0, dadd(dmul(dx, dx), dmul(dy, dy)));
         if (attn > 0.0) {
-            const long long lx = bxi + c_lat_pt[index + k][0], ly = byi + c_lat_pt[index + k][1];
-            // (plain loads: the table may live in shared memory, see fill_kernel)
-            const unsigned h = perm[perm[(unsigned)(lx & 0xff)] ^ (unsigned)(ly & 0xff)];
-            // gradient::grad2(h % 8) = (1,0) (-1,0) (0,1) (0,-1) (d,d) (-d,d) (d,-d) (-d,-d), as selects: a switch diverges eight ways
-            const double gx = (h & 4u) ? ((h & 1u) ? -kDiag : kDiag) : ((h & 2u) ? 0.0 : ((h & 1u) ? -1.0 : 1.0));
-            const double gy = (h & 4u) ? ((h & 2u) ? -kDiag : kDiag) : ((h & 2u) ? ((h & 1u) ? -1.0 : 1.0) : 0.0);
+            // (plain loads: the tables may live in shared memory, see fill_kernel)
+            const unsigned h = perm[perm[(bxi + lpx) & 0xffu] ^ ((byi + lpy) & 0xffu)];
+            // gradient::grad2(h % 8) = (1,0) (-1,0) (0,1) (0,-1) (d,d) (-d,d) (d,-d) (-d,-d): one 16-byte table load
+            const double2 gr = *reinterpret_cast<const double2 *>(T->grad[h & 7u]);
             const double a2 = dmul(attn, attn);
-            value = dadd(value, dmul(dmul(a2, a2), dadd(dmul(gx, dx), dmul(gy, dy))));
+            value = dadd(value, dmul(dmul(a2, a2), dadd(dmul(gr.x, dx), dmul(gr.y, dy))));
         }
+    };
+    // lattice points 0 and 1 are (0, 0) and (1, 1) in every group; 2 and 3 come from the group's table rows
+    point(0.0, 0.0, 0u, 0u);
+    point(-LC, -LC, 1u, 1u);
+#pragma unroll
+    for (unsigned k = 0; k < 2; k++) {
+        const LatticeEntry *e = &T->lat[group][k];
+        const double2 o = *reinterpret_cast<const double2 *>(&e->ox);
+        const int2 lp = *reinterpret_cast<const int2 *>(&e->px);
+        point(o.x, o.y, (unsigned)lp.x, (unsigned)lp.y);
     }
     return dmul(value, kNorm);
 }
@@ -81,43 +87,49 @@ __device__ __noinline__ double super_simplex_2d(const uint8_t *__restrict__ perm
 // 10^4 an f32 position has an error of 10^-3, which would move lattice decisions and broke the 1e-5 bound in round 1 -- so the
 // same lattice points and gradients are used as in the f64 path. Everything after that works on the relative coordinates in
 // [0, 1): offsets, attenuation, gradient dot products and the sum are f32 (about 80 % of the arithmetic).
-__device__ __noinline__ float super_simplex_2d_f32(const uint8_t *__restrict__ perm, double px, double py) {
+__device__ __noinline__ float super_simplex_2d_f32(const GenTables *__restrict__ T, int which, double px, double py) {
+    const uint8_t *perm = T->perm[which];
     const double to_simplex_offset = dmul(dadd(px, py), kToSimplex);
     const double sx = dadd(px, to_simplex_offset), sy = dadd(py, to_simplex_offset);
     const double bxf = floor(sx), byf = floor(sy);
-    const long long bxi = __double2ll_rz(bxf), byi = __double2ll_rz(byf);
+    const unsigned bxi = (unsigned)__double2ll_rz(bxf), byi = (unsigned)__double2ll_rz(byf);
     const double rxd = dsub(sx, bxf), ryd = dsub(sy, byf);
     const double region_sum = floor(dadd(rxd, ryd));
     const double half_rs = dmul(region_sum, 0.5);
-    unsigned index = (region_sum >= 1.0 ? 1u : 0u) << 2;
-    index |= (dsub(dadd(dsub(rxd, dmul(ryd, 0.5)), 1.0), half_rs) >= 1.0 ? 1u : 0u) << 3;
-    index |= (dsub(dadd(dsub(ryd, dmul(rxd, 0.5)), 1.0), half_rs) >= 1.0 ? 1u : 0u) << 4;
+    unsigned group = region_sum >= 1.0 ? 1u : 0u;
+    group |= (dsub(dadd(dsub(rxd, dmul(ryd, 0.5)), 1.0), half_rs) >= 1.0 ? 1u : 0u) << 1;
+    group |= (dsub(dadd(dsub(ryd, dmul(rxd, 0.5)), 1.0), half_rs) >= 1.0 ? 1u : 0u) << 2;
     const float rx = (float)rxd, ry = (float)ryd;
     const float to_real_offset = __fmul_rn(__fadd_rn(rx, ry), (float)kToReal);
     const float qx = __fadd_rn(rx, to_real_offset), qy = __fadd_rn(ry, to_real_offset);
     float value = 0.0f;
-#pragma unroll
-    for (unsigned k = 0; k < 4; k++) {
-        const float dx = __fadd_rn(qx, (float)c_lat_off[index + k][0]), dy = __fadd_rn(qy, (float)c_lat_off[index + k][1]);
+    auto point = [&](float ox, float oy, unsigned lpx, unsigned lpy) {
+        const float dx = __fadd_rn(qx, ox), dy = __fadd_rn(qy, oy);
         const float attn = __fsub_rn(2.0f / 3.0f, __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
         if (attn > 0.0f) {
-            const long long lx = bxi + c_lat_pt[index + k][0], ly = byi + c_lat_pt[index + k][1];
-            const unsigned h = perm[perm[(unsigned)(lx & 0xff)] ^ (unsigned)(ly & 0xff)];
-            const float diag = (float)kDiag;
-            const float gx = (h & 4u) ? ((h & 1u) ? -diag : diag) : ((h & 2u) ? 0.0f : ((h & 1u) ? -1.0f : 1.0f));
-            const float gy = (h & 4u) ? ((h & 2u) ? -diag : diag) : ((h & 2u) ? ((h & 1u) ? -1.0f : 1.0f) : 0.0f);
+            const unsigned h = perm[perm[(bxi + lpx) & 0xffu] ^ ((byi + lpy) & 0xffu)];
+            const double2 gr = *reinterpret_cast<const double2 *>(T->grad[h & 7u]);
             const float a2 = __fmul_rn(attn, attn);
-            value = __fadd_rn(value, __fmul_rn(__fmul_rn(a2, a2), __fadd_rn(__fmul_rn(gx, dx), __fmul_rn(gy, dy))));
+            value = __fadd_rn(value, __fmul_rn(__fmul_rn(a2, a2), __fadd_rn(__fmul_rn((float)gr.x, dx), __fmul_rn((float)gr.y, dy))));
         }
+    };
+    point(0.0f, 0.0f, 0u, 0u);
+    point((float)-LC, (float)-LC, 1u, 1u);
+#pragma unroll
+    for (unsigned k = 0; k < 2; k++) {
+        const LatticeEntry *e = &T->lat[group][k];
+        const double2 o = *reinterpret_cast<const double2 *>(&e->ox);
+        const int2 lp = *reinterpret_cast<const int2 *>(&e->px);
+        point((float)o.x, (float)o.y, (unsigned)lp.x, (unsigned)lp.y);
     }
     return __fmul_rn(value, (float)kNorm);
 }
 
 // precision-generic noise returning double
 template <int PREC>
-__device__ __forceinline__ double noise_at(const uint8_t *perm, double px, double py) {
-    if (PREC == 32) return (double)super_simplex_2d_f32(perm, px, py);
-    return super_simplex_2d(perm, px, py);
+__device__ __forceinline__ double noise_at(const GenTables *T, int which, double px, double py) {
+    if (PREC == 32) return (double)super_simplex_2d_f32(T, which, px, py);
+    return super_simplex_2d(T, which, px, py);
 }
 
 // The scaled column coordinates x / sf, z / sf of the four noise scales (elevation 2560, plains 1200, hills 1600, mountains
@@ -142,7 +154,7 @@ __device__ __forceinline__ ColCoords col_coords(int32_t x, int32_t z) {
 // (n + 1) / 2 of the reference is computed as (n + 1) * 0.5: halving is exact in binary floating point either way
 template <int PREC>
 __device__ __forceinline__ double elevation_noise_at(const GenTables *T, double ex, double ez) {
-    return dmul(dadd(noise_at<PREC>(T->perm[5], ex, ez), 1.0), 0.5);
+    return dmul(dadd(noise_at<PREC>(T, 5, ex, ez), 1.0), 0.5);
 }
 
 template <int PREC>
@@ -154,7 +166,7 @@ __device__ __forceinline__ double elevation_noise(const GenTables *T, int32_t x,
 
 template <int PREC>
 __device__ __forceinline__ double h_n(const GenTables *T, int i, double px, double pz) {
-    return dmul(dadd(noise_at<PREC>(T->perm[i], px, pz), 1.0), 0.5); // stdgen.rs:178-180 ((n + 1) / 2, exact as * 0.5)
+    return dmul(dadd(noise_at<PREC>(T, i, px, pz), 1.0), 0.5); // stdgen.rs:178-180 ((n + 1) / 2, exact as * 0.5)
 }
 template <int PREC>
 __device__ __forceinline__ double h_rn(const GenTables *T, int i, double px, double pz) {
@@ -234,8 +246,8 @@ __global__ void cellpoints_kernel(uint64_t seed, int32_t cell_x0, int32_t cell_z
 template <int PREC>
 // cands != nullptr: the 36 cell points around the column's super-cell in the reference's visiting order (cdx outer, cdy inner,
 // point index innermost), gathered once per CTA (every column of a chunk lies in one super-cell); T: the permutation tables
-__device__ __forceinline__ int32_t column_params(const GenParams &p, const GenTables *T, const CellPointDev *cands, int ix, int iz,
-                                                 double *raw_out, const ColCoords &cc) {
+__device__ __forceinline__ int32_t column_params(const GenParams &p, const GenTables *T, const CellPointDev *cands, int n_cands, int ix,
+                                                 int iz, double *raw_out, const ColCoords &cc) {
     const int32_t x = p.x0 + ix, z = p.z0 + iz;
 
     // find_nearest_cell_points(pos, 1) (stdgen.rs:149-169): truncating division, first minimum wins
@@ -244,7 +256,7 @@ __device__ __forceinline__ int32_t column_params(const GenParams &p, const GenTa
     bool have = false;
     if (cands) {
 #pragma unroll 4
-        for (int k = 0; k < 36; k++) {
+        for (int k = 0; k < n_cands; k++) {
             const int32_t dx = cands[k].px - x, dz = cands[k].pz - z;
             const int32_t dist = dx * dx + dz * dz;
             if (!have || dist < best) {
@@ -299,7 +311,7 @@ __device__ __forceinline__ int32_t column_params(const GenParams &p, const GenTa
         elevation = 0;
     } else if (cec < 0.5 || (!(cec < 0.7) && cec < 0.8)) {
         const int lo = cec < 0.5 ? 0 : 1;
-        elevation = noise_at<PREC>(T->perm[4], (double)x, (double)z) < 0.0 ? lo : lo + 1;
+        elevation = noise_at<PREC>(T, 4, (double)x, (double)z) < 0.0 ? lo : lo + 1;
     } else if (cec < 0.7) {
         elevation = 1;
     } else {
@@ -323,7 +335,7 @@ __global__ void __launch_bounds__(128) heightmap_kernel(GenParams p) {
     const int iz = blockIdx.y;
     if (ix >= p.W) return;
     double raw;
-    p.hmap[(size_t)iz * p.W + ix] = column_params<PREC>(p, p.tables, nullptr, ix, iz, &raw, col_coords(p.x0 + ix, p.z0 + iz));
+    p.hmap[(size_t)iz * p.W + ix] = column_params<PREC>(p, p.tables, nullptr, 0, ix, iz, &raw, col_coords(p.x0 + ix, p.z0 + iz));
     if (p.raw) p.raw[(size_t)iz * p.W + ix] = raw;
 }
 
@@ -364,7 +376,9 @@ __global__ void __launch_bounds__(256, 4) fill_kernel(FillParams p, GenParams g)
         // scaled coordinates of the CTA's 32 x values and 32 z values at the four noise scales: one division per thread
         __shared__ double s_coord[4][2][32];
         __shared__ GenTables s_tab;         // the seven permutation tables (1.8 KB): two dependent lookups per lattice point
-        __shared__ CellPointDev s_cand[36]; // the cell points around this chunk column's super-cell, in visiting order
+        __shared__ CellPointDev s_cand[36]; // the cell points around this chunk column's super-cell, in visiting order ...
+        __shared__ CellPointDev s_near[36]; // ... and those of them that can be the nearest one of some column of this chunk
+        __shared__ int s_keep[36], s_bound, s_ncand;
         for (int i = threadIdx.x; i < (int)(sizeof(GenTables) / 4); i += 256)
             reinterpret_cast<uint32_t *>(&s_tab)[i] = reinterpret_cast<const uint32_t *>(g.tables)[i];
         // A chunk is 32 columns wide and a super-cell 128, so its columns share pos / 128 -- unless the chunk starts at a
@@ -372,10 +386,21 @@ __global__ void __launch_bounds__(256, 4) fill_kernel(FillParams p, GenParams g)
         // search per column.
         const int32_t cx_lo = g.x0 + sx * 32, cz_lo = g.z0 + sz * 32;
         const bool one_cell = (cx_lo / 128 == (cx_lo + 31) / 128) && (cz_lo / 128 == (cz_lo + 31) / 128);
+        // Pruning: a point whose smallest distance to the chunk's 32 x 32 columns exceeds the LARGEST distance of some other
+        // point is farther than that one from every column, so it can neither win nor tie (find_nearest_cell_points keeps the
+        // first minimum, stdgen.rs:149-169; the survivors keep their visiting order). 36 -> typically 5-10 candidates.
+        int32_t c_min = 0, c_max = 0;
+        if (threadIdx.x == 0) s_bound = 0x7FFFFFFF;
         if (threadIdx.x < 36 && one_cell) {
             const int32_t cellx = cx_lo / 128, cellz = cz_lo / 128;
             const int k = threadIdx.x, cdx = k / 12 - 1, cdy = (k / 4) % 3 - 1;
-            s_cand[k] = g.cells[((size_t)(cellz + cdy - g.cell_z0) * g.cells_w + (cellx + cdx - g.cell_x0)) * 4 + (k & 3)];
+            const CellPointDev c = g.cells[((size_t)(cellz + cdy - g.cell_z0) * g.cells_w + (cellx + cdx - g.cell_x0)) * 4 + (k & 3)];
+            s_cand[k] = c;
+            const int32_t ax = cx_lo - c.px, bx = c.px - (cx_lo + 31), az = cz_lo - c.pz, bz = c.pz - (cz_lo + 31);
+            const int32_t nx = max(max(ax, bx), 0), nz = max(max(az, bz), 0);   // nearest column
+            const int32_t fx = max(abs(ax), abs(bx)), fz = max(abs(az), abs(bz)); // farthest column
+            c_min = nx * nx + nz * nz;
+            c_max = fx * fx + fz * fz;
         }
         {
             const int t = threadIdx.x, sc = t >> 6, axis = (t >> 5) & 1, i = t & 31;
@@ -384,6 +409,18 @@ __global__ void __launch_bounds__(256, 4) fill_kernel(FillParams p, GenParams g)
             s_coord[sc][axis][i] = ddiv((double)coord, sf);
         }
         __syncthreads();
+        if (threadIdx.x < 36 && one_cell) atomicMin(&s_bound, c_max);
+        __syncthreads();
+        if (threadIdx.x < 36 && one_cell) s_keep[threadIdx.x] = c_min <= s_bound;
+        __syncthreads();
+        if (threadIdx.x < 36 && one_cell) {
+            int pos = 0;
+            for (int k = 0; k < (int)threadIdx.x; k++) pos += s_keep[k];
+            if (s_keep[threadIdx.x]) s_near[pos] = s_cand[threadIdx.x];
+            if (threadIdx.x == 35) s_ncand = pos + s_keep[35];
+        }
+        __syncthreads();
+        const int n_cands = one_cell ? s_ncand : 0;
         int hv[4];
 #pragma unroll 1
         for (int k = 0; k < 4; k++) {
@@ -397,7 +434,7 @@ __global__ void __launch_bounds__(256, 4) fill_kernel(FillParams p, GenParams g)
             cc.hz = s_coord[2][1][zr];
             cc.mx = s_coord[3][0][xi];
             cc.mz = s_coord[3][1][zr];
-            hv[k] = column_params<(GEN == 0 ? 64 : GEN)>(g, &s_tab, one_cell ? s_cand : nullptr, sx * 32 + q * 4 + k, sz * 32 + zr, nullptr, cc);
+            hv[k] = column_params<(GEN == 0 ? 64 : GEN)>(g, &s_tab, one_cell ? s_near : nullptr, n_cands, sx * 32 + q * 4 + k, sz * 32 + zr, nullptr, cc);
         }
         hm = make_int4(hv[0], hv[1], hv[2], hv[3]);
         *reinterpret_cast<int4 *>(g.hmap + (size_t)(sz * 32 + zr) * p.W + sx * 32 + q * 4) = hm;
@@ -417,6 +454,7 @@ __global__ void __launch_bounds__(256, 4) fill_kernel(FillParams p, GenParams g)
     int lz0 = zr == 0 ? lo : big, lz1 = zr == 31 ? lo : big;
     lo = __reduce_min_sync(0xFFFFFFFFu, lo);
     hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+    const int w_lo = lo, w_hi = hi; // lowest / highest surface among this warp's 128 columns
     lx0 = __reduce_min_sync(0xFFFFFFFFu, lx0);
     lx1 = __reduce_min_sync(0xFFFFFFFFu, lx1);
     lz0 = __reduce_min_sync(0xFFFFFFFFu, lz0);
@@ -464,8 +502,14 @@ __global__ void __launch_bounds__(256, 4) fill_kernel(FillParams p, GenParams g)
         if (p.page && threadIdx.x == 0) p.page[c] = pg;
         if (pg != c) continue;
         uint4 *dst = reinterpret_cast<uint4 *>(p.blocks + (size_t)c * kChunkVoxels + zr * 32 + q * 4);
+        // layers [0, y_mixed) are stone and layers [y_void, 32) are void for every column of this WARP (4 z rows; terrain is
+        // smooth, so the per-voxel selection runs for a handful of layers only); 1024 voxels per y layer = 256 uint4
+        const int y_mixed = min(max(w_lo - 5 - ybase, 0), 32), y_void = min(max(w_hi + 1 - ybase, y_mixed), 32);
+        const uint4 stone4 = make_uint4(p.id_stone, p.id_stone, p.id_stone, p.id_stone), void4 = make_uint4(p.id_void, p.id_void, p.id_void, p.id_void);
 #pragma unroll 4
-        for (int yc = 0; yc < 32; yc++) {
+        for (int yc = 0; yc < y_mixed; yc++) __stcs(&dst[yc * 256], stone4); // streaming stores
+#pragma unroll 2
+        for (int yc = y_mixed; yc < y_void; yc++) {
             const int y = ybase + yc;
             uint32_t o[4];
 #pragma unroll
@@ -473,8 +517,10 @@ __global__ void __launch_bounds__(256, 4) fill_kernel(FillParams p, GenParams g)
                 const int t = hh[k] - y; // depth below the surface (stdgen.rs:359-372)
                 o[k] = t < 0 ? p.id_void : (t == 0 ? top[k] : (t <= 5 ? p.id_dirt : p.id_stone));
             }
-            __stcs(&dst[yc * 256], make_uint4(o[0], o[1], o[2], o[3])); // 1024 voxels per y layer = 256 uint4; streaming store
+            __stcs(&dst[yc * 256], make_uint4(o[0], o[1], o[2], o[3]));
         }
+#pragma unroll 4
+        for (int yc = y_void; yc < 32; yc++) __stcs(&dst[yc * 256], void4);
     }
 }
 
@@ -518,24 +564,28 @@ __global__ void __launch_bounds__(64) fill_xface_kernel(FillParams p) {
 template <int PREC>
 __global__ void noise_samples_kernel(const GenTables *T, int which, const double *xs, const double *ys, size_t n, double *out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = noise_at<PREC>(T->perm[which], xs[i], ys[i]);
-}
-
-unsigned long long g_const_devices = 0; // bit d set: __constant__ tables uploaded on device d
-void ensure_constants() {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 64 && (g_const_devices >> dev) & 1ull) return;
-    cudaMemcpyToSymbol(c_lat_off, h_lat_off, sizeof h_lat_off);
-    cudaMemcpyToSymbol(c_lat_pt, h_lat_pt, sizeof h_lat_pt);
-    if (dev < 64) g_const_devices |= 1ull << dev;
+    if (i < n) out[i] = noise_at<PREC>(T, which, xs[i], ys[i]);
 }
 
 } // namespace
 
+void fill_noise_constants(GenTables &t) {
+    const double d = kDiag;
+    const double g[8][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}, {d, d}, {-d, d}, {d, -d}, {-d, -d}};
+    for (int i = 0; i < 8; i++) t.grad[i][0] = g[i][0], t.grad[i][1] = g[i][1];
+    for (int grp = 0; grp < 8; grp++)
+        for (int k = 0; k < 2; k++) {
+            LatticeEntry &e = t.lat[grp][k];
+            e.ox = h_lat_off[grp * 4 + 2 + k][0];
+            e.oy = h_lat_off[grp * 4 + 2 + k][1];
+            e.px = h_lat_pt[grp * 4 + 2 + k][0];
+            e.py = h_lat_pt[grp * 4 + 2 + k][1];
+            e.pad[0] = e.pad[1] = 0;
+        }
+}
+
 void launch_cellpoints_kernel(uint64_t seed, int32_t cell_x0, int32_t cell_z0, int32_t cells_w, int32_t cells_d,
                               const GenTables *tables, CellPointDev *cells, int precision, cudaStream_t stream) {
-    ensure_constants();
     const int n = cells_w * cells_d;
     if (precision == 32)
         cellpoints_kernel<32><<<(n + 127) / 128, 128, 0, stream>>>(seed, cell_x0, cell_z0, cells_w, cells_d, tables, cells);
@@ -545,7 +595,6 @@ void launch_cellpoints_kernel(uint64_t seed, int32_t cell_x0, int32_t cell_z0, i
 
 void launch_noise_samples(const GenTables *tables, int which, const double *xs, const double *ys, size_t n, double *out, int precision,
                           cudaStream_t stream) {
-    ensure_constants();
     if (!n) return;
     const unsigned nb = (unsigned)((n + 127) / 128);
     if (precision == 32) noise_samples_kernel<32><<<nb, 128, 0, stream>>>(tables, which, xs, ys, n, out);
@@ -553,7 +602,6 @@ void launch_noise_samples(const GenTables *tables, int which, const double *xs, 
 }
 
 void launch_heightmap_kernel(const GenParams &p, int precision, cudaStream_t stream) {
-    ensure_constants();
     dim3 grid((p.W + 127) / 128, p.D);
     if (precision == 32) heightmap_kernel<32><<<grid, 128, 0, stream>>>(p);
     else heightmap_kernel<64><<<grid, 128, 0, stream>>>(p);
@@ -572,7 +620,6 @@ void launch_fill_kernel(const FillParams &p, cudaStream_t stream) {
 }
 
 void launch_gen_fill_kernel(const FillParams &p, const GenParams &g, int precision, cudaStream_t stream) {
-    ensure_constants();
     if (p.list && !p.n_list) return;
     if (precision == 32) fill_kernel<32><<<fill_grid(p), 256, 0, stream>>>(p, g);
     else fill_kernel<64><<<fill_grid(p), 256, 0, stream>>>(p, g);
