@@ -39,10 +39,44 @@ __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a,
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
 
+// Where the generator's tables are read from. Global: a pointer (height map / sample kernels). Shared: fill_kernel stages the
+// tables per CTA, and the noise subroutine -- which is not inlined, so a pointer would arrive as a GENERIC address: 64-bit
+// address arithmetic and generic loads for its 16 lookups -- gets the 32-bit shared-memory address and uses ld.shared.
+constexpr uint32_t kTabGrad = (uint32_t)offsetof(GenTables, grad), kTabLat = (uint32_t)offsetof(GenTables, lat);
+struct TabsGlobal {
+    const GenTables *T;
+    __device__ __forceinline__ unsigned u8(uint32_t off) const { return reinterpret_cast<const uint8_t *>(T)[off]; }
+    __device__ __forceinline__ double2 f64x2(uint32_t off) const {
+        return *reinterpret_cast<const double2 *>(reinterpret_cast<const uint8_t *>(T) + off);
+    }
+    __device__ __forceinline__ int2 s32x2(uint32_t off) const {
+        return *reinterpret_cast<const int2 *>(reinterpret_cast<const uint8_t *>(T) + off);
+    }
+};
+struct TabsShared {
+    uint32_t ts; // shared-window address of the CTA's GenTables copy (written before a __syncthreads, read-only afterwards)
+    __device__ __forceinline__ unsigned u8(uint32_t off) const {
+        unsigned v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(ts + off));
+        return v;
+    }
+    __device__ __forceinline__ double2 f64x2(uint32_t off) const {
+        double2 v;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(ts + off));
+        return v;
+    }
+    __device__ __forceinline__ int2 s32x2(uint32_t off) const {
+        int2 v;
+        asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(ts + off));
+        return v;
+    }
+};
+
 // noise::SuperSimplex::get([x, y]) (f64). One copy per kernel (not inlined): the height map kernel calls it from 11 sites and
 // fully inlined it was 141 KB of SASS, more than half of its warp stalls were instruction-cache misses.
-__device__ __noinline__ double super_simplex_2d(const GenTables *__restrict__ T, int which, double px, double py) {
-    const uint8_t *perm = T->perm[which];
+template <class TB>
+__device__ __noinline__ double super_simplex_2d(const TB T, int which, double px, double py) {
+    const uint32_t perm = (uint32_t)which * 256u;
     const double to_simplex_offset = dmul(dadd(px, py), kToSimplex);
     const double sx = dadd(px, to_simplex_offset), sy = dadd(py, to_simplex_offset);
     const double bxf = floor(sx), byf = floor(sy);
@@ -61,10 +95,9 @@ __device__ __noinline__ double super_simplex_2d(const GenTables *__restrict__ T,
         const double dx = dadd(qx, ox), dy = dadd(qy, oy);
         const double attn = dsub(2.0 / 3.0, dadd(dmul(dx, dx), dmul(dy, dy)));
         if (attn > 0.0) {
-            // (plain loads: the tables may live in shared memory, see fill_kernel)
-            const unsigned h = perm[perm[(bxi + lpx) & 0xffu] ^ ((byi + lpy) & 0xffu)];
+            const unsigned h = T.u8(perm + (T.u8(perm + ((bxi + lpx) & 0xffu)) ^ ((byi + lpy) & 0xffu)));
             // gradient::grad2(h % 8) = (1,0) (-1,0) (0,1) (0,-1) (d,d) (-d,d) (d,-d) (-d,-d): one 16-byte table load
-            const double2 gr = *reinterpret_cast<const double2 *>(T->grad[h & 7u]);
+            const double2 gr = T.f64x2(kTabGrad + (h & 7u) * 16u);
             const double a2 = dmul(attn, attn);
             value = dadd(value, dmul(dmul(a2, a2), dadd(dmul(gr.x, dx), dmul(gr.y, dy))));
         }
@@ -74,9 +107,9 @@ __device__ __noinline__ double super_simplex_2d(const GenTables *__restrict__ T,
     point(-LC, -LC, 1u, 1u);
 #pragma unroll
     for (unsigned k = 0; k < 2; k++) {
-        const LatticeEntry *e = &T->lat[group][k];
-        const double2 o = *reinterpret_cast<const double2 *>(&e->ox);
-        const int2 lp = *reinterpret_cast<const int2 *>(&e->px);
+        const uint32_t e = kTabLat + (group * 2u + k) * (uint32_t)sizeof(LatticeEntry);
+        const double2 o = T.f64x2(e);
+        const int2 lp = T.s32x2(e + 16u);
         point(o.x, o.y, (unsigned)lp.x, (unsigned)lp.y);
     }
     return dmul(value, kNorm);
@@ -87,8 +120,9 @@ __device__ __noinline__ double super_simplex_2d(const GenTables *__restrict__ T,
 // 10^4 an f32 position has an error of 10^-3, which would move lattice decisions and broke the 1e-5 bound in round 1 -- so the
 // same lattice points and gradients are used as in the f64 path. Everything after that works on the relative coordinates in
 // [0, 1): offsets, attenuation, gradient dot products and the sum are f32 (about 80 % of the arithmetic).
-__device__ __noinline__ float super_simplex_2d_f32(const GenTables *__restrict__ T, int which, double px, double py) {
-    const uint8_t *perm = T->perm[which];
+template <class TB>
+__device__ __noinline__ float super_simplex_2d_f32(const TB T, int which, double px, double py) {
+    const uint32_t perm = (uint32_t)which * 256u;
     const double to_simplex_offset = dmul(dadd(px, py), kToSimplex);
     const double sx = dadd(px, to_simplex_offset), sy = dadd(py, to_simplex_offset);
     const double bxf = floor(sx), byf = floor(sy);
@@ -107,8 +141,8 @@ __device__ __noinline__ float super_simplex_2d_f32(const GenTables *__restrict__
         const float dx = __fadd_rn(qx, ox), dy = __fadd_rn(qy, oy);
         const float attn = __fsub_rn(2.0f / 3.0f, __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
         if (attn > 0.0f) {
-            const unsigned h = perm[perm[(bxi + lpx) & 0xffu] ^ ((byi + lpy) & 0xffu)];
-            const double2 gr = *reinterpret_cast<const double2 *>(T->grad[h & 7u]);
+            const unsigned h = T.u8(perm + (T.u8(perm + ((bxi + lpx) & 0xffu)) ^ ((byi + lpy) & 0xffu)));
+            const double2 gr = T.f64x2(kTabGrad + (h & 7u) * 16u);
             const float a2 = __fmul_rn(attn, attn);
             value = __fadd_rn(value, __fmul_rn(__fmul_rn(a2, a2), __fadd_rn(__fmul_rn((float)gr.x, dx), __fmul_rn((float)gr.y, dy))));
         }
@@ -117,17 +151,17 @@ __device__ __noinline__ float super_simplex_2d_f32(const GenTables *__restrict__
     point((float)-LC, (float)-LC, 1u, 1u);
 #pragma unroll
     for (unsigned k = 0; k < 2; k++) {
-        const LatticeEntry *e = &T->lat[group][k];
-        const double2 o = *reinterpret_cast<const double2 *>(&e->ox);
-        const int2 lp = *reinterpret_cast<const int2 *>(&e->px);
+        const uint32_t e = kTabLat + (group * 2u + k) * (uint32_t)sizeof(LatticeEntry);
+        const double2 o = T.f64x2(e);
+        const int2 lp = T.s32x2(e + 16u);
         point((float)o.x, (float)o.y, (unsigned)lp.x, (unsigned)lp.y);
     }
     return __fmul_rn(value, (float)kNorm);
 }
 
 // precision-generic noise returning double
-template <int PREC>
-__device__ __forceinline__ double noise_at(const GenTables *T, int which, double px, double py) {
+template <int PREC, class TB>
+__device__ __forceinline__ double noise_at(const TB T, int which, double px, double py) {
     if (PREC == 32) return (double)super_simplex_2d_f32(T, which, px, py);
     return super_simplex_2d(T, which, px, py);
 }
@@ -152,37 +186,37 @@ __device__ __forceinline__ ColCoords col_coords(int32_t x, int32_t z) {
 }
 
 // (n + 1) / 2 of the reference is computed as (n + 1) * 0.5: halving is exact in binary floating point either way
-template <int PREC>
-__device__ __forceinline__ double elevation_noise_at(const GenTables *T, double ex, double ez) {
+template <int PREC, class TB>
+__device__ __forceinline__ double elevation_noise_at(const TB T, double ex, double ez) {
     return dmul(dadd(noise_at<PREC>(T, 5, ex, ez), 1.0), 0.5);
 }
 
-template <int PREC>
-__device__ __forceinline__ double elevation_noise(const GenTables *T, int32_t x, int32_t z) {
+template <int PREC, class TB>
+__device__ __forceinline__ double elevation_noise(const TB T, int32_t x, int32_t z) {
     // stdgen.rs:171-175: GLOBAL_BIOME_SCALE * GLOBAL_SCALE_MOD = 2560
     const double sf = 256.0 * 10.0;
     return elevation_noise_at<PREC>(T, ddiv((double)x, sf), ddiv((double)z, sf));
 }
 
-template <int PREC>
-__device__ __forceinline__ double h_n(const GenTables *T, int i, double px, double pz) {
+template <int PREC, class TB>
+__device__ __forceinline__ double h_n(const TB T, int i, double px, double pz) {
     return dmul(dadd(noise_at<PREC>(T, i, px, pz), 1.0), 0.5); // stdgen.rs:178-180 ((n + 1) / 2, exact as * 0.5)
 }
-template <int PREC>
-__device__ __forceinline__ double h_rn(const GenTables *T, int i, double px, double pz) {
+template <int PREC, class TB>
+__device__ __forceinline__ double h_rn(const TB T, int i, double px, double pz) {
     return dmul(2.0, dsub(0.5, fabs(dsub(0.5, h_n<PREC>(T, i, px, pz))))); // stdgen.rs:183-185
 }
 
-template <int PREC>
-__device__ double plains_height(const GenTables *T, double px, double pz) {
+template <int PREC, class TB>
+__device__ double plains_height(const TB T, double px, double pz) {
     // stdgen.rs:187-192; px, pz = pos / (10 * 120)
     const double a = dmul(0.75, h_n<PREC>(T, 0, px, pz));
     const double b = dmul(0.25, h_n<PREC>(T, 1, dmul(px, 2.0), dmul(pz, 2.0)));
     return dadd(dmul(dadd(a, b), 5.0), 10.0);
 }
 
-template <int PREC>
-__device__ double hills_height(const GenTables *T, double px, double pz) {
+template <int PREC, class TB>
+__device__ double hills_height(const TB T, double px, double pz) {
     // stdgen.rs:194-200; px, pz = pos / (10 * 160)
     const double a = dmul(0.60, h_n<PREC>(T, 0, px, pz));
     const double b = dmul(0.25, h_n<PREC>(T, 1, dmul(px, 1.5), dmul(pz, 1.5)));
@@ -190,8 +224,8 @@ __device__ double hills_height(const GenTables *T, double px, double pz) {
     return dadd(dmul(dadd(dadd(a, b), c), 30.0), 15.0);
 }
 
-template <int PREC>
-__device__ double mountains_height(const GenTables *T, double px, double pz) {
+template <int PREC, class TB>
+__device__ double mountains_height(const TB T, double px, double pz) {
     // stdgen.rs:202-213; px, pz = pos / (10 * 200)
     const double h0 = dmul(0.50, h_rn<PREC>(T, 0, px, pz));
     const double h01 = dadd(dmul(0.25, h_rn<PREC>(T, 1, dmul(px, 2.0), dmul(pz, 2.0))), h0);
@@ -237,16 +271,16 @@ __global__ void cellpoints_kernel(uint64_t seed, int32_t cell_x0, int32_t cell_z
         CellPointDev cp;
         cp.px = cx * 128 + bx[k] + ((int32_t)(r[0] % 32u) - 16);
         cp.pz = cz * 128 + bz[k] + ((int32_t)(r[1] % 32u) - 16);
-        cp.elevation_class = elevation_noise<PREC>(T, cp.px, cp.pz);
+        cp.elevation_class = elevation_noise<PREC>(TabsGlobal{T}, cp.px, cp.pz);
         cells[i * 4 + k] = cp;
     }
 }
 
 // CellGen::calc_voxel_params (stdgen.rs:215-276) of column (ix, iz) of the height map: returns height*4 + elevation class
-template <int PREC>
+template <int PREC, class TB>
 // cands != nullptr: the 36 cell points around the column's super-cell in the reference's visiting order (cdx outer, cdy inner,
 // point index innermost), gathered once per CTA (every column of a chunk lies in one super-cell); T: the permutation tables
-__device__ __forceinline__ int32_t column_params(const GenParams &p, const GenTables *T, const CellPointDev *cands, int n_cands, int ix,
+__device__ __forceinline__ int32_t column_params(const GenParams &p, const TB T, const CellPointDev *cands, int n_cands, int ix,
                                                  int iz, double *raw_out, const ColCoords &cc) {
     const int32_t x = p.x0 + ix, z = p.z0 + iz;
 
@@ -335,7 +369,7 @@ __global__ void __launch_bounds__(128) heightmap_kernel(GenParams p) {
     const int iz = blockIdx.y;
     if (ix >= p.W) return;
     double raw;
-    p.hmap[(size_t)iz * p.W + ix] = column_params<PREC>(p, p.tables, nullptr, 0, ix, iz, &raw, col_coords(p.x0 + ix, p.z0 + iz));
+    p.hmap[(size_t)iz * p.W + ix] = column_params<PREC>(p, TabsGlobal{p.tables}, nullptr, 0, ix, iz, &raw, col_coords(p.x0 + ix, p.z0 + iz));
     if (p.raw) p.raw[(size_t)iz * p.W + ix] = raw;
 }
 
@@ -434,7 +468,7 @@ __global__ void __launch_bounds__(256, 4) fill_kernel(FillParams p, GenParams g)
             cc.hz = s_coord[2][1][zr];
             cc.mx = s_coord[3][0][xi];
             cc.mz = s_coord[3][1][zr];
-            hv[k] = column_params<(GEN == 0 ? 64 : GEN)>(g, &s_tab, one_cell ? s_near : nullptr, n_cands, sx * 32 + q * 4 + k, sz * 32 + zr, nullptr, cc);
+            hv[k] = column_params<(GEN == 0 ? 64 : GEN)>(g, TabsShared{(uint32_t)__cvta_generic_to_shared(&s_tab)}, one_cell ? s_near : nullptr, n_cands, sx * 32 + q * 4 + k, sz * 32 + zr, nullptr, cc);
         }
         hm = make_int4(hv[0], hv[1], hv[2], hv[3]);
         *reinterpret_cast<int4 *>(g.hmap + (size_t)(sz * 32 + zr) * p.W + sx * 32 + q * 4) = hm;
@@ -564,7 +598,7 @@ __global__ void __launch_bounds__(64) fill_xface_kernel(FillParams p) {
 template <int PREC>
 __global__ void noise_samples_kernel(const GenTables *T, int which, const double *xs, const double *ys, size_t n, double *out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = noise_at<PREC>(T, which, xs[i], ys[i]);
+    if (i < n) out[i] = noise_at<PREC>(TabsGlobal{T}, which, xs[i], ys[i]);
 }
 
 } // namespace
