@@ -50,11 +50,11 @@ struct Scratch { // phases B, S, C
     uint32_t rowV[1028];   // exclusive prefix over rows: first vertex of the row (chunk-relative); [1024] = total
     uint32_t rowI[1028];
     uint32_t rowF[1028];
-    // record tile: written by C1
+    // record tile of a cubes-and-void chunk: written by C1
     uint32_t frecA[FC];   // row | x<<10 | dir<<15 | vstart<<18 (tile-relative first vertex)
-    uint32_t frecB[FC];   // tile-relative first index (tiles with non-quad sides)
-    uint32_t frecC[FC];   // block id | class<<16 (tiles with non-quad sides)
-    uint32_t frecE[FC];   // occupancy of the cell's 3x3x3 neighbourhood, bit (dy+1)*9 + (dz+1)*3 + (dx+1) (ditto)
+    // chunks with other shapes: the visible-side mask of every cell, kept from phase B for phase C (the general test costs
+    // six class lookups + six table lookups per cell)
+    uint8_t vis[32 * 32 * 32];
 };
 struct ScratchLean { // the cubes-only kernel: every side is a quad, C2 recomputes the rest
     uint32_t rowV[1028];
@@ -697,7 +697,7 @@ __global__ void __launch_bounds__(NT, LEAN ? 4 : 2) mesh_kernel(MeshParams p) {
                 const uint32_t nf = __popcll(vw[0]) + __popcll(vw[1]) + __popcll(vw[2]) + __popcll(vw[3]) + __popcll(vw[4]) + __popcll(vw[5]);
                 s.sc.rowV[row] = (nf * 4u) | ((nf * 6u) << 10) | (nf << 21);
             }
-        } else if (!LEAN) {
+        } else if constexpr (!LEAN) {
             for (int row = warp; row < 1024; row += NW) {
                 const int y = row >> 5, z = row & 31;
                 const int at = (y + 1) * PLANE + (z + 1) * ROWB + XOFF + lane;
@@ -705,7 +705,9 @@ __global__ void __launch_bounds__(NT, LEAN ? 4 : 2) mesh_kernel(MeshParams p) {
                 uint32_t cnt = 0;
                 if (__any_sync(FULL, c != 0)) {
                     const uint32_t t = s.ctab[c];
-                    cnt = __reduce_add_sync(FULL, cell_counts(s, cell_visibility(s, at, t), t));
+                    const uint32_t vis = cell_visibility(s, at, t);
+                    s.sc.vis[row * 32 + lane] = (uint8_t)vis; // (rows without a side are skipped by phase C)
+                    cnt = __reduce_add_sync(FULL, cell_counts(s, vis, t));
                 }
                 if (lane == 0) s.sc.rowV[row] = cnt;
             }
@@ -817,7 +819,50 @@ __global__ void __launch_bounds__(NT, LEAN ? 4 : 2) mesh_kernel(MeshParams p) {
         const uint32_t *center = p.blocks + (size_t)s.nbr[13] * kChunkVoxels;
         const unsigned long long fbase = s.fbase;
         const bool quads_only = LEAN || !has_shapes; // every side has 4 vertices / 6 indices
-        for (uint32_t r0 = 0; r0 < 1024;) {
+        if constexpr (!LEAN) {
+            if (!quads_only) {
+                // Chunks with slopes / corners: warp per row, lane per cell; every lane writes the finished records of its cell's
+                // visible sides straight to the record buffer (a row's records are one contiguous run, so the scattered 16-byte
+                // stores of a warp fall into a few lines). No staging tile, no second pass, no block barriers.
+                PHASE_MARK(t_t1);
+                for (uint32_t row = warp; row < 1024; row += NW) {
+                    const uint32_t rf = s.sc.rowF[row];
+                    if (s.sc.rowF[row + 1] - rf == 0) continue;
+                    const int at = ((row >> 5) + 1) * PLANE + ((row & 31) + 1) * ROWB + XOFF + lane;
+                    const uint32_t c = s.cls[at];
+                    const uint32_t t = s.ctab[c];
+                    const uint32_t vis = s.sc.vis[row * 32 + lane];
+                    const uint32_t pk = cell_counts(s, vis, t);
+                    uint32_t incl = pk;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t a = __shfl_up_sync(FULL, incl, o);
+                        if (lane >= o) incl += a;
+                    }
+                    const uint32_t excl = incl - pk;
+                    if (vis) {
+                        const uint32_t nb = neighbourhood27(s, (int)(row >> 5), (int)(row & 31), lane); // row words are warp-uniform loads
+                        const uint32_t id = __ldg(center + row * 32 + lane) >> 16; // an L2 hit: phase A just streamed the chunk
+                        uint32_t vs = s.sc.rowV[row] + (excl & 1023u), is = s.sc.rowI[row] + ((excl >> 10) & 2047u);
+                        uint4 *out = p.frec + fbase + rf + (excl >> 21);
+                        const uint32_t codes = t >> 18;
+                        const uint32_t a0 = row | ((uint32_t)lane << 10) | (c << 18), idlo = (id & 0xFFFu) << 20, idhi = (id >> 12) << 21;
+#pragma unroll
+                        for (int d = 0; d < 6; d++) {
+                            if ((vis >> d) & 1u) {
+                                const uint32_t code = (codes >> (2 * d)) & 3u;
+                                *out++ = make_uint4(a0 | ((uint32_t)d << 15), vs | idlo, is | idhi, nb);
+                                vs += code + 2u + (code == 3u);
+                                is += (code == 1u ? 3u : 6u);
+                            }
+                        }
+                    }
+                }
+                PHASE_MARK(t_t2);
+                PHASE_ADD(7, t_t1, t_t2);
+            }
+        }
+        for (uint32_t r0 = quads_only ? 0u : 1024u; r0 < 1024;) {
             PHASE_MARK(t_t0);
             // largest r1 with faces(r0..r1) <= FC and vertices(r0..r1) <= VC (a single row never exceeds 192 / 768). The test is
             // monotone in r1: every warp finds it with two 32-way votes (rows r0+1, r0+33, ... then the 32 rows behind the hit).
@@ -862,42 +907,6 @@ __global__ void __launch_bounds__(NT, LEAN ? 4 : 2) mesh_kernel(MeshParams p) {
                         }
                     }
                 }
-            } else if constexpr (!LEAN) {
-                for (uint32_t row = r0 + warp; row < r1; row += NW) {
-                    if (s.sc.rowF[row + 1] - s.sc.rowF[row] == 0) continue;
-                    const int at = ((row >> 5) + 1) * PLANE + ((row & 31) + 1) * ROWB + XOFF + lane;
-                    const uint32_t c = s.cls[at];
-                    const uint32_t t = s.ctab[c];
-                    const uint32_t vis = c ? cell_visibility(s, at, t) : 0u;
-                    const uint32_t pk = cell_counts(s, vis, t);
-                    uint32_t incl = pk;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t a = __shfl_up_sync(FULL, incl, o);
-                        if (lane >= o) incl += a;
-                    }
-                    const uint32_t excl = incl - pk;
-                    const uint32_t nb = neighbourhood27(s, (int)(row >> 5), (int)(row & 31), lane); // row words are warp-uniform loads
-                    const uint32_t idc = (__ldg(center + row * 32 + lane) >> 16) | (c << 16); // block id | class, one coalesced row load
-                    if (vis) {
-                        uint32_t vs = s.sc.rowV[row] - v0 + (excl & 1023u), is = s.sc.rowI[row] - i0 + ((excl >> 10) & 2047u),
-                                 f = s.sc.rowF[row] - f0 + (excl >> 21);
-                        const uint32_t codes = t >> 18;
-#pragma unroll
-                        for (int d = 0; d < 6; d++) {
-                            if ((vis >> d) & 1u) {
-                                const uint32_t code = (codes >> (2 * d)) & 3u;
-                                s.sc.frecA[f] = row | ((uint32_t)lane << 10) | ((uint32_t)d << 15) | (vs << 18);
-                                s.sc.frecB[f] = is;
-                                s.sc.frecE[f] = nb;
-                                s.sc.frecC[f] = idc;
-                                f++;
-                                vs += code + 2u + (code == 3u);
-                                is += (code == 1u ? 3u : 6u);
-                            }
-                        }
-                    }
-                }
             }
             __syncthreads();
             PHASE_MARK(t_t2);
@@ -907,25 +916,17 @@ __global__ void __launch_bounds__(NT, LEAN ? 4 : 2) mesh_kernel(MeshParams p) {
                 const uint32_t a = s.sc.frecA[f];
                 const uint32_t row = a & 1023u, x = (a >> 10) & 31u;
                 const uint32_t y = row >> 5, z = row & 31u;
-                uint32_t id = 0, cx = 0, nb = 0, is = 0;
-                if (quads_only) {
-                    const uint32_t datum = __ldg(center + row * 32 + x); // an L2 hit: phase A just streamed the chunk
-                    id = datum >> 16;
-                    if (LEAN) { // no class table: a cube's class is 1 + its orientation
-                        uint32_t e2 = 0;
-                        cx = classify(datum, s, p.reg, e2);
-                    } else {
-                        cx = s.cls[(y + 1) * PLANE + (z + 1) * ROWB + XOFF + (int)x];
-                    }
-                    nb = neighbourhood27(s, (int)y, (int)z, (int)x);
-                    is = f * 6u;
-                } else if constexpr (!LEAN) { // recorded by C1
-                    const uint32_t icr = s.sc.frecC[f];
-                    id = icr & 0xFFFFu;
-                    cx = icr >> 16;
-                    nb = s.sc.frecE[f];
-                    is = s.sc.frecB[f];
+                const uint32_t datum = __ldg(center + row * 32 + x); // an L2 hit: phase A just streamed the chunk
+                const uint32_t id = datum >> 16;
+                uint32_t cx;
+                if (LEAN) { // no class table: a cube's class is 1 + its orientation
+                    uint32_t e2 = 0;
+                    cx = classify(datum, s, p.reg, e2);
+                } else {
+                    cx = s.cls[(y + 1) * PLANE + (z + 1) * ROWB + XOFF + (int)x];
                 }
+                const uint32_t nb = neighbourhood27(s, (int)y, (int)z, (int)x);
+                const uint32_t is = f * 6u;
                 p.frec[fbase + f0 + f] = make_uint4((a & 0x3FFFFu) | (cx << 18), (v0 + (a >> 18)) | ((id & 0xFFFu) << 20),
                                                     (i0 + is) | ((id >> 12) << 21), nb);
             }
