@@ -15,16 +15,25 @@
 #include "device_common.cuh"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 
 namespace bxw {
 namespace {
 
-constexpr int ENT = 256;      // threads per CTA
-constexpr int ENW = ENT / 32; // warps per CTA
-constexpr int EREGC = 64;     // registry entries cached in shared memory
-constexpr int STGW = 328;     // staging words per warp: 32 vertices x 10 words + 2 words of misalignment, rounded to 16 bytes
+// Kernel shape. Measured on B200 (tools/exp_emit_variants.sh; hashed shapes / bench terrain, ms): the kernel is issue bound
+// per scheduler and its stores like few, large pieces: 12 warps per SM in ONE CTA with passes of up to 160 vertices (a batch
+// of 32 sides is ~128 vertices, so a batch leaves as one bulk copy of ~5 KB) 9.04 / 0.744; 16 warps x 64 vertices 9.0-9.1 /
+// 0.85-0.86; 24 warps x 32 vertices (round 2's first shape) 9.73 / 0.90; 13, 14, 20, 24 warps are 10-20 % slower (the warp
+// count has to divide evenly over the four schedulers, and more writers slow the write stream down).
+#ifndef BXW_EMIT_THREADS
+#define BXW_EMIT_THREADS 384
+#endif
+#ifndef BXW_EMIT_PV
+#define BXW_EMIT_PV 160
+#endif
+constexpr int EREGC = 32;     // registry entries cached in shared memory (ids beyond take the per-side fetch path)
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 
 struct alignas(16) SideRec { // what the vertex pass needs of a side (written by its lane in the side pass)
@@ -42,7 +51,11 @@ struct alignas(16) SideRec { // what the vertex pass needs of a side (written by
 constexpr uint32_t kVdPos = (1u << 24) | (1u << 14) | (1u << 4);
 constexpr uint32_t kVdFlags = 7u << 17;
 
-struct ESmem {
+template <int ENT, int PV>
+struct ESmemT {
+    static constexpr int ENW = ENT / 32;                 // warps per CTA
+    static constexpr int STGW = (PV * 10 + 2 + 3) / 4 * 4; // staging words per warp: PV vertices x 10 words + 2 of misalignment, rounded to 16 bytes
+    static_assert(PV % 16 == 0 && STGW >= 196, "a pass ends on a multiple of 16 vertices; the index run of a batch is staged in the same buffer");
     alignas(16) uint32_t wstage[ENW][2][STGW]; // two staging buffers per warp: one is filled while the bulk copy drains the other
     SideRec rec[ENW][32];
     float4 bigreg[ENW][32];           // debug_color + local-side texture id of sides whose block id is not in the cached registry
@@ -108,10 +121,13 @@ __device__ __forceinline__ void warp_bulk_out_vertices(uint32_t *dst, const uint
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-    // lane 1: head half (run starts odd), lane 2: tail half (run ends odd)
-    const uint32_t w = lane == 1u ? 2u : nfull * 4u;
-    if ((lane == 1u && misal) || (lane == 2u && (total & 2u)))
-        __stcs(reinterpret_cast<uint2 *>(dst - misal + w), *reinterpret_cast<const uint2 *>(stage16 + w));
+    // lane 1: head half (run starts odd), lane 2: tail half (run ends odd). Pieces end on multiples of 16 vertices, so only a
+    // batch's first piece can start odd and only its last can end odd: the (warp-uniform) test skips this for the others.
+    if (misal | (total & 2u)) {
+        const uint32_t w = lane == 1u ? 2u : nfull * 4u;
+        if ((lane == 1u && misal) || (lane == 2u && (total & 2u)))
+            __stcs(reinterpret_cast<uint2 *>(dst - misal + w), *reinterpret_cast<const uint2 *>(stage16 + w));
+    }
 }
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
@@ -125,13 +141,16 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
     return v;
 }
 
+// ENT threads per CTA; PV vertices per pass (PV / 32 per lane).
 // PIPE = false: launched after mesh_kernel has finished, over the f_alloc / 32 batches it left.
 // PIPE = true: launched NEXT TO mesh_kernel (another stream; mesh_kernel is compute / latency bound, this kernel memory bound):
 // a batch is consumed as soon as its chunk's record block is published -- mesh_kernel writes the batch's fslot entry last,
 // tagged with the pass's epoch, after a fence -- and the loop ends when every mesh CTA has retired (counters->mesh_done) and
 // the batch index has passed the final f_alloc.
-template <bool PIPE>
-__global__ void __launch_bounds__(ENT, 4) emit_kernel(MeshParams p) {
+template <bool PIPE, int ENT, int PV>
+__global__ void __launch_bounds__(ENT, PIPE ? 4 : 1) emit_kernel(MeshParams p) {
+    using ESmem = ESmemT<ENT, PV>;
+    constexpr int ENW = ESmem::ENW, STGW = ESmem::STGW;
     extern __shared__ __align__(16) unsigned char esmem_raw[];
     ESmem &s = *reinterpret_cast<ESmem *>(esmem_raw);
     const int tid = threadIdx.x;
@@ -294,58 +313,63 @@ __global__ void __launch_bounds__(ENT, 4) emit_kernel(MeshParams p) {
         // record: position, color, texcoord (u, v, texture id), index | barycentric flags, barycentric_color_offset[4]
         // (src/client/render/voxrender.rs:39-49). A vertex is 40 bytes and v_off is a multiple of 4 vertices, so an even vertex
         // index is 16-byte aligned: passes are cut at even indices (the first takes 31 vertices when the batch starts odd) and
-        // every pass leaves as whole 16-byte units except for one 8-byte half at the very start / end of the batch's run.
+        // every pass leaves as whole 16-byte units except for one 8-byte half at the very start / end of the batch's run. A pass
+        // takes up to PV vertices, two per lane.
         const uint32_t nvt = vqe - vq0;
         for (uint32_t tb = 0; tb < nvt;) {
             const uint32_t mis = ((vq0 + tb) & 1u) * 2u;
             // passes end on multiples of 16 vertices of the chunk's span (which starts on a 128-byte line): every piece but the
             // first and last of a batch is then ten whole lines
-            const uint32_t cnt = min(nvt - tb, 32u - ((vq0 + tb) & 15u));
+            const uint32_t cnt = min(nvt - tb, (uint32_t)PV - ((vq0 + tb) & 15u));
             uint32_t *const buf = stw + (npass & 1u) * STGW;
             uint2 *const st2 = reinterpret_cast<uint2 *>(buf);
             npass++;
             // the bulk copy that last read this buffer (two passes ago) must be through with it
             if (lane == 0u) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             __syncwarp();
+#pragma unroll
+            for (uint32_t h = 0; h < ((uint32_t)PV + 31u) / 32u; h++) {
+                const uint32_t v = lane + 32u * h; // vertex of the pass
 #ifdef BXW_EXP_NO_COMPUTE
-            if (lane < cnt) {
-                uint2 *o = st2 + (mis >> 1) + lane * 5u;
-                o[0] = make_uint2(tb, lane);
-                o[1] = make_uint2(tb, lane);
-                o[2] = make_uint2(tb, lane);
-                o[3] = make_uint2(tb, lane);
-                o[4] = make_uint2(tb, lane);
-            }
-            if (false) {
-#else
-            if (lane < cnt) {
-#endif
-                const uint32_t m = vmap[tb + lane];
-                const SideRec *sr = &rec[m >> 3];
-                const uint4 a = *reinterpret_cast<const uint4 *>(sr);
-                const uint4 fbv = *reinterpret_cast<const uint4 *>(&sr->fb[0]);
-                const uint32_t j = m & 7u;
-                const uint32_t cell = a.x & 0x7FFFu, id = a.x >> 16;
-                const uint32_t vd = s.vd32[(a.y >> 18) + j];
-                const uint32_t k = (a.y >> (3u * j)) & 7u;
-                uint32_t col;
-                if (id < (uint32_t)EREGC) {
-                    col = s.col_lut[id * 8 + k];
-                } else { // as_rgba8(debug_color * ao) (voxmesh.rs:29-34,147-152)
-                    const float aj = s.ao_lut[k];
-                    const float4 bc = s.bigreg[warp][m >> 3];
-                    const float c0f = __fmul_rn(bc.x, aj), c1f = __fmul_rn(bc.y, aj), c2f = __fmul_rn(bc.z, aj);
-                    col = ((__float2uint_rz(__fmul_rn(c0f, 255.0f)) & 0xFFu) << 24) | ((__float2uint_rz(__fmul_rn(c1f, 255.0f)) & 0xFFu) << 16) |
-                          ((__float2uint_rz(__fmul_rn(c2f, 255.0f)) & 0xFFu) << 8) | 0xFFu;
+                if (v < cnt) {
+                    uint2 *o = st2 + (mis >> 1) + v * 5u;
+                    o[0] = make_uint2(tb, lane);
+                    o[1] = make_uint2(tb, lane);
+                    o[2] = make_uint2(tb, lane);
+                    o[3] = make_uint2(tb, lane);
+                    o[4] = make_uint2(tb, lane);
                 }
-                // as_wxyz10 of (ipos + voffset + 0.5)/32 (voxmesh.rs:36-41,139-145,165): every vertex sits on a voxel corner, so
-                // each 10-bit field is 16 * corner coordinate (<= 512); w = (1/32*2) as u32 = 0
-                uint2 *o = st2 + (mis >> 1) + lane * 5u; // lanes 40 bytes apart: conflict-free 8-byte stores
-                o[0] = make_uint2(a.w + (vd & kVdPos), col);
-                o[1] = make_uint2((vd & 1u) * 0x3F800000u, ((vd >> 1) & 1u) * 0x3F800000u); // texcoord u, v: 0.0f or 1.0f
-                o[2] = make_uint2(a.z, cell | (vd & kVdFlags));
-                o[3] = make_uint2(fbv.x, fbv.y);
-                o[4] = make_uint2(fbv.z, fbv.w);
+                if (false) {
+#else
+                if (v < cnt) {
+#endif
+                    const uint32_t m = vmap[tb + v];
+                    const SideRec *sr = &rec[m >> 3];
+                    const uint4 a = *reinterpret_cast<const uint4 *>(sr);
+                    const uint4 fbv = *reinterpret_cast<const uint4 *>(&sr->fb[0]);
+                    const uint32_t j = m & 7u;
+                    const uint32_t cell = a.x & 0x7FFFu, id = a.x >> 16;
+                    const uint32_t vd = s.vd32[(a.y >> 18) + j];
+                    const uint32_t k = (a.y >> (3u * j)) & 7u;
+                    uint32_t col;
+                    if (id < (uint32_t)EREGC) {
+                        col = s.col_lut[id * 8 + k];
+                    } else { // as_rgba8(debug_color * ao) (voxmesh.rs:29-34,147-152)
+                        const float aj = s.ao_lut[k];
+                        const float4 bc = s.bigreg[warp][m >> 3];
+                        const float c0f = __fmul_rn(bc.x, aj), c1f = __fmul_rn(bc.y, aj), c2f = __fmul_rn(bc.z, aj);
+                        col = ((__float2uint_rz(__fmul_rn(c0f, 255.0f)) & 0xFFu) << 24) | ((__float2uint_rz(__fmul_rn(c1f, 255.0f)) & 0xFFu) << 16) |
+                              ((__float2uint_rz(__fmul_rn(c2f, 255.0f)) & 0xFFu) << 8) | 0xFFu;
+                    }
+                    // as_wxyz10 of (ipos + voffset + 0.5)/32 (voxmesh.rs:36-41,139-145,165): every vertex sits on a voxel corner, so
+                    // each 10-bit field is 16 * corner coordinate (<= 512); w = (1/32*2) as u32 = 0
+                    uint2 *o = st2 + (mis >> 1) + v * 5u; // lanes 40 bytes apart: conflict-free 8-byte stores
+                    o[0] = make_uint2(a.w + (vd & kVdPos), col);
+                    o[1] = make_uint2((vd & 1u) * 0x3F800000u, ((vd >> 1) & 1u) * 0x3F800000u); // texcoord u, v: 0.0f or 1.0f
+                    o[2] = make_uint2(a.z, cell | (vd & kVdFlags));
+                    o[3] = make_uint2(fbv.x, fbv.y);
+                    o[4] = make_uint2(fbv.z, fbv.w);
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // staging writes -> visible to the bulk copy engine
             __syncwarp();
@@ -378,24 +402,29 @@ __global__ void __launch_bounds__(ENT, 4) emit_kernel(MeshParams p) {
 
 } // namespace
 
-static_assert(sizeof(ESmem) <= 56 * 1024, "emit_kernel's shared memory no longer fits four times on an SM");
+// the sequential pass: one CTA per SM; the pipelined pass has to share the SMs with mesh_kernel: round 2's first shape
+using ESmemSeq = ESmemT<BXW_EMIT_THREADS, BXW_EMIT_PV>;
+using ESmemPipe = ESmemT<256, 32>;
+static_assert(sizeof(ESmemSeq) <= 226 * 1024, "emit_kernel's shared memory no longer fits an SM");
+static_assert(sizeof(ESmemPipe) <= 56 * 1024, "the pipelined emit_kernel no longer fits beside mesh_kernel");
 
 void launch_emit_kernel(const MeshParams &p, int sm_count, cudaStream_t stream) {
-    cudaFuncSetAttribute(emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ESmem));
+    auto kern = emit_kernel<false, BXW_EMIT_THREADS, BXW_EMIT_PV>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ESmemSeq));
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, emit_kernel<false>, ENT, sizeof(ESmem));
-    // three CTAs per SM, not four: the kernel is bound by the write stream, and with fewer writers in flight DRAM takes it
-    // faster (hashed-block chunks 10.9 -> 9.9 ms, terrain 0.95 -> 0.92 ms)
-    per_sm = std::min(per_sm, 3);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BXW_EMIT_THREADS, sizeof(ESmemSeq));
+    if (getenv("BXW_DEBUG_OCCUPANCY"))
+        fprintf(stderr, "emit_kernel: %d CTAs/SM possible, %zu bytes of shared memory per CTA\n", per_sm, sizeof(ESmemSeq));
+    per_sm = std::min(per_sm, 1);
     if (per_sm < 1) per_sm = 1;
-    if (const char *e = getenv("BXW_EXP_EMIT_CTAS")) per_sm = std::min(per_sm, std::max(1, atoi(e))); // experiments only
-    emit_kernel<false><<<(unsigned)(sm_count * per_sm), ENT, sizeof(ESmem), stream>>>(p);
+    kern<<<(unsigned)(sm_count * per_sm), BXW_EMIT_THREADS, sizeof(ESmemSeq), stream>>>(p);
 }
 
 void launch_emit_kernel_pipelined(const MeshParams &p, int sm_count, int ctas_per_sm, cudaStream_t stream) {
-    cudaFuncSetAttribute(emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ESmem));
-    cudaFuncSetAttribute(emit_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-    emit_kernel<true><<<(unsigned)(sm_count * ctas_per_sm), ENT, sizeof(ESmem), stream>>>(p);
+    auto kern = emit_kernel<true, 256, 32>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ESmemPipe));
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    kern<<<(unsigned)(sm_count * ctas_per_sm), 256, sizeof(ESmemPipe), stream>>>(p);
 }
 
 } // namespace bxw
