@@ -55,6 +55,8 @@ struct Scratch { // phases B, S, C
     // chunks with other shapes: the visible-side mask of every cell, kept from phase B for phase C (the general test costs
     // six class lookups + six table lookups per cell)
     uint8_t vis[32 * 32 * 32];
+    // ... and the 34-bit solid words (row + x-halo bits) combined once, for the 27-cell occupancy of every visible cell
+    unsigned long long solid64[34 * 34];
 };
 struct ScratchLean { // the cubes-only kernel: every side is a quad, C2 recomputes the rest
     uint32_t rowV[1028];
@@ -184,6 +186,19 @@ __device__ __forceinline__ uint32_t neighbourhood27(const S &s, int y, int z, in
         for (int dz = 0; dz < 3; dz++) {
             const unsigned long long w = solid_word(s, (y + dy) * 34 + (z + dz)); // rows y-1..y+1, z-1..z+1 (+1 halo offset)
             nb |= ((uint32_t)(w >> x) & 7u) << (3 * (dy * 3 + dz)); // bit x of w is cell x-1
+        }
+    return nb;
+}
+
+// the same from the combined words (low / high halves; bit x of a word is cell x-1)
+__device__ __forceinline__ uint32_t neighbourhood27_words(const unsigned long long *w64, int y, int z, int x) {
+    uint32_t nb = 0;
+#pragma unroll
+    for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+        for (int dz = 0; dz < 3; dz++) {
+            const uint2 w = *reinterpret_cast<const uint2 *>(&w64[(y + dy) * 34 + (z + dz)]);
+            nb |= (__funnelshift_r(w.x, w.y, x) & 7u) << (3 * (dy * 3 + dz));
         }
     return nb;
 }
@@ -825,6 +840,8 @@ __global__ void __launch_bounds__(NT, LEAN ? 4 : 2) mesh_kernel(MeshParams p) {
                 // visible sides straight to the record buffer (a row's records are one contiguous run, so the scattered 16-byte
                 // stores of a warp fall into a few lines). No staging tile, no second pass, no block barriers.
                 PHASE_MARK(t_t1);
+                for (int i = tid; i < 34 * 34; i += NT) s.sc.solid64[i] = solid_word(s, i);
+                __syncthreads();
                 for (uint32_t row = warp; row < 1024; row += NW) {
                     const uint32_t rf = s.sc.rowF[row];
                     if (s.sc.rowF[row + 1] - rf == 0) continue;
@@ -841,7 +858,7 @@ __global__ void __launch_bounds__(NT, LEAN ? 4 : 2) mesh_kernel(MeshParams p) {
                     }
                     const uint32_t excl = incl - pk;
                     if (vis) {
-                        const uint32_t nb = neighbourhood27(s, (int)(row >> 5), (int)(row & 31), lane); // row words are warp-uniform loads
+                        const uint32_t nb = neighbourhood27_words(s.sc.solid64, (int)(row >> 5), (int)(row & 31), lane); // warp-uniform loads
                         const uint32_t id = __ldg(center + row * 32 + lane) >> 16; // an L2 hit: phase A just streamed the chunk
                         uint32_t vs = s.sc.rowV[row] + (excl & 1023u), is = s.sc.rowI[row] + ((excl >> 10) & 2047u);
                         uint4 *out = p.frec + fbase + rf + (excl >> 21);
