@@ -842,7 +842,12 @@ __global__ void __launch_bounds__(NT, LEAN ? 4 : 2) mesh_kernel(MeshParams p) {
                 PHASE_MARK(t_t1);
                 for (int i = tid; i < 34 * 34; i += NT) s.sc.solid64[i] = solid_word(s, i);
                 __syncthreads();
+                // block ids of the row come from global memory (an L2 hit: phase A just streamed the chunk); the load for the
+                // next row is issued a whole iteration ahead
+                uint32_t datum_next = __ldg(center + warp * 32 + lane);
                 for (uint32_t row = warp; row < 1024; row += NW) {
+                    const uint32_t datum = datum_next;
+                    if (row + NW < 1024u) datum_next = __ldg(center + (row + NW) * 32 + lane);
                     const uint32_t rf = s.sc.rowF[row];
                     if (s.sc.rowF[row + 1] - rf == 0) continue;
                     const int at = ((row >> 5) + 1) * PLANE + ((row & 31) + 1) * ROWB + XOFF + lane;
@@ -859,7 +864,7 @@ __global__ void __launch_bounds__(NT, LEAN ? 4 : 2) mesh_kernel(MeshParams p) {
                     const uint32_t excl = incl - pk;
                     if (vis) {
                         const uint32_t nb = neighbourhood27_words(s.sc.solid64, (int)(row >> 5), (int)(row & 31), lane); // warp-uniform loads
-                        const uint32_t id = __ldg(center + row * 32 + lane) >> 16; // an L2 hit: phase A just streamed the chunk
+                        const uint32_t id = datum >> 16;
                         uint32_t vs = s.sc.rowV[row] + (excl & 1023u), is = s.sc.rowI[row] + ((excl >> 10) & 2047u);
                         uint4 *out = p.frec + fbase + rf + (excl >> 21);
                         const uint32_t codes = t >> 18;
@@ -869,8 +874,8 @@ __global__ void __launch_bounds__(NT, LEAN ? 4 : 2) mesh_kernel(MeshParams p) {
                             if ((vis >> d) & 1u) {
                                 const uint32_t code = (codes >> (2 * d)) & 3u;
                                 *out++ = make_uint4(a0 | ((uint32_t)d << 15), vs | idlo, is | idhi, nb);
-                                vs += code + 2u + (code == 3u);
-                                is += (code == 1u ? 3u : 6u);
+                                vs += (0x6430u >> (4u * code)) & 15u; // 3 / 4 / 6 vertices
+                                is += (0x6630u >> (4u * code)) & 15u; // 3 / 6 / 6 indices
                             }
                         }
                     }
