@@ -88,6 +88,7 @@ struct SmemT {
     uint32_t ctab[kNumClasses + 3];
     uint16_t spread6[64];            // bit d of the index -> bits 2d, 2d+1 (mask over the 2-bit per-direction codes)
     uint8_t reg_kind[256];
+    uint32_t kpack;                  // reg_kind[0..15], two bits each
     uint32_t nbr[27 + 5];
     uint32_t warp_tot[3][NW];
     unsigned long long vbase, ibase, fbase;
@@ -129,10 +130,18 @@ __device__ __forceinline__ uint32_t classify(uint32_t d, const S &s, const Devic
 
 // The cubes-only kernel needs less of a voxel in phase A: 0 = no mesh, 1 = a cube (any orientation), 25 = another shape (which
 // sends the chunk to the general kernel).
+// kpack: the registry kinds of block ids 0..15, two bits each (SmemT::kpack) -- a register lookup for the ids of generated
+// terrain instead of a shared-memory load per voxel; other ids take the table (a real branch, so that the common path holds no
+// load).
 template <class S>
-__device__ __forceinline__ uint32_t classify_lean(uint32_t d, const S &s, const DeviceRegistry &reg, uint32_t &err) {
+__device__ __noinline__ uint32_t kind_from_table(const S &s, const DeviceRegistry &reg, uint32_t id) {
+    return id < 256u ? (uint32_t)s.reg_kind[id] : (id < reg.n ? (uint32_t)__ldg(reg.kind + id) : 0u);
+}
+template <class S>
+__device__ __forceinline__ uint32_t classify_lean(uint32_t d, const S &s, const DeviceRegistry &reg, uint32_t &err, uint32_t kpack) {
     const uint32_t id = d >> 16;
-    const uint32_t k = id < 256u ? (uint32_t)s.reg_kind[id] : (id < reg.n ? (uint32_t)__ldg(reg.kind + id) : 0u);
+    uint32_t k = (kpack >> (2u * (id & 15u))) & 3u;
+    if (id >= 16u) k = kind_from_table(s, reg, id);
     if (k == 0u) err = 1u;
     if (k != 2u) return 0u;
     const uint32_t shape = d & 63u;
@@ -247,8 +256,8 @@ __device__ __forceinline__ void halo_store(SmemT<LEAN> &s, int lane, int yy, uin
 }
 
 template <bool LEAN>
-__device__ __forceinline__ uint32_t classify_any(uint32_t d, const SmemT<LEAN> &s, const DeviceRegistry &reg, uint32_t &err) {
-    return LEAN ? classify_lean(d, s, reg, err) : classify(d, s, reg, err);
+__device__ __forceinline__ uint32_t classify_any(uint32_t d, const SmemT<LEAN> &s, const DeviceRegistry &reg, uint32_t &err, uint32_t kpack) {
+    return LEAN ? classify_lean(d, s, reg, err, kpack) : classify(d, s, reg, err);
 }
 
 // A staged unit (a third of a layer: 12 rows + in the first third the layer's x-halo) that is NOT one single datum: per-voxel
@@ -264,12 +273,13 @@ __device__ __forceinline__ uint32_t classify_unit_body(SmemT<LEAN> &s, const uin
     reg.texf = nullptr;
     reg.color = nullptr;
     reg.n = reg_n;
+    const uint32_t kpack = LEAN ? s.kpack : 0u;
     uint32_t err = 0, shapes = 0;
     uint32_t last_d = 0xFFFFFFFFu, last_c = 0; // (datum 0xFFFFFFFF: block id 65535 with meta 65535 -- classified like any other on a miss)
     bool have = false;
     if (PART == 0) {
-        const uint32_t cm = classify_any<LEAN>(hm, s, reg, err), cp = classify_any<LEAN>(hp, s, reg, err);
-        const uint32_t ce = lane < 4 ? classify_any<LEAN>(he, s, reg, err) : 0u;
+        const uint32_t cm = classify_any<LEAN>(hm, s, reg, err, kpack), cp = classify_any<LEAN>(hp, s, reg, err, kpack);
+        const uint32_t ce = lane < 4 ? classify_any<LEAN>(he, s, reg, err, kpack) : 0u;
         const uint32_t co = __shfl_xor_sync(FULL, ce, 1); // the other side of the same corner row
         shapes |= (cm > 24u) | (cp > 24u) | (ce > 24u);
         halo_store<LEAN>(s, lane, yy, cm, cp, ce, co);
@@ -285,15 +295,15 @@ __device__ __forceinline__ uint32_t classify_unit_body(SmemT<LEAN> &s, const uin
             if (!have || first != last_d) {
                 have = true;
                 last_d = first;
-                last_c = classify_any<LEAN>(first, s, reg, err);
+                last_c = classify_any<LEAN>(first, s, reg, err, kpack);
             }
             b = last_c * 0x01010101u;
             rowmask = last_c ? 0xFFFFFFFFu : 0u;
             shapes |= (last_c > 24u);
         } else {
             const bool valid = zz < 34;
-            const uint32_t k0 = valid ? classify_any<LEAN>(v.x, s, reg, err) : 0u, k1 = valid ? classify_any<LEAN>(v.y, s, reg, err) : 0u,
-                           k2 = valid ? classify_any<LEAN>(v.z, s, reg, err) : 0u, k3 = valid ? classify_any<LEAN>(v.w, s, reg, err) : 0u;
+            const uint32_t k0 = valid ? classify_any<LEAN>(v.x, s, reg, err, kpack) : 0u, k1 = valid ? classify_any<LEAN>(v.y, s, reg, err, kpack) : 0u,
+                           k2 = valid ? classify_any<LEAN>(v.z, s, reg, err, kpack) : 0u, k3 = valid ? classify_any<LEAN>(v.w, s, reg, err, kpack) : 0u;
             b = k0 | (k1 << 8) | (k2 << 16) | (k3 << 24);
             shapes |= (k0 > 24u) | (k1 > 24u) | (k2 > 24u) | (k3 > 24u);
             uint32_t m = ((k0 != 0u) | ((k1 != 0u) << 1) | ((k2 != 0u) << 2) | ((k3 != 0u) << 3)) << (q * 4);
@@ -336,6 +346,11 @@ __global__ void __launch_bounds__(NT, LEAN ? 4 : 2) mesh_kernel(MeshParams p) {
 
     for (int i = tid; i < kNumClasses; i += NT) s.ctab[i] = T->ctab[i];
     for (int i = tid; i < 256; i += NT) s.reg_kind[i] = (uint32_t)i < p.reg.n ? p.reg.kind[i] : (uint8_t)0;
+    if (tid == 0) {
+        uint32_t kp = 0;
+        for (uint32_t i = 0; i < 16u && i < p.reg.n; i++) kp |= ((uint32_t)p.reg.kind[i] & 3u) << (2u * i);
+        s.kpack = kp;
+    }
     if (tid < 64) {
         uint32_t m = 0;
         for (int d = 0; d < 6; d++) m |= ((tid >> d) & 1) ? (3u << (2 * d)) : 0u;
@@ -483,7 +498,7 @@ __global__ void __launch_bounds__(NT, LEAN ? 4 : 2) mesh_kernel(MeshParams p) {
         } else {
             const int q = lane & 7, zsub = lane >> 3;
             auto cls_of = [&](uint32_t d, const SM &sm, const DeviceRegistry &rg, uint32_t &e) {
-                return LEAN ? classify_lean(d, sm, rg, e) : classify(d, sm, rg, e);
+                return LEAN ? classify_lean(d, sm, rg, e, sm.kpack) : classify(d, sm, rg, e);
             };
             uint32_t last_d = 0, last_c = 0, wref = 0;
             bool have_ref = false;
