@@ -118,8 +118,9 @@ struct bxw_ctx {
     bool lean_mesher = true;                                       // BXW_OPT_CUBES_ONLY_MESHER
     int pipeline_mode = 0;                                         // BXW_OPT_PIPELINED_MESHER: 0 off (default), 1 auto, 2 always
     uint32_t mesh_epoch = 0;                                       // tag of the last pipelined pass (24 bits)
-    cudaStream_t emit_stream = nullptr;                            // emit_kernel of a pipelined pass
+    cudaStream_t emit_stream = nullptr;                            // side stream: emit_kernel of a pipelined pass; part 2 of a split generation
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_gen_fork = nullptr, ev_gen_join = nullptr;
     double last_faces_per_item = 0.0;                              // statistics of the last pass (the auto mode's heuristic)
     bool mesh_from_hmap = false;                                   // BXW_OPT_MESH_FROM_HEIGHT_MAP
     uint32_t last_candidates = 0, last_candidates_of = 0;          // last whole-region mesh: chunks listed / interior chunks
@@ -471,16 +472,31 @@ int region_generate(bxw_ctx *ctx, Region &r, uint64_t seed, int precision, bool 
     fill_params(ctx, r, elide, fp);
     fp.col_mode = part;
     for (int i = 0; i < 5; i++) r.fill_ids[i] = ctx->gen_ids[i];
-    launch_gen_fill_kernel(fp, gp, precision, ctx->stream);
-    if (part != 1) { // the fill timer covers part 1 + part 2 (and whatever ran between them on this stream)
-        CK(cudaEventRecord(ctx->ev_g2, ctx->stream));
+    // Part 2 runs on the side stream, ordered after everything that preceded part 1 (tables, cell points, shared pages, the
+    // previous pass over this storage) but NOT after part 1 itself and what the caller queued behind it -- the plane export and
+    // the transfer to the neighbour ranks -- so it fills the SMs the short part-1 launch leaves idle and hides the exchange.
+    // The caller's stream continues when part 2 is done.
+    cudaStream_t gs = ctx->stream;
+    if (part == 1) CK(cudaEventRecord(ctx->ev_gen_fork, ctx->stream));
+    if (part == 2) {
+        gs = ctx->emit_stream;
+        CK(cudaStreamWaitEvent(gs, ctx->ev_gen_fork, 0));
+    }
+    launch_gen_fill_kernel(fp, gp, precision, gs);
+    if (part == 0) CK(cudaEventRecord(ctx->ev_g2, ctx->stream)); // the fill timer of an unsplit generation: the fill kernel alone
+    launch_fill_xface_kernel(fp, gs);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    if (part != 1 && r.blk_loaded) CK(cudaMemsetAsync(r.blk_loaded, 1, r.n_storage(), gs)); // every chunk now holds block data
+    if (part == 2) {
+        CK(cudaEventRecord(ctx->ev_gen_join, gs));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_gen_join, 0));
+    }
+    if (part == 2) CK(cudaEventRecord(ctx->ev_g2, ctx->stream)); // split: part 1 .. the join (whatever ran between them included)
+    if (part != 1) {
         ctx->gen_pending = true;
         ctx->gen_pending_fused = true;
     }
-    launch_fill_xface_kernel(fp, ctx->stream);
-    ctx->launches += 2;
-    CK(cudaGetLastError());
-    if (part != 1 && r.blk_loaded) CK(cudaMemsetAsync(r.blk_loaded, 1, r.n_storage(), ctx->stream)); // every chunk now holds block data
     r.have_hmap = part != 1;
     r.shape_hint = 0;
     r.gen_seed = seed;
@@ -862,6 +878,8 @@ int bxw_create(int device, bxw_ctx **out) {
         cudaStreamCreateWithFlags(&ctx->emit_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_gen_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_gen_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_mesh_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_copy_done, cudaEventDisableTiming) != cudaSuccess)
         return bail(BXW_E_CUDA);
@@ -914,6 +932,8 @@ void bxw_destroy(bxw_ctx *ctx) {
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_gen_fork) cudaEventDestroy(ctx->ev_gen_fork);
+    if (ctx->ev_gen_join) cudaEventDestroy(ctx->ev_gen_join);
     if (ctx->ev_mesh_done) cudaEventDestroy(ctx->ev_mesh_done);
     if (ctx->ev_copy_done) cudaEventDestroy(ctx->ev_copy_done);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
