@@ -89,6 +89,7 @@ struct SmemT {
     uint16_t spread6[64];            // bit d of the index -> bits 2d, 2d+1 (mask over the 2-bit per-direction codes)
     uint8_t reg_kind[256];
     uint32_t kpack;                  // reg_kind[0..15], two bits each
+    uint32_t klut[2];                // byte i of the pair: bit 0 = block id i (0..7) has a mesh, bit 7 = id i is not registered
     uint32_t nbr[27 + 5];
     uint32_t warp_tot[3][NW];
     unsigned long long vbase, ibase, fbase;
@@ -274,7 +275,8 @@ __device__ __forceinline__ uint32_t classify_unit_body(SmemT<LEAN> &s, const uin
     reg.color = nullptr;
     reg.n = reg_n;
     const uint32_t kpack = LEAN ? s.kpack : 0u;
-    uint32_t err = 0, shapes = 0;
+    const uint32_t lut0 = LEAN ? s.klut[0] : 0u, lut1 = LEAN ? s.klut[1] : 0u;
+    uint32_t err = 0, shapes = 0, tiny_seen = 0;
     uint32_t last_d = 0xFFFFFFFFu, last_c = 0; // (datum 0xFFFFFFFF: block id 65535 with meta 65535 -- classified like any other on a miss)
     bool have = false;
     if (PART == 0) {
@@ -300,6 +302,19 @@ __device__ __forceinline__ uint32_t classify_unit_body(SmemT<LEAN> &s, const uin
             b = last_c * 0x01010101u;
             rowmask = last_c ? 0xFFFFFFFFu : 0u;
             shapes |= (last_c > 24u);
+        } else if (LEAN && __all_sync(FULL, (((v.x | v.y) | (v.z | v.w)) & 0xFFF8FFFFu) == 0u)) {
+            // Cubes-only kernel, all 128 datums are block ids 0..7 with meta 0 (all of generated terrain): the four lookups of a
+            // lane are ONE byte permute -- the selector's nibbles are the four ids, the two lookup words hold a byte per id -- and
+            // the four "has a mesh" bits are gathered with one multiply.
+            const uint32_t sel = ((v.x >> 16) | (v.y >> 12)) | ((v.z >> 8) | (v.w >> 4));
+            const uint32_t r = zz < 34 ? __byte_perm(lut0, lut1, sel) : 0u; // (rows 34, 35 of the last third hold stale ring data)
+            tiny_seen |= r;
+            uint32_t m = (((r & 0x01010101u) * 0x01020408u) >> 24) << (q * 4);
+            m |= __shfl_xor_sync(FULL, m, 1);
+            m |= __shfl_xor_sync(FULL, m, 2);
+            m |= __shfl_xor_sync(FULL, m, 4);
+            b = 0;
+            rowmask = m; // (a row beyond the 34 is not stored)
         } else {
             const bool valid = zz < 34;
             const uint32_t k0 = valid ? classify_any<LEAN>(v.x, s, reg, err, kpack) : 0u, k1 = valid ? classify_any<LEAN>(v.y, s, reg, err, kpack) : 0u,
@@ -317,6 +332,7 @@ __device__ __forceinline__ uint32_t classify_unit_body(SmemT<LEAN> &s, const uin
             if (q == 0) s.solid[yy * 34 + zz] = rowmask;
         }
     }
+    if (tiny_seen & 0x80808080u) err = 1u; // an unregistered id among them (voxregistry.rs:141-143 would panic)
     return shapes | (err << 1);
 }
 template <bool LEAN>
@@ -350,6 +366,13 @@ __global__ void __launch_bounds__(NT, LEAN ? 4 : 2) mesh_kernel(MeshParams p) {
         uint32_t kp = 0;
         for (uint32_t i = 0; i < 16u && i < p.reg.n; i++) kp |= ((uint32_t)p.reg.kind[i] & 3u) << (2u * i);
         s.kpack = kp;
+        uint32_t lut[2] = {0u, 0u};
+        for (uint32_t i = 0; i < 8u; i++) {
+            const uint32_t k = i < p.reg.n ? (uint32_t)p.reg.kind[i] : 0u;
+            lut[i >> 2] |= ((k == 2u ? 1u : 0u) | (k == 0u ? 0x80u : 0u)) << (8u * (i & 3u));
+        }
+        s.klut[0] = lut[0];
+        s.klut[1] = lut[1];
     }
     if (tid < 64) {
         uint32_t m = 0;
