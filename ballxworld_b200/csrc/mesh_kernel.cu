@@ -286,7 +286,7 @@ __device__ __forceinline__ uint32_t classify_unit_body(SmemT<LEAN> &s, const uin
         shapes |= (cm > 24u) | (cp > 24u) | (ce > 24u);
         halo_store<LEAN>(s, lane, yy, cm, cp, ce, co);
     }
-#pragma unroll 1
+#pragma unroll
     for (int jj = 0; jj < 3; jj++) {
         const uint4 v = jj == 0 ? v0 : (jj == 1 ? v1 : v2);
         const int zz = 4 * (3 * PART + jj) + zsub;
