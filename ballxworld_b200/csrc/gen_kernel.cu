@@ -484,11 +484,14 @@ __global__ void __launch_bounds__(256, 4) fill_kernel(FillParams p, GenParams g)
     __shared__ int red[6][8];
     const int big = 0x7FFFFFFF;
     int lo = min(min(hh[0], hh[1]), min(hh[2], hh[3])), hi = max(max(hh[0], hh[1]), max(hh[2], hh[3]));
+    const int t_lo = lo, t_hi = hi; // lowest / highest surface among this thread's four columns
     int lx0 = q == 0 ? hh[0] : big, lx1 = q == 7 ? hh[3] : big;
     int lz0 = zr == 0 ? lo : big, lz1 = zr == 31 ? lo : big;
     lo = __reduce_min_sync(0xFFFFFFFFu, lo);
     hi = __reduce_max_sync(0xFFFFFFFFu, hi);
-    const int w_lo = lo, w_hi = hi; // lowest / highest surface among this warp's 128 columns
+    // range of the per-voxel selection in the store loop: per thread when only the surface chunks are written (fewer selected
+    // layers), per warp when every chunk is (most chunks are all stone / all void: no divergence)
+    const int b_lo = p.elide ? t_lo : lo, b_hi = p.elide ? t_hi : hi;
     lx0 = __reduce_min_sync(0xFFFFFFFFu, lx0);
     lx1 = __reduce_min_sync(0xFFFFFFFFu, lx1);
     lz0 = __reduce_min_sync(0xFFFFFFFFu, lz0);
@@ -523,23 +526,34 @@ __global__ void __launch_bounds__(256, 4) fill_kernel(FillParams p, GenParams g)
             p.summary[(size_t)(sx + p.SX * (sz + p.SZ * sy))] = sum | ((unsigned long long)solid << kSolidShift);
         }
     }
-    for (int sy = sy_lo; sy < sy_hi; sy++) {
+    // Uniform chunks are not materialised: their page entry points at the shared all-void / all-stone page (every reader goes
+    // through the page table; the first writer materialises the chunk). Same test as the summary above; thread per chunk.
+    if (p.page) {
+        for (int sy = sy_lo + (int)threadIdx.x; sy < sy_hi; sy += 256) {
+            const uint32_t c = (uint32_t)(sx + p.SX * (sz + p.SZ * sy));
+            const int ybase = (p.cy_min + sy) * 32;
+            uint32_t pg = c;
+            if (p.elide) {
+                if (ybase > hi) pg = p.page_void;
+                else if (ybase + 31 < lo - 5) pg = p.page_stone;
+            }
+            p.page[c] = pg;
+        }
+    }
+    // the chunks in between are written: ybase <= hi and ybase + 31 >= lo - 5 (floor divisions: heights may be negative)
+    int sy_m0 = sy_lo, sy_m1 = sy_hi;
+    if (p.elide) {
+        sy_m0 = max(sy_lo, ((lo - 5) >> 5) - p.cy_min);
+        sy_m1 = min(sy_hi, (hi >> 5) - p.cy_min + 1);
+    }
+    const uint4 stone4 = make_uint4(p.id_stone, p.id_stone, p.id_stone, p.id_stone), void4 = make_uint4(p.id_void, p.id_void, p.id_void, p.id_void);
+    for (int sy = sy_m0; sy < sy_m1; sy++) {
         const uint32_t c = (uint32_t)(sx + p.SX * (sz + p.SZ * sy));
         const int ybase = (p.cy_min + sy) * 32;
-        // Uniform chunks are not materialised: their page entry points at the shared all-void / all-stone page (every reader
-        // goes through the page table; the first writer materialises the chunk). Same test as the summary above.
-        uint32_t pg = c;
-        if (p.elide) {
-            if (ybase > hi) pg = p.page_void;
-            else if (ybase + 31 < lo - 5) pg = p.page_stone;
-        }
-        if (p.page && threadIdx.x == 0) p.page[c] = pg;
-        if (pg != c) continue;
         uint4 *dst = reinterpret_cast<uint4 *>(p.blocks + (size_t)c * kChunkVoxels + zr * 32 + q * 4);
-        // layers [0, y_mixed) are stone and layers [y_void, 32) are void for every column of this WARP (4 z rows; terrain is
-        // smooth, so the per-voxel selection runs for a handful of layers only); 1024 voxels per y layer = 256 uint4
-        const int y_mixed = min(max(w_lo - 5 - ybase, 0), 32), y_void = min(max(w_hi + 1 - ybase, y_mixed), 32);
-        const uint4 stone4 = make_uint4(p.id_stone, p.id_stone, p.id_stone, p.id_stone), void4 = make_uint4(p.id_void, p.id_void, p.id_void, p.id_void);
+        // layers [0, y_mixed) are stone and layers [y_void, 32) are void for the four columns of this thread (terrain is smooth:
+        // the per-voxel selection runs for six or seven layers); 1024 voxels per y layer = 256 uint4
+        const int y_mixed = min(max(b_lo - 5 - ybase, 0), 32), y_void = min(max(b_hi + 1 - ybase, y_mixed), 32);
 #pragma unroll 4
         for (int yc = 0; yc < y_mixed; yc++) __stcs(&dst[yc * 256], stone4); // streaming stores
 #pragma unroll 2

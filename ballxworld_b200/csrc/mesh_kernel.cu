@@ -1106,6 +1106,7 @@ unsigned mesh_kernel_grid(const MeshParams &p, int sm_count, bool lean, int max_
 }
 
 void launch_mesh_kernel(const MeshParams &p, int sm_count, cudaStream_t stream, bool lean, bool mostly_uniform, int max_per_sm) {
+    if (const char *e = getenv("BXW_EXP_MESH_INLINE")) mostly_uniform = atoi(e) != 0; // experiments only
     if (!lean) launch_mesh_kernel_t<false, false>(p, sm_count, stream, max_per_sm);
     else if (mostly_uniform) launch_mesh_kernel_t<true, false>(p, sm_count, stream, max_per_sm);
     else launch_mesh_kernel_t<true, true>(p, sm_count, stream, max_per_sm);
