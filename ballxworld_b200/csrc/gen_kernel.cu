@@ -94,13 +94,16 @@ __device__ __noinline__ double super_simplex_2d(const TB T, int which, double px
     auto point = [&](double ox, double oy, unsigned lpx, unsigned lpy) {
         const double dx = dadd(qx, ox), dy = dadd(qy, oy);
         const double attn = dsub(2.0 / 3.0, dadd(dmul(dx, dx), dmul(dy, dy)));
-        if (attn > 0.0) {
-            const unsigned h = T.u8(perm + (T.u8(perm + ((bxi + lpx) & 0xffu)) ^ ((byi + lpy) & 0xffu)));
-            // gradient::grad2(h % 8) = (1,0) (-1,0) (0,1) (0,-1) (d,d) (-d,d) (d,-d) (-d,-d): one 16-byte table load
-            const double2 gr = T.f64x2(kTabGrad + (h & 7u) * 16u);
-            const double a2 = dmul(attn, attn);
-            value = dadd(value, dmul(dmul(a2, a2), dadd(dmul(gr.x, dx), dmul(gr.y, dy))));
-        }
+        // The reference adds the term only if attn > 0. Here the term is always computed and +0.0 is added otherwise: the sum
+        // starts at +0.0 and can never become -0.0 under round-to-nearest, so adding +0.0 leaves it bit for bit unchanged -- and
+        // without the four branches the lookup chains of the four lattice points overlap (a warp nearly always had a lane
+        // inside every point's radius anyway).
+        const unsigned h = T.u8(perm + (T.u8(perm + ((bxi + lpx) & 0xffu)) ^ ((byi + lpy) & 0xffu)));
+        // gradient::grad2(h % 8) = (1,0) (-1,0) (0,1) (0,-1) (d,d) (-d,d) (d,-d) (-d,-d): one 16-byte table load
+        const double2 gr = T.f64x2(kTabGrad + (h & 7u) * 16u);
+        const double a2 = dmul(attn, attn);
+        const double term = dmul(dmul(a2, a2), dadd(dmul(gr.x, dx), dmul(gr.y, dy)));
+        value = dadd(value, attn > 0.0 ? term : 0.0);
     };
     // lattice points 0 and 1 are (0, 0) and (1, 1) in every group; 2 and 3 come from the group's table rows
     point(0.0, 0.0, 0u, 0u);
@@ -140,12 +143,11 @@ __device__ __noinline__ float super_simplex_2d_f32(const TB T, int which, double
     auto point = [&](float ox, float oy, unsigned lpx, unsigned lpy) {
         const float dx = __fadd_rn(qx, ox), dy = __fadd_rn(qy, oy);
         const float attn = __fsub_rn(2.0f / 3.0f, __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
-        if (attn > 0.0f) {
-            const unsigned h = T.u8(perm + (T.u8(perm + ((bxi + lpx) & 0xffu)) ^ ((byi + lpy) & 0xffu)));
-            const double2 gr = T.f64x2(kTabGrad + (h & 7u) * 16u);
-            const float a2 = __fmul_rn(attn, attn);
-            value = __fadd_rn(value, __fmul_rn(__fmul_rn(a2, a2), __fadd_rn(__fmul_rn((float)gr.x, dx), __fmul_rn((float)gr.y, dy))));
-        }
+        const unsigned h = T.u8(perm + (T.u8(perm + ((bxi + lpx) & 0xffu)) ^ ((byi + lpy) & 0xffu)));
+        const double2 gr = T.f64x2(kTabGrad + (h & 7u) * 16u);
+        const float a2 = __fmul_rn(attn, attn);
+        const float term = __fmul_rn(__fmul_rn(a2, a2), __fadd_rn(__fmul_rn((float)gr.x, dx), __fmul_rn((float)gr.y, dy)));
+        value = __fadd_rn(value, attn > 0.0f ? term : 0.0f); // (as in the f64 path: adding +0.0 is exact)
     };
     point(0.0f, 0.0f, 0u, 0u);
     point((float)-LC, (float)-LC, 1u, 1u);
