@@ -593,9 +593,20 @@ __global__ void __launch_bounds__(64) fill_xface_kernel(FillParams p) {
     const int side = threadIdx.x >> 5, z = threadIdx.x & 31;
     const int hm = __ldg(p.hmap + (size_t)(sz * 32 + z) * p.W + sx * 32 + (side ? 31 : 0));
     const int h = hm >> 2, el = hm & 3;
+    // which chunks of the stack are materialised: one page-table load per thread up front (inside the loop below it was a
+    // dependent global load per chunk, 18 memory latencies in a row)
+    __shared__ uint32_t s_mat[32];
+    if (threadIdx.x < 32) s_mat[threadIdx.x] = 0u;
+    __syncthreads();
+    for (int sy = sy_lo + (int)threadIdx.x; sy < sy_hi; sy += 64) {
+        const uint32_t c = (uint32_t)(sx + p.SX * (sz + p.SZ * sy));
+        if (!p.page || p.page[c] == c) atomicOr(&s_mat[((sy - sy_lo) >> 5) & 31], 1u << ((sy - sy_lo) & 31));
+    }
+    __syncthreads();
     for (int sy = sy_lo; sy < sy_hi; sy++) {
         const uint32_t c = (uint32_t)(sx + p.SX * (sz + p.SZ * sy));
-        if (p.page && p.page[c] != c) continue; // not materialised: the shared page carries its planes
+        if (sy - sy_lo < 1024 ? !((s_mat[(sy - sy_lo) >> 5] >> ((sy - sy_lo) & 31)) & 1u) : (p.page && p.page[c] != c))
+            continue; // not materialised: the shared page carries its planes
         uint32_t *dst = p.xface + (size_t)c * 2048 + side * 1024 + z;
         const int ybase = (p.cy_min + sy) * 32;
         for (int yc = 0; yc < 32; yc++) {
