@@ -178,3 +178,79 @@ def test_large_and_sparse_block_ids(ctx, oracle):
         assert gv.tobytes() == wv.tobytes() and np.array_equal(gi, wi)
     finally:
         bxw.standard_registry().bind(ctx)
+
+
+@pytest.mark.gpu
+def test_cubes_only_kernel_class_lookup_paths(ctx, oracle):
+    """The cubes-only mesh_kernel finds a voxel's class three ways: one byte permute per four voxels when a 128-voxel group holds
+    block ids 0..7 with meta 0, a register table for ids below 16, the shared-memory table beyond. All of them against the
+    oracle (cubes with every orientation / unknown shape numbers, ids up to 40, a block without a mesh), and a hole in the
+    registry among the small ids must still be the reference's panic (voxregistry.rs:141-143)."""
+    import ballxworld_b200 as bxw
+
+    n = 41
+    defs = (oracle.BlockDef * n)()
+    std = oracle.standard_registry_defs()
+    for i in range(8):
+        defs[i] = std[i]
+    for i in range(8, n):
+        defs[i].present = 1
+        defs[i].mesh_kind = 0 if i in (12, 33) else 1
+        for k in range(3):
+            defs[i].debug_color[k] = [i / 41.0, 0.5, 1.0 - i / 41.0][k]
+        for k in range(6):
+            defs[i].tex[k] = i + k
+    nx, ny, nz = 2, 1, 2
+    rng = np.random.default_rng(11)
+
+    def chunk(kind):
+        c = np.zeros((32, 32, 32), np.uint32)  # [y][z][x]
+        if kind == 0:  # terrain-like: ids 1..7, meta 0, in long runs along x (the byte-permute path) under a ragged surface
+            h = rng.integers(8, 24, (32, 32))
+            ids = rng.integers(1, 8, (32, 32, 4)).repeat(8, axis=2)
+            c = np.where(np.arange(32)[:, None, None] <= h[None, :, :], ids.astype(np.uint32) << 16, 0).astype(np.uint32)
+        elif kind == 1:  # cubes of ids up to 40 with orientations and unknown shape numbers (all are cubes: stdshapes.rs:59)
+            ids = rng.integers(1, n, (32, 32, 32)).astype(np.uint32)
+            orient = rng.integers(0, 30, (32, 32, 32)).astype(np.uint32)  # >= 24 falls back to the default orientation
+            shape = np.where(rng.random((32, 32, 32)) < 0.5, 0, rng.integers(4, 64, (32, 32, 32))).astype(np.uint32)
+            c = np.where(rng.random((32, 32, 32)) < 0.4, (ids << 16) | (orient * 64 + shape), 0).astype(np.uint32)
+        elif kind == 2:  # mostly small ids with a few large ones sprinkled in (groups that leave the fast path half way)
+            ids = np.where(rng.random((32, 32, 32)) < 0.02, rng.integers(8, n, (32, 32, 32)), rng.integers(0, 8, (32, 32, 32)))
+            c = (ids.astype(np.uint32) << 16)
+        return np.ascontiguousarray(c.reshape(-1))
+
+    try:
+        ctx.set_registry(oracle.defs_to_numpy(defs))
+        oreg = oracle.OracleRegistry(defs)
+        ctx.region_create(-3, 2, 7, nx, ny, nz)
+        chunks = {}
+        for ly in range(-1, ny + 1):
+            for lz in range(-1, nz + 1):
+                for lx in range(-1, nx + 1):
+                    chunks[(lx, ly, lz)] = chunk((lx + 2 * lz + ly) % 3)
+                    ctx.region_upload_chunk(lx, ly, lz, chunks[(lx, ly, lz)])
+        av, ai = ctx.region_mesh()
+        spans = ctx.region_mesh_spans()
+        V, I = ctx.region_mesh_fetch(av, ai)
+        for iz in range(nz):
+            for ix in range(nx):
+                s = spans[ix + nx * iz]
+                d = [chunks[(ix + dx, dy, iz + dz)] for dy in (-1, 0, 1) for dz in (-1, 0, 1) for dx in (-1, 0, 1)]
+                wv, wi = oracle.mesh_from_dense27(oreg, d)
+                assert int(s["v_count"]) == len(wv) and int(s["i_count"]) == len(wi) and len(wv) > 0
+                v0, i0 = int(s["v_off"]), int(s["i_off"])
+                assert V[v0:v0 + len(wv)].tobytes() == wv.tobytes(), f"vertices of chunk ({ix}, 0, {iz})"
+                assert np.array_equal(I[i0:i0 + len(wi)], wi), f"indices of chunk ({ix}, 0, {iz})"
+        # a hole among the small ids: block id 5 is not registered and sits in a group of small ids with meta 0
+        defs[5].present = 0
+        ctx.set_registry(oracle.defs_to_numpy(defs))
+        bad = chunks[(0, 0, 0)].copy()
+        bad[3 + 32 * 4 + 1024 * 2] = 5 << 16
+        ctx.region_upload_chunk(0, 0, 0, bad)
+        with pytest.raises(bxw.BxwError) as e:
+            ctx.region_mesh()
+        assert e.value.code == -4
+    finally:
+        ctx.region_destroy()
+        ctx.set_registry(oracle.defs_to_numpy(oracle.standard_registry_defs()))
+        ctx._bound_registry = None
