@@ -143,7 +143,10 @@ int bxw_region_destroy(bxw_ctx *ctx);
 int bxw_region_generate(bxw_ctx *ctx, uint64_t seed, int precision);
 /* The same in two calls, for multi-GPU steps: part 1 fills only the two chunk columns next to the x- and x+ faces of the
  * interior (everything bxw_region_halo_export reads), part 2 all the others. Between the two the caller exports the boundary
- * planes and starts their transfer, which then overlaps part 2; the received planes are imported after part 2. */
+ * planes and starts their transfer, which then overlaps part 2; the received planes are imported after part 2. Part 2 is
+ * queued on an internal side stream that is ordered after everything preceding part 1 but not after part 1 and what the caller
+ * queued behind it; the context's stream waits for it before the call returns control of the stream to the caller (later work
+ * on the stream sees all of the generation). */
 int bxw_region_generate_part(bxw_ctx *ctx, uint64_t seed, int precision, int part);
 /* Column parameters of the last generate: height (round(h) as i32) and elevation class (0 LowLand,1 Hill,
  * 2 Mountain) for the (nx+2)*32 x (nz+2)*32 columns, row-major [z][x]; raw f64 height optional (may be NULL). */
