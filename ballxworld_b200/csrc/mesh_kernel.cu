@@ -972,11 +972,21 @@ __global__ void __launch_bounds__(NT, LEAN ? 4 : 2) mesh_kernel(MeshParams p) {
             PHASE_MARK(t_t2);
             PHASE_ADD(7, t_t1, t_t2);
             // ---- C2: complete the records and hand them to emit_kernel (coalesced: thread = face) ----
+            // (the side's block datum is the only global load -- an L2 hit, phase A just streamed the chunk --: the one of the
+            // thread's next side is issued before this side's record is built)
+            uint32_t a_next = 0, datum_next = 0;
+            if (tid < tileF) {
+                a_next = s.sc.frecA[tid];
+                datum_next = __ldg(center + (a_next & 1023u) * 32 + ((a_next >> 10) & 31u));
+            }
             for (uint32_t f = tid; f < tileF; f += NT) {
-                const uint32_t a = s.sc.frecA[f];
+                const uint32_t a = a_next, datum = datum_next;
+                if (f + NT < tileF) {
+                    a_next = s.sc.frecA[f + NT];
+                    datum_next = __ldg(center + (a_next & 1023u) * 32 + ((a_next >> 10) & 31u));
+                }
                 const uint32_t row = a & 1023u, x = (a >> 10) & 31u;
                 const uint32_t y = row >> 5, z = row & 31u;
-                const uint32_t datum = __ldg(center + row * 32 + x); // an L2 hit: phase A just streamed the chunk
                 const uint32_t id = datum >> 16;
                 uint32_t cx;
                 if (LEAN) { // no class table: a cube's class is 1 + its orientation
