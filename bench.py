@@ -531,18 +531,19 @@ def main():
         ut = torch.tensor([tot_v, tot_i], dtype=torch.int64, device="cuda")
         dist.all_reduce(ut)
         history, best = [], None
-        for it in range(4):
+        CUTS, MEASURE_STEPS = 6, 3
+        for it in range(CUTS):
             for k in (ctx.KERNEL_MESH, ctx.KERNEL_FILL):
                 ctx.kernel_time_ms(k, reset=True)
-            for _ in range(2):
+            for _ in range(MEASURE_STEPS):
                 step()
             barrier()
-            cost = (ctx.kernel_time_ms(ctx.KERNEL_MESH, reset=True)[0] + ctx.kernel_time_ms(ctx.KERNEL_FILL, reset=True)[0]) / 2
+            cost = (ctx.kernel_time_ms(ctx.KERNEL_MESH, reset=True)[0] + ctx.kernel_time_ms(ctx.KERNEL_FILL, reset=True)[0]) / MEASURE_STEPS
             new_w, costs = agree_on_widths(dist, widths, cost, "cuda", min_width=32)
             history.append({"widths": list(widths), "own_kernel_ms": [round(c, 3) for c in costs]})
             if best is None or max(costs) < best[0]:
                 best = (max(costs), list(widths))
-            done = it == 3 or max(costs) < 1.01 * sum(costs) / world or new_w == widths
+            done = it == CUTS - 1 or max(costs) < 1.005 * sum(costs) / world or new_w == widths
             target = best[1] if done else new_w  # at the end: the best cut that was measured
             if target != widths:
                 widths = target
@@ -557,7 +558,7 @@ def main():
         rt = torch.tensor([tot_v, tot_i], dtype=torch.int64, device="cuda")
         dist.all_reduce(rt)
         rebalance = {"widths": list(widths), "measured": history, "world_totals_unchanged": bool((rt == ut).all().item()),
-                     "how": "per-rank device time of fill + mesh kernels over 2 steps, one scalar all_gather, every rank computes the same "
+                     "how": "per-rank device time of fill + mesh kernels over 3 steps, one scalar all_gather, every rank computes the same "
                             "new cut (slabs.rebalance_slabs); total columns and the global mesh are unchanged"}
         if not rebalance["world_totals_unchanged"]:
             raise RuntimeError("rebalanced slabs changed the global mesh totals")
