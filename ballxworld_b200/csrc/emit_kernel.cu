@@ -1,12 +1,13 @@
 // emit_kernel.cu — second half of mesh_from_chunk (src/client/render/voxmesh.rs:122-177): vertices and indices of every
 // side that mesh_kernel found visible.
 //
-// mesh_kernel needs ~110 KB of shared memory per CTA (the 34^3 class table) and therefore runs 16 warps per SM, too few to
-// hide the dependent table lookups of vertex construction. Here the work is one face per lane with no large shared state,
-// so many warps are resident. Input: the face records mesh_kernel wrote in the reference's emission order
-// (device_common.cuh: kFacePad); every chunk's records start on a multiple of 32, so the 32 faces of a warp belong to one
-// chunk and their vertices / indices form one contiguous run of its arena span. The warp transposes that run through its
-// private shared-memory slice and writes it with coalesced 16-byte stores.
+// The work here is table-driven vertex construction with no large shared state, split from mesh_kernel (whose shared memory
+// holds the 34^3 neighbourhood) so that each half gets the kernel shape it needs. Input: the face records mesh_kernel wrote in
+// the reference's emission order (device_common.cuh: kFacePad); every chunk's records start on a multiple of 32, so the 32
+// sides of a batch belong to one chunk and their vertices / indices form one contiguous run of its arena span. A warp takes a
+// batch: a side pass (lane = side) leaves a 32-byte side record per lane in shared memory, a vertex pass (lane = vertex, up
+// to five vertices per lane) builds the 40-byte vertices in a warp-private staging buffer, from which the run -- normally
+// the whole batch, ~5 KB -- leaves with one bulk copy; the index run is staged and copied out with 16-byte stores.
 //
 // Bit-exactness: colours are as_rgba8(debug_color * ao) with ao = the sequential f32 product of 0.88 factors
 // (voxmesh.rs:27-34,128-152; only the *number* of occluding samples matters), the barycentric colour offset is the in-order

@@ -6,22 +6,24 @@
 // Output: per chunk its arena span (vertex / index counts and offsets) and one face record per visible side in the
 // reference's emission order; emit_kernel.cu turns the records into vertices and indices (voxmesh.rs:122-177).
 //
-// One persistent CTA (256 threads, two per SM) takes one chunk at a time:
-//   A  stage the chunk plus its 1-voxel halo (34^3) in shared memory as one CLASS BYTE per voxel (class = shape x
-//      orientation of the datum, 0 = no mesh) plus one 34-bit SOLID word per (y,z) row. The rows stream through
-//      warp-private cp.async rings (16-byte copies, three units ahead); the x-halo comes from the neighbour chunks'
+// One persistent CTA (256 threads) takes one chunk at a time. Two instantiations (SmemT below): the general kernel with the
+// class table (two CTAs per SM) and the cubes-only kernel without it (four per SM; generated terrain).
+//   A  stage the chunk plus its 1-voxel halo (34^3) in shared memory as one 34-bit SOLID word per (y,z) row and, in the
+//      general kernel, one CLASS BYTE per voxel (class = shape x orientation of the datum, 0 = no mesh). The rows stream
+//      through warp-private cp.async rings (16-byte copies, a few units ahead); the x-halo comes from the neighbour chunks'
 //      x-face planes. A unit (384 voxels) that is one single datum costs one match + one vote (terrain is mostly
 //      uniform); a 34^3 neighbourhood that is one void/cube datum ends the chunk after one barrier. In height-map mode
 //      (bxw_region_generate_and_mesh) the table is derived from the 34x34 column parameters instead of reading voxels.
 //   B  per-row vertex/index/face counts. Cubes-and-void chunks: one thread per row, visibility by bit operations
 //      on the solid words (voxmesh.rs:119 reduces to solid & ~neighbour-solid). Chunks containing slopes/corners:
-//      one warp per row, lane = x, the general orientation-aware test (voxmesh.rs:105-121).
+//      one warp per row, lane = x, the general orientation-aware test (voxmesh.rs:105-121); the side masks are kept for C.
 //   S  block-wide exclusive scan of the 1024 row counts = the reference's emission order (cells y,z,x-major,
 //      directions 0..5 minor, voxmesh.rs:94,104); one atomicAdd triple reserves the chunk's vertex span, index span and
-//      face records.
-//   C  face records in tiles of <=1024 sides: (C1) the sides in emission order with their first vertex / index; (C2) thread per
-//      side: class, block id, the 27-bit occupancy of the cell's 3x3x3 neighbourhood (all the AO test needs,
-//      voxmesh.rs:128-137), written as one uint4 (device_common.cuh).
+//      face records (or the chunk's old reservation is reused, in re-mesh passes).
+//   C  face records: one uint4 per visible side (device_common.cuh) with its first vertex / index, class, block id and the
+//      27-bit occupancy of the cell's 3x3x3 neighbourhood (all the AO test needs, voxmesh.rs:128-137). Cubes-and-void
+//      chunks: tiles of <=1024 sides, (C1) thread per row orders the sides, (C2) thread per side completes the record.
+//      Chunks with other shapes: warp per row, every lane writes the records of its cell directly.
 #include <algorithm>
 #include <cstdlib>
 #include <type_traits>
