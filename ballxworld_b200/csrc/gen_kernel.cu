@@ -1,9 +1,11 @@
 // gen_kernel.cu — bxw_world::stdgen::StdGenerator as sm_100a kernels.
 //
 // The reference evaluates calc_voxel_params for the 1024 columns of EVERY chunk (stdgen.rs:335-347), so a vertical
-// stack of chunks recomputes the same columns; here the column parameters are computed once per (x,z) of the
-// region (heightmap kernel), then a fill kernel streams the block ids of whole vertical stacks with 16-byte
-// coalesced stores (stdgen.rs:349-373).
+// stack of chunks recomputes the same columns. Here one CTA owns a vertical stack: it computes the parameters of its 32x32
+// columns once (fill_kernel<64 / 32>; they also go to the region's height map), derives the chunk summaries and the page
+// table from them -- a chunk that is all void or all stone is not written at all, its page-table entry points at a shared
+// page -- and writes the block ids of the chunks in between with 16-byte coalesced stores (stdgen.rs:349-373).
+// heightmap_kernel computes the same parameters alone (raw getters, FP32 report).
 //
 // The f64 path performs exactly the IEEE operations of the reference, in its order, with explicit
 // round-to-nearest intrinsics so that nvcc never contracts a*b+c into an FMA (Rust/LLVM does not contract).
