@@ -281,6 +281,31 @@ class Gpu {
         bound_version_ = reg.version();
     }
     uint64_t kernel_launches() const { return bxw_kernel_launches(raw()); }
+    // everything the context launches goes to this CUDA stream (a cudaStream_t; nullptr = the context's own)
+    void set_stream(void *cuda_stream) { check(bxw_set_stream(raw(), cuda_stream)); }
+    void set_option(int option, int value) { check(bxw_set_option(raw(), option, value)); } // BXW_OPT_*
+    void synchronize() { check(bxw_synchronize(raw())); }
+    // device time of the library's own launches since the last reset: {milliseconds, launches} (BXW_KERNEL_*)
+    std::pair<float, uint64_t> kernel_time_ms(int which, bool reset = false) {
+        float ms = 0.0f;
+        uint64_t n = 0;
+        check(bxw_kernel_time_ms(raw(), which, &ms, &n, reset ? 1 : 0));
+        return {ms, n};
+    }
+    // raw SuperSimplex samples: StdGenerator's seven noise functions (stdgen.rs:82-114; which = 0..6) and bxw_terragen's
+    // (bxw_terragen/src/supersimplex.rs)
+    std::vector<double> stdgen_noise(uint64_t seed, int which, const std::vector<double> &xs, const std::vector<double> &ys, int precision = 64) {
+        if (xs.size() != ys.size()) throw std::invalid_argument("xs and ys differ in length");
+        std::vector<double> out(xs.size());
+        check(bxw_stdgen_noise(raw(), seed, which, precision, xs.data(), ys.data(), xs.size(), out.data()));
+        return out;
+    }
+    std::vector<double> terragen_noise2(uint64_t seed, const std::vector<double> &xs, const std::vector<double> &ys) {
+        if (xs.size() != ys.size()) throw std::invalid_argument("xs and ys differ in length");
+        std::vector<double> out(xs.size());
+        check(bxw_terragen_noise2(raw(), seed, xs.data(), ys.data(), xs.size(), out.data()));
+        return out;
+    }
 
   private:
     struct Del {
@@ -506,6 +531,101 @@ class Region {
     ChunkBuffers fetch() const {
         const auto a = arena();
         return fetch_arena(a.first, a.second);
+    }
+    // one chunk's ChunkBuffers (voxrender.rs:34-37) from its span
+    ChunkBuffers fetch_chunk(const bxw_mesh_span &sp) const {
+        ChunkBuffers b;
+        b.vertices.resize(sp.v_count);
+        b.indices.resize(sp.i_count);
+        if (sp.v_count | sp.i_count)
+            gpu_.check(bxw_region_mesh_fetch_range(gpu_.raw(), sp.v_off, sp.v_count, b.vertices.data(), sp.i_off, sp.i_count, b.indices.data()));
+        return b;
+    }
+    // the arena into caller-owned (pinned) memory on the copy stream; valid after fetch_wait(). The next generate / mesh pass
+    // overlaps the transfer.
+    void fetch_async(bxw_vertex *vertices, uint64_t n_vertices, uint32_t *indices, uint64_t n_indices) {
+        gpu_.check(bxw_region_mesh_fetch_async(gpu_.raw(), vertices, n_vertices, indices, n_indices));
+    }
+    void fetch_wait() { gpu_.check(bxw_region_fetch_wait(gpu_.raw())); }
+    // dense chunk in / out (UncompressedChunk::blocks_yzx, lib.rs:222-235), local coordinates, shell = -1 and n
+    void upload(int32_t lx, int32_t ly, int32_t lz, const UncompressedChunk &c) {
+        gpu_.check(bxw_region_upload_chunk(gpu_.raw(), lx, ly, lz, c.blocks_yzx.data()));
+    }
+    UncompressedChunk download(int32_t lx, int32_t ly, int32_t lz) const {
+        UncompressedChunk c;
+        c.position = {origin_.x + lx, origin_.y + ly, origin_.z + lz};
+        gpu_.check(bxw_region_download_chunk(gpu_.raw(), lx, ly, lz, c.blocks_yzx.data()));
+        return c;
+    }
+    // multi-GPU steps (one Region per rank, slabs along x): the boundary chunk columns first, their planes exported and sent
+    // while the rest is generated, the neighbours' planes imported before meshing
+    void generate_part(const StdGenerator &g, int part) {
+        if (part == 1) {
+            const auto ids = StdGenerator::resolve_ids(registry_);
+            gpu_.check(bxw_set_gen_ids(gpu_.raw(), ids[0], ids[1], ids[2], ids[3], ids[4]));
+        }
+        gpu_.check(bxw_region_generate_part(gpu_.raw(), g.seed(), 64, part));
+    }
+    size_t halo_bytes() const { return bxw_region_halo_bytes(gpu_.raw()); }
+    void halo_export(int face, void *device_buffer) { gpu_.check(bxw_region_halo_export(gpu_.raw(), face, device_buffer)); }
+    void halo_import(int face, const void *device_buffer) { gpu_.check(bxw_region_halo_import(gpu_.raw(), face, device_buffer)); }
+    // the box moves (its content is dropped: load deltas or generate fill it again)
+    void set_origin(ChunkPosition origin) {
+        gpu_.check(bxw_region_set_origin(gpu_.raw(), origin.x, origin.y, origin.z));
+        origin_ = origin;
+    }
+    // CellGen::calc_voxel_params of every column of the box, shell included (stdgen.rs:215-276): height, elevation class and
+    // the unrounded height
+    struct HeightMap {
+        uint32_t width = 0, depth = 0; // columns along x, z
+        std::vector<int32_t> height;
+        std::vector<uint8_t> elevation;
+        std::vector<double> raw_height;
+    };
+    HeightMap heightmap() const {
+        HeightMap h;
+        h.width = (dims_[0] + 2) * 32;
+        h.depth = (dims_[2] + 2) * 32;
+        const size_t n = (size_t)h.width * h.depth;
+        h.height.resize(n);
+        h.elevation.resize(n);
+        h.raw_height.resize(n);
+        gpu_.check(bxw_region_heightmap(gpu_.raw(), h.height.data(), h.elevation.data(), h.raw_height.data()));
+        return h;
+    }
+    // mesh the chunks inside one load-anchor sphere, nearest first (iter_coords_to_load, worldmgr.rs:734-746): {chunks meshed,
+    // arena vertices, arena indices}
+    std::array<uint64_t, 3> mesh_sphere(ChunkPosition anchor, uint32_t radius) {
+        gpu_.bind(registry_);
+        uint32_t n = 0;
+        uint64_t v = 0, i = 0;
+        gpu_.check(bxw_region_mesh_sphere(gpu_.raw(), anchor.x, anchor.y, anchor.z, radius, &n, &v, &i));
+        return {{n, v, i}};
+    }
+    bxw_arena_stats arena_stats() const {
+        bxw_arena_stats st{};
+        gpu_.check(bxw_region_arena_stats(gpu_.raw(), &st));
+        return st;
+    }
+    std::pair<uint64_t, uint64_t> compact_arena() { // spans' offsets change
+        uint64_t v = 0, i = 0;
+        gpu_.check(bxw_region_compact_arena(gpu_.raw(), &v, &i));
+        return {v, i};
+    }
+    // the two load states of the reference's handlers (CHUNK_BLOCK_DATA, CHUNK_MESH_DATA): {blocks loaded: every chunk of the box
+    // with its shell, storage order x + SX (z + SZ y); mesh loaded: interior chunks, span order}
+    std::pair<std::vector<uint8_t>, std::vector<uint8_t>> load_state() const {
+        std::vector<uint8_t> b((size_t)(dims_[0] + 2) * (dims_[1] + 2) * (dims_[2] + 2)), m(n_chunks());
+        gpu_.check(bxw_region_load_state(gpu_.raw(), b.data(), m.data()));
+        return {b, m};
+    }
+    // hashed random blocks incl. oriented slopes / corners (BASELINE configs[1])
+    void fill_synthetic(uint64_t seed, uint32_t void_threshold) { gpu_.check(bxw_region_fill_synthetic(gpu_.raw(), seed, void_threshold)); }
+    // {chunks listed by the last whole-region mesh pass, interior chunks}
+    std::pair<uint32_t, uint32_t> mesh_candidates() const {
+        uint32_t a = 0, b = 0;
+        gpu_.check(bxw_region_mesh_candidates(gpu_.raw(), &a, &b));
+        return {a, b};
     }
 
   private:

@@ -282,6 +282,88 @@ static void load_anchor_ticks() {
     CHECK(sorted);
 }
 
+// ---- the rest of the C ABI through the mirror: dense chunks in / out, per-chunk fetch, raw column parameters, split
+// generation, sphere pass, arena bookkeeping, moving the box ----
+static void region_plumbing() {
+    Region region(*g_gpu, {3, 0, -4}, {4, 3, 3}, *g_reg);
+    StdGenerator gen(*g_gpu, 7);
+    region.generate(gen);
+    // split generation (boundary columns, then the rest on the side stream) = one call
+    const UncompressedChunk whole = region.download(0, 1, 1), shell = region.download(-1, 0, 3);
+    region.generate_part(gen, 1);
+    region.generate_part(gen, 2);
+    CHECK(region.download(0, 1, 1).blocks_yzx == whole.blocks_yzx && region.download(-1, 0, 3).blocks_yzx == shell.blocks_yzx);
+    // the generator's chunk = the region's chunk
+    UncompressedChunk one;
+    one.position = {3 + 2, 0 + 1, -4 + 1};
+    gen.generate_chunk(one, *g_reg);
+    CHECK(region.download(2, 1, 1).blocks_yzx == one.blocks_yzx);
+    // raw column parameters against the oracle
+    const auto hm = region.heightmap();
+    CHECK(hm.width == 6 * 32 && hm.depth == 5 * 32);
+    bxo_stdgen *og = bxo_stdgen_new(7);
+    bool same = true;
+    for (uint32_t k = 0; k < 200; k++) {
+        const uint32_t ix = (k * 37u) % hm.width, iz = (k * 91u) % hm.depth;
+        bxo_voxel_params vp;
+        bxo_calc_voxel_params(og, (3 - 1) * 32 + (int32_t)ix, (-4 - 1) * 32 + (int32_t)iz, &vp);
+        same &= hm.height[(size_t)iz * hm.width + ix] == vp.height;
+    }
+    bxo_stdgen_free(og);
+    CHECK(same);
+    // whole pass, then one chunk's buffers by range = the same bytes inside the arena
+    const auto arena = region.mesh();
+    const auto spans = region.spans();
+    const ChunkBuffers all = region.fetch_arena(arena.first, arena.second);
+    size_t best = 0;
+    for (size_t i = 0; i < spans.size(); i++)
+        if (spans[i].v_count > spans[best].v_count) best = i;
+    const ChunkBuffers mine = region.fetch_chunk(spans[best]);
+    CHECK(mine.vertices.size() == spans[best].v_count && spans[best].v_count > 0);
+    CHECK(std::memcmp(mine.vertices.data(), all.vertices.data() + spans[best].v_off, mine.vertices.size() * sizeof(bxw_vertex)) == 0);
+    CHECK(std::memcmp(mine.indices.data(), all.indices.data() + spans[best].i_off, mine.indices.size() * sizeof(uint32_t)) == 0);
+    // asynchronous fetch = synchronous fetch
+    ChunkBuffers again;
+    again.vertices.resize(arena.first);
+    again.indices.resize(arena.second);
+    region.fetch_async(again.vertices.data(), arena.first, again.indices.data(), arena.second);
+    region.fetch_wait();
+    CHECK(std::memcmp(again.vertices.data(), all.vertices.data(), arena.first * sizeof(bxw_vertex)) == 0);
+    const auto cand = region.mesh_candidates();
+    CHECK(cand.second == 4 * 3 * 3 && cand.first <= cand.second && cand.first > 0);
+    // arena bookkeeping: nothing is garbage after a whole pass; compaction keeps every mesh
+    const bxw_arena_stats st = region.arena_stats();
+    CHECK(st.vertices_used == arena.first && st.vertices_garbage == 0 && st.vertices_capacity >= st.vertices_used);
+    const auto compacted = region.compact_arena();
+    CHECK(compacted.first <= arena.first);
+    const ChunkBuffers moved = region.fetch_chunk(region.spans()[best]);
+    CHECK(moved.vertices.size() == mine.vertices.size() &&
+          std::memcmp(moved.vertices.data(), mine.vertices.data(), mine.vertices.size() * sizeof(bxw_vertex)) == 0);
+    // the sphere pass meshes a subset, every chunk of the box holds block data, and meshes only inside the sphere
+    const auto sph = region.mesh_sphere({4, 1, -3}, 1);
+    CHECK(sph[0] == 7); // centre + six neighbours, all inside the box
+    const auto ls = region.load_state();
+    CHECK(ls.first.size() == 6 * 5 * 5 && ls.second.size() == 4 * 3 * 3);
+    // upload a dense chunk, read it back
+    UncompressedChunk custom;
+    for (size_t i = 0; i < custom.blocks_yzx.size(); i++) custom.blocks_yzx[i] = (i % 3 == 0) ? VoxelDatum(4, 0).repr : 0u;
+    region.upload(1, 1, 1, custom);
+    CHECK(region.download(1, 1, 1).blocks_yzx == custom.blocks_yzx);
+    // the box moves: generation there equals the generator's chunks at the new position
+    region.set_origin({-20, 0, 11});
+    region.generate(gen);
+    one.position = {-20 + 1, 0, 11 + 2};
+    gen.generate_chunk(one, *g_reg);
+    CHECK(region.download(1, 0, 2).blocks_yzx == one.blocks_yzx);
+    // raw noise: the generator's elevation noise through the mirror equals the oracle's
+    const std::vector<double> xs = {0.25, -3.5, 100.125}, ys = {7.0, 0.5, -42.75};
+    const auto ns = g_gpu->stdgen_noise(7, 5, xs, ys);
+    CHECK(ns.size() == 3 && ns[0] >= -1.0 && ns[0] <= 1.0);
+    g_gpu->synchronize();
+    const auto kt = g_gpu->kernel_time_ms(BXW_KERNEL_MESH, true);
+    CHECK(kt.second > 0);
+}
+
 int main() {
     try {
         Gpu gpu(0);
@@ -303,6 +385,7 @@ int main() {
         RUN(region_generate_and_mesh_cfg1);
         RUN(apply_voxel_changes_and_remesh);
         RUN(load_anchor_ticks);
+        RUN(region_plumbing);
         std::printf("test result: %s. %d passed; %d failed; %llu kernel launches\n", g_failed ? "FAILED" : "ok", g_run - g_failed, g_failed,
                     (unsigned long long)gpu.kernel_launches());
     } catch (const std::exception &e) {
