@@ -61,29 +61,14 @@ def finish_exchange(slab, works, bufs, import_plane):
 
 
 def exchange_halos(slab, dist, bufs, export_plane, import_plane):
-    """One halo exchange.
+    """One halo exchange, start to finish (nothing overlapped).
 
     bufs: dict with tensors send_lo, send_hi, recv_lo, recv_hi (same shape/dtype/device).
     export_plane(face, tensor): pack this rank's own boundary plane at face 0 (x-) / 1 (x+) into tensor.
     import_plane(face, tensor): write a received plane into this rank's shell at that face.
     The x- plane of rank r becomes the x+ shell of rank r-1 and vice versa.
     """
-    ops = []
-    if slab.has_lo:
-        export_plane(0, bufs["send_lo"])
-        ops.append(dist.P2POp(dist.isend, bufs["send_lo"], slab.rank - 1))
-        ops.append(dist.P2POp(dist.irecv, bufs["recv_lo"], slab.rank - 1))
-    if slab.has_hi:
-        export_plane(1, bufs["send_hi"])
-        ops.append(dist.P2POp(dist.isend, bufs["send_hi"], slab.rank + 1))
-        ops.append(dist.P2POp(dist.irecv, bufs["recv_hi"], slab.rank + 1))
-    if ops:
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-    if slab.has_lo:
-        import_plane(0, bufs["recv_lo"])
-    if slab.has_hi:
-        import_plane(1, bufs["recv_hi"])
+    finish_exchange(slab, start_exchange(slab, dist, bufs, export_plane), bufs, import_plane)
 
 
 def rebalance_slabs(widths, costs, min_width=8):
