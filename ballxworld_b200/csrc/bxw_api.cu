@@ -61,7 +61,8 @@ struct Region {
     bxw_mesh_span *spans_bak = nullptr;    // re-mesh passes: spans / reservations before the pass (restored if the arena must grow)
     uint2 *span_cap_bak = nullptr;
     // cubes-only mesher: chunks it hands over to the general kernel; shape_hint: 0 = storage holds generator output and edits
-    // only (cubes, the odd edited shape), 2 = bulk content of unknown shapes (synthetic fill, uploads, imports)
+    // with cubes only, 1 = an edit placed a slope / corner (re-mesh passes over the dirty chunks then go straight to the general
+    // kernel instead of failing over chunk by chunk), 2 = bulk content of unknown shapes (synthetic fill)
     uint32_t *fb_work = nullptr, *fb_span = nullptr, *fb_count = nullptr;
     int shape_hint = 0;
     bool streaming = false;                // load-anchor mode (bxw_region_unload_all / _update_anchors): chunks carry load states
@@ -638,7 +639,7 @@ int region_mesh(bxw_ctx *ctx, Region &r, const uint32_t *work, const uint32_t *w
         p.work_span = r.dirty_span;
         p.n_work_dev = r.dirty_count;
     }
-    const bool lean = ctx->lean_mesher && !from_hmap && r.shape_hint < 2;
+    const bool lean = ctx->lean_mesher && !from_hmap && r.shape_hint < 2 && !(append && r.shape_hint == 1);
     p.fallback_work = r.fb_work;
     p.fallback_span = r.fb_span;
     p.fallback_count = r.fb_count;
@@ -1624,6 +1625,8 @@ int bxw_region_apply_changes(bxw_ctx *ctx, const bxw_voxel_change *changes, uint
     };
     std::vector<Keyed> keyed;
     keyed.reserve(n);
+    for (uint32_t i = 0; i < n && r.shape_hint == 0; i++)
+        if ((changes[i].to & 63u) - 1u < 3u) r.shape_hint = 1; // a slope / corner arrives (StdMeta: shape = meta % 64)
     for (uint32_t i = 0; i < n; i++) {
         const int64_t gx = (int64_t)changes[i].x - x_min, gy = (int64_t)changes[i].y - y_min, gz = (int64_t)changes[i].z - z_min;
         if (gx < 0 || gy < 0 || gz < 0 || gx >= (int64_t)r.SX * 32 || gy >= (int64_t)r.SY * 32 || gz >= (int64_t)r.SZ * 32) continue;
