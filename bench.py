@@ -771,7 +771,9 @@ def main():
             "everything_materialised": {"ms_per_step": mat_ms, "value": total_chunks / (mat_ms / 1000.0), "unit": UNIT,
                                         "note": "BXW_OPT_ELIDE_UNIFORM=0 (round 1's storage): every chunk written voxel by voxel"},
             "fused_generate_and_mesh": None if fused_ms is None else {"ms_per_step": fused_ms, "value": n_chunks / (fused_ms / 1000.0), "unit": UNIT,
-                                                                      "note": "bxw_region_generate_and_mesh with BXW_OPT_MESH_FROM_HEIGHT_MAP=1"},
+                                                                      "note": "bxw_region_generate_and_mesh with BXW_OPT_MESH_FROM_HEIGHT_MAP=1 (phase A derives the 34^3 table from the column "
+                                                                              "parameters instead of reading voxels; since the cubes-only kernel of round 2 it is SLOWER than the "
+                                                                              "default step and stays an option)"},
             "mesh": {"vertices": tot_v_all, "indices": tot_i_all, "arena_vertices": av, "arena_indices": ai},
             "per_rank": per_rank, "slab_rebalance": rebalance, "multi_gpu_parity": parity, "cfg5_edits": edits_leg, "cfg2_mesh_only": cfg2, "cfg4_literal": cfg4,
         }
