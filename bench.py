@@ -9,6 +9,10 @@ slab (shell included) -> [N>1: slab-boundary halo exchange over NCCL] -> mesh ev
   value : chunks/s, device-resident (CUDA events on the library's stream, max over ranks), whole job
   e2e   : the same metric through the public API with HOST buffers: generate+mesh, then the meshes and the span
           table are copied to pinned host memory inside the timed region
+N>1: the world is N x 128 chunk columns wide; after the warm-up the ranks re-cut it into slabs of equal measured cost (same world,
+same total; `slab_rebalance` in the line), and the timed steps run on that cut.
+Extra legs in the same line (skipped with --no-extra-legs): everything_materialised, the streaming mesher figure
+(`roofline.frac`), fused_generate_and_mesh, cfg2_mesh_only (N=1), cfg5_edits, and for N>1 multi_gpu_parity, per_rank, cfg4_literal.
 Rank 0 prints ONE JSON line. See DESIGN.md "Measurement" for the roofline / cpu_baseline definitions.
 """
 import argparse
